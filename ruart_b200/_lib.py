@@ -1,0 +1,86 @@
+"""ctypes binding of libruart_b200.so (the C ABI declared in include/ruart_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  `lib()` loads the in-tree .so (building it with nvcc if it is absent
+and a compiler is available).
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libruart_b200.so")
+_HEADER = os.path.join(os.path.dirname(_HERE), "include", "ruart_b200.h")
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_i64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "ruart_last_error": [],
+    "ruart_version": [],
+    "ruart_num_sms": [],
+    "ruart_phoc_batch": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p],
+    "ruart_phoc_batch_packed": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p],
+    "ruart_phoc_batch_host": [ctypes.c_char_p, c_void_p, c_i64, c_void_p,
+                              ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int32)],
+    "ruart_gemm_bf16": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
+                        c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
+                        c_ll, c_int, c_void_p],
+}
+_RESTYPES = {"ruart_last_error": ctypes.c_char_p}
+
+
+def declared_symbols():
+    """Every function name declared in include/ruart_b200.h."""
+    with open(_HEADER) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"RUART_API\s+[\w\s\*]+?\b(ruart_\w+)\s*\(", text)))
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError("ruart_b200: %s is missing and could not be built; there is no "
+                           "non-CUDA fallback" % _LIB_PATH)
+    L = ctypes.CDLL(_LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().ruart_last_error()
+        raise RuntimeError("ruart_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def call(name, *args):
+    """Call a C-ABI function by name and raise on a non-zero return code."""
+    check(getattr(lib(), name)(*args))
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

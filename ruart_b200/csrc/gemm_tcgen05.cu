@@ -1,0 +1,406 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T (+ epilogue)
+//
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> 4-stage smem ring -> tcgen05.mma (kind::f16,
+//   fp32 accumulators in TMEM, double-buffered 2 x 256 columns) -> tcgen05.ld epilogue.
+//
+// It replaces every nn.Linear / F.linear on RUArt's hot path:
+//   BERT  query/key/value (Models/Bert/modeling.py:225-227, fused into one N=2304 GEMM),
+//         BertSelfOutput.dense (:261), BertIntermediate.dense + gelu (:287-288),
+//         BertOutput.dense (:300)
+//   SDNet AttentionScore.linear (+ReLU, *diagonal) (Models/Layers.py:226-231),
+//         the LSTM input projections W_ih x + b_ih + b_hh of every nn.LSTM (Layers.py:137,166).
+//
+// "Split" operands give fp32-grade accuracy on bf16 tensor cores: an fp32 matrix X is stored as
+// up to three bf16 parts X = X0 + X1 + X2 laid side by side ([rows, nparts*Kp]); the K loop then
+// walks a list of (part_a, part_b) terms (1 term: plain bf16; 3 terms: ~2^-16; 6 terms: ~2^-24).
+#include <cuda.h>
+#include "common.cuh"
+#include "ruart_b200.h"
+
+namespace {
+
+using namespace ruart;
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int MAX_BN = 256;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
+constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;  // 32 KB
+constexpr int BAR_BYTES = 256;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + BAR_BYTES + 1024;
+constexpr int GEMM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+struct GemmParams {
+  int M, N, Kp;
+  int block_n;
+  int n_terms;
+  uint32_t term_a, term_b;  // 4 bits per term: which part of A / W
+  int epi;
+  const float* bias;   // [N] or nullptr
+  const float* scale;  // [N] (scale_stride = 1) or [1] (scale_stride = 0), epi == RELU_SCALE
+  int scale_stride;
+  float* out_f32;
+  long long ldo_f32;
+  __nv_bfloat16* out_bf16;
+  long long ldo_bf16;
+  int out_parts;           // 1: plain bf16; 2/3: hi|mid|lo split parts
+  long long out_part_stride;  // elements between parts inside one row
+  int fast_gelu;
+};
+
+__device__ __forceinline__ float apply_epi(float acc, int epi, float b, float s, int fast_gelu) {
+  switch (epi) {
+    case RUART_EPI_NONE:
+      return acc;
+    case RUART_EPI_BIAS:
+      return acc + b;
+    case RUART_EPI_BIAS_GELU:
+      return fast_gelu ? gelu_erf_fast(acc + b) : gelu_erf(acc + b);
+    case RUART_EPI_RELU_SCALE:
+      return fmaxf(acc, 0.0f) * s;
+    case RUART_EPI_BIAS_RELU:
+      return fmaxf(acc + b, 0.0f);
+    default:
+      return acc;
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + p.block_n - 1) / p.block_n;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = p.Kp / BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BK * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles;
+        const int n_blk = tile - m_blk * n_tiles;
+        for (int t = 0; t < p.n_terms; ++t) {
+          const int pa = (p.term_a >> (4 * t)) & 0xF;
+          const int pb = (p.term_b >> (4 * t)) & 0xF;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * A_STAGE_BYTES,
+                        pa * p.Kp + kb * BK, m_blk * BM);
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * B_STAGE_BYTES,
+                        pb * p.Kp + kb * BK, n_blk * p.block_n);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(BM, p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int iters = p.n_terms * k_blocks;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * MAX_BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may touch
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                               static_cast<uint32_t>(acc * MAX_BN + c0);
+        __syncwarp();
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * p.block_n + c0;
+        if (col0 >= p.N) break;  // warp-uniform: the rest of this tile is past the last column
+        const bool full_chunk = (col0 + 32 <= p.N);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float b = 0.0f, s = 1.0f;
+          if (full_chunk || col < p.N) {
+            if (p.bias != nullptr) b = __ldg(p.bias + col);
+            if (p.epi == RUART_EPI_RELU_SCALE) s = __ldg(p.scale + col * p.scale_stride);
+          }
+          f[j] = apply_epi(__uint_as_float(v[j]), p.epi, b, s, p.fast_gelu);
+        }
+        if (row_ok && p.out_f32 != nullptr) {
+          float* dst = p.out_f32 + static_cast<long long>(row) * p.ldo_f32 + col0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = f[j];
+          }
+        }
+        if (row_ok && p.out_bf16 != nullptr) {
+#pragma unroll 1
+          for (int part = 0; part < p.out_parts; ++part) {
+            __nv_bfloat16* dst = p.out_bf16 + static_cast<long long>(row) * p.ldo_bf16 +
+                                 static_cast<long long>(part) * p.out_part_stride + col0;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(f[j]);
+              const __nv_bfloat16 h1 = __float2bfloat16_rn(f[j + 1]);
+              pk[j / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                          (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+              f[j] -= __bfloat162float(h0);  // residual feeds the next (finer) part
+              f[j + 1] -= __bfloat162float(h1);
+            }
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4*>(dst + 2 * j) =
+                    make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N)
+                  dst[j] = __ushort_as_bfloat16(
+                      static_cast<unsigned short>((pk[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// --------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64].
+int make_tmap_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld,
+                   int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    ruart_set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return RUART_ERR_NO_DRIVER;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ruart_set_error("cuTensorMapEncodeTiled failed: %d (base=%p rows=%lld cols=%lld ld=%lld box=%d)",
+                    (int)r, base, rows, cols, ld, box_rows);
+    return RUART_ERR_CUDA;
+  }
+  return RUART_OK;
+}
+
+int pick_block_n(int N) {
+  // N tile: multiple of 32 (epilogue chunk) and <= 256; prefer the largest tile that wastes the
+  // least of the last column block.
+  if (N >= 256) {
+    int best = 256, best_waste = 1 << 30;
+    for (int bn = 256; bn >= 128; bn -= 32) {
+      const int tiles = (N + bn - 1) / bn;
+      const int waste = tiles * bn - N;
+      if (waste < best_waste) {
+        best_waste = waste;
+        best = bn;
+      }
+    }
+    return best;
+  }
+  return ((N + 31) / 32) * 32;
+}
+
+}  // namespace
+
+extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const void* W,
+                               long long ldw, int w_parts, int M, int N, int Kp, int n_terms,
+                               int epi, const float* bias, const float* scale, int scale_len,
+                               float* out_f32, long long ldo_f32, void* out_bf16,
+                               long long ldo_bf16, int out_parts, long long out_part_stride,
+                               int fast_gelu, void* stream) {
+  RUART_ARG_CHECK(M >= 0 && N > 0 && Kp > 0 && (Kp % BK) == 0);
+  RUART_ARG_CHECK(a_parts >= 1 && a_parts <= 3 && w_parts >= 1 && w_parts <= 3);
+  RUART_ARG_CHECK(n_terms == 1 || n_terms == 3 || n_terms == 6);
+  RUART_ARG_CHECK((lda % 8) == 0 && (ldw % 8) == 0);
+  RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(A) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(W) & 15u) == 0);
+  RUART_ARG_CHECK(out_f32 != nullptr || out_bf16 != nullptr);
+  RUART_ARG_CHECK(out_parts >= 1 && out_parts <= 3);
+  if (epi == RUART_EPI_RELU_SCALE) RUART_ARG_CHECK(scale != nullptr && scale_len >= 1);
+  if (epi == RUART_EPI_BIAS || epi == RUART_EPI_BIAS_GELU || epi == RUART_EPI_BIAS_RELU)
+    RUART_ARG_CHECK(bias != nullptr);
+  if (M == 0) return RUART_OK;
+
+  // term tables: (a part, w part).  Order: smallest products first so they are not swamped.
+  uint32_t ta = 0, tb = 0;
+  if (n_terms == 1) {
+    ta = 0;
+    tb = 0;
+  } else if (n_terms == 3) {
+    RUART_ARG_CHECK(a_parts >= 2 && w_parts >= 2);
+    // (1,0) (0,1) (0,0)
+    ta = 0x001;
+    tb = 0x010;
+  } else {
+    RUART_ARG_CHECK(a_parts >= 3 && w_parts >= 3);
+    // (1,1) (2,0) (0,2) (1,0) (0,1) (0,0)
+    ta = 0x001021;
+    tb = 0x010201;
+  }
+
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.Kp = Kp;
+  p.block_n = pick_block_n(N);
+  p.n_terms = n_terms;
+  p.term_a = ta;
+  p.term_b = tb;
+  p.epi = epi;
+  p.bias = bias;
+  p.scale = scale;
+  p.scale_stride = (scale_len > 1) ? 1 : 0;
+  p.out_f32 = out_f32;
+  p.ldo_f32 = ldo_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.ldo_bf16 = ldo_bf16;
+  p.out_parts = out_parts;
+  p.out_part_stride = out_part_stride;
+  p.fast_gelu = fast_gelu;
+
+  CUtensorMap tma, tmb;
+  int rc = make_tmap_bf16(&tma, A, M, (long long)a_parts * Kp, lda, BM);
+  if (rc != RUART_OK) return rc;
+  rc = make_tmap_bf16(&tmb, W, N, (long long)w_parts * Kp, ldw, p.block_n);
+  if (rc != RUART_OK) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          GEMM_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + p.block_n - 1) / p.block_n;
+  const int total = m_tiles * n_tiles;
+  const int grid = total < ruart_num_sms() ? total : ruart_num_sms();
+  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb,
+                                                                                          p);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}

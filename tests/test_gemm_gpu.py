@@ -1,0 +1,99 @@
+"""GPU: tcgen05 GEMM against torch fp32 matmul of the same (bf16-rounded) operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias, epi, scale):
+    c = a.float() @ w.float().t()
+    if epi in (1, 2, 4):
+        c = c + bias
+    if epi == 2:
+        c = torch.nn.functional.gelu(c)
+    if epi == 3:
+        c = torch.relu(c) * scale
+    if epi == 4:
+        c = torch.relu(c)
+    return c
+
+
+@pytest.mark.parametrize("M,N,K,epi", [
+    (128, 256, 64, 0), (128, 256, 768, 0), (256, 768, 768, 1), (1000, 2304, 768, 1),
+    (333, 3072, 768, 2), (517, 768, 3072, 1), (77, 1000, 320, 1), (4096, 1200, 1408, 1),
+    (130, 250, 832, 3), (64, 125, 256, 3), (1, 32, 64, 0), (5000, 768, 768, 1),
+    (40000, 2304, 768, 1),
+])
+def test_gemm_bf16(M, N, K, epi):
+    from ruart_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    scale = torch.rand(N, device="cuda", generator=g) + 0.5
+    out32 = torch.full((M, N), float("nan"), device="cuda")
+    out16 = torch.zeros((M, N + 8), device="cuda", dtype=torch.bfloat16)[:, :N]
+    ops.gemm(a, w, M, N, K, epi=epi, bias=bias if epi in (1, 2, 4) else None,
+             scale=scale if epi == 3 else None, out_f32=out32, out_bf16=out16)
+    torch.cuda.synchronize()
+    want = _ref(a, w, bias, epi, scale)
+    err = (out32 - want).abs().max().item()
+    tol = 2e-3 * max(1.0, want.abs().max().item())
+    assert err < tol, (err, tol)
+    err16 = (out16.float() - want).abs().max().item()
+    assert err16 < 1e-2 * max(1.0, want.abs().max().item())
+
+
+def test_gemm_scalar_scale_and_fast_gelu():
+    from ruart_b200 import ops
+    M, N, K = 300, 300, 320
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    s = torch.tensor([0.0577], device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(a, w, M, N, K, epi=3, scale=s, out_f32=out)
+    want = torch.relu(a.float() @ w.float().t()) * s
+    assert (out - want).abs().max().item() < 1e-3
+    bias = torch.randn(N, device="cuda")
+    ops.gemm(a, w, M, N, K, epi=2, bias=bias, out_f32=out, fast_gelu=True)
+    want = torch.nn.functional.gelu(a.float() @ w.float().t() + bias)
+    assert (out - want).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("terms,tol", [(3, 3e-5), (6, 2e-6)])
+def test_gemm_split_terms_reach_fp32_accuracy(terms, tol):
+    from ruart_b200 import ops
+    M, N, K = 513, 384, 300
+    Kp = 320
+    parts = 2 if terms == 3 else 3
+    a = torch.randn(M, K, device="cuda", dtype=torch.float64)
+    w = torch.randn(N, K, device="cuda", dtype=torch.float64) * 0.1
+
+    def split(x):
+        x = x.float()
+        buf = torch.zeros(x.shape[0], parts * Kp, device="cuda", dtype=torch.bfloat16)
+        r = x.clone()
+        for p in range(parts):
+            h = r.bfloat16()
+            buf[:, p * Kp:p * Kp + K] = h
+            r = r - h.float()
+        return buf
+
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(split(a), split(w), M, N, Kp, a_parts=parts, w_parts=parts, n_terms=terms, out_f32=out)
+    want = a.float().double() @ w.float().double().t()
+    rel = ((out.double() - want).abs().max() / want.abs().max()).item()
+    assert rel < tol, rel
+
+
+def test_gemm_split_output_parts():
+    from ruart_b200 import ops
+    M, N, K = 200, 128, 128
+    a = (torch.randn(M, K, device="cuda")).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    out = torch.zeros(M, 3 * 192, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, M, N, K, out_bf16=out, out_parts=3, out_part_stride=192)
+    want = a.float() @ w.float().t()
+    recon = out[:, 0:N].float() + out[:, 192:192 + N].float() + out[:, 384:384 + N].float()
+    assert (recon - want).abs().max().item() < 2e-5 * want.abs().max().item() + 1e-6
+    assert out[:, N:192].abs().max().item() == 0
