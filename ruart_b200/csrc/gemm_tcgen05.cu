@@ -27,55 +27,79 @@ constexpr int MAX_BN = 256;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;  // 32 KB
+constexpr int C_STAGE_BYTES = BM * 64 * 2;      // 16 KB: 128 rows x 64 bf16, TMA-store staging
+constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+constexpr int OFF_C = OFF_B + STAGES * B_STAGE_BYTES;
+constexpr int OFF_VEC = OFF_C + 2 * C_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_VEC + MAX_BN * 4;
 constexpr int BAR_BYTES = 256;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + BAR_BYTES + 1024;
+constexpr int GEMM_SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
 constexpr int GEMM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
+static_assert(GEMM_SMEM_BYTES <= 232448, "shared memory budget");
+
+// epilogue kinds as compiled (the ABI's RUART_EPI_BIAS_GELU maps to one of the two GELUs)
+enum : int { K_NONE = 0, K_BIAS, K_GELU_FAST, K_GELU_EXACT, K_RELU_SCALE, K_BIAS_RELU, K_NUM };
 
 struct GemmParams {
   int M, N, Kp;
   int block_n;
   int n_terms;
   uint32_t term_a, term_b;  // 4 bits per term: which part of A / W
-  int epi;
-  const float* bias;   // [N] or nullptr
-  const float* scale;  // [N] (scale_stride = 1) or [1] (scale_stride = 0), epi == RELU_SCALE
-  int scale_stride;
+  const float* vec;         // bias [N] or scale ([N] or [1]); nullptr for K_NONE
+  int vec_stride;           // 1, or 0 for a broadcast scalar
   float* out_f32;
   long long ldo_f32;
   __nv_bfloat16* out_bf16;
   long long ldo_bf16;
-  int out_parts;           // 1: plain bf16; 2/3: hi|mid|lo split parts
+  int out_parts;              // 1: plain bf16; 2/3: hi|mid|lo split parts
   long long out_part_stride;  // elements between parts inside one row
-  int fast_gelu;
 };
 
-__device__ __forceinline__ float apply_epi(float acc, int epi, float b, float s, int fast_gelu) {
-  switch (epi) {
-    case RUART_EPI_NONE:
-      return acc;
-    case RUART_EPI_BIAS:
-      return acc + b;
-    case RUART_EPI_BIAS_GELU:
-      return fast_gelu ? gelu_erf_fast(acc + b) : gelu_erf(acc + b);
-    case RUART_EPI_RELU_SCALE:
-      return fmaxf(acc, 0.0f) * s;
-    case RUART_EPI_BIAS_RELU:
-      return fmaxf(acc + b, 0.0f);
-    default:
-      return acc;
-  }
+template <int EPI>
+__device__ __forceinline__ float epi_fn(float acc, float v) {
+  if constexpr (EPI == K_NONE) return acc;
+  if constexpr (EPI == K_BIAS) return acc + v;
+  if constexpr (EPI == K_GELU_FAST) return gelu_erf_fast(acc + v);
+  if constexpr (EPI == K_GELU_EXACT) return gelu_erf(acc + v);
+  if constexpr (EPI == K_RELU_SCALE) return fmaxf(acc, 0.0f) * v;
+  if constexpr (EPI == K_BIAS_RELU) return fmaxf(acc + v, 0.0f);
+  return acc;
 }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   tmap),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// EPI: epilogue kind.  TMA_OUT: plain bf16 output written with swizzled smem staging + TMA
+// stores (the BERT path); otherwise generic direct stores (fp32 and/or split bf16 outputs).
+template <int EPI, bool TMA_OUT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* smem_b = smem + OFF_B;
+  uint8_t* smem_c = smem + OFF_C;
+  float* s_vec = reinterpret_cast<float*>(smem + OFF_VEC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full_bar = bars + 2 * STAGES;
@@ -88,6 +112,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (TMA_OUT) tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -177,83 +202,135 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps)
     const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may touch
+    const int et = threadIdx.x - 128;
+    const int r_local = ew * 32 + lane;
+    const bool issuer = (et == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
+      const int tile_col0 = n_blk * p.block_n;
+      // stage this tile's bias / scale slice (previous tile's readers are past their last barrier)
+      if (EPI != K_NONE) {
+        for (int i = et; i < p.block_n; i += 128) {
+          const int col = tile_col0 + i;
+          s_vec[i] = (col < p.N) ? __ldg(p.vec + static_cast<long long>(col) * p.vec_stride) : 0.0f;
+        }
+      }
+      if (!TMA_OUT) epi_bar_sync();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + ew * 32 + lane;
-      const bool row_ok = row < p.M;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
-                               static_cast<uint32_t>(acc * MAX_BN + c0);
-        __syncwarp();
-        tmem_ld_32x32b_x32(taddr, v);
-        tmem_ld_wait();
-        const int col0 = n_blk * p.block_n + c0;
-        if (col0 >= p.N) break;  // warp-uniform: the rest of this tile is past the last column
-        const bool full_chunk = (col0 + 32 <= p.N);
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float b = 0.0f, s = 1.0f;
-          if (full_chunk || col < p.N) {
-            if (p.bias != nullptr) b = __ldg(p.bias + col);
-            if (p.epi == RUART_EPI_RELU_SCALE) s = __ldg(p.scale + col * p.scale_stride);
+      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                                static_cast<uint32_t>(acc * MAX_BN);
+      if constexpr (TMA_OUT) {
+        for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+          uint8_t* cbuf = smem_c + (chunk_ctr & 1u) * C_STAGE_BYTES;
+          if (issuer) bulk_wait_read<1>();  // the store that last used this buffer has read it
+          epi_bar_sync();                   // ... and everybody knows (also publishes s_vec)
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(tmem_acc + c0, v0);
+          tmem_ld_32x32b_x32(tmem_acc + c0 + 32, v1);
+          tmem_ld_wait();
+          if (c0 + 64 >= p.block_n) {  // last TMEM read of this tile: hand the accumulator back
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[acc]);
           }
-          f[j] = apply_epi(__uint_as_float(v[j]), p.epi, b, s, p.fast_gelu);
-        }
-        if (row_ok && p.out_f32 != nullptr) {
-          float* dst = p.out_f32 + static_cast<long long>(row) * p.ldo_f32 + col0;
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+          uint8_t* row_ptr = cbuf + r_local * 128;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
+          for (int c = 0; c < 8; ++c) {
+            uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) dst[j] = f[j];
-          }
-        }
-        if (row_ok && p.out_bf16 != nullptr) {
-#pragma unroll 1
-          for (int part = 0; part < p.out_parts; ++part) {
-            __nv_bfloat16* dst = p.out_bf16 + static_cast<long long>(row) * p.ldo_bf16 +
-                                 static_cast<long long>(part) * p.out_part_stride + col0;
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(f[j]);
-              const __nv_bfloat16 h1 = __float2bfloat16_rn(f[j + 1]);
-              pk[j / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                          (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-              f[j] -= __bfloat162float(h0);  // residual feeds the next (finer) part
-              f[j + 1] -= __bfloat162float(h1);
+            for (int q = 0; q < 4; ++q) {
+              const int j = c * 8 + q * 2;  // column inside the 64-wide chunk
+              float x0, x1;
+              if (j < 32) {
+                x0 = __uint_as_float(v0[j]);
+                x1 = __uint_as_float(v0[j + 1]);
+              } else {
+                x0 = __uint_as_float(v1[j - 32]);
+                x1 = __uint_as_float(v1[j - 31]);
+              }
+              const float2 bv = *reinterpret_cast<const float2*>(s_vec + c0 + j);
+              pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x), epi_fn<EPI>(x1, bv.y));
             }
+            *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (issuer) {
+            tma_store_2d(&tmap_c, cbuf, tile_col0 + c0, m_blk * BM);
+            bulk_commit();
+          }
+          ++chunk_ctr;
+        }
+      } else {
+        const int row = m_blk * BM + r_local;
+        const bool row_ok = row < p.M;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(tmem_acc + c0, v);
+          tmem_ld_wait();
+          const int col0 = tile_col0 + c0;
+          if (col0 >= p.N) break;  // warp-uniform: the rest of this tile is past the last column
+          const bool full_chunk = (col0 + 32 <= p.N);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = epi_fn<EPI>(__uint_as_float(v[j]), s_vec[c0 + j]);
+          if (row_ok && p.out_f32 != nullptr) {
+            float* dst = p.out_f32 + static_cast<long long>(row) * p.ldo_f32 + col0;
             if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<uint4*>(dst + 2 * j) =
-                    make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N)
-                  dst[j] = __ushort_as_bfloat16(
-                      static_cast<unsigned short>((pk[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
+                if (col0 + j < p.N) dst[j] = f[j];
+            }
+          }
+          if (row_ok && p.out_bf16 != nullptr) {
+#pragma unroll 1
+            for (int part = 0; part < p.out_parts; ++part) {
+              __nv_bfloat16* dst = p.out_bf16 + static_cast<long long>(row) * p.ldo_bf16 +
+                                   static_cast<long long>(part) * p.out_part_stride + col0;
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(f[j]);
+                const __nv_bfloat16 h1 = __float2bfloat16_rn(f[j + 1]);
+                pk[j / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                            (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                f[j] -= __bfloat162float(h0);  // residual feeds the next (finer) part
+                f[j + 1] -= __bfloat162float(h1);
+              }
+              if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<uint4*>(dst + 2 * j) =
+                      make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N)
+                    dst[j] = __ushort_as_bfloat16(
+                        static_cast<unsigned short>((pk[j / 2] >> (16 * (j & 1))) & 0xFFFFu));
+              }
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        epi_bar_sync();  // s_vec may be overwritten for the next tile only after all reads
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (TMA_OUT && issuer) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -306,12 +383,12 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, long long rows, long long 
   return RUART_OK;
 }
 
-int pick_block_n(int N) {
-  // N tile: multiple of 32 (epilogue chunk) and <= 256; prefer the largest tile that wastes the
-  // least of the last column block.
+int pick_block_n(int N, int gran) {
+  // N tile: multiple of `gran` (32 for the direct-store epilogue, 64 for TMA stores), <= 256;
+  // prefer the largest tile that wastes the least of the last column block.
   if (N >= 256) {
     int best = 256, best_waste = 1 << 30;
-    for (int bn = 256; bn >= 128; bn -= 32) {
+    for (int bn = 256; bn >= 128; bn -= gran) {
       const int tiles = (N + bn - 1) / bn;
       const int waste = tiles * bn - N;
       if (waste < best_waste) {
@@ -321,7 +398,27 @@ int pick_block_n(int N) {
     }
     return best;
   }
-  return ((N + 31) / 32) * 32;
+  return ((N + gran - 1) / gran) * gran;
+}
+
+typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const GemmParams);
+
+template <int EPI>
+GemmKernel pick_kernel(bool tma_out) {
+  return tma_out ? gemm_bf16_tcgen05_kernel<EPI, true> : gemm_bf16_tcgen05_kernel<EPI, false>;
+}
+
+GemmKernel kernel_for(int kind, bool tma_out) {
+  switch (kind) {
+    case K_NONE: return pick_kernel<K_NONE>(tma_out);
+    case K_BIAS: return pick_kernel<K_BIAS>(tma_out);
+    case K_GELU_FAST: return pick_kernel<K_GELU_FAST>(tma_out);
+    case K_GELU_EXACT: return pick_kernel<K_GELU_EXACT>(tma_out);
+    case K_RELU_SCALE: return pick_kernel<K_RELU_SCALE>(tma_out);
+    case K_BIAS_RELU: return pick_kernel<K_BIAS_RELU>(tma_out);
+  }
+  return nullptr;
 }
 
 }  // namespace
@@ -340,67 +437,82 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
                   (reinterpret_cast<uintptr_t>(W) & 15u) == 0);
   RUART_ARG_CHECK(out_f32 != nullptr || out_bf16 != nullptr);
   RUART_ARG_CHECK(out_parts >= 1 && out_parts <= 3);
-  if (epi == RUART_EPI_RELU_SCALE) RUART_ARG_CHECK(scale != nullptr && scale_len >= 1);
-  if (epi == RUART_EPI_BIAS || epi == RUART_EPI_BIAS_GELU || epi == RUART_EPI_BIAS_RELU)
-    RUART_ARG_CHECK(bias != nullptr);
+  int kind = K_NONE;
+  const float* vec = nullptr;
+  int vec_stride = 1;
+  switch (epi) {
+    case RUART_EPI_NONE: kind = K_NONE; break;
+    case RUART_EPI_BIAS: kind = K_BIAS; vec = bias; break;
+    case RUART_EPI_BIAS_GELU: kind = fast_gelu ? K_GELU_FAST : K_GELU_EXACT; vec = bias; break;
+    case RUART_EPI_BIAS_RELU: kind = K_BIAS_RELU; vec = bias; break;
+    case RUART_EPI_RELU_SCALE:
+      kind = K_RELU_SCALE;
+      vec = scale;
+      RUART_ARG_CHECK(scale_len == 1 || scale_len >= N);
+      vec_stride = (scale_len > 1) ? 1 : 0;
+      break;
+    default: RUART_ARG_CHECK(!"unknown epilogue");
+  }
+  if (kind != K_NONE) RUART_ARG_CHECK(vec != nullptr);
   if (M == 0) return RUART_OK;
 
   // term tables: (a part, w part).  Order: smallest products first so they are not swamped.
   uint32_t ta = 0, tb = 0;
-  if (n_terms == 1) {
-    ta = 0;
-    tb = 0;
-  } else if (n_terms == 3) {
+  if (n_terms == 3) {
     RUART_ARG_CHECK(a_parts >= 2 && w_parts >= 2);
-    // (1,0) (0,1) (0,0)
-    ta = 0x001;
+    ta = 0x001;  // (1,0) (0,1) (0,0)
     tb = 0x010;
-  } else {
+  } else if (n_terms == 6) {
     RUART_ARG_CHECK(a_parts >= 3 && w_parts >= 3);
-    // (1,1) (2,0) (0,2) (1,0) (0,1) (0,0)
-    ta = 0x001021;
+    ta = 0x001021;  // (1,1) (2,0) (0,2) (1,0) (0,1) (0,0)
     tb = 0x010201;
   }
+
+  // plain bf16 output with TMA-compatible alignment -> staged TMA-store epilogue
+  const bool tma_out = out_f32 == nullptr && out_bf16 != nullptr && out_parts == 1 &&
+                       (ldo_bf16 % 8) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15u) == 0;
 
   GemmParams p;
   p.M = M;
   p.N = N;
   p.Kp = Kp;
-  p.block_n = pick_block_n(N);
+  p.block_n = pick_block_n(N, tma_out ? 64 : 32);
   p.n_terms = n_terms;
   p.term_a = ta;
   p.term_b = tb;
-  p.epi = epi;
-  p.bias = bias;
-  p.scale = scale;
-  p.scale_stride = (scale_len > 1) ? 1 : 0;
+  p.vec = vec;
+  p.vec_stride = vec_stride;
   p.out_f32 = out_f32;
   p.ldo_f32 = ldo_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.ldo_bf16 = ldo_bf16;
   p.out_parts = out_parts;
   p.out_part_stride = out_part_stride;
-  p.fast_gelu = fast_gelu;
 
-  CUtensorMap tma, tmb;
+  CUtensorMap tma, tmb, tmc;
   int rc = make_tmap_bf16(&tma, A, M, (long long)a_parts * Kp, lda, BM);
   if (rc != RUART_OK) return rc;
   rc = make_tmap_bf16(&tmb, W, N, (long long)w_parts * Kp, ldw, p.block_n);
   if (rc != RUART_OK) return rc;
+  if (tma_out) {
+    rc = make_tmap_bf16(&tmc, out_bf16, M, N, ldo_bf16, BM);
+    if (rc != RUART_OK) return rc;
+  } else {
+    tmc = tma;
+  }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    RUART_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+  GemmKernel kern = kernel_for(kind, tma_out);
+  static bool attr_set[K_NUM][2] = {};
+  if (!attr_set[kind][tma_out ? 1 : 0]) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           GEMM_SMEM_BYTES));
-    attr_set = true;
+    attr_set[kind][tma_out ? 1 : 0] = true;
   }
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + p.block_n - 1) / p.block_n;
   const int total = m_tiles * n_tiles;
   const int grid = total < ruart_num_sms() ? total : ruart_num_sms();
-  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb,
-                                                                                          p);
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, p);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

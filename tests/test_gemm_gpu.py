@@ -42,6 +42,16 @@ def test_gemm_bf16(M, N, K, epi):
     assert err < tol, (err, tol)
     err16 = (out16.float() - want).abs().max().item()
     assert err16 < 1e-2 * max(1.0, want.abs().max().item())
+    # bf16-only output: the TMA-store epilogue when the row pitch allows it (N % 8 == 0)
+    pitch = N + 8 if N % 8 == 0 else N
+    buf = torch.full((M + 1, pitch), 7.0, device="cuda", dtype=torch.bfloat16)
+    out_t = buf[:M, :N]
+    ops.gemm(a, w, M, N, K, epi=epi, bias=bias if epi in (1, 2, 4) else None,
+             scale=scale if epi == 3 else None, out_bf16=out_t)
+    torch.cuda.synchronize()
+    err_t = (out_t.float() - want).abs().max().item()
+    assert err_t < 1e-2 * max(1.0, want.abs().max().item()), err_t
+    assert (buf[M] == 7.0).all() and (buf[:, N:] == 7.0).all()  # nothing written out of bounds
 
 
 def test_gemm_scalar_scale_and_fast_gelu():

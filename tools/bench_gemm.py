@@ -1,0 +1,48 @@
+"""Micro-benchmark of the tcgen05 GEMM at the BERT shapes of BASELINE cfg-3 (valid tokens only).
+Usage (GPU box): python tools/bench_gemm.py [M]"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from ruart_b200 import ops  # noqa: E402
+
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 113664
+shapes = [("qkv", 2304, 768, 1), ("attn_out", 768, 768, 1), ("ffn_up+gelu", 3072, 768, 2), ("ffn_down", 768, 3072, 1)]
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+tot_t = tot_f = 0.0
+for name, N, K, epi in shapes:
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda")
+    o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=True)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = sorted(ts)[len(ts) // 2]
+    fl = 2.0 * M * N * K
+    tot_t += t
+    tot_f += fl
+    # cuBLAS for context
+    for _ in range(3):
+        torch.matmul(a, w.t())
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        torch.matmul(a, w.t())
+    e1.record()
+    torch.cuda.synchronize()
+    tc = e0.elapsed_time(e1) / 5
+    print("%-12s M=%d N=%d K=%d  ours %.3f ms  %.1f TFLOP/s | cublas %.3f ms %.1f TFLOP/s" %
+          (name, M, N, K, t, fl / t / 1e9, tc, fl / tc / 1e9))
+print("layer total: %.3f ms, %.1f TFLOP/s ; x12 layers = %.1f ms" % (tot_t, tot_f / tot_t / 1e9, 12 * tot_t))
