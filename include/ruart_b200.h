@@ -73,6 +73,85 @@ RUART_API int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const v
                     void* out_bf16, long long ldo_bf16, int out_parts, long long out_part_stride,
                     int fast_gelu, void* stream);
 
+/* ---------------------------------------------------------------- BERT (packed, pad-free rows)
+ * Activations are [T, hidden] row-major over the T real wordpieces of all sequences; every
+ * kernel accepts fp32 and/or bf16 pointers (exactly one input representation, any outputs).
+ * bf16 outputs may be written as `out_parts` split parts ([T, parts*hidden]).                */
+
+/* BertEmbeddings.forward, modeling.py:185-199: LN(word[ids] + position[pos] + token_type[0]) */
+RUART_API int ruart_bert_embed_ln(const int32_t* ids, const int32_t* pos, const float* word_emb,
+                                  const float* pos_emb, const float* type_emb, const float* gamma,
+                                  const float* beta, float eps, int T, int hidden, float* out_f32,
+                                  void* out_bf16, int out_parts, void* stream);
+/* BertSelfOutput / BertOutput tail, modeling.py:260-264,299-303: LN(x + residual)           */
+RUART_API int ruart_add_layernorm(const float* x_f32, const void* x_bf16, const float* res_f32,
+                                  const void* res_bf16, const float* gamma, const float* beta,
+                                  float eps, int T, int hidden, float* out_f32, void* out_bf16,
+                                  int out_parts, void* stream);
+/* BertSelfAttention.forward core, modeling.py:229-250, on fused qkv [T, 3*hidden]; sequences are
+ * rows cu_seqlens[s] .. cu_seqlens[s+1]; head_dim 64; max_len = longest sequence (host hint). */
+RUART_API int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
+                                   const int32_t* cu_seqlens, int n_seq, int n_heads, float scale,
+                                   int max_len, float* out_f32, void* out_bf16, int out_parts,
+                                   void* stream);
+/* Bert.combine_forward's subword->word mean (Bert.py:149-165) fused with SDNet.linear_sum
+ * (SDNet.py:573-583).  words = int32 [4][n_words]: item row, word slot j, st, ed (the reference's
+ * x_bert_offset[item][j]); row_start[item] = packed index of the row's first token; x_mask =
+ * uint8 [N, W] (words with 0 are skipped, Bert.py:155); the word's slot is
+ * dst + (item*W + j)*dst_stride.  dst (+)= mean(h[st..ed)) * softmax(alpha)[layer] * gamma;
+ * alpha == NULL means coefficient 1 (the per-layer outputs of plain Bert.forward).            */
+RUART_API int ruart_subword_avg_accum(const float* h_f32, const void* h_bf16, const int32_t* words,
+                                      int n_words, const int32_t* row_start, const uint8_t* x_mask,
+                                      int W, float* dst, long long dst_stride, const float* alpha,
+                                      int n_layers, const float* gamma, int layer, int first,
+                                      int hidden, void* stream);
+/* fp32 [*, K] (row pitch ld) -> bf16 split operand [rows, parts*Kp] for ruart_gemm_bf16; output
+ * row r reads source row row_idx[r] (NULL = r)                                                 */
+RUART_API int ruart_split_bf16(const float* src, long long ld, const int32_t* row_idx,
+                               long long rows, int K, int Kp, int parts, void* dst, void* stream);
+
+/* ---------------------------------------------------------------- SDNet fusion stack (fp32)
+ * Pitches are in floats.  Masks are uint8 (0 = pad), exactly the reference's ByteTensor /
+ * bool masks.                                                                                */
+
+/* dst[dst_idx[k]] = src[src_idx[k]] (D floats; optional second copy dst2): nn.Embedding lookups
+ * (SDNet.py:447-492), pre-align pack/unpack (SDNet.py:504-520,540-550), slot scatter
+ * (SDNet.py:300-318).  NULL index = identity; negative index = skip.                          */
+RUART_API int ruart_gather_rows(const float* src, long long src_pitch, const void* src_idx,
+                                float* dst, long long dst_pitch, const void* dst_idx, float* dst2,
+                                long long dst2_pitch, long long n, int D, int idx_is_64,
+                                void* stream);
+/* F.layer_norm(x, x.size()) — one mean/var over the whole [rows, cols] block, in place
+ * (Layers.py:167-168).  workspace: >= 2048 doubles.                                           */
+RUART_API int ruart_whole_layernorm(float* x, long long rows, int cols, long long pitch, float eps,
+                                    double* workspace, void* stream);
+/* Attention.forward after the projections (Layers.py:272-288): out = softmax(mask(p1 p2^T)) x3  */
+RUART_API int ruart_attention_tail(const float* p1, long long p1_pitch, const float* p2,
+                                   long long p2_pitch, int hidden, const uint8_t* mask,
+                                   const float* x3, long long x3_pitch, int D3, float* out,
+                                   long long out_pitch, int B, int L1, int L2, int add_to_out,
+                                   void* stream);
+/* LinearSelfAttn + weighted_avg (Layers.py:328-341,529-534): out[b] = softmax(mask(x w + b)) x  */
+RUART_API int ruart_self_attn_pool(const float* x, long long x_pitch, int B, int L, int D,
+                                   const uint8_t* mask, const float* w, const float* bias,
+                                   float* out, long long out_pitch, void* stream);
+/* GetFinalScores.forward (Layers.py:373-432) given wy = [attn | attn2 | noanswer_linear](h0)
+ * [B, 3X]: probabilities [B, M+1] (and optional pre-softmax logits); nan_flag is set to 1 if any
+ * probability is NaN (replaces the reference's isnan asserts, Layers.py:430,462,467).         */
+RUART_API int ruart_final_scores(const float* x, long long x_pitch, int B, int M, int X,
+                                 const float* wy, const uint8_t* mask, int es_len,
+                                 const float* noans_w, const float* noans_b, float* probs,
+                                 float* logits, int* nan_flag, void* stream);
+/* One step of the step-synchronous uni-LSTM `multi2one` (SDNet.py:137,270-271,304,310).        */
+RUART_API int ruart_lstm_cell(const float* gx, const int32_t* row_gx, const float* gh, float* c,
+                              void* h_split, int Kp, int H, int n_rows, const int32_t* last_step,
+                              int step, const long long* slot_off, float* slots, void* stream);
+/* Persistent (Bi)LSTM recurrence of StackedBRNN (Layers.py:137,166): xg = x W_ih^T + b_ih + b_hh
+ * [B*L, ndir*4H] -> out[:, dir*H + j]; w_hh [ndir][4H][H]; H <= 128; pads are processed.      */
+RUART_API int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const float* w_hh,
+                                    float* out, long long out_pitch, int B, int L, int H,
+                                    int ndir, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

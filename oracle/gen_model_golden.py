@@ -1,0 +1,64 @@
+"""TEST INFRASTRUCTURE — golden vectors for the model path, made by running the UNMODIFIED
+reference (oracle/ref_harness.py) on seeded synthetic inputs.  Build-container only:
+
+    python -m oracle.gen_model_golden
+
+Writes tests/golden/model_<case>.npz with the reference's probabilities, pre-softmax logits,
+selected answer indices (SDNetTrainer.py:402-412 rule) and a few slices of intermediate tensors.
+Weights and inputs are NOT stored: both are regenerated from seeds by ruart_b200.synth
+(fill_state_dict / make_batch), which is what the tests do.
+"""
+import os
+
+import numpy as np
+import torch
+
+from ruart_b200 import synth
+
+from . import ref_harness
+
+CASES = {
+    # name: (config, ragged, bert_init, weight seed)
+    "tiny_uniform_random": ("tiny", False, "random", 1033),
+    "tiny_ragged_pretrained": ("tiny", True, "pretrained_like", 1033),
+    "small_ragged_random": ("small", True, "random", 77),
+    "small_uniform_pretrained": ("small", False, "pretrained_like", 5),
+}
+CAPTURE = ("Bert", "multi2one", "context_rnn", "ques_rnn", "deep_attn", "high_lvl_context_rnn", "ques_self_attn")
+
+
+def first(x):
+    return x[0] if isinstance(x, (tuple, list)) else x
+
+
+def main():
+    if not ref_harness.available():
+        raise SystemExit("needs the reference tree (build container only)")
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    for name, (cfg, ragged, init, seed) in CASES.items():
+        torch.manual_seed(0)
+        opt = synth.make_opt(cfg)
+        net = ref_harness.build_reference(opt, seed=seed, bert_init=init)
+        batch = synth.make_batch(cfg, ragged=ragged)
+        probs, logits, cap = ref_harness.run_reference(net, batch, capture=CAPTURE)
+        picks = synth.select_answers(probs, batch[1]["num_cnt"])
+        bert_calls = cap["Bert"]  # q, ocr, od: each a list of 12 [N, W, 768]
+        data = {
+            "probs": probs.numpy(), "logits": logits.numpy(), "picks": np.asarray(picks, np.int64),
+            "bert_q_l0": bert_calls[0][0][:2, :4].numpy(), "bert_q_l11": bert_calls[0][-1][:2, :4].numpy(),
+            "bert_ocr_l0": bert_calls[1][0][:6, :2].numpy(), "bert_ocr_l11": bert_calls[1][-1][:6, :2].numpy(),
+            "bert_od_l11": bert_calls[2][-1][:4, :2].numpy(),
+            "multi2one_ocr": first(cap["multi2one"][0])[:6, :3].numpy(),
+            "context_rnn_ocr_last": first(cap["context_rnn"][0])[:, :12, :16].numpy(),
+            "ques_rnn_last": first(cap["ques_rnn"][0])[:, :8, :16].numpy(),
+            "deep_attn_ocr_after": first(cap["deep_attn"][0])[:, :12, :16].numpy(),
+            "high_lvl_context_ocr": first(cap["high_lvl_context_rnn"][0])[:, :12, :16].numpy(),
+            "ques_self_attn": first(cap["ques_self_attn"][0])[:, :8, :16].numpy(),
+        }
+        meta = "cfg=%s ragged=%s bert_init=%s seed=%d torch=%s" % (cfg, ragged, init, seed, torch.__version__)
+        np.savez_compressed(os.path.join(out_dir, "model_%s.npz" % name), meta=np.asarray(meta), **data)
+        print(name, meta, "picks", picks, "bytes", os.path.getsize(os.path.join(out_dir, "model_%s.npz" % name)))
+
+
+if __name__ == "__main__":
+    main()

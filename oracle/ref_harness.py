@@ -1,0 +1,141 @@
+"""TEST INFRASTRUCTURE — drives the UNMODIFIED reference (xiaojino/RUArt under /root/reference).
+
+Only usable in the build container (the reference tree does not travel to the GPU box).  It is
+used to (a) pin oracle/sdnet_oracle.py and (b) generate the golden fixtures under tests/golden/
+(see oracle/gen_model_golden.py).  Nothing in ruart_b200/ imports this.
+
+Shims, all outside the reference tree:
+  (i)   stub modules `spacy`, `fasttext`, `h5py` — Models/SDNet.py:12 imports POS/ENT from
+        Utils/CoQAUtils.py, which loads spaCy at import (Utils/GeneralUtils.py:7,13) and fastText
+        (Utils/CoQAUtils.py:26); |POS|, |ENT| are fixed to synth.POS_SIZE / synth.ENT_SIZE;
+  (ii)  on a CPU-only host `.cuda()` becomes the identity (hard-coded `.cuda()` calls at
+        Models/SDNet.py:288-299, Models/Bert/Bert.py:42,173);
+  (iii) a temp dir with bert_config.json + pytorch_model.bin ('bert.'-prefixed BertModel state);
+  (iv)  `opt` from ruart_b200.synth.make_opt (the shipped conf restated) ;
+  (v)   net.drop_emb = False, net.eval().
+"""
+import contextlib
+import json
+import os
+import sys
+import tempfile
+import types
+
+import torch
+
+from ruart_b200 import synth
+
+REF_ROOT = os.environ.get("RUART_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, "Models", "SDNet.py"))
+
+
+def _install_stubs():
+    if "spacy" not in sys.modules:
+        spacy = types.ModuleType("spacy")
+
+        class _Tagger:
+            labels = tuple("P%d" % i for i in range(synth.POS_SIZE - 1))
+
+        class _Entity:
+            move_names = ["E%d" % i for i in range(synth.ENT_SIZE - 1)]
+
+        class _NLP:
+            tagger = _Tagger()
+            entity = _Entity()
+
+        spacy.load = lambda *a, **k: _NLP()
+        sys.modules["spacy"] = spacy
+    if "fasttext" not in sys.modules:
+        ft = types.ModuleType("fasttext")
+        ft.load_model = lambda *a, **k: None
+        sys.modules["fasttext"] = ft
+    if "h5py" not in sys.modules:
+        sys.modules["h5py"] = types.ModuleType("h5py")
+
+
+@contextlib.contextmanager
+def _cpu_cuda_identity():
+    """(ii): make `.cuda()` a no-op when there is no GPU."""
+    if torch.cuda.is_available():
+        yield
+        return
+    t_cuda, m_cuda = torch.Tensor.cuda, torch.nn.Module.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, torch.nn.Module.cuda = t_cuda, m_cuda
+
+
+def import_reference():
+    """Import Models.SDNet etc. from the reference tree; returns the `Models.SDNet` module."""
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    _install_stubs()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    # our package mirrors the names Models/ and Utils/ *inside* ruart_b200/, so there is no clash
+    import Models.SDNet as ref_sdnet  # noqa: E402
+    return ref_sdnet
+
+
+def build_reference(opt, embedding=None, seed=1033, bert_init="random", bert_layers=12):
+    """Construct the reference SDNet with weights from synth.fill_state_dict (same names as ours)."""
+    ref_sdnet = import_reference()
+    from Models.Bert.modeling import BertConfig, BertModel
+    if embedding is None:
+        embedding = synth.make_embedding(seed)
+    opt = dict(opt)
+    with tempfile.TemporaryDirectory() as tmp, _cpu_cuda_identity():
+        cfg = BertConfig(synth.BERT_VOCAB, num_hidden_layers=bert_layers)
+        with open(os.path.join(tmp, "bert_config.json"), "w") as f:
+            json.dump(cfg.to_dict(), f)
+        bm = BertModel(cfg)
+        torch.save({"bert." + k: v for k, v in bm.state_dict().items()}, os.path.join(tmp, "pytorch_model.bin"))
+        del bm
+        opt["datadir"] = ""
+        opt["BERT_model_file"] = tmp
+        net = ref_sdnet.SDNet(opt, {k: v.clone() for k, v in embedding.items()})
+    synth.fill_state_dict(net, seed=seed, bert_init=bert_init)
+    net.eval()
+    net.drop_emb = False
+    return net
+
+
+def run_reference(net, batch, capture=()):
+    """Forward of the unmodified reference on a synth batch (CPU or CUDA).  Returns
+    (probs, logits, captured) — logits are the pre-softmax row (hook on F.softmax input at
+    Models/Layers.py:416-418), captured maps module names to their outputs."""
+    import copy
+    q, ocr, od = copy.deepcopy(batch)
+    captured = {}
+    hooks = []
+    mods = dict(net.named_modules())
+    for name in capture:
+        def _mk(nm):
+            def hook(_m, _inp, out):
+                captured.setdefault(nm, []).append(out)
+            return hook
+        hooks.append(mods[name].register_forward_hook(_mk(name)))
+    logits = {}
+    F = torch.nn.functional
+    orig_softmax = F.softmax
+
+    def spy_softmax(x, dim=None, **kw):
+        if x.dim() == 2 and dim == -1:
+            logits["final"] = x.detach().clone()
+        return orig_softmax(x, dim=dim, **kw)
+
+    F.softmax = spy_softmax
+    try:
+        with torch.no_grad(), _cpu_cuda_identity():
+            probs, _ = net(q, ocr, od)
+    finally:
+        F.softmax = orig_softmax
+        for h in hooks:
+            h.remove()
+    return probs.detach(), logits.get("final"), captured

@@ -1,0 +1,393 @@
+"""Drop-in for the reference's Models/Layers.py: same classes, constructor signatures, parameter
+names (state_dict compatible) and forward signatures — with the arithmetic done by the sm_100a
+kernels of libruart_b200.so.  Inference only: every forward needs CUDA tensors and raises
+otherwise (no CPU / eager fallback); dropout is the identity in eval mode exactly as in the
+reference (Layers.py:23-39), and training mode is rejected.
+
+Reference map: StackedBRNN Layers.py:124-180 | AttentionScore :182-245 | Attention :247-295 |
+RNN_from_opt :297-317 | LinearSelfAttn :320-341 | GetFinalScores :352-432 |
+BilinearSeqAttn :435-468 | DeepAttention :471-524 | weighted_avg :529-534.
+"""
+import torch
+import torch.nn as nn
+from torch.nn.parameter import Parameter
+
+from .. import ops
+from .. import sdnet_ops as K
+from .._lib import call, current_stream, ptr
+
+dropout_p = 0.0
+do_seq_dropout = False
+sdnet_parts = 3  # split parts of the SDNet-stack GEMM operands (3 = fp32-grade)
+
+
+def set_dropout_prob(p):
+    global dropout_p
+    dropout_p = p
+
+
+def set_seq_dropout(option):  # option = True or False
+    global do_seq_dropout
+    do_seq_dropout = option
+
+
+def set_sdnet_precision(parts):
+    global sdnet_parts
+    assert parts in (1, 2, 3)
+    sdnet_parts = parts
+
+
+def _no_training(module, p):
+    if module.training and p > 0:
+        raise NotImplementedError("ruart_b200 implements the inference path; call .eval() "
+                                  "(training-time dropout/backward is not part of this build)")
+
+
+def seq_dropout(x, p=0, training=False):
+    if training == False or p == 0:
+        return x
+    raise NotImplementedError("training-time variational dropout is not part of this build")
+
+
+def dropout(x, p=0, training=False):
+    if training == False or p == 0:
+        return x
+    raise NotImplementedError("training-time dropout is not part of this build")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and torch.is_tensor(t) and not t.is_cuda:
+            raise RuntimeError("ruart_b200 layers run on CUDA tensors only; there is no CPU fallback")
+
+
+class StackedBRNN(nn.Module):
+    def __init__(self, input_size, hidden_size, num_layers, rnn_type=nn.LSTM, concat_layers=False,
+                 bidirectional=True, add_feat=0, LN=False, batch_size=None, max_len=None):
+        super(StackedBRNN, self).__init__()
+        assert rnn_type is nn.LSTM, "only nn.LSTM is on RUArt's path"
+        self.bidir_coef = 2 if bidirectional else 1
+        self.num_layers = num_layers
+        self.concat_layers = concat_layers
+        self.hidden_size = hidden_size
+        self.rnns = nn.ModuleList()
+        self.LN = LN
+        if LN:
+            self.ln = nn.LayerNorm([batch_size, max_len, self.bidir_coef * self.hidden_size])
+        for i in range(num_layers):
+            in_size = input_size if i == 0 else (
+                self.bidir_coef * hidden_size + add_feat if i == 1 else self.bidir_coef * hidden_size)
+            # parameter holder only (weight_ih_l0, weight_hh_l0, bias_*_l0[_reverse]); never called
+            self.rnns.append(nn.LSTM(in_size, hidden_size, num_layers=1, bidirectional=bidirectional,
+                                     batch_first=True))
+
+    @property
+    def output_size(self):
+        if self.concat_layers:
+            return self.num_layers * self.bidir_coef * self.hidden_size
+        return self.bidir_coef * self.hidden_size
+
+    def _dir_params(self, i):
+        r = self.rnns[i]
+        sfx = ["", "_reverse"][:self.bidir_coef]
+        return ([getattr(r, "weight_ih_l0" + s) for s in sfx], [getattr(r, "weight_hh_l0" + s) for s in sfx],
+                [getattr(r, "bias_ih_l0" + s) for s in sfx], [getattr(r, "bias_hh_l0" + s) for s in sfx])
+
+    def run_layer(self, i, x, out=None, LN=None):
+        """Layer i on [B, L, in] -> [B, L, ndir*H] (optionally into the strided view `out`)."""
+        H = self.hidden_size
+        if out is None:
+            out = torch.empty((x.shape[0], x.shape[1], self.bidir_coef * H), dtype=torch.float32, device=x.device)
+        w_ih, w_hh, b_ih, b_hh = self._dir_params(i)
+        if H <= 128:
+            K.lstm_layer(x, (id(self), i), w_ih, w_hh, b_ih, b_hh, H, sdnet_parts, out, whole_ln=bool(LN))
+        else:
+            self._run_layer_stepwise(i, x, out)
+            if LN:
+                K.whole_layernorm_(out)
+        return out
+
+    def _run_layer_stepwise(self, i, x, out):
+        """Hidden sizes that do not fit the persistent kernel (multi2one: 300): one recurrent GEMM
+        + cell kernel per step.  Unidirectional only (the shipped conf's multi2one)."""
+        assert self.bidir_coef == 1, "step-synchronous path is unidirectional"
+        H = self.hidden_size
+        B, L, _ = x.shape
+        w_ih, w_hh, b_ih, b_hh = self._dir_params(i)
+        parts = 3  # the cell kernel always emits a 3-part split of h
+        a, Kp_in = K.split_act(x, parts)
+        wi, _ = K.prep_weight((id(self), i, "w_ih"), w_ih, parts)
+        wh, Kp_h = K.prep_weight((id(self), i, "w_hh"), w_hh, parts)
+        bias = K.prep_vector((id(self), i, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
+        gx = torch.empty((B * L, 4 * H), dtype=torch.float32, device=x.device)
+        K.linear(a, Kp_in, wi, B * L, 4 * H, parts, gx, epi=ops.EPI_BIAS, bias=bias)
+        c = torch.zeros((B, H), dtype=torch.float32, device=x.device)
+        hs = torch.zeros((B, 3 * Kp_h), dtype=torch.bfloat16, device=x.device)
+        gh = torch.empty((B, 4 * H), dtype=torch.float32, device=x.device)
+        last = torch.zeros(B, dtype=torch.int32, device=x.device)
+        op = K.rows2d(out)[2]
+        rows_b = torch.arange(B, device=x.device, dtype=torch.int32) * L
+        offs_b = torch.arange(B, device=x.device, dtype=torch.int64) * L * op
+        for t in range(L):
+            if t > 0:
+                K.linear(hs, Kp_h, wh, B, 4 * H, parts, gh)
+            last.fill_(t)
+            call("ruart_lstm_cell", ptr(gx), ptr(rows_b + t), ptr(gh) if t > 0 else None, ptr(c), ptr(hs), Kp_h, H,
+                 B, ptr(last), t, ptr(offs_b + t * op), ptr(out), current_stream())
+
+    def forward(self, x, x_mask, return_list=False, x_additional=None, LN=None):
+        _need_cuda(x)
+        _no_training(self, dropout_p)
+        hiddens = [x]
+        for i in range(self.num_layers):
+            rnn_input = hiddens[-1]
+            if i == 1 and x_additional is not None:
+                rnn_input = torch.cat((rnn_input, x_additional), 2)
+            hiddens.append(self.run_layer(i, rnn_input.contiguous(), LN=LN))
+        output = torch.cat(hiddens[1:], 2) if self.concat_layers else hiddens[-1]
+        if return_list:
+            return output, hiddens[1:]
+        return output
+
+
+class AttentionScore(nn.Module):
+    """correlation_func 3: s_ij = relu(W x1_i) D relu(W x2_j) (the only variant RUArt constructs)."""
+
+    def __init__(self, input_size, hidden_size, correlation_func=1, do_similarity=False):
+        super(AttentionScore, self).__init__()
+        self.correlation_func = correlation_func
+        self.hidden_size = hidden_size
+        if correlation_func == 2 or correlation_func == 3:
+            self.linear = nn.Linear(input_size, hidden_size, bias=False)
+            if do_similarity:
+                self.diagonal = Parameter(torch.ones(1, 1, 1) / (hidden_size ** 0.5), requires_grad=False)
+            else:
+                self.diagonal = Parameter(torch.ones(1, 1, hidden_size), requires_grad=True)
+        if correlation_func == 4:
+            self.linear = nn.Linear(input_size, input_size, bias=False)
+        if correlation_func == 5:
+            self.linear = nn.Linear(input_size, hidden_size, bias=False)
+
+    def project(self, x, with_diag, a_split=None):
+        """relu(x W^T) (* diagonal) for [B, L, D] rows -> fp32 [B*L, hidden]; returns (proj, split)."""
+        assert self.correlation_func == 3, "only correlation_func=3 is on RUArt's path"
+        rows = x.shape[0] * x.shape[1]
+        if a_split is None:
+            a_split = K.split_act(x, sdnet_parts)
+        a, Kp = a_split
+        w, _ = K.prep_weight((id(self), "w"), [self.linear.weight], sdnet_parts)
+        out = torch.empty((rows, self.hidden_size), dtype=torch.float32, device=x.device)
+        if with_diag:
+            d = K.prep_vector((id(self), "d"), lambda: self.diagonal.reshape(-1), [self.diagonal])
+        else:
+            d = K.ones(x.device)
+        K.linear(a, Kp, w, rows, self.hidden_size, sdnet_parts, out, epi=ops.EPI_RELU_SCALE, scale=d)
+        return out, a_split
+
+    def forward(self, x1, x2):
+        raise NotImplementedError("raw score matrices are never materialised; use Attention.forward")
+
+
+class Attention(nn.Module):
+    def __init__(self, input_size, hidden_size, correlation_func=1, do_similarity=False):
+        super(Attention, self).__init__()
+        self.scoring = AttentionScore(input_size, hidden_size, correlation_func, do_similarity)
+
+    def forward(self, x1, x2, x2_mask, x3=None, drop_diagonal=False, return_score=False, out=None,
+                add_to_out=False, p2_cache=None):
+        """attended[b, i] = sum_j softmax_j(score(x1_i, x2_j) | x2_mask) x3_j   (Layers.py:253-295).
+        `out` (strided view) / `add_to_out` / `p2_cache` are extensions used by SDNet.forward."""
+        _need_cuda(x1, x2, x3)
+        _no_training(self, dropout_p)
+        if drop_diagonal or return_score:
+            raise NotImplementedError("drop_diagonal / return_score are not used on RUArt's path")
+        if x3 is None:
+            x3 = x2
+        B, L1, L2 = x1.shape[0], x1.shape[1], x2.shape[1]
+        p1, sp = self.scoring.project(x1, True)
+        if p2_cache is not None and "p2" in p2_cache:
+            p2 = p2_cache["p2"]
+        else:
+            p2, _ = self.scoring.project(x2, False, a_split=sp if x2 is x1 else None)
+            if p2_cache is not None:
+                p2_cache["p2"] = p2
+        if out is None:
+            out = torch.empty((B, L1, x3.shape[2]), dtype=torch.float32, device=x1.device)
+        K.attention_tail(p1, p2, K.as_u8(x2_mask), x3, out, B, L1, L2, add=add_to_out)
+        return out
+
+
+def RNN_from_opt(input_size_, hidden_size_, num_layers=1, concat_rnn=False, add_feat=0, bidirectional=True,
+                 rnn_type=nn.LSTM, LN=False, batch_size=None, max_len=None):
+    new_rnn = StackedBRNN(input_size=input_size_, hidden_size=hidden_size_, num_layers=num_layers,
+                          rnn_type=rnn_type, concat_layers=concat_rnn, bidirectional=bidirectional,
+                          add_feat=add_feat, LN=False, batch_size=batch_size, max_len=max_len)
+    output_size = hidden_size_
+    if bidirectional:
+        output_size *= 2
+    if concat_rnn:
+        output_size *= num_layers
+    return new_rnn, output_size
+
+
+class LinearSelfAttn(nn.Module):
+    """alpha = softmax(mask(W x_i)) over the sequence (Layers.py:320-341)."""
+
+    def __init__(self, input_size):
+        super(LinearSelfAttn, self).__init__()
+        self.linear = nn.Linear(input_size, 1)
+
+    def pooled(self, x, x_mask):
+        """weighted_avg(x, self(x, x_mask)) in one kernel (SDNet.py:414-415)."""
+        _need_cuda(x)
+        B, L, D = x.shape
+        out = torch.empty((B, D), dtype=torch.float32, device=x.device)
+        call("ruart_self_attn_pool", ptr(x), K.rows2d(x)[2], B, L, D, ptr(K.as_u8(x_mask)),
+             ptr(self.linear.weight.detach().reshape(-1).contiguous()), ptr(self.linear.bias.detach()),
+             ptr(out), D, current_stream())
+        return out
+
+    def forward(self, x, x_mask):
+        raise NotImplementedError("use LinearSelfAttn.pooled(x, mask) (alpha is fused with weighted_avg)")
+
+
+def generate_mask(new_data, dropout_p=0.0):
+    raise NotImplementedError("training-time helper; not part of the inference path")
+
+
+class GetFinalScores(nn.Module):
+    def __init__(self, x_size, h_size, yesno, no_answer, useES):
+        super(GetFinalScores, self).__init__()
+        self.no_answer = no_answer
+        self.yesno = yesno
+        self.useES = useES
+        if no_answer:
+            self.noanswer_linear = nn.Linear(h_size, x_size)
+            self.noanswer_w = nn.Linear(x_size, 1, bias=True)
+        if yesno:
+            self.no_linear = nn.Linear(h_size, x_size)
+            self.no_w = nn.Linear(x_size, 1, bias=True)
+            self.yes_linear = nn.Linear(h_size, x_size)
+            self.yes_w = nn.Linear(x_size, 1, bias=True)
+            self.no_read_linear = nn.Linear(h_size, x_size)
+            self.no_read_w = nn.Linear(x_size, 1, bias=True)
+        self.attn = BilinearSeqAttn(x_size, h_size)
+        self.rnn = nn.GRUCell(x_size, h_size)  # parameters kept; its output is unused (Layers.py:395-397)
+        self.attn2 = BilinearSeqAttn(x_size, h_size)
+        self.x_size = x_size
+        self.last_logits = None
+
+    def forward(self, x, h0, x_mask, ES_len, mask_flag=None, nan_flag=None, want_logits=False):
+        """softmax([ES scores | OCR scores | no-answer]) (Layers.py:373-419)."""
+        _need_cuda(x, h0)
+        _no_training(self, dropout_p)
+        if self.yesno or not self.no_answer or not self.useES or not mask_flag:
+            raise NotImplementedError("only the shipped conf's scorer (useES, label_no_answer, mask_score, "
+                                      "no yes/no heads) is implemented")
+        B, M, X = x.shape
+        parts = sdnet_parts
+        w, _ = K.prep_weight((id(self), "w3"), [self.attn.linear.weight, self.attn2.linear.weight,
+                                                 self.noanswer_linear.weight], parts)
+        b3 = K.prep_vector((id(self), "b3"), lambda: torch.cat([self.attn.linear.bias, self.attn2.linear.bias,
+                                                                 self.noanswer_linear.bias]),
+                           [self.attn.linear.bias, self.attn2.linear.bias, self.noanswer_linear.bias])
+        a, Kp = K.split_act(h0, parts)
+        wy = torch.empty((B, 3 * X), dtype=torch.float32, device=x.device)
+        K.linear(a, Kp, w, B, 3 * X, parts, wy, epi=ops.EPI_BIAS, bias=b3)
+        probs = torch.empty((B, M + 1), dtype=torch.float32, device=x.device)
+        logits = torch.empty((B, M + 1), dtype=torch.float32, device=x.device) if want_logits else None
+        call("ruart_final_scores", ptr(x), K.rows2d(x)[2], B, M, X, ptr(wy), ptr(K.as_u8(x_mask)), int(ES_len),
+             ptr(self.noanswer_w.weight.detach().reshape(-1).contiguous()), ptr(self.noanswer_w.bias.detach()),
+             ptr(probs), ptr(logits), ptr(nan_flag), current_stream())
+        self.last_logits = logits
+        return probs
+
+    def get_single_score(self, x, h, x_mask, linear, w):
+        raise NotImplementedError("fused into GetFinalScores.forward")
+
+
+class BilinearSeqAttn(nn.Module):
+    """o_i = x_i' (W y + b); parameter holder — evaluated inside GetFinalScores' fused kernel."""
+
+    def __init__(self, x_size, y_size, identity=False):
+        super(BilinearSeqAttn, self).__init__()
+        self.linear = nn.Linear(y_size, x_size) if not identity else None
+
+    def forward(self, x, y, x_mask, mask_flag=True):
+        raise NotImplementedError("fused into GetFinalScores.forward")
+
+
+class DeepAttention(nn.Module):
+    def __init__(self, opt, abstr_list_cnt, deep_att_hidden_size_per_abstr, correlation_func=1,
+                 word_hidden_size=None):
+        super(DeepAttention, self).__init__()
+        word_hidden_size = opt['embedding_dim'] if word_hidden_size is None else word_hidden_size
+        abstr_hidden_size = opt['hidden_size'] * 2
+        if 'no_DeepAttention' in opt:
+            att_size = 0
+            rnn_input_size = abstr_hidden_size * abstr_list_cnt
+        else:
+            att_size = abstr_hidden_size * abstr_list_cnt + word_hidden_size
+            self.int_attn_list = nn.ModuleList()
+            for i in range(abstr_list_cnt + 1):
+                self.int_attn_list.append(Attention(att_size, deep_att_hidden_size_per_abstr,
+                                                    correlation_func=correlation_func))
+            rnn_input_size = abstr_hidden_size * abstr_list_cnt * 2 + (opt['highlvl_hidden_size'] * 2)
+        self.att_size = att_size
+        self.rnn_input_size = rnn_input_size
+        self.rnn, self.output_size = RNN_from_opt(rnn_input_size, opt['highlvl_hidden_size'], num_layers=1)
+        self.opt = opt
+
+    def forward(self, x1_word, x1_abstr, x2_word, x2_abstr, x1_mask, x2_mask, return_bef_rnn=False,
+                return_score=False):
+        """History-of-word multi-level inter-attention (Layers.py:493-524)."""
+        if return_score or 'no_DeepAttention' in self.opt:
+            raise NotImplementedError("return_score / no_DeepAttention are not on the shipped conf's path")
+        x1_att = torch.cat(x1_word + x1_abstr, 2)
+        x2_att = torch.cat(x2_word + x2_abstr[:-1], 2)
+        B, L1 = x1_att.shape[0], x1_att.shape[1]
+        widths = [t.shape[2] for t in x1_abstr] + [t.shape[2] for t in x2_abstr]
+        x1 = torch.empty((B, L1, sum(widths)), dtype=torch.float32, device=x1_att.device)
+        col = 0
+        for t in x1_abstr:
+            x1[:, :, col:col + t.shape[2]] = t
+            col += t.shape[2]
+        sp1 = K.split_act(x1_att, sdnet_parts)
+        sp2 = K.split_act(x2_att, sdnet_parts)
+        mask = K.as_u8(x2_mask)
+        for i in range(len(x2_abstr)):
+            sc = self.int_attn_list[i].scoring
+            p1, _ = sc.project(x1_att, True, a_split=sp1)
+            p2, _ = sc.project(x2_att, False, a_split=sp2)
+            x3 = x2_abstr[i]
+            K.attention_tail(p1, p2, mask, x3, x1[:, :, col:col + x3.shape[2]], B, L1, x2_att.shape[1])
+            col += x3.shape[2]
+        x1_hiddens = self.rnn(x1, x1_mask)
+        if return_bef_rnn:
+            return x1_hiddens, x1
+        return x1_hiddens
+
+
+def weighted_avg(x, weights):
+    raise NotImplementedError("fused into LinearSelfAttn.pooled")
+
+
+# Present in the reference but never constructed with the shipped conf.
+class CNN(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("CNN is unused on RUArt's inference path")
+
+
+class MaxPooling(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("MaxPooling is unused on RUArt's inference path")
+
+
+class AveragePooling(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("AveragePooling is unused on RUArt's inference path")
+
+
+class LinearTransform(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("LinearTransform is unused on RUArt's inference path")

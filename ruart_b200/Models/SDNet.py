@@ -1,0 +1,355 @@
+"""Drop-in for the reference's Models/SDNet.py: `SDNet(opt, embedding)` with the same constructor
+contract, attribute / state_dict names and `forward(q_list, ocr_list, od_list) -> (score_s,
+att_score)`, whose arithmetic runs on the sm_100a kernels of libruart_b200.so.
+
+Scope: the inference path of the shipped `conf`: q embedding
+glove,pos,ent,bert; ocr/od embedding fasttext,pos,ent,bert; PRE_ALIGN_befor_rnn; LN;
+position_mod qk+; pos_att_merge_mod cat; useES (ES_using_way as_ocr); label_no_answer; mask_score.
+Other option combinations raise NotImplementedError at construction / forward.
+
+How it differs from the reference's forward (same results, different schedule):
+  * one packed, pad-free BERT pass for question + OCR + OD tokens; the subword mean and the learned
+    layer sum (Bert.py:149-165, SDNet.py:573-583) are accumulated layer by layer straight into
+    the [word300 | bert768 | pos12 | ent8 | prealign300] concat buffers;
+  * the host loops of SDNet.py:300-318 and :498-550 become index tensors built once per batch
+    with numpy from `num_cnt` / `len_cnt`, consumed by gather kernels;
+  * `multi2one` only runs the real word steps (the LSTM is causal and only step len-1 is read,
+    SDNet.py:304,310) and scatters straight into the slot tensors;
+  * the NaN asserts (Layers.py:169,290,430,462,467) are one device flag checked once per forward.
+"""
+import logging
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .. import sdnet_ops as K
+from .._lib import call, current_stream, ptr
+from . import Layers
+from .Bert.Bert import Bert
+from .Layers import (Attention, DeepAttention, GetFinalScores, LinearSelfAttn, RNN_from_opt, dropout,
+                     set_dropout_prob, set_seq_dropout)
+
+log = logging.getLogger(__name__)
+
+_REQUIRED = ("PRE_ALIGN", "PRE_ALIGN_befor_rnn", "BERT", "BERT_LINEAR_COMBINE", "useES", "label_no_answer",
+             "mask_score", "position_dim", "GLOVE", "FastText")
+_UNSUPPORTED = ("PHOC", "img_feature", "fixed_answers", "ModelParallel", "label_yesno", "no_Context_Self_Attention",
+                "no_DeepAttention", "PRE_ALIGN_after_rnn", "BERT_LARGE_only")
+
+
+def _pos_ent_sizes(opt):
+    """len(POS), len(ENT): the reference takes them from spaCy at import (Utils/CoQAUtils.py:31-32)."""
+    if "pos_size" in opt and "ent_size" in opt:
+        return int(opt["pos_size"]), int(opt["ent_size"])
+    try:  # running inside the reference tree: use its tables
+        from Utils.CoQAUtils import ENT, POS
+        return len(POS), len(ENT)
+    except Exception as e:
+        raise RuntimeError("opt['pos_size'] / opt['ent_size'] are required when Utils.CoQAUtils (spaCy) is "
+                           "not importable: %r" % (e,))
+
+
+class SDNet(nn.Module):
+    def __init__(self, opt, embedding):
+        super(SDNet, self).__init__()
+        print('SDNet model\n')
+        self.opt = opt
+        for k in _REQUIRED:
+            if k not in opt:
+                raise NotImplementedError("ruart_b200.SDNet implements the shipped conf; option %s is required" % k)
+        for k in _UNSUPPORTED:
+            if k in opt:
+                raise NotImplementedError("ruart_b200.SDNet: option %s is outside the implemented path" % k)
+        if opt['position_mod'] != 'qk+' or opt['pos_att_merge_mod'] != 'cat' or opt.get('ES_using_way') != 'as_ocr':
+            raise NotImplementedError("only position_mod qk+, pos_att_merge_mod cat, ES_using_way as_ocr")
+        if opt['q_embedding'] != 'glove,pos,ent,bert' or opt['ocr_embedding'] != 'fasttext,pos,ent,bert':
+            raise NotImplementedError("only q_embedding glove,pos,ent,bert / ocr_embedding fasttext,pos,ent,bert")
+        self.vocab_dim = 300
+        self.use_cuda = (opt['cuda'] == True)
+        self.q_embedding = opt['q_embedding'].split(',')
+        self.ocr_embedding = opt['ocr_embedding'].split(',')
+        self.LN_flag = 'LN' in opt
+        self.LN = 'LN' in opt
+        self.drop_emb = False
+        set_dropout_prob(0.0 if 'DROPOUT' not in opt else float(opt['DROPOUT']))
+        set_seq_dropout('VARIATIONAL_DROPOUT' in opt)
+        if 'SDNET_precision' in opt:
+            Layers.set_sdnet_precision({'fp32': 3, 'bf16x2': 2, 'bf16': 1}[opt['SDNET_precision']])
+
+        self.vocab_size = int(opt['vocab_size'])
+        self.fast_dim = int(opt['fast_dim'])
+        self.glove_dim = int(opt['glove_dim'])
+        self.fast_embed = nn.Embedding(self.vocab_size, self.fast_dim, padding_idx=1)
+        self.fast_embed.weight.data = embedding['fast_embedding']
+        self.glove_embed = nn.Embedding(self.vocab_size, self.glove_dim, padding_idx=1)
+        self.glove_embed.weight.data = embedding['glove_embedding']
+        if 'TUNE_PARTIAL' in opt:
+            print('TUNE_PARTIAL')
+            self.fixed_embedding_fast = embedding['fast_embedding'][opt['tune_partial']:]
+            self.fixed_embedding_glove = embedding['glove_embedding'][opt['tune_partial']:]
+        else:
+            self.fast_embed.weight.requires_grad = False
+            self.glove_embed.weight.requires_grad = False
+
+        print('Using BERT')
+        self.Bert = Bert(opt)
+        if 'LOCK_BERT' in opt:
+            print('Lock BERT\'s weights')
+            for p in self.Bert.parameters():
+                p.requires_grad = False
+        bert_dim = self.Bert.bert_dim
+        bert_layers = self.Bert.bert_layer
+        print('BERT dim:', bert_dim, 'BERT_LAYERS:', bert_layers)
+        self.alphaBERT = nn.Parameter(torch.Tensor(bert_layers), requires_grad=True)
+        self.gammaBERT = nn.Parameter(torch.Tensor(1, 1), requires_grad=True)
+        torch.nn.init.constant_(self.alphaBERT, 1.0)
+        torch.nn.init.constant_(self.gammaBERT, 1.0)
+
+        pos_dim, ent_dim = opt['pos_dim'], opt['ent_dim']
+        n_pos, n_ent = _pos_ent_sizes(opt)
+        x_input_size = self.fast_dim + bert_dim + self.vocab_dim + pos_dim + ent_dim
+        ques_input_size = self.glove_dim + bert_dim + pos_dim + ent_dim
+        self.pre_align = Attention(self.vocab_dim, opt['prealign_hidden'], correlation_func=3, do_similarity=True)
+        self.pos_embedding = nn.Embedding(n_pos, pos_dim)
+        self.ent_embedding = nn.Embedding(n_ent, ent_dim)
+        print('Initially, the vector_sizes [ocr, query] are', x_input_size, ques_input_size)
+        self.x_input_size, self.ques_input_size, self.bert_dim = x_input_size, ques_input_size, bert_dim
+
+        self.multi2one, multi2one_output_size = RNN_from_opt(
+            x_input_size, opt['multi2one_hidden_size'], num_layers=1, concat_rnn=opt['concat_rnn'], add_feat=0,
+            bidirectional=opt['multi2one_bidir'])
+        if opt['multi2one_bidir']:
+            raise NotImplementedError("multi2one_bidir True is outside the implemented path")
+        self.multi2one_output_size = multi2one_output_size
+        self.context_rnn, context_rnn_output_size = RNN_from_opt(
+            multi2one_output_size, opt['hidden_size'], num_layers=opt['in_rnn_layers'],
+            concat_rnn=opt['concat_rnn'], add_feat=0)
+        self.ques_rnn, ques_rnn_output_size = RNN_from_opt(
+            ques_input_size, opt['hidden_size'], num_layers=opt['in_rnn_layers'], concat_rnn=opt['concat_rnn'],
+            add_feat=0)
+        print('After Input LSTM, the vector_sizes [doc, query] are [', context_rnn_output_size,
+              ques_rnn_output_size, '] *', opt['in_rnn_layers'])
+        self.deep_attn = DeepAttention(opt, abstr_list_cnt=opt['in_rnn_layers'],
+                                       deep_att_hidden_size_per_abstr=opt['deep_att_hidden_size_per_abstr'],
+                                       correlation_func=3, word_hidden_size=multi2one_output_size)
+        self.deep_attn_input_size = self.deep_attn.rnn_input_size
+        self.deep_attn_output_size = self.deep_attn.output_size
+        self.high_lvl_ques_rnn, high_lvl_ques_rnn_output_size = RNN_from_opt(
+            ques_rnn_output_size * opt['in_rnn_layers'], opt['highlvl_hidden_size'],
+            num_layers=opt['question_high_lvl_rnn_layers'], concat_rnn=True)
+        self.after_deep_attn_size = self.deep_attn_output_size + self.deep_attn_input_size + multi2one_output_size
+        self.self_attn_input_size = self.after_deep_attn_size
+        self.highlvl_self_att = Attention(self.self_attn_input_size, opt['deep_att_hidden_size_per_abstr'],
+                                          correlation_func=3)
+        self.high_lvl_context_rnn, high_lvl_context_rnn_output_size = RNN_from_opt(
+            self.deep_attn_output_size * 2, opt['highlvl_hidden_size'], num_layers=1, concat_rnn=False)
+        context_final_size = high_lvl_context_rnn_output_size
+        self.ques_self_attn = Attention(high_lvl_ques_rnn_output_size, opt['query_self_attn_hidden_size'],
+                                        correlation_func=3)
+        ques_final_size = high_lvl_ques_rnn_output_size
+        self.od_ocr_attn = Attention(context_final_size, opt['hidden_size'], correlation_func=3, do_similarity=True)
+        self.position_attn = Attention(opt['position_dim'], opt['hidden_size'], correlation_func=3,
+                                       do_similarity=True)
+        self.ques_merger = LinearSelfAttn(ques_final_size)
+        ocr_final_size = context_final_size * 2
+        self.get_answer = GetFinalScores(ocr_final_size, ques_final_size, yesno=False, no_answer=True, useES=True)
+        self.check_nan = bool(opt.get('CHECK_NAN', True))
+        log.debug('Network build successes')
+
+    # ------------------------------------------------------------------ host-side index building
+    @staticmethod
+    def _item_index(num_cnt, len_cnt, W, M):
+        """numpy indices replacing the loops of SDNet.py:300-318 and :498-550 for one item list."""
+        B = len(num_cnt)
+        num = np.asarray(num_cnt, dtype=np.int64)
+        lens = np.fromiter((l for img in len_cnt for l in img), dtype=np.int64, count=int(num.sum()))
+        if lens.size and lens.min() < 1:
+            raise ValueError("every item must have at least one word (len_cnt >= 1)")
+        if int(num.max()) > M:
+            raise ValueError("num_cnt exceeds the slot count of `position`")
+        n_items = lens.size
+        item_img = np.repeat(np.arange(B, dtype=np.int64), num)
+        first_item = np.cumsum(num) - num
+        item_slot = np.arange(n_items, dtype=np.int64) - first_item[item_img]
+        word_off = np.cumsum(lens) - lens                      # first word of each item, global
+        img_words = np.add.reduceat(lens, first_item) if n_items else np.zeros(B, np.int64)
+        img_first_word = word_off[first_item]
+        t0_item = word_off - img_first_word[item_img]          # word offset of the item inside its image
+        T_max = int(img_words.max())
+        total = int(lens.sum())
+        item_of_word = np.repeat(np.arange(n_items, dtype=np.int64), lens)
+        w = np.arange(total, dtype=np.int64) - np.repeat(word_off, lens)
+        word_src = item_of_word * W + w                        # row in the [items*W] word layout
+        word_dst = item_img[item_of_word] * T_max + t0_item[item_of_word] + w   # row in [B*T_max]
+        mask = (np.arange(M)[None, :] < num[:, None]).astype(np.uint8)
+        return dict(B=B, n_items=n_items, lens=lens, item_img=item_img, item_slot=item_slot, T_max=T_max,
+                    word_src=word_src, word_dst=word_dst, mask=mask, total_words=total)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, q_list, ocr_list, od_list, return_score=False):
+        if self.training and (Layers.dropout_p > 0 or self.drop_emb):
+            raise NotImplementedError("ruart_b200.SDNet implements inference; call .eval() and set drop_emb=False")
+        att_score = {} if return_score else None
+        dev = ocr_list['fasttext'].device
+        if dev.type != 'cuda':
+            raise RuntimeError("ruart_b200.SDNet.forward needs CUDA inputs (ToCUDA, SDNetTrainer.py:208-230); "
+                               "there is no CPU fallback")
+        opt = self.opt
+        st = current_stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        B = len(ocr_list['num_cnt'])
+        M, M_od = ocr_list['position'].size(1), od_list['position'].size(1)
+        Wq, Wo, Wd = q_list['glove'].size(1), ocr_list['fasttext'].size(1), od_list['fasttext'].size(1)
+        N_ocr, N_od = ocr_list['fasttext'].size(0), od_list['fasttext'].size(0)
+        XD, QD, BD, VD = self.x_input_size, self.ques_input_size, self.bert_dim, self.vocab_dim
+        pos_dim, ent_dim = opt['pos_dim'], opt['ent_dim']
+        H = opt['hidden_size']
+
+        # ---- host indices (one upload) -------------------------------------------------------
+        io = self._item_index(ocr_list['num_cnt'], ocr_list['len_cnt'], Wo, M)
+        id_ = self._item_index(od_list['num_cnt'], od_list['len_cnt'], Wd, M_od)
+        if io['n_items'] != N_ocr or id_['n_items'] != N_od:
+            raise ValueError("num_cnt does not match the number of item rows")
+        # multi2one over OCR and OD items together (shared weights, SDNet.py:270-271)
+        lens_all = np.concatenate([io['lens'], id_['lens']])
+        base_all = np.concatenate([np.arange(N_ocr, dtype=np.int64) * Wo,
+                                   N_ocr * Wo + np.arange(N_od, dtype=np.int64) * Wd])
+        slot_all = np.concatenate([io['item_img'] * M + io['item_slot'],
+                                   B * M + id_['item_img'] * M_od + id_['item_slot']])
+        perm = np.argsort(-lens_all, kind='stable')
+        max_len = int(lens_all.max())
+        n_t = [(lens_all > t).sum() for t in range(max_len)]
+        a_rows = np.concatenate([base_all[perm[:n]] + t for t, n in enumerate(n_t)])
+        i32 = np.concatenate([io['word_src'], io['word_dst'], id_['word_src'], id_['word_dst'], a_rows,
+                              lens_all[perm] - 1]).astype(np.int32)
+        i32_d = torch.from_numpy(i32).to(dev, non_blocking=True)
+        i64_d = torch.from_numpy((slot_all[perm] * self.multi2one_output_size).astype(np.int64)).to(dev, non_blocking=True)
+        masks_d = torch.from_numpy(np.concatenate([io['mask'].reshape(-1), id_['mask'].reshape(-1)])).to(dev, non_blocking=True)
+        cuts = np.cumsum([0, io['total_words'], io['total_words'], id_['total_words'], id_['total_words'],
+                          a_rows.size, lens_all.size])
+        ocr_wsrc, ocr_wdst, od_wsrc, od_wdst, a_rows_d, last_d = [i32_d[cuts[i]:cuts[i + 1]] for i in range(6)]
+        ocr_mask = masks_d[:B * M].view(B, M)
+        od_mask = masks_d[B * M:].view(B, M_od)
+        q_mask = K.as_u8(q_list['glove_mask'])
+
+        # ---- embeddings: [word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) -------------
+        q_in = torch.zeros((B, Wq, QD), **f32)
+        items_in = torch.zeros((N_ocr * Wo + N_od * Wd, XD), **f32)
+        ocr_in = items_in[:N_ocr * Wo].view(N_ocr, Wo, XD)
+        od_in = items_in[N_ocr * Wo:].view(N_od, Wd, XD)
+        q_word = torch.empty((B, Wq, VD), **f32)
+        ocr_word = torch.empty((N_ocr, Wo, VD), **f32)
+        od_word = torch.empty((N_od, Wd, VD), **f32)
+        c_pos, c_ent = VD + BD, VD + BD + pos_dim
+
+        def embed(lst, key, table, buf, raw, n_rows):
+            K.gather_rows(table.weight.detach(), lst[key].reshape(-1), buf, None, n_rows, VD, dst2=raw)
+            K.gather_rows(self.pos_embedding.weight.detach(), lst['pos'].reshape(-1), buf[..., c_pos:], None,
+                          n_rows, pos_dim)
+            K.gather_rows(self.ent_embedding.weight.detach(), lst['ent'].reshape(-1), buf[..., c_ent:], None,
+                          n_rows, ent_dim)
+
+        embed(q_list, 'glove', self.glove_embed, q_in, q_word, B * Wq)
+        embed(ocr_list, 'fasttext', self.fast_embed, ocr_in, ocr_word, N_ocr * Wo)
+        embed(od_list, 'fasttext', self.fast_embed, od_in, od_word, N_od * Wd)
+        q_list['glove_emb'] = q_word          # side effect of the reference (SDNet.py:449-450,458-459)
+        ocr_list['fasttext_emb'] = ocr_word
+        od_list['fasttext_emb'] = od_word
+
+        # ---- BERT: one packed pass, subword mean + layer sum into the concat buffers ------------
+        self.Bert.encode_into(
+            [(q_list['bert'], q_list['bert_mask'], q_list['bert_offsets'], q_list['glove_mask']),
+             (ocr_list['bert'], ocr_list['bert_mask'], ocr_list['bert_offsets'], ocr_list['fasttext_mask']),
+             (od_list['bert'], od_list['bert_mask'], od_list['bert_offsets'], od_list['fasttext_mask'])],
+            [(q_in, QD, VD), (ocr_in, XD, VD), (od_in, XD, VD)], self.alphaBERT, self.gammaBERT)
+
+        # ---- word-level pre-alignment (SDNet.py:495-551) --------------------------------------
+        c_pre = VD + BD + pos_dim + ent_dim
+        p2_cache = {}
+        for idx, word, wsrc, wdst, buf in ((io, ocr_word, ocr_wsrc, ocr_wdst, ocr_in),
+                                           (id_, od_word, od_wsrc, od_wdst, od_in)):
+            T_max = idx['T_max']
+            packed = torch.zeros((B, T_max, VD), **f32)
+            K.gather_rows(word, wsrc, packed, wdst, idx['total_words'], VD)
+            att = self.pre_align(packed, q_word, q_mask, p2_cache=p2_cache)
+            K.gather_rows(att, wdst, buf[..., c_pre:], wsrc, idx['total_words'], VD)
+
+        # ---- multi2one: real word steps only, last step -> slot (SDNet.py:270-271,300-318) ----
+        HS = self.multi2one_output_size
+        slots = torch.zeros((B * M + B * M_od, HS), **f32)
+        m2o = self.multi2one
+        w_ih, w_hh, b_ih, b_hh = m2o._dir_params(0)
+        a_sp, Kp_in = K.split_act(items_in, 3, row_idx=a_rows_d, n_rows=int(a_rows.size))
+        wi, _ = K.prep_weight((id(m2o), 0, "w_ih"), w_ih, 3)
+        wh, Kp_h = K.prep_weight((id(m2o), 0, "w_hh"), w_hh, 3)
+        bias = K.prep_vector((id(m2o), 0, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
+        gx = torch.empty((int(a_rows.size), 4 * HS), **f32)
+        K.linear(a_sp, Kp_in, wi, int(a_rows.size), 4 * HS, 3, gx, epi=ops.EPI_BIAS, bias=bias)
+        n_all = lens_all.size
+        c_state = torch.zeros((n_all, HS), **f32)
+        h_split = torch.zeros((n_all, 3 * Kp_h), dtype=torch.bfloat16, device=dev)
+        gh = torch.empty((n_all, 4 * HS), **f32)
+        row0 = 0
+        for t, n in enumerate(n_t):
+            n = int(n)
+            if t > 0:
+                K.linear(h_split, Kp_h, wh, n, 4 * HS, 3, gh)
+            call("ruart_lstm_cell", gx.data_ptr() + row0 * 4 * HS * 4, None, ptr(gh) if t > 0 else None,
+                 ptr(c_state), ptr(h_split), Kp_h, HS, n, ptr(last_d), t, ptr(i64_d), ptr(slots), st)
+            row0 += n
+        ocr_x = slots[:B * M].view(B, M, HS)
+        od_x = slots[B * M:].view(B, M_od, HS)
+
+        # ---- encoders with whole-tensor LN (SDNet.py:338-350) ----------------------------------
+        L_in = opt['in_rnn_layers']
+
+        def encode(rnn, x, n_layers):
+            outs, cur = [], x
+            for i in range(n_layers):
+                cur = rnn.run_layer(i, cur, LN=True)
+                outs.append(cur)
+            return outs
+
+        ocr_layers = encode(self.context_rnn, ocr_x, L_in)
+        q_layers = encode(self.ques_rnn, q_in, L_in)
+        od_layers = encode(self.context_rnn, od_x, L_in)
+        q_cat = torch.cat(q_layers, 2)
+        q_high = encode(self.high_lvl_ques_rnn, q_cat, opt['question_high_lvl_rnn_layers'])[-1]
+        q_layers = q_layers + [q_high]
+
+        # ---- deep inter-attention + context self-attention (SDNet.py:376-390) ------------------
+        def context_branch(x, layers, mask, Mx):
+            after, before = self.deep_attn([x], layers, [q_word], q_layers, mask, q_mask, return_bef_rnn=True)
+            s_in = torch.cat([after, before, x], 2)
+            DA = self.deep_attn_output_size
+            hl_in = torch.empty((B, Mx, 2 * DA), **f32)
+            hl_in[:, :, :DA] = after
+            self.highlvl_self_att(s_in, s_in, mask, x3=after, out=hl_in[:, :, DA:])
+            return self.high_lvl_context_rnn.run_layer(0, hl_in, LN=True)
+
+        ocr_high = context_branch(ocr_x, ocr_layers, ocr_mask, M)
+        od_high = context_branch(od_x, od_layers, od_mask, M_od)
+
+        # ---- OD <-> OCR + position attention (SDNet.py:393-405) -------------------------------
+        CF = ocr_high.shape[2]
+        ocr_final = torch.empty((B, M, 2 * CF), **f32)
+        ocr_final[:, :, :CF] = ocr_high
+        x_od_ocr = ocr_final[:, :, CF:]
+        self.od_ocr_attn(ocr_high, od_high, od_mask, out=x_od_ocr)
+        self.position_attn(ocr_list['position'].float(), od_list['position'].float(), od_mask, x3=od_high,
+                           out=x_od_ocr, add_to_out=True)
+
+        # ---- question summary + answer scores (SDNet.py:411-431) -------------------------------
+        q_final = self.ques_self_attn(q_high, q_high, q_mask)
+        q_merged = self.ques_merger.pooled(q_final, q_mask)
+        nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        score_s = self.get_answer(ocr_final, q_merged, ocr_mask, opt['ES_ocr_len'], mask_flag='mask_score' in opt,
+                                  nan_flag=nan_flag, want_logits=bool(opt.get('KEEP_LOGITS', False)))
+        if self.check_nan and int(nan_flag.item()) != 0:
+            raise AssertionError("NaN in answer scores (reference: assert torch.sum(torch.isnan(...)) == 0)")
+        return score_s, att_score
+
+    def linear_sum(self, output, alpha, gamma):
+        raise NotImplementedError("fused into Bert.encode_into (subword mean + layer sum per layer)")

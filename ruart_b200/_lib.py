@@ -31,6 +31,25 @@ _SIGNATURES = {
     "ruart_gemm_bf16": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
                         c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
                         c_ll, c_int, c_void_p],
+    "ruart_bert_embed_ln": [c_void_p] * 7 + [c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "ruart_add_layernorm": [c_void_p] * 6 + [c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "ruart_bert_attention": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p,
+                             c_void_p, c_int, c_void_p],
+    "ruart_subword_avg_accum": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                c_ll, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    "ruart_split_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p],
+    "ruart_gather_rows": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_int,
+                          c_int, c_void_p],
+    "ruart_whole_layernorm": [c_void_p, c_ll, c_int, c_ll, c_float, c_void_p, c_void_p],
+    "ruart_attention_tail": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_int,
+                             c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p],
+    "ruart_self_attn_pool": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_ll, c_void_p],
+    "ruart_final_scores": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "ruart_lstm_cell": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                        c_int, c_void_p, c_void_p, c_void_p],
+    "ruart_lstm_recurrence": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"ruart_last_error": ctypes.c_char_p}
 

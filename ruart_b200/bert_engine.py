@@ -1,0 +1,248 @@
+"""Packed (pad-free) BERT encoder on sm_100a kernels.
+
+Replaces BertModel.forward (reference Models/Bert/modeling.py:585-614) + Bert.combine_forward
+(Models/Bert/Bert.py:130-176) + SDNet.linear_sum (Models/SDNet.py:573-583) for inference:
+
+    rows of real wordpieces  --embed+LN-->  h
+    12 x [ QKV GEMM (tcgen05) -> varlen attention -> out-proj GEMM -> add+LN
+           -> FFN-up GEMM + erf-GELU epilogue -> FFN-down GEMM -> add+LN
+           -> subword mean * softmax(alpha)[l] * gamma accumulated into the word slots ]
+
+The 12 per-layer outputs are never materialised ([N, L, 9216] in the reference, Bert.py:137).
+
+Two numeric modes
+  "bf16": activations and GEMM operands bf16, fp32 accumulation (tensor cores, 1 term)
+  "fp32": activations fp32; GEMM operands are 3-part bf16 splits multiplied as 6 terms (~2^-24)
+"""
+import itertools
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import call, current_stream, ptr
+
+WINDOW = 512  # BERT_MAX_LEN, Models/Bert/Bert.py:18
+
+
+class Segment(object):
+    """One Bert.forward call's worth of input: ids/mask [N, L], word offsets, word mask [N, W]."""
+
+    def __init__(self, ids, mask, offsets, word_mask):
+        self.ids, self.mask, self.offsets, self.word_mask = ids, mask, offsets, word_mask
+        self.N, self.L = ids.shape
+        self.W = word_mask.shape[1]
+
+
+def flatten_offsets(offsets, n_rows):
+    """list[N][n_words][2] -> int32 [4, n_words_total] rows (item, j, st, ed)."""
+    try:
+        counts = np.fromiter(map(len, offsets), dtype=np.int64, count=n_rows)
+        total = int(counts.sum())
+        flat = np.fromiter(itertools.chain.from_iterable(itertools.chain.from_iterable(offsets)),
+                           dtype=np.int32, count=2 * total)
+    except TypeError:
+        # VQA_Dataset.bertify emits a flat [1, 1] for an item without words (VQA_Dataset.py:426-427)
+        norm = [[o] if (len(o) == 2 and not isinstance(o[0], (list, tuple))) else o for o in offsets]
+        counts = np.fromiter(map(len, norm), dtype=np.int64, count=n_rows)
+        total = int(counts.sum())
+        flat = np.fromiter(itertools.chain.from_iterable(itertools.chain.from_iterable(norm)),
+                           dtype=np.int32, count=2 * total)
+    words = np.empty((4, total), dtype=np.int32)
+    words[0] = np.repeat(np.arange(n_rows, dtype=np.int32), counts)
+    starts = np.cumsum(counts) - counts
+    words[1] = np.arange(total, dtype=np.int64) - np.repeat(starts, counts)
+    pair = flat.reshape(total, 2)
+    words[2] = pair[:, 0]
+    words[3] = pair[:, 1]
+    return words
+
+
+class BertEngine(object):
+    def __init__(self, bert_model, mode="bf16"):
+        assert mode in ("bf16", "fp32")
+        self.model = bert_model
+        self.mode = mode
+        cfg = bert_model.config
+        self.H = cfg.hidden_size
+        self.I = cfg.intermediate_size
+        self.heads = cfg.num_attention_heads
+        self.n_layers = cfg.num_hidden_layers
+        assert self.H // self.heads == 64, "attention kernel is specialised for head_dim 64"
+        self._key = None
+        self._w = None
+
+    # ------------------------------------------------------------------ weights
+    def _weights_key(self, dev):
+        return (str(dev), self.mode, tuple(p._version for p in self.model.parameters()),
+                tuple(p.data_ptr() for p in self.model.parameters()))
+
+    def _prep_matrix(self, w):
+        """fp32 [N, K] -> bf16 GEMM operand ([N, K] or 3-part split [N, 3K])."""
+        w = w.detach().float().contiguous()
+        N, K = w.shape
+        assert K % 64 == 0
+        if self.mode == "bf16":
+            out = torch.empty((N, K), dtype=torch.bfloat16, device=w.device)
+            call("ruart_split_bf16", ptr(w), K, None, N, K, K, 1, ptr(out), current_stream())
+        else:
+            out = torch.empty((N, 3 * K), dtype=torch.bfloat16, device=w.device)
+            call("ruart_split_bf16", ptr(w), K, None, N, K, K, 3, ptr(out), current_stream())
+        return out
+
+    def prepare(self, dev):
+        key = self._weights_key(dev)
+        if key == self._key:
+            return self._w
+        m = self.model
+        f = lambda t: t.detach().float().contiguous()
+        W = {"word": f(m.embeddings.word_embeddings.weight), "pos": f(m.embeddings.position_embeddings.weight),
+             "type": f(m.embeddings.token_type_embeddings.weight),
+             "eg": f(m.embeddings.LayerNorm.gamma), "eb": f(m.embeddings.LayerNorm.beta),
+             "eps": float(m.embeddings.LayerNorm.variance_epsilon), "layers": []}
+        for lay in m.encoder.layer:
+            s = lay.attention.self
+            wqkv = torch.cat([s.query.weight, s.key.weight, s.value.weight], 0)
+            bqkv = torch.cat([s.query.bias, s.key.bias, s.value.bias], 0)
+            W["layers"].append({
+                "wqkv": self._prep_matrix(wqkv), "bqkv": f(bqkv),
+                "wo": self._prep_matrix(lay.attention.output.dense.weight), "bo": f(lay.attention.output.dense.bias),
+                "g1": f(lay.attention.output.LayerNorm.gamma), "b1": f(lay.attention.output.LayerNorm.beta),
+                "wi": self._prep_matrix(lay.intermediate.dense.weight), "bi": f(lay.intermediate.dense.bias),
+                "wd": self._prep_matrix(lay.output.dense.weight), "bd": f(lay.output.dense.bias),
+                "g2": f(lay.output.LayerNorm.gamma), "b2": f(lay.output.LayerNorm.beta),
+                "eps": float(lay.output.LayerNorm.variance_epsilon),
+            })
+        self._key, self._w = key, W
+        return W
+
+    # ------------------------------------------------------------------ packing
+    @staticmethod
+    def pack(segments):
+        """Token packing for a list of Segments (device int ops only; one host sync for T).
+
+        Returns dict: ids/pos int32 [T]; cu_seqlens int32 [S+1] over 512-token windows; per
+        segment (row_start int32 [N], seq range, max_len)."""
+        dev = segments[0].ids.device
+        row_lens, win_lens, meta = [], [], []
+        for sg in segments:
+            rl = sg.mask.sum(1, dtype=torch.int32)
+            row_lens.append(rl)
+            nwin = (sg.L + WINDOW - 1) // WINDOW
+            if nwin == 1:
+                win_lens.append(rl)
+            else:
+                base = torch.arange(nwin, device=dev, dtype=torch.int32) * WINDOW
+                win_lens.append((rl[:, None] - base[None, :]).clamp_(0, WINDOW).reshape(-1))
+            meta.append(nwin)
+        all_rows = torch.cat(row_lens)
+        cu_rows = torch.zeros(all_rows.numel() + 1, dtype=torch.int32, device=dev)
+        cu_rows[1:] = torch.cumsum(all_rows, 0)
+        all_win = torch.cat(win_lens)
+        cu_seq = torch.zeros(all_win.numel() + 1, dtype=torch.int32, device=dev)
+        cu_seq[1:] = torch.cumsum(all_win, 0)
+        maxes = torch.stack([w.max() if w.numel() else torch.zeros((), dtype=torch.int32, device=dev)
+                             for w in win_lens])
+        host = torch.cat([cu_rows[-1:].to(torch.int64), maxes.to(torch.int64)]).cpu()  # the one sync
+        T = int(host[0])
+        ids = torch.empty(T, dtype=torch.int32, device=dev)
+        pos = torch.empty(T, dtype=torch.int32, device=dev)
+        segs = []
+        r0 = s0 = 0
+        for k, sg in enumerate(segments):
+            # valid tokens are a prefix of each row, so row-major order == packed order
+            sel = torch.nonzero(sg.mask.reshape(-1), as_tuple=False).squeeze(1)
+            segs.append({"row_start": cu_rows[r0:r0 + sg.N].contiguous(), "seq0": s0,
+                         "seq1": s0 + sg.N * meta[k], "max_len": int(host[1 + k]), "sel": sel,
+                         "n_tok": sel.numel()})
+            r0 += sg.N
+            s0 += sg.N * meta[k]
+        off = 0
+        for k, sg in enumerate(segments):
+            sel = segs[k].pop("sel")
+            n = segs[k]["n_tok"]
+            ids[off:off + n] = sg.ids.reshape(-1)[sel].to(torch.int32)
+            pos[off:off + n] = (sel % sg.L % WINDOW).to(torch.int32)
+            off += n
+        assert off == T
+        return {"ids": ids, "pos": pos, "cu_seqlens": cu_seq, "T": T, "segments": segs}
+
+    # ------------------------------------------------------------------ forward
+    def _gemm(self, a, w, bias, N, K, epi, out_kind, fast_gelu=False):
+        """a: activation GEMM operand; returns (f32, bf16) outputs according to mode/out_kind."""
+        T = a.shape[0]
+        dev = a.device
+        if self.mode == "bf16":
+            out = torch.empty((T, N), dtype=torch.bfloat16, device=dev)
+            ops.gemm(a, w, T, N, K, epi=epi, bias=bias, out_bf16=out, fast_gelu=fast_gelu)
+            return None, out
+        if out_kind == "split":  # consumer is another GEMM only
+            out = torch.empty((T, 3 * N), dtype=torch.bfloat16, device=dev)
+            ops.gemm(a, w, T, N, K, a_parts=3, w_parts=3, n_terms=6, epi=epi, bias=bias,
+                     out_bf16=out, out_parts=3, out_part_stride=N)
+            return None, out
+        out = torch.empty((T, N), dtype=torch.float32, device=dev)
+        ops.gemm(a, w, T, N, K, a_parts=3, w_parts=3, n_terms=6, epi=epi, bias=bias, out_f32=out)
+        return out, None
+
+    def encode(self, segments, sinks, alpha=None, gamma=None):
+        """segments: list[Segment]; sinks: per segment (dst fp32 tensor, dst_stride floats, col_off)
+        or a list of n_layers such triples when alpha is None (per-layer outputs).
+
+        With alpha/gamma: dst[item, j, col_off:col_off+H] = sum_l mean_subwords(h_l) * softmax(alpha)_l * gamma.
+        """
+        dev = segments[0].ids.device
+        if dev.type != "cuda":
+            raise RuntimeError("ruart_b200 BERT runs on CUDA only; there is no CPU fallback")
+        W = self.prepare(dev)
+        pk = self.pack(segments)
+        T, H, I = pk["T"], self.H, self.I
+        st = current_stream()
+        fp32 = self.mode == "fp32"
+        parts = 3 if fp32 else 1
+        words = []
+        for k, sg in enumerate(segments):
+            wt = flatten_offsets(sg.offsets, sg.N)
+            words.append((torch.from_numpy(wt).to(dev, non_blocking=True), wt.shape[1],
+                          sg.word_mask.to(torch.uint8).contiguous()))
+        # embeddings
+        h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if fp32 else None
+        h_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
+        call("ruart_bert_embed_ln", ptr(pk["ids"]), ptr(pk["pos"]), ptr(W["word"]), ptr(W["pos"]),
+             ptr(W["type"]), ptr(W["eg"]), ptr(W["eb"]), W["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
+        scale = 1.0 / 8.0
+        for li, lw in enumerate(W["layers"]):
+            q_f, q_b = self._gemm(h_b, lw["wqkv"], lw["bqkv"], 3 * H, H, ops.EPI_BIAS, "act")
+            ctx = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
+            for sgm in pk["segments"]:
+                n_seq = sgm["seq1"] - sgm["seq0"]
+                if n_seq == 0:
+                    continue
+                cu = pk["cu_seqlens"][sgm["seq0"]:sgm["seq1"] + 1]
+                call("ruart_bert_attention", ptr(q_f), ptr(q_b), ptr(cu), n_seq, self.heads, scale,
+                     sgm["max_len"], None, ptr(ctx), parts, st)
+            a_f, a_b = self._gemm(ctx, lw["wo"], lw["bo"], H, H, ops.EPI_BIAS, "act")
+            h1_f = torch.empty((T, H), dtype=torch.float32, device=dev) if fp32 else None
+            h1_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
+            call("ruart_add_layernorm", ptr(a_f), ptr(a_b), ptr(h_f), ptr(h_b) if not fp32 else None,
+                 ptr(lw["g1"]), ptr(lw["b1"]), lw["eps"], T, H, ptr(h1_f), ptr(h1_b), parts, st)
+            _, ff = self._gemm(h1_b, lw["wi"], lw["bi"], I, H, ops.EPI_BIAS_GELU, "split",
+                               fast_gelu=not fp32)
+            d_f, d_b = self._gemm(ff, lw["wd"], lw["bd"], H, I, ops.EPI_BIAS, "act")
+            h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if fp32 else None
+            h_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
+            call("ruart_add_layernorm", ptr(d_f), ptr(d_b), ptr(h1_f), ptr(h1_b) if not fp32 else None,
+                 ptr(lw["g2"]), ptr(lw["b2"]), lw["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
+            for k, sg in enumerate(segments):
+                wt, nw, wmask = words[k]
+                if alpha is not None:
+                    dst, stride, col = sinks[k]
+                    first = 1 if li == 0 else 0
+                else:
+                    dst, stride, col = sinks[k][li]
+                    first = 1
+                base = dst.data_ptr() + 4 * col
+                call("ruart_subword_avg_accum", ptr(h_f), None if fp32 else ptr(h_b), ptr(wt), nw,
+                     ptr(pk["segments"][k]["row_start"]), ptr(wmask), sg.W, base, stride,
+                     ptr(alpha), self.n_layers, ptr(gamma), li, first, H, st)
+        return pk

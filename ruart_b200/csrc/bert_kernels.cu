@@ -1,0 +1,516 @@
+// Memory-bound BERT kernels for sm_100a over PACKED (pad-free) token rows.
+//
+// The reference runs BertModel on padded [N, L] id matrices (Models/Bert/modeling.py:585-614).
+// Pad keys receive an additive -10000 (modeling.py:604) whose exp underflows to exactly 0 in
+// fp32, and pad query rows are never read downstream (Models/Bert/Bert.py:153-165 only reads
+// [st,ed) of real words), so we keep only the real tokens: row t of every activation matrix is
+// one real wordpiece, sequences are delimited by cu_seqlens.  See DESIGN.md §"Pad skipping".
+//
+// Activations are either bf16 ("bf16 mode") or fp32 + a 3-part bf16 split for the next GEMM
+// ("fp32 mode"); every kernel takes both kinds of pointers and uses the non-null ones.
+//
+// One warp owns one 768- (or 1024-) wide row: lane l holds columns c*256 + l*8 .. +7 of chunk c,
+// i.e. 16-byte vector accesses for bf16 and 2 x 16 bytes for fp32, fully coalesced.
+#include "common.cuh"
+#include "ruart_b200.h"
+
+namespace {
+
+using namespace ruart;
+
+constexpr int ROWS_PER_CTA = 8;  // 8 warps
+
+template <int HC>
+struct RowVec {
+  float v[HC * 8];
+};
+
+template <int HC>
+__device__ __forceinline__ void load_row_f32(const float* __restrict__ p, int lane, RowVec<HC>& r) {
+#pragma unroll
+  for (int c = 0; c < HC; ++c) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + c * 256 + lane * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + c * 256 + lane * 8 + 4));
+    r.v[c * 8 + 0] = a.x; r.v[c * 8 + 1] = a.y; r.v[c * 8 + 2] = a.z; r.v[c * 8 + 3] = a.w;
+    r.v[c * 8 + 4] = b.x; r.v[c * 8 + 5] = b.y; r.v[c * 8 + 6] = b.z; r.v[c * 8 + 7] = b.w;
+  }
+}
+template <int HC>
+__device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* __restrict__ p, int lane,
+                                              RowVec<HC>& r) {
+#pragma unroll
+  for (int c = 0; c < HC; ++c) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + c * 256 + lane * 8));
+    r.v[c * 8 + 0] = bf16_lo(u.x); r.v[c * 8 + 1] = bf16_hi(u.x);
+    r.v[c * 8 + 2] = bf16_lo(u.y); r.v[c * 8 + 3] = bf16_hi(u.y);
+    r.v[c * 8 + 4] = bf16_lo(u.z); r.v[c * 8 + 5] = bf16_hi(u.z);
+    r.v[c * 8 + 6] = bf16_lo(u.w); r.v[c * 8 + 7] = bf16_hi(u.w);
+  }
+}
+// Activation row from whichever representation exists.
+template <int HC>
+__device__ __forceinline__ void load_act(const float* f32, const __nv_bfloat16* b16, long long row,
+                                         int lane, RowVec<HC>& r) {
+  constexpr int H = HC * 256;
+  if (f32 != nullptr) load_row_f32<HC>(f32 + row * H, lane, r);
+  else load_row_bf16<HC>(b16 + row * H, lane, r);
+}
+// Store a row: fp32 (if out_f32) and bf16 in `parts` split parts (part p at column p*H).
+template <int HC>
+__device__ __forceinline__ void store_act(float* out_f32, __nv_bfloat16* out_b16, int parts,
+                                          long long row, int lane, RowVec<HC>& r) {
+  constexpr int H = HC * 256;
+  if (out_f32 != nullptr) {
+    float* p = out_f32 + row * H;
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+      *reinterpret_cast<float4*>(p + c * 256 + lane * 8) =
+          make_float4(r.v[c * 8 + 0], r.v[c * 8 + 1], r.v[c * 8 + 2], r.v[c * 8 + 3]);
+      *reinterpret_cast<float4*>(p + c * 256 + lane * 8 + 4) =
+          make_float4(r.v[c * 8 + 4], r.v[c * 8 + 5], r.v[c * 8 + 6], r.v[c * 8 + 7]);
+    }
+  }
+  if (out_b16 != nullptr) {
+    for (int part = 0; part < parts; ++part) {
+      __nv_bfloat16* p = out_b16 + row * (static_cast<long long>(parts) * H) + part * H;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(r.v[c * 8 + 2 * q]);
+          const __nv_bfloat16 h1 = __float2bfloat16_rn(r.v[c * 8 + 2 * q + 1]);
+          pk[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                  (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+          r.v[c * 8 + 2 * q] -= __bfloat162float(h0);
+          r.v[c * 8 + 2 * q + 1] -= __bfloat162float(h1);
+        }
+        *reinterpret_cast<uint4*>(p + c * 256 + lane * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+}
+
+// BertLayerNorm (modeling.py:155-168): u = mean, s = mean((x-u)^2), (x-u)/sqrt(s+eps)*gamma+beta
+template <int HC>
+__device__ __forceinline__ void layer_norm_row(RowVec<HC>& r, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, int lane) {
+  constexpr int H = HC * 256;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < HC * 8; ++i) s += r.v[i];
+  const float u = warp_sum(s) * (1.0f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < HC * 8; ++i) {
+    const float d = r.v[i] - u;
+    q = fmaf(d, d, q);
+  }
+  const float var = warp_sum(q) * (1.0f / H);
+  const float inv = 1.0f / sqrtf(var + eps);
+#pragma unroll
+  for (int c = 0; c < HC; ++c) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 256 + lane * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 256 + lane * 8 + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[c * 8 + i] = fmaf(g[i], (r.v[c * 8 + i] - u) * inv, b[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// BertEmbeddings (modeling.py:185-199): word[id] + position[pos] + token_type[0] -> LayerNorm
+template <int HC>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos,
+                     const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
+                     const float* __restrict__ type_emb, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, int T, float* out_f32,
+                     __nv_bfloat16* out_b16, int parts) {
+  constexpr int H = HC * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (row >= T) return;
+  const int id = ids[row];
+  const int ps = pos[row];
+  RowVec<HC> w, p, t;
+  load_row_f32<HC>(word_emb + static_cast<long long>(id) * H, lane, w);
+  load_row_f32<HC>(pos_emb + static_cast<long long>(ps) * H, lane, p);
+  load_row_f32<HC>(type_emb, lane, t);
+#pragma unroll
+  for (int i = 0; i < HC * 8; ++i) w.v[i] = (w.v[i] + p.v[i]) + t.v[i];
+  layer_norm_row<HC>(w, gamma, beta, eps, lane);
+  store_act<HC>(out_f32, out_b16, parts, row, lane, w);
+}
+
+// BertSelfOutput / BertOutput tail (modeling.py:260-264, 299-303): LayerNorm(dense_out + input)
+// (the dense bias is already added by the GEMM epilogue).
+template <int HC>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+add_ln_kernel(const float* x_f32, const __nv_bfloat16* x_b16, const float* res_f32,
+              const __nv_bfloat16* res_b16, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, int T, float* out_f32,
+              __nv_bfloat16* out_b16, int parts) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (row >= T) return;
+  RowVec<HC> x, r;
+  load_act<HC>(x_f32, x_b16, row, lane, x);
+  load_act<HC>(res_f32, res_b16, row, lane, r);
+#pragma unroll
+  for (int i = 0; i < HC * 8; ++i) x.v[i] += r.v[i];
+  layer_norm_row<HC>(x, gamma, beta, eps, lane);
+  store_act<HC>(out_f32, out_b16, parts, row, lane, x);
+}
+
+// ---------------------------------------------------------------------------------------
+// BertSelfAttention core (modeling.py:229-250) for packed sequences, head_dim 64.
+// One warp per (sequence, head).  K and V of the sequence's head are staged in shared memory
+// (bf16, 16-byte chunks XOR-swizzled by row) when the sequence has <= kMaxStage tokens; longer
+// sequences stream K/V from global memory (L2) block by block.  Online softmax over blocks of 32
+// keys; lane j scores key j, lane l accumulates output dims (2l, 2l+1).
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_MAX_STAGE = 64;  // most tokens whose K,V the per-warp staging buffer may hold
+
+template <typename T>
+__device__ __forceinline__ float2 ld2(const T* p);
+template <>
+__device__ __forceinline__ float2 ld2<float>(const float* p) {
+  return *reinterpret_cast<const float2*>(p);
+}
+template <>
+__device__ __forceinline__ float2 ld2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(bf16_lo(u), bf16_hi(u));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+bert_attention_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu_seqlens, int n_seq,
+                      int n_heads, float scale, int stage_tokens, float* out_f32,
+                      __nv_bfloat16* out_b16, int parts) {
+  // per warp: K and V [stage_tokens][64] fp32 + the scaled query row [64]
+  extern __shared__ float att_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float* sK = att_smem + warp * (2 * stage_tokens * 64 + 64);
+  float* sV = sK + stage_tokens * 64;
+  float* sQ = sV + stage_tokens * 64;
+  const long long task = static_cast<long long>(blockIdx.x) * ATT_WARPS + warp;
+  if (task >= static_cast<long long>(n_seq) * n_heads) return;
+  const int seq = static_cast<int>(task / n_heads);
+  const int head = static_cast<int>(task - static_cast<long long>(seq) * n_heads);
+  const int t0 = cu_seqlens[seq];
+  const int len = cu_seqlens[seq + 1] - t0;
+  const int H = n_heads * 64;
+  const long long ld = 3LL * H;
+  const T* qbase = qkv + static_cast<long long>(t0) * ld + head * 64;
+  const T* kbase = qbase + H;
+  const T* vbase = qbase + 2 * H;
+  const bool staged = len <= stage_tokens;
+  if (staged) {
+    // row j, float index d stored at j*64 + (d ^ ((j & 7) << 2)) : conflict-free for "lane = row"
+    for (int j = 0; j < len; ++j) {
+      const float2 kk = ld2<T>(kbase + j * ld + 2 * lane);
+      const float2 vv = ld2<T>(vbase + j * ld + 2 * lane);
+      const int sw = (2 * lane) ^ ((j & 7) << 2);
+      *reinterpret_cast<float2*>(sK + j * 64 + sw) = kk;
+      *reinterpret_cast<float2*>(sV + j * 64 + 2 * lane) = vv;
+    }
+  }
+  __syncwarp();
+  for (int i = 0; i < len; ++i) {
+    const float2 qq = ld2<T>(qbase + i * ld + 2 * lane);
+    __syncwarp();
+    *reinterpret_cast<float2*>(sQ + 2 * lane) = make_float2(qq.x * scale, qq.y * scale);
+    __syncwarp();
+    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int kb = 0; kb < len; kb += 32) {
+      const int j = kb + lane;
+      float s = -INFINITY;
+      if (j < len) {
+        float acc = 0.f;
+        if (staged) {
+          const float* kr = sK + j * 64;
+          const int x = (j & 7) << 2;
+#pragma unroll
+          for (int d = 0; d < 64; d += 4) {
+            const float4 kv = *reinterpret_cast<const float4*>(kr + (d ^ x));
+            const float4 qv = *reinterpret_cast<const float4*>(sQ + d);
+            acc = fmaf(qv.x, kv.x, acc);
+            acc = fmaf(qv.y, kv.y, acc);
+            acc = fmaf(qv.z, kv.z, acc);
+            acc = fmaf(qv.w, kv.w, acc);
+          }
+        } else {
+          const T* kr = kbase + j * ld;
+#pragma unroll 8
+          for (int d = 0; d < 64; d += 2) {
+            const float2 kv = ld2<T>(kr + d);
+            acc = fmaf(sQ[d], kv.x, acc);
+            acc = fmaf(sQ[d + 1], kv.y, acc);
+          }
+        }
+        s = acc;
+      }
+      const float m_new = fmaxf(m, warp_max(s));
+      const float corr = __expf(m - m_new);  // m = -inf on the first block -> 0
+      const float pj = (j < len) ? __expf(s - m_new) : 0.f;
+      l = l * corr + warp_sum(pj);
+      o0 *= corr;
+      o1 *= corr;
+      const int nk = min(32, len - kb);
+      for (int jj = 0; jj < nk; ++jj) {
+        const float pb = __shfl_sync(0xffffffffu, pj, jj);
+        float2 vv;
+        if (staged) vv = *reinterpret_cast<const float2*>(sV + (kb + jj) * 64 + 2 * lane);
+        else vv = ld2<T>(vbase + (kb + jj) * ld + 2 * lane);
+        o0 = fmaf(pb, vv.x, o0);
+        o1 = fmaf(pb, vv.y, o1);
+      }
+      m = m_new;
+    }
+    const float inv = 1.0f / l;
+    o0 *= inv;
+    o1 *= inv;
+    const long long orow = static_cast<long long>(t0 + i);
+    const int ocol = head * 64 + 2 * lane;
+    if (out_f32 != nullptr)
+      *reinterpret_cast<float2*>(out_f32 + orow * H + ocol) = make_float2(o0, o1);
+    if (out_b16 != nullptr) {
+      float r0 = o0, r1 = o1;
+      for (int part = 0; part < parts; ++part) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(r0);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+        __nv_bfloat162 hh;
+        hh.x = h0;
+        hh.y = h1;
+        *reinterpret_cast<__nv_bfloat162*>(out_b16 + orow * (static_cast<long long>(parts) * H) +
+                                           part * H + ocol) = hh;
+        r0 -= __bfloat162float(h0);
+        r1 -= __bfloat162float(h1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Subword -> word averaging (Models/Bert/Bert.py:149-165) fused with the learned layer sum
+// (Models/SDNet.py:573-583): for encoder layer `layer`,
+//     dst[item, j] (+)= (mean_{t in [st,ed)} h[row_start[item] + t]) * softmax(alpha)[layer] * gamma
+// One warp per word (item, j, st, ed).  Words whose x_mask[item, j] is 0 are skipped
+// (Bert.py:155-156); ed == st+1 copies the row, ed > st+1 divides the sum by float(ed-st),
+// ed <= st contributes zeros (Bert.py:160-165).  `first` overwrites instead of accumulating.
+// alpha == nullptr: coefficient 1 (per-layer outputs of the plain Bert.forward API).
+template <int HC>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+subword_avg_accum_kernel(const float* h_f32, const __nv_bfloat16* h_b16,
+                         const int32_t* __restrict__ words, int n_words,
+                         const int32_t* __restrict__ row_start, const uint8_t* __restrict__ x_mask,
+                         int W, float* __restrict__ dst, long long dst_stride,
+                         const float* __restrict__ alpha, int n_layers,
+                         const float* __restrict__ gamma_p, int layer, int first) {
+  const int lane = threadIdx.x & 31;
+  const long long w = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (w >= n_words) return;
+  const int item = words[w];
+  const int j = words[n_words + w];
+  const int st = words[2LL * n_words + w];
+  const int ed = words[3LL * n_words + w];
+  if (j >= W) return;
+  if (x_mask != nullptr && x_mask[static_cast<long long>(item) * W + j] == 0) return;
+  float a = 1.0f, g = 1.0f;
+  if (alpha != nullptr) {
+    // softmax(alpha)[layer] (F.softmax(alpha, dim=0), SDNet.py:574)
+    float mx = -INFINITY;
+    for (int i = 0; i < n_layers; ++i) mx = fmaxf(mx, alpha[i]);
+    float den = 0.f;
+    for (int i = 0; i < n_layers; ++i) den += expf(alpha[i] - mx);
+    a = expf(alpha[layer] - mx) / den;
+    g = gamma_p[0];
+  }
+  const int cnt = ed - st;
+  const long long t0 = static_cast<long long>(row_start[item]) + st;
+  RowVec<HC> acc;
+#pragma unroll
+  for (int i = 0; i < HC * 8; ++i) acc.v[i] = 0.f;
+  for (int t = 0; t < cnt; ++t) {
+    RowVec<HC> r;
+    load_act<HC>(h_f32, h_b16, t0 + t, lane, r);
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) acc.v[i] += r.v[i];
+  }
+  if (cnt > 1) {
+    const float fc = static_cast<float>(cnt);
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) acc.v[i] = acc.v[i] / fc;
+  }
+  float* d = dst + (static_cast<long long>(item) * W + j) * dst_stride;
+#pragma unroll
+  for (int c = 0; c < HC; ++c) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4* pp = reinterpret_cast<float4*>(d + c * 256 + lane * 8 + q * 4);
+      float4 o = make_float4((acc.v[c * 8 + q * 4 + 0] * a) * g, (acc.v[c * 8 + q * 4 + 1] * a) * g,
+                             (acc.v[c * 8 + q * 4 + 2] * a) * g, (acc.v[c * 8 + q * 4 + 3] * a) * g);
+      if (!first) {
+        const float4 old = *pp;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *pp = o;
+    }
+  }
+}
+
+// fp32 [rows, K] (row stride ld) -> bf16 split [rows, parts*Kp], zero padded to Kp per part.
+__global__ void split_bf16_kernel(const float* __restrict__ src, long long ld,
+                                  const int32_t* __restrict__ row_idx, long long rows, int K,
+                                  int Kp, int parts, __nv_bfloat16* __restrict__ dst) {
+  const long long total = rows * (Kp / 2);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / (Kp / 2);
+    const int c = static_cast<int>(i - r * (Kp / 2)) * 2;
+    const long long sr = row_idx ? static_cast<long long>(row_idx[r]) : r;
+    float x0 = (c < K) ? src[sr * ld + c] : 0.f;
+    float x1 = (c + 1 < K) ? src[sr * ld + c + 1] : 0.f;
+    for (int p = 0; p < parts; ++p) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0);
+      const __nv_bfloat16 h1 = __float2bfloat16_rn(x1);
+      __nv_bfloat162 hh;
+      hh.x = h0;
+      hh.y = h1;
+      *reinterpret_cast<__nv_bfloat162*>(dst + r * (static_cast<long long>(parts) * Kp) +
+                                         static_cast<long long>(p) * Kp + c) = hh;
+      x0 -= __bfloat162float(h0);
+      x1 -= __bfloat162float(h1);
+    }
+  }
+}
+
+inline unsigned row_grid(long long rows) {
+  return static_cast<unsigned>((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+}
+
+}  // namespace
+
+extern "C" int ruart_bert_embed_ln(const int32_t* ids, const int32_t* pos, const float* word_emb,
+                                   const float* pos_emb, const float* type_emb, const float* gamma,
+                                   const float* beta, float eps, int T, int hidden, float* out_f32,
+                                   void* out_bf16, int out_parts, void* stream) {
+  RUART_ARG_CHECK(hidden == 768 || hidden == 1024);
+  RUART_ARG_CHECK(out_f32 != nullptr || out_bf16 != nullptr);
+  if (T == 0) return RUART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hidden == 768)
+    bert_embed_ln_kernel<3><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        ids, pos, word_emb, pos_emb, type_emb, gamma, beta, eps, T, out_f32,
+        (__nv_bfloat16*)out_bf16, out_parts);
+  else
+    bert_embed_ln_kernel<4><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        ids, pos, word_emb, pos_emb, type_emb, gamma, beta, eps, T, out_f32,
+        (__nv_bfloat16*)out_bf16, out_parts);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_add_layernorm(const float* x_f32, const void* x_bf16, const float* res_f32,
+                                   const void* res_bf16, const float* gamma, const float* beta,
+                                   float eps, int T, int hidden, float* out_f32, void* out_bf16,
+                                   int out_parts, void* stream) {
+  RUART_ARG_CHECK(hidden == 768 || hidden == 1024);
+  RUART_ARG_CHECK((x_f32 != nullptr) != (x_bf16 != nullptr));
+  RUART_ARG_CHECK((res_f32 != nullptr) != (res_bf16 != nullptr));
+  RUART_ARG_CHECK(out_f32 != nullptr || out_bf16 != nullptr);
+  if (T == 0) return RUART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hidden == 768)
+    add_ln_kernel<3><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        x_f32, (const __nv_bfloat16*)x_bf16, res_f32, (const __nv_bfloat16*)res_bf16, gamma, beta,
+        eps, T, out_f32, (__nv_bfloat16*)out_bf16, out_parts);
+  else
+    add_ln_kernel<4><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        x_f32, (const __nv_bfloat16*)x_bf16, res_f32, (const __nv_bfloat16*)res_bf16, gamma, beta,
+        eps, T, out_f32, (__nv_bfloat16*)out_bf16, out_parts);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
+                                    const int32_t* cu_seqlens, int n_seq, int n_heads, float scale,
+                                    int max_len, float* out_f32, void* out_bf16, int out_parts,
+                                    void* stream) {
+  RUART_ARG_CHECK((qkv_f32 != nullptr) != (qkv_bf16 != nullptr));
+  RUART_ARG_CHECK(out_f32 != nullptr || out_bf16 != nullptr);
+  RUART_ARG_CHECK(n_heads > 0);
+  if (n_seq == 0) return RUART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int stage_tokens = max_len < 1 ? 1 : (max_len > ATT_MAX_STAGE ? ATT_MAX_STAGE : max_len);
+  stage_tokens = (stage_tokens + 7) / 8 * 8;
+  if (stage_tokens > 24) stage_tokens = (stage_tokens > 48) ? 64 : 48;
+  const size_t smem = ATT_WARPS * (2 * stage_tokens * 64 + 64) * sizeof(float);
+  const size_t smem_max = ATT_WARPS * (2 * ATT_MAX_STAGE * 64 + 64) * sizeof(float);
+  const long long tasks = static_cast<long long>(n_seq) * n_heads;
+  const unsigned grid = static_cast<unsigned>((tasks + ATT_WARPS - 1) / ATT_WARPS);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<float>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem_max));
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<__nv_bfloat16>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem_max));
+    attr_set = true;
+  }
+  if (qkv_f32 != nullptr)
+    bert_attention_kernel<float><<<grid, ATT_WARPS * 32, smem, st>>>(
+        qkv_f32, cu_seqlens, n_seq, n_heads, scale, stage_tokens, out_f32, (__nv_bfloat16*)out_bf16,
+        out_parts);
+  else
+    bert_attention_kernel<__nv_bfloat16><<<grid, ATT_WARPS * 32, smem, st>>>(
+        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, stage_tokens, out_f32,
+        (__nv_bfloat16*)out_bf16, out_parts);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_subword_avg_accum(const float* h_f32, const void* h_bf16, const int32_t* words,
+                                       int n_words, const int32_t* row_start,
+                                       const uint8_t* x_mask, int W, float* dst,
+                                       long long dst_stride, const float* alpha, int n_layers,
+                                       const float* gamma, int layer, int first, int hidden,
+                                       void* stream) {
+  RUART_ARG_CHECK(hidden == 768 || hidden == 1024);
+  RUART_ARG_CHECK((h_f32 != nullptr) != (h_bf16 != nullptr));
+  RUART_ARG_CHECK(alpha == nullptr || (layer >= 0 && layer < n_layers && gamma != nullptr));
+  RUART_ARG_CHECK((dst_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+  if (n_words == 0) return RUART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hidden == 768)
+    subword_avg_accum_kernel<3><<<row_grid(n_words), ROWS_PER_CTA * 32, 0, st>>>(
+        h_f32, (const __nv_bfloat16*)h_bf16, words, n_words, row_start, x_mask, W, dst, dst_stride,
+        alpha, n_layers, gamma, layer, first);
+  else
+    subword_avg_accum_kernel<4><<<row_grid(n_words), ROWS_PER_CTA * 32, 0, st>>>(
+        h_f32, (const __nv_bfloat16*)h_bf16, words, n_words, row_start, x_mask, W, dst, dst_stride,
+        alpha, n_layers, gamma, layer, first);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_split_bf16(const float* src, long long ld, const int32_t* row_idx,
+                                long long rows, int K, int Kp, int parts, void* dst, void* stream) {
+  RUART_ARG_CHECK(K > 0 && Kp >= K && (Kp % 64) == 0 && parts >= 1 && parts <= 3);
+  if (rows == 0) return RUART_OK;
+  const long long total = rows * (Kp / 2);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  split_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
+      src, ld, row_idx, rows, K, Kp, parts, (__nv_bfloat16*)dst);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}

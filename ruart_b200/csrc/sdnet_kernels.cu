@@ -1,0 +1,486 @@
+// fp32 kernels of the SDNet fusion stack (reference Models/Layers.py, Models/SDNet.py) for sm_100a.
+// All of them are small, HBM/L2- or latency-bound; the dense projections that feed them go
+// through the tcgen05 GEMM (gemm_tcgen05.cu) with split-bf16 operands.
+#include "common.cuh"
+#include "ruart_b200.h"
+
+namespace {
+
+using namespace ruart;
+
+// ------------------------------------------------------------------------------------------
+// Row gather: dst[dst_idx[k]] <- table[src_idx[k]]  (D floats per row, independent row pitches).
+// Covers nn.Embedding lookups (SDNet.py:447-492), the pre-align pack/unpack loops
+// (SDNet.py:504-520,540-550) and the item -> slot scatter (SDNet.py:300-318).
+// idx arrays are int64 (the collate's dtype) or int32; a null dst_idx means k itself.
+template <typename I>
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long src_pitch,
+                                   const I* __restrict__ src_idx, float* __restrict__ dst,
+                                   long long dst_pitch, const I* __restrict__ dst_idx,
+                                   float* __restrict__ dst2, long long dst2_pitch, long long n,
+                                   int D) {
+  const int lanes = (D + 3) / 4;  // float4 lanes per row
+  const long long total = n * lanes;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long k = i / lanes;
+    const int c = static_cast<int>(i - k * lanes) * 4;
+    const long long s = src_idx ? static_cast<long long>(src_idx[k]) : k;
+    const long long d = dst_idx ? static_cast<long long>(dst_idx[k]) : k;
+    if (s < 0 || d < 0) continue;
+    const float* sp = src + s * src_pitch + c;
+    float* dp = dst + d * dst_pitch + c;
+    if (c + 4 <= D && ((reinterpret_cast<uintptr_t>(sp) | reinterpret_cast<uintptr_t>(dp)) & 15u) == 0) {
+      const float4 v = *reinterpret_cast<const float4*>(sp);
+      *reinterpret_cast<float4*>(dp) = v;
+      if (dst2) {
+        float* d2 = dst2 + d * dst2_pitch + c;
+        d2[0] = v.x; d2[1] = v.y; d2[2] = v.z; d2[3] = v.w;
+      }
+    } else {
+      for (int e = 0; e < 4 && c + e < D; ++e) {
+        const float v = sp[e];
+        dp[e] = v;
+        if (dst2) dst2[d * dst2_pitch + c + e] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole-tensor LayerNorm, F.layer_norm(x, x.size()) of Layers.py:167-168: ONE mean / variance over
+// every element of the [rows, cols] block (pads included), eps 1e-5, no affine.
+// Pass 1 writes per-CTA partial (sum, sum of squares) in double; pass 2 re-reduces the partials in
+// a fixed order (deterministic) and normalises in place.
+constexpr int LN_THREADS = 256;
+constexpr int LN_MAX_PARTS = 1024;
+
+__global__ void __launch_bounds__(LN_THREADS)
+whole_ln_stats_kernel(const float* __restrict__ x, long long rows, int cols, long long pitch,
+                      double* __restrict__ partials) {
+  __shared__ double s_sum[LN_THREADS / 32], s_sq[LN_THREADS / 32];
+  const long long total = rows * cols;
+  double sum = 0.0, sq = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const float v = x[r * pitch + (i - r * cols)];
+    sum += v;
+    sq += static_cast<double>(v) * v;
+  }
+  sum = warp_sum_d(sum);
+  sq = warp_sum_d(sq);
+  if ((threadIdx.x & 31) == 0) {
+    s_sum[threadIdx.x >> 5] = sum;
+    s_sq[threadIdx.x >> 5] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < LN_THREADS / 32; ++w) {
+      a += s_sum[w];
+      b += s_sq[w];
+    }
+    partials[2 * blockIdx.x] = a;
+    partials[2 * blockIdx.x + 1] = b;
+  }
+}
+
+__global__ void __launch_bounds__(LN_THREADS)
+whole_ln_apply_kernel(float* __restrict__ x, long long rows, int cols, long long pitch,
+                      const double* __restrict__ partials, int n_parts, float eps) {
+  __shared__ float s_mean, s_inv;
+  if (threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n_parts; i += 32) {
+      a += partials[2 * i];
+      b += partials[2 * i + 1];
+    }
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    if (threadIdx.x == 0) {
+      const double n = static_cast<double>(rows) * cols;
+      const double mean = a / n;
+      double var = b / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean = static_cast<float>(mean);
+      s_inv = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+  __syncthreads();
+  const float mean = s_mean, inv = s_inv;
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    float* p = x + r * pitch + (i - r * cols);
+    *p = (*p - mean) * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused tail of Attention.forward (Layers.py:272-288) after the two projections:
+//   scores = p1 p2^T ; masked_fill(x2_mask == 0, -inf) ; softmax over keys ; out = alpha x3
+// p1 [B, L1, Hd] = relu(x1 W^T) * D,  p2 [B, L2, Hd] = relu(x2 W^T) come from the GEMM.
+// One CTA per (batch b, tile of QT query rows).  Phase 1: each warp owns keys k = w, w+8, ...;
+// lanes stride the hidden dim (coalesced p2 reads), p1 tile lives in smem.  Phase 2: one warp per
+// query row does the masked softmax.  Phase 3: threads stride the value dim.
+// If add_to_out != 0 the result is added to what `out` already holds (x_od_ocr += pos_att,
+// SDNet.py:399-401).
+constexpr int ATT_QT = 16;
+constexpr int ATT_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_tail_kernel(const float* __restrict__ p1, long long p1_pitch, const float* __restrict__ p2,
+                      long long p2_pitch, int Hd, const uint8_t* __restrict__ mask,
+                      const float* __restrict__ x3, long long x3_pitch, int D3,
+                      float* __restrict__ out, long long out_pitch, int L1, int L2, int add_to_out) {
+  extern __shared__ float smem[];
+  float* s_p1 = smem;                    // [QT][Hd]
+  float* s_sc = smem + ATT_QT * Hd;      // [QT][L2]
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * ATT_QT;
+  const int nq = min(ATT_QT, L1 - q0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* p1b = p1 + (static_cast<long long>(b) * L1 + q0) * p1_pitch;
+  const float* p2b = p2 + static_cast<long long>(b) * L2 * p2_pitch;
+  for (int i = threadIdx.x; i < ATT_QT * Hd; i += ATT_THREADS) {
+    const int q = i / Hd, h = i - q * Hd;
+    s_p1[i] = (q < nq) ? p1b[q * p1_pitch + h] : 0.f;
+  }
+  __syncthreads();
+  // phase 1: scores
+  for (int k = warp; k < L2; k += ATT_THREADS / 32) {
+    float acc[ATT_QT];
+#pragma unroll
+    for (int q = 0; q < ATT_QT; ++q) acc[q] = 0.f;
+    const float* kr = p2b + k * p2_pitch;
+    for (int h = lane; h < Hd; h += 32) {
+      const float kv = kr[h];
+#pragma unroll
+      for (int q = 0; q < ATT_QT; ++q) acc[q] = fmaf(s_p1[q * Hd + h], kv, acc[q]);
+    }
+    const bool keep = mask[static_cast<long long>(b) * L2 + k] != 0;
+#pragma unroll
+    for (int q = 0; q < ATT_QT; ++q) {
+      const float v = warp_sum(acc[q]);
+      if (lane == 0) s_sc[q * L2 + k] = keep ? v : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // phase 2: softmax over keys (F.softmax(scores, dim=1), Layers.py:284)
+  for (int q = warp; q < nq; q += ATT_THREADS / 32) {
+    float* row = s_sc + q * L2;
+    float m = -INFINITY;
+    for (int k = lane; k < L2; k += 32) m = fmaxf(m, row[k]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int k = lane; k < L2; k += 32) {
+      const float e = expf(row[k] - m);
+      row[k] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int k = lane; k < L2; k += 32) row[k] *= inv;
+  }
+  __syncthreads();
+  // phase 3: out = alpha @ x3
+  const float* x3b = x3 + static_cast<long long>(b) * L2 * x3_pitch;
+  float* ob = out + (static_cast<long long>(b) * L1 + q0) * out_pitch;
+  for (int d = threadIdx.x; d < D3; d += ATT_THREADS) {
+    float acc[ATT_QT];
+#pragma unroll
+    for (int q = 0; q < ATT_QT; ++q) acc[q] = 0.f;
+    for (int k = 0; k < L2; ++k) {
+      const float v = x3b[k * x3_pitch + d];
+#pragma unroll
+      for (int q = 0; q < ATT_QT; ++q) acc[q] = fmaf(s_sc[q * L2 + k], v, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < ATT_QT; ++q)
+      if (q < nq) {
+        float* o = ob + q * out_pitch + d;
+        *o = add_to_out ? (*o + acc[q]) : acc[q];
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LinearSelfAttn + weighted_avg (Layers.py:328-341,529-534; SDNet.py:414-415):
+//   alpha = softmax(mask(x w + b)) over the sequence ; out[b] = sum_l alpha_l x[b, l]
+// One CTA per batch row.
+__global__ void __launch_bounds__(256)
+self_attn_pool_kernel(const float* __restrict__ x, long long x_pitch, int L, int D,
+                      const uint8_t* __restrict__ mask, const float* __restrict__ w,
+                      const float* __restrict__ bias, float* __restrict__ out, long long out_pitch) {
+  extern __shared__ float s_al[];  // [L]
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + static_cast<long long>(b) * L * x_pitch;
+  for (int l = warp; l < L; l += 8) {
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(xb[l * x_pitch + d], w[d], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_al[l] = (mask[static_cast<long long>(b) * L + l] != 0) ? acc + bias[0] : -INFINITY;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int l = lane; l < L; l += 32) m = fmaxf(m, s_al[l]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      const float e = expf(s_al[l] - m);
+      s_al[l] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int l = lane; l < L; l += 32) s_al[l] *= inv;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += 256) {
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) acc = fmaf(s_al[l], xb[l * x_pitch + d], acc);
+    out[static_cast<long long>(b) * out_pitch + d] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GetFinalScores.forward (Layers.py:373-419) with useES + no_answer, after the three
+// `linear(h0)` products (attn, attn2, noanswer_linear; Layers.py:422,457) were computed by the GEMM
+// into wy [B, 3*X] = [attn | attn2 | noanswer].  One CTA per question:
+//   logit[m] = x[m] . (m < es_len ? wy_attn2 : wy_attn), pads -> -inf   (BilinearSeqAttn, :446-468)
+//   xWh[m]   = x[m] . wy_noans, pads -> -inf ; pooled = softmax(xWh) x ; noans = w . pooled + b
+//   probs = softmax([logits..., noans])                                              (:413-419)
+// A sticky NaN flag replaces the reference's `assert isnan == 0` host syncs (Layers.py:430,462).
+__global__ void __launch_bounds__(256)
+final_scores_kernel(const float* __restrict__ x, long long x_pitch, int M, int X,
+                    const float* __restrict__ wy, const uint8_t* __restrict__ mask, int es_len,
+                    const float* __restrict__ noans_w, const float* __restrict__ noans_b,
+                    float* __restrict__ probs, float* __restrict__ logits, int* nan_flag) {
+  extern __shared__ float sm[];
+  float* s_logit = sm;          // [M + 1]
+  float* s_xwh = sm + (M + 1);  // [M]
+  float* s_red = s_xwh + M;     // [8]
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + static_cast<long long>(b) * M * x_pitch;
+  const float* wa = wy + static_cast<long long>(b) * 3 * X;
+  const float* wa2 = wa + X;
+  const float* wn = wa + 2 * X;
+  for (int m = warp; m < M; m += 8) {
+    const float* xr = xb + m * x_pitch;
+    const float* wv = (m < es_len) ? wa2 : wa;
+    float a = 0.f, c = 0.f;
+    for (int d = lane; d < X; d += 32) {
+      const float xv = xr[d];
+      a = fmaf(xv, wv[d], a);
+      c = fmaf(xv, wn[d], c);
+    }
+    a = warp_sum(a);
+    c = warp_sum(c);
+    if (lane == 0) {
+      const bool keep = mask[static_cast<long long>(b) * M + m] != 0;
+      s_logit[m] = keep ? a : -INFINITY;
+      s_xwh[m] = keep ? c : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // softmax(xWh) (all threads need it): warp 0 normalises in place
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int m = lane; m < M; m += 32) mx = fmaxf(mx, s_xwh[m]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int m = lane; m < M; m += 32) {
+      const float e = expf(s_xwh[m] - mx);
+      s_xwh[m] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    for (int m = lane; m < M; m += 32) s_xwh[m] *= inv;
+  }
+  __syncthreads();
+  // noans = noanswer_w . (sum_m p_m x[m]) + b
+  float part = 0.f;
+  for (int d = threadIdx.x; d < X; d += 256) {
+    float pooled = 0.f;
+    for (int m = 0; m < M; ++m) pooled = fmaf(s_xwh[m], xb[m * x_pitch + d], pooled);
+    part = fmaf(pooled, noans_w[d], part);
+  }
+  part = warp_sum(part);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    s_logit[M] = t + noans_b[0];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int m = lane; m <= M; m += 32) mx = fmaxf(mx, s_logit[m]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int m = lane; m <= M; m += 32) s += expf(s_logit[m] - mx);
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+    bool bad = false;
+    for (int m = lane; m <= M; m += 32) {
+      const float lg = s_logit[m];
+      const float p = expf(lg - mx) * inv;
+      probs[static_cast<long long>(b) * (M + 1) + m] = p;
+      if (logits) logits[static_cast<long long>(b) * (M + 1) + m] = lg;
+      bad |= (p != p);
+    }
+    if (bad && nan_flag) atomicExch(nan_flag, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LSTM cell update for the step-synchronous multi2one path (uni-LSTM 1388 -> 300 over item words,
+// SDNet.py:137,270-271): rows are the still-active items at this step.
+//   g = gx[row_gx[r]] (+ gh[r])  ;  i,f,g,o ;  c = f*c + i*g ;  h = o*tanh(c)
+// h is written as fp32, as the 3-part bf16 split operand of the next step's recurrent GEMM, and,
+// when this is an item's last word (last_step[r] == step), into its slot row (SDNet.py:304,310).
+__global__ void lstm_cell_kernel(const float* __restrict__ gx, const int32_t* __restrict__ row_gx,
+                                 const float* __restrict__ gh, float* __restrict__ c,
+                                 __nv_bfloat16* __restrict__ h_split, int Kp, int H, int n_rows,
+                                 const int32_t* __restrict__ last_step, int step,
+                                 const long long* __restrict__ slot_off, float* __restrict__ slots) {
+  const long long total = static_cast<long long>(n_rows) * H;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / H);
+    const int j = static_cast<int>(i - static_cast<long long>(r) * H);
+    const float* g = gx + static_cast<long long>(row_gx ? row_gx[r] : r) * 4 * H;
+    float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+    float cp = 0.f;
+    if (gh != nullptr) {
+      const float* q = gh + static_cast<long long>(r) * 4 * H;
+      gi += q[j]; gf += q[H + j]; gg += q[2 * H + j]; go += q[3 * H + j];
+      cp = c[i];
+    }
+    const float si = 1.0f / (1.0f + expf(-gi));
+    const float sf = 1.0f / (1.0f + expf(-gf));
+    const float so = 1.0f / (1.0f + expf(-go));
+    const float cn = sf * cp + si * tanhf(gg);
+    const float hn = so * tanhf(cn);
+    c[i] = cn;
+    float rem = hn;
+    for (int p = 0; p < 3; ++p) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(rem);
+      h_split[static_cast<long long>(r) * 3 * Kp + static_cast<long long>(p) * Kp + j] = hb;
+      rem -= __bfloat162float(hb);
+    }
+    if (last_step[r] == step) slots[slot_off[r] + j] = hn;
+  }
+}
+
+inline unsigned cap_grid(long long work_items, int per_cta) {
+  long long g = (work_items + per_cta - 1) / per_cta;
+  const long long cap = static_cast<long long>(ruart_num_sms()) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+
+extern "C" int ruart_gather_rows(const float* src, long long src_pitch, const void* src_idx,
+                                 float* dst, long long dst_pitch, const void* dst_idx, float* dst2,
+                                 long long dst2_pitch, long long n, int D, int idx_is_64,
+                                 void* stream) {
+  RUART_ARG_CHECK(src != nullptr && dst != nullptr && D > 0 && n >= 0);
+  if (n == 0) return RUART_OK;
+  const unsigned grid = cap_grid(n * ((D + 3) / 4), 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (idx_is_64)
+    gather_rows_kernel<long long><<<grid, 256, 0, st>>>(src, src_pitch, (const long long*)src_idx,
+                                                        dst, dst_pitch, (const long long*)dst_idx,
+                                                        dst2, dst2_pitch, n, D);
+  else
+    gather_rows_kernel<int32_t><<<grid, 256, 0, st>>>(src, src_pitch, (const int32_t*)src_idx, dst,
+                                                      dst_pitch, (const int32_t*)dst_idx, dst2,
+                                                      dst2_pitch, n, D);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_whole_layernorm(float* x, long long rows, int cols, long long pitch, float eps,
+                                     double* workspace, void* stream) {
+  RUART_ARG_CHECK(x != nullptr && workspace != nullptr && rows > 0 && cols > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  long long g = (rows * cols + LN_THREADS * 8 - 1) / (LN_THREADS * 8);
+  if (g > LN_MAX_PARTS) g = LN_MAX_PARTS;
+  if (g < 1) g = 1;
+  whole_ln_stats_kernel<<<static_cast<unsigned>(g), LN_THREADS, 0, st>>>(x, rows, cols, pitch,
+                                                                          workspace);
+  RUART_LAUNCH_CHECK();
+  whole_ln_apply_kernel<<<cap_grid(rows * cols, LN_THREADS * 4), LN_THREADS, 0, st>>>(
+      x, rows, cols, pitch, workspace, static_cast<int>(g), eps);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_attention_tail(const float* p1, long long p1_pitch, const float* p2,
+                                    long long p2_pitch, int hidden, const uint8_t* mask,
+                                    const float* x3, long long x3_pitch, int D3, float* out,
+                                    long long out_pitch, int B, int L1, int L2, int add_to_out,
+                                    void* stream) {
+  RUART_ARG_CHECK(B > 0 && L1 > 0 && L2 > 0 && hidden > 0 && D3 > 0);
+  const size_t smem = (static_cast<size_t>(ATT_QT) * hidden + static_cast<size_t>(ATT_QT) * L2) *
+                      sizeof(float);
+  RUART_ARG_CHECK(smem <= 200 * 1024);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(attention_tail_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = 200 * 1024;
+  }
+  dim3 grid((L1 + ATT_QT - 1) / ATT_QT, B);
+  attention_tail_kernel<<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(
+      p1, p1_pitch, p2, p2_pitch, hidden, mask, x3, x3_pitch, D3, out, out_pitch, L1, L2,
+      add_to_out);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_self_attn_pool(const float* x, long long x_pitch, int B, int L, int D,
+                                    const uint8_t* mask, const float* w, const float* bias,
+                                    float* out, long long out_pitch, void* stream) {
+  RUART_ARG_CHECK(B > 0 && L > 0 && D > 0 && L * sizeof(float) <= 48 * 1024);
+  self_attn_pool_kernel<<<B, 256, L * sizeof(float), (cudaStream_t)stream>>>(x, x_pitch, L, D, mask,
+                                                                            w, bias, out, out_pitch);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_final_scores(const float* x, long long x_pitch, int B, int M, int X,
+                                  const float* wy, const uint8_t* mask, int es_len,
+                                  const float* noans_w, const float* noans_b, float* probs,
+                                  float* logits, int* nan_flag, void* stream) {
+  RUART_ARG_CHECK(B > 0 && M > 0 && X > 0 && es_len >= 0 && es_len <= M);
+  const size_t smem = (2 * static_cast<size_t>(M) + 1 + 8) * sizeof(float);
+  RUART_ARG_CHECK(smem <= 48 * 1024);
+  final_scores_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(x, x_pitch, M, X, wy, mask, es_len,
+                                                              noans_w, noans_b, probs, logits,
+                                                              nan_flag);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_lstm_cell(const float* gx, const int32_t* row_gx, const float* gh, float* c,
+                               void* h_split, int Kp, int H, int n_rows, const int32_t* last_step,
+                               int step, const long long* slot_off, float* slots, void* stream) {
+  RUART_ARG_CHECK(H > 0 && Kp >= H && (Kp % 64) == 0);
+  if (n_rows == 0) return RUART_OK;
+  lstm_cell_kernel<<<cap_grid(static_cast<long long>(n_rows) * H, 256), 256, 0,
+                     (cudaStream_t)stream>>>(gx, row_gx, gh, c, (__nv_bfloat16*)h_split, Kp, H,
+                                             n_rows, last_step, step, slot_off, slots);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}

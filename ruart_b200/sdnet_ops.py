@@ -1,0 +1,138 @@
+"""Functional building blocks of the SDNet stack on top of the C ABI (fp32 activations).
+
+Dense products go through the tcgen05 GEMM with split-bf16 operands (`parts` = 3 -> 6 partial
+products, fp32-grade; 2 -> 3 products, ~2^-16; 1 -> plain bf16).  Everything else is one of the
+fused kernels of csrc/sdnet_kernels.cu / csrc/lstm.cu.  No torch math here: torch allocates.
+"""
+import torch
+
+from . import ops
+from ._lib import call, current_stream, ptr
+
+_TERMS = {1: 1, 2: 3, 3: 6}
+_wcache = {}
+_consts = {}
+
+
+def rows2d(t):
+    """View a [.., D] tensor whose leading dims are uniformly strided as (rows, cols, pitch)."""
+    assert t.dtype == torch.float32 and t.stride(-1) == 1, "need fp32 rows with unit inner stride"
+    if t.dim() == 1:
+        return 1, t.shape[0], t.shape[0]
+    pitch = t.stride(-2)
+    rows = 1
+    exp = pitch
+    for d in range(t.dim() - 2, -1, -1):
+        assert t.shape[d] == 1 or t.stride(d) == exp, "rows are not uniformly strided"
+        exp = exp * t.shape[d]
+        rows *= t.shape[d]
+    return rows, t.shape[-1], pitch
+
+
+def ones(dev):
+    k = ("ones", str(dev))
+    if k not in _consts:
+        _consts[k] = torch.ones(1, dtype=torch.float32, device=dev)
+    return _consts[k]
+
+
+def ln_workspace(dev):
+    k = ("lnws", str(dev), torch.cuda.current_stream().cuda_stream)
+    if k not in _consts:
+        _consts[k] = torch.empty(2048, dtype=torch.float64, device=dev)
+    return _consts[k]
+
+
+def split_act(x, parts, row_idx=None, n_rows=None):
+    """fp32 rows -> bf16 split operand [rows, parts*Kp]."""
+    rows, K, pitch = rows2d(x)
+    if row_idx is not None:
+        rows = n_rows if n_rows is not None else row_idx.numel()
+    Kp = ops.round_up(K, 64)
+    out = torch.empty((rows, parts * Kp), dtype=torch.bfloat16, device=x.device)
+    call("ruart_split_bf16", ptr(x), pitch, ptr(row_idx), rows, K, Kp, parts, ptr(out), current_stream())
+    return out, Kp
+
+
+def prep_weight(key, tensors, parts):
+    """Cache the split-bf16 form of a weight matrix (concatenation of `tensors` along dim 0)."""
+    ver = tuple((t.data_ptr(), t._version) for t in tensors) + (parts,)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    w = torch.cat([t.detach().float() for t in tensors], 0).contiguous() if len(tensors) > 1 \
+        else tensors[0].detach().float().contiguous()
+    out, Kp = split_act(w, parts)
+    _wcache[key] = (ver, out, Kp)
+    return out, Kp
+
+
+def prep_vector(key, fn, tensors):
+    ver = tuple((t.data_ptr(), t._version) for t in tensors)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    v = fn().detach().float().contiguous()
+    _wcache[key] = (ver, v)
+    return v
+
+
+def linear(a_split, Kp, w_split, rows, N, parts, out, epi=ops.EPI_NONE, bias=None, scale=None):
+    """out[rows, N] (fp32, pitch from `out`) = epi(A W^T)."""
+    _, _, pitch = rows2d(out)
+    call("ruart_gemm_bf16", ptr(a_split), a_split.stride(0), parts, ptr(w_split), w_split.stride(0), parts,
+         rows, N, Kp, _TERMS[parts], epi, ptr(bias), ptr(scale), 0 if scale is None else scale.numel(),
+         ptr(out), pitch, None, 0, 1, 0, 0, current_stream())
+    return out
+
+
+def gather_rows(src, src_idx, dst, dst_idx, n, D, dst2=None):
+    _, _, sp = rows2d(src)
+    _, _, dp = rows2d(dst)
+    is64 = 1
+    for ix in (src_idx, dst_idx):
+        if ix is not None:
+            is64 = 1 if ix.dtype == torch.int64 else 0
+    d2p = rows2d(dst2)[2] if dst2 is not None else 0
+    call("ruart_gather_rows", ptr(src), sp, ptr(src_idx), ptr(dst), dp, ptr(dst_idx), ptr(dst2), d2p, n, D,
+         is64, current_stream())
+
+
+def whole_layernorm_(x, eps=1e-5):
+    rows, cols, pitch = rows2d(x)
+    call("ruart_whole_layernorm", ptr(x), rows, cols, pitch, eps, ptr(ln_workspace(x.device)), current_stream())
+    return x
+
+
+def attention_tail(p1, p2, mask_u8, x3, out, B, L1, L2, add=False):
+    _, hid, p1p = rows2d(p1)
+    _, _, p2p = rows2d(p2)
+    _, D3, x3p = rows2d(x3)
+    _, _, op = rows2d(out)
+    call("ruart_attention_tail", ptr(p1), p1p, ptr(p2), p2p, hid, ptr(mask_u8), ptr(x3), x3p, D3, ptr(out), op,
+         B, L1, L2, 1 if add else 0, current_stream())
+    return out
+
+
+def as_u8(mask):
+    if mask.dtype == torch.uint8:
+        return mask.contiguous()
+    return mask.to(torch.uint8).contiguous()
+
+
+def lstm_layer(x, key, w_ih, w_hh, b_ih, b_hh, H, parts, out, whole_ln=False):
+    """One (Bi)LSTM layer of StackedBRNN (Layers.py:156-170) for H <= 128 on [B, L, in] input.
+    w_ih/w_hh/b_ih/b_hh are lists over directions.  `out` [B, L, ndir*H] may be a strided view."""
+    B, L = x.shape[0], x.shape[1]
+    ndir = len(w_ih)
+    a, Kp = split_act(x, parts)
+    w, _ = prep_weight((key, "w_ih"), w_ih, parts)
+    bias = prep_vector((key, "bias"), lambda: torch.cat([bi + bh for bi, bh in zip(b_ih, b_hh)], 0), b_ih + b_hh)
+    whh = prep_vector((key, "w_hh"), lambda: torch.stack(w_hh, 0), w_hh)
+    xg = torch.empty((B * L, ndir * 4 * H), dtype=torch.float32, device=x.device)
+    linear(a, Kp, w, B * L, ndir * 4 * H, parts, xg, epi=ops.EPI_BIAS, bias=bias)
+    _, _, op = rows2d(out)
+    call("ruart_lstm_recurrence", ptr(xg), xg.stride(0), ptr(whh), ptr(out), op, B, L, H, ndir, current_stream())
+    if whole_ln:
+        whole_layernorm_(out)
+    return out

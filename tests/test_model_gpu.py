@@ -1,0 +1,94 @@
+"""GPU: the CUDA product (ruart_b200.Models.SDNet) against the CPU oracle on the same seeded
+weights/inputs and against the reference's golden vectors.  Tolerances are BASELINE.json's:
+logits within 1e-4 relative (fp32 mode) / 2e-2 (bf16 mode), answer agreement."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sdnet_oracle
+from ruart_b200 import synth
+
+from helpers import CASES, build_ours, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ours(net, batch):
+    b = synth.batch_to(copy.deepcopy(batch), "cuda")
+    with torch.no_grad():
+        probs, att = net(*b)
+    torch.cuda.synchronize()
+    assert att is None
+    return probs.cpu(), net.get_answer.last_logits.cpu(), b
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_forward_matches_reference_golden(name, mode, tol):
+    cfg, ragged, init, seed = CASES[name]
+    g = load_golden(name)
+    net, opt = build_ours(cfg, seed=seed, bert_init=init, device="cuda", BERT_precision=mode, KEEP_LOGITS=True)
+    batch = synth.make_batch(cfg, ragged=ragged)
+    probs, logits, b = run_ours(net, batch)
+    assert probs.shape == g["probs"].shape
+    assert rel_err(logits, g["logits"]) < tol
+    assert np.abs(probs.numpy() - g["probs"]).max() < (5 * tol)
+    assert abs(float(probs.sum(1).min()) - 1.0) < 1e-4
+    # masked slots are exactly zero (Appendix A.10)
+    assert (probs.numpy()[g["probs"] == 0] == 0).all()
+    picks = synth.select_answers(probs, batch[1]["num_cnt"])
+    top2 = np.sort(g["probs"], 1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 10 * tol
+    assert [p for p, c in zip(picks, clear) if c] == [p for p, c in zip(g["picks"].tolist(), clear) if c]
+    # side effects of the reference forward (SDNet.py:449-450,458-459)
+    assert b[0]["glove_emb"].shape == (probs.shape[0], 40, 300) and "fasttext_emb" in b[1] and "fasttext_emb" in b[2]
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_forward_matches_oracle_cfg1_shape(mode, tol):
+    # BASELINE config 1 shape at a reduced batch so the CPU oracle finishes in seconds
+    cfg = dict(B=6, n_ocr=50, n_od=10, max_ocr_num=100, max_od_num=30)
+    net, opt = build_ours(cfg, seed=11, bert_init="pretrained_like", device="cuda", BERT_precision=mode,
+                          KEEP_LOGITS=True)
+    batch = synth.make_batch(cfg, seed=2001, ragged=True)
+    cpu_sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch))
+    probs, logits, _ = run_ours(net, batch)
+    assert rel_err(logits, want_l) < tol
+    agree = (probs.argmax(1) == want_p.argmax(1)).float().mean().item()
+    assert agree == 1.0
+
+
+def test_bert_wrapper_api_returns_per_layer_word_tensors():
+    from ruart_b200.Models.Bert.Bert import Bert
+    net, opt = build_ours("tiny", device="cuda", BERT_precision="fp32")
+    batch = synth.make_batch("tiny")
+    q = synth.batch_to(batch, "cuda")[1]
+    outs = net.Bert(q["bert"], q["bert_mask"], q["bert_offsets"], q["fasttext_mask"])
+    assert isinstance(outs, list) and len(outs) == 12 and outs[0].shape == (q["bert"].shape[0], 20, 768)
+    sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    want = sdnet_oracle.bert_words(sd, opt, batch[1]["bert"], batch[1]["bert_mask"], batch[1]["bert_offsets"],
+                                   batch[1]["fasttext_mask"], 12, 12)
+    for l in (0, 5, 11):
+        assert rel_err(outs[l].cpu(), want[l]) < 1e-4
+
+
+def test_cpu_inputs_fail_loudly():
+    net, opt = build_ours("tiny", device="cuda")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(*synth.make_batch("tiny"))
+
+
+def test_sharded_forward_equals_oracle_per_shard():
+    # whole-tensor LN couples a batch, so each shard reproduces the reference run on
+    # that shard's sub-batch.
+    net, opt = build_ours("small", seed=77, device="cuda", BERT_precision="fp32", KEEP_LOGITS=True)
+    batch = synth.make_batch("small", ragged=True)
+    cpu_sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    for r in range(2):
+        sh = synth.shard_batch(batch, r, 2)
+        want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(sh))
+        probs, logits, _ = run_ours(net, sh)
+        assert rel_err(logits, want_l) < 1e-4

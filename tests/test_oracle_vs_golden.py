@@ -1,0 +1,53 @@
+"""CPU: oracle/sdnet_oracle.py against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/model_*.npz, made by oracle/gen_model_golden.py), plus the state_dict contract."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sdnet_oracle
+from ruart_b200 import synth
+
+from helpers import CASES, GOLDEN, build_ours, load_golden, rel_err
+
+
+def test_state_dict_names_shapes_order_match_reference():
+    with open(os.path.join(GOLDEN, "state_dict_manifest.json")) as f:
+        want = json.load(f)
+    net, _ = build_ours("tiny")
+    got = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert list(got) == list(want)
+    assert got == want
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == 12246007
+
+
+@pytest.mark.parametrize("name", ["tiny_uniform_random", "tiny_ragged_pretrained", "small_ragged_random"])
+def test_oracle_reproduces_reference(name):
+    cfg, ragged, init, seed = CASES[name]
+    g = load_golden(name)
+    net, opt = build_ours(cfg, seed=seed, bert_init=init)
+    batch = synth.make_batch(cfg, ragged=ragged)
+    probs, logits, inter = sdnet_oracle.sdnet_forward(net.state_dict(), opt, *batch, keep=True)
+    assert rel_err(logits, g["logits"]) < 2e-5
+    assert np.abs(probs.numpy() - g["probs"]).max() < 2e-5
+    assert synth.select_answers(probs, batch[1]["num_cnt"]) == g["picks"].tolist()
+    assert rel_err(inter["ocr_layers"][-1][:, :12, :16], g["context_rnn_ocr_last"]) < 1e-4
+    assert rel_err(inter["ocr_high"][:, :12, :16], g["high_lvl_context_ocr"]) < 1e-4
+    assert rel_err(inter["q_final"][:, :8, :16], g["ques_self_attn"]) < 1e-4
+
+
+def test_answer_selection_rule():
+    # SDNetTrainer.py:402-412: skip the <OCR> end slot, stop at no-answer, accept idx < num_cnt
+    p = torch.tensor([[0.1, 0.5, 0.3, 0.0, 0.1], [0.1, 0.2, 0.6, 0.0, 0.1], [0.0, 0.1, 0.2, 0.0, 0.7]])
+    assert synth.select_answers(p, [3, 3, 3]) == [1, 1, 4]
+
+
+def test_shard_batch_partitions_questions_and_items():
+    batch = synth.make_batch("small", ragged=True)
+    parts = [synth.shard_batch(batch, r, 2) for r in range(2)]
+    assert sum(len(p[1]["num_cnt"]) for p in parts) == len(batch[1]["num_cnt"])
+    assert torch.equal(torch.cat([p[1]["fasttext"] for p in parts]), batch[1]["fasttext"])
+    assert torch.equal(torch.cat([p[0]["bert"] for p in parts]), batch[0]["bert"])
+    assert parts[0][2]["bert_offsets"] + parts[1][2]["bert_offsets"] == batch[2]["bert_offsets"]
