@@ -42,6 +42,7 @@ class Bert(nn.Module):
         self.bert_dim = self.bert_model.config.hidden_size
         self.bert_layer = self.bert_model.config.num_hidden_layers
         self.precision = opt.get('BERT_precision', 'bf16')
+        self.residual_fp32 = bool(opt.get('BERT_residual_fp32', False))
         if torch.cuda.is_available():
             self.bert_model.cuda()
         self.bert_model.eval()
@@ -49,8 +50,9 @@ class Bert(nn.Module):
         print('Finished loading')
 
     def engine(self):
-        if self._engine is None or self._engine.mode != self.precision:
-            self._engine = BertEngine(self.bert_model, self.precision)
+        if self._engine is None or self._engine.mode != self.precision \
+                or self._engine.residual_fp32 != self.residual_fp32:
+            self._engine = BertEngine(self.bert_model, self.precision, self.residual_fp32)
         return self._engine
 
     def forward(self, x_bert, x_bert_mask, x_bert_offset, x_mask, device=None):

@@ -59,10 +59,14 @@ def flatten_offsets(offsets, n_rows):
 
 
 class BertEngine(object):
-    def __init__(self, bert_model, mode="bf16"):
+    def __init__(self, bert_model, mode="bf16", residual_fp32=False):
         assert mode in ("bf16", "fp32")
         self.model = bert_model
         self.mode = mode
+        # bf16 mode: keep the residual stream / LayerNorm outputs in fp32 as well (what autocast
+        # does); the GEMM operands stay bf16.  Measured (tools/bert_error.py): no consistent gain —
+        # the bf16 error is dominated by operand rounding — so it is off by default.
+        self.residual_fp32 = residual_fp32
         cfg = bert_model.config
         self.H = cfg.hidden_size
         self.I = cfg.intermediate_size
@@ -199,6 +203,7 @@ class BertEngine(object):
         T, H, I = pk["T"], self.H, self.I
         st = current_stream()
         fp32 = self.mode == "fp32"
+        keep32 = fp32 or self.residual_fp32   # fp32 copy of the residual stream
         parts = 3 if fp32 else 1
         words = []
         for k, sg in enumerate(segments):
@@ -206,7 +211,7 @@ class BertEngine(object):
             words.append((torch.from_numpy(wt).to(dev, non_blocking=True), wt.shape[1],
                           sg.word_mask.to(torch.uint8).contiguous()))
         # embeddings
-        h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if fp32 else None
+        h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if keep32 else None
         h_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
         call("ruart_bert_embed_ln", ptr(pk["ids"]), ptr(pk["pos"]), ptr(W["word"]), ptr(W["pos"]),
              ptr(W["type"]), ptr(W["eg"]), ptr(W["eb"]), W["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
@@ -222,16 +227,16 @@ class BertEngine(object):
                 call("ruart_bert_attention", ptr(q_f), ptr(q_b), ptr(cu), n_seq, self.heads, scale,
                      sgm["max_len"], None, ptr(ctx), parts, st)
             a_f, a_b = self._gemm(ctx, lw["wo"], lw["bo"], H, H, ops.EPI_BIAS, "act")
-            h1_f = torch.empty((T, H), dtype=torch.float32, device=dev) if fp32 else None
+            h1_f = torch.empty((T, H), dtype=torch.float32, device=dev) if keep32 else None
             h1_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
-            call("ruart_add_layernorm", ptr(a_f), ptr(a_b), ptr(h_f), ptr(h_b) if not fp32 else None,
+            call("ruart_add_layernorm", ptr(a_f), ptr(a_b), ptr(h_f), ptr(h_b) if not keep32 else None,
                  ptr(lw["g1"]), ptr(lw["b1"]), lw["eps"], T, H, ptr(h1_f), ptr(h1_b), parts, st)
             _, ff = self._gemm(h1_b, lw["wi"], lw["bi"], I, H, ops.EPI_BIAS_GELU, "split",
                                fast_gelu=not fp32)
             d_f, d_b = self._gemm(ff, lw["wd"], lw["bd"], H, I, ops.EPI_BIAS, "act")
-            h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if fp32 else None
+            h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if keep32 else None
             h_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
-            call("ruart_add_layernorm", ptr(d_f), ptr(d_b), ptr(h1_f), ptr(h1_b) if not fp32 else None,
+            call("ruart_add_layernorm", ptr(d_f), ptr(d_b), ptr(h1_f), ptr(h1_b) if not keep32 else None,
                  ptr(lw["g2"]), ptr(lw["b2"]), lw["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
             for k, sg in enumerate(segments):
                 wt, nw, wmask = words[k]
@@ -242,7 +247,7 @@ class BertEngine(object):
                     dst, stride, col = sinks[k][li]
                     first = 1
                 base = dst.data_ptr() + 4 * col
-                call("ruart_subword_avg_accum", ptr(h_f), None if fp32 else ptr(h_b), ptr(wt), nw,
+                call("ruart_subword_avg_accum", ptr(h_f), None if keep32 else ptr(h_b), ptr(wt), nw,
                      ptr(pk["segments"][k]["row_start"]), ptr(wmask), sg.W, base, stride,
                      ptr(alpha), self.n_layers, ptr(gamma), li, first, H, st)
         return pk

@@ -199,7 +199,7 @@ bert_attention_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu_
   float* sK = att_smem + warp * (2 * stage_tokens * 64 + 64);
   float* sV = sK + stage_tokens * 64;
   float* sQ = sV + stage_tokens * 64;
-  const long long task = static_cast<long long>(blockIdx.x) * ATT_WARPS + warp;
+  const long long task = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (task >= static_cast<long long>(n_seq) * n_heads) return;
   const int seq = static_cast<int>(task / n_heads);
   const int head = static_cast<int>(task - static_cast<long long>(seq) * n_heads);
@@ -451,10 +451,11 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
   int stage_tokens = max_len < 1 ? 1 : (max_len > ATT_MAX_STAGE ? ATT_MAX_STAGE : max_len);
   stage_tokens = (stage_tokens + 7) / 8 * 8;
   if (stage_tokens > 24) stage_tokens = (stage_tokens > 48) ? 64 : 48;
-  const size_t smem = ATT_WARPS * (2 * stage_tokens * 64 + 64) * sizeof(float);
-  const size_t smem_max = ATT_WARPS * (2 * ATT_MAX_STAGE * 64 + 64) * sizeof(float);
+  const int warps = stage_tokens <= 24 ? ATT_WARPS : 4;
+  const size_t smem = warps * (2 * stage_tokens * 64 + 64) * sizeof(float);
+  const size_t smem_max = 4 * (2 * ATT_MAX_STAGE * 64 + 64) * sizeof(float);
   const long long tasks = static_cast<long long>(n_seq) * n_heads;
-  const unsigned grid = static_cast<unsigned>((tasks + ATT_WARPS - 1) / ATT_WARPS);
+  const unsigned grid = static_cast<unsigned>((tasks + warps - 1) / warps);
   static bool attr_set = false;
   if (!attr_set) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<float>,
@@ -466,11 +467,11 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     attr_set = true;
   }
   if (qkv_f32 != nullptr)
-    bert_attention_kernel<float><<<grid, ATT_WARPS * 32, smem, st>>>(
+    bert_attention_kernel<float><<<grid, warps * 32, smem, st>>>(
         qkv_f32, cu_seqlens, n_seq, n_heads, scale, stage_tokens, out_f32, (__nv_bfloat16*)out_bf16,
         out_parts);
   else
-    bert_attention_kernel<__nv_bfloat16><<<grid, ATT_WARPS * 32, smem, st>>>(
+    bert_attention_kernel<__nv_bfloat16><<<grid, warps * 32, smem, st>>>(
         (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, stage_tokens, out_f32,
         (__nv_bfloat16*)out_bf16, out_parts);
   RUART_LAUNCH_CHECK();
