@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of RUArt's per-question inference path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg cfg3]
+
+One "step" = one SDNet.forward over one synthetic ST-VQA-shaped batch (cfg-3: 256 questions x
+20 q-words, 50+1 OCR items, 36+1 OD items, bf16 BERT).  N > 1 is launched with torchrun, one rank
+per GPU; every rank runs its own seeded batch of the same size (weak scaling, no data-path
+collective — SURVEY.md §8e) and rank 0 prints ONE JSON line.
+
+  value      questions/s with the batch's tensors already resident in HBM
+  e2e        same through the public API with the batch in pinned HOST memory: H2D of every input
+             tensor + forward + D2H of the probabilities inside the timed region
+  roofline   all tcgen05 GEMM launches of the BERT encoder in the timed steps: algorithmic FLOPs
+             (2*T*N*K over the REAL tokens) / CUDA-event time, against the measured sustained bf16
+             peak in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port (oracle/sdnet_oracle.py, plain torch fp32 on all host threads)
+             on a bounded sample of the same workload (rank 0, N=1 only)
+
+--impl reference times that same CPU port as the reference arm (the reference itself is Python
+and does not travel to the GPU box; the port is pinned to it by tests/golden/).
+"""
+import argparse
+import contextlib
+import copy
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ruart_b200 import synth  # noqa: E402
+
+METRIC = "ST-VQA questions/sec"
+UNIT = "questions/s"
+
+
+def workload_desc(cfg):
+    c = synth.CONFIGS[cfg]
+    return ("%s: B=%d questions x 20 q-words, %d+1 OCR items, %d+1 OD labels per image "
+            "(max_ocr_num %d, max_od_num %d), synthetic ids, random-init BERT-base + SDNet" %
+            (cfg, c["B"], c["n_ocr"], c["n_od"], c["max_ocr_num"], c["max_od_num"]))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_step(cpu_sd, opt, batch):
+    from oracle import sdnet_oracle
+    probs, _, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch))
+    return probs
+
+
+def build_net(cfg, device):
+    from ruart_b200.Models.SDNet import SDNet
+    opt = synth.make_opt(cfg, BERT_precision="bf16")
+    torch.manual_seed(1033)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = SDNet(opt, synth.make_embedding(1033))
+    synth.fill_state_dict(net, seed=1033, bert_init="random")
+    net.eval()
+    net.drop_emb = False
+    if device is not None:
+        net.to(device)
+    return net, opt
+
+
+def sample_cfg(cfg, n_questions):
+    c = dict(synth.CONFIGS[cfg])
+    c["B"] = n_questions
+    return c
+
+
+def run_reference_arm(args, rank, world):
+    """CPU port on the host cores; each step is a bounded sample of the workload."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_q = max(1, min(32, int(budget / 0.8)))
+    net, opt = build_net(sample_cfg(args.cfg, n_q), None)
+    sd = net.state_dict()
+    batch = synth.make_batch(sample_cfg(args.cfg, n_q), seed=2003)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            cpu_port_step(sd, opt, batch)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_port_step(sd, opt, batch)
+        dt = time.perf_counter() - t0
+    qps = n_q * args.steps / dt
+    sample = "%d questions of the %s shape per step (fp32, torch CPU, %d threads)" % (n_q, args.cfg, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_desc(args.cfg)},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", default="cfg3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ruart_b200 import _lib
+    net, opt = build_net(args.cfg, dev)
+    B = synth.CONFIGS[args.cfg]["B"]
+    host_batch = synth.make_batch(args.cfg, seed=2003 + rank)
+    # pinned host copies for the e2e leg
+    pinned = tuple({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in d.items()} for d in host_batch)
+    h2d_bytes = sum(v.numel() * v.element_size() for d in pinned for v in d.values() if torch.is_tensor(v))
+    dev_batch = synth.batch_to(host_batch, dev)
+
+    def fresh(b):
+        # forward adds '*_emb' keys to its input dicts (reference side effect): reuse shallow copies
+        return tuple(dict(d) for d in b)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- GEMM timing hook (roofline): CUDA events around every BERT-shaped GEMM launch ----------
+    gemm_events = []
+    H = 768
+
+    class _Timed(object):
+        def __init__(self, flops):
+            self.flops = flops
+
+        def __enter__(self):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+        def __exit__(self, *a):
+            self.e1.record()
+            gemm_events.append((self.e0, self.e1, self.flops))
+
+    null = contextlib.nullcontext()
+
+    def hook(name, a):
+        if name != "ruart_gemm_bf16":
+            return null
+        M_, N_, Kp_, terms = a[6], a[7], a[8], a[9]
+        if terms == 1 and N_ in (3 * H, H, 4 * H) and Kp_ in (H, 4 * H):
+            return _Timed(2.0 * M_ * N_ * Kp_)
+        return null
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            probs, _ = net(*fresh(dev_batch))
+        barrier()
+        # -------- device-resident throughput --------------------------------------------------
+        _lib.set_timing_hook(hook)
+        launches0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                probs, _ = net(*fresh(dev_batch))
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count - launches0
+        _lib.set_timing_hook(None)
+        g_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
+        g_fl = sum(f for _, _, f in gemm_events)
+        n_gemm = len(gemm_events)
+        # -------- end to end: pinned host -> device -> forward -> host -------------------------
+        out_host = torch.empty((B, probs.shape[1]), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            b = synth.batch_to(pinned, dev)
+            p, _ = net(*b)
+            out_host.copy_(p, non_blocking=True)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(args.steps):
+            b = synth.batch_to(pinned, dev)
+            p, _ = net(*b)
+            out_host.copy_(p, non_blocking=True)
+        e3.record()
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    total_q = B * world * args.steps
+    value = total_q / (ms / 1e3)
+    e2e = total_q / (ms_e2e / 1e3)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        n_q = 16
+        cnet, copt = build_net(sample_cfg(args.cfg, n_q), None)
+        cb = synth.make_batch(sample_cfg(args.cfg, n_q), seed=2003)
+        csd = cnet.state_dict()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            cpu_port_step(csd, copt, cb)
+            dt = time.perf_counter() - t0
+        cpu_base = {"value": n_q / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": "one forward over %d questions of the %s shape (oracle/sdnet_oracle.py, fp32 torch CPU)" % (n_q, args.cfg)}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_desc(args.cfg), "per_gpu_batch": B, "global_batch": B * world,
+                       "parallelism": "batch-sharded x%d, no collective" % world,
+                       "precision": "BERT bf16 operands / fp32 accumulate; SDNet stack fp32-grade (3-part bf16 split)",
+                       "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_host.numel() * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (ach / peak) if ach else None, "traffic": None,
+                         "kernel": "gemm_bf16_tcgen05_kernel (all %d BERT GEMM launches of the timed steps)" % n_gemm,
+                         "kernel_ms_per_step": g_ms / args.steps, "peak_source": peak_src},
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,7 +14,8 @@ from torch.nn.parameter import Parameter
 
 from .. import ops
 from .. import sdnet_ops as K
-from .._lib import call, current_stream, ptr
+from .._lib import current_stream, ptr
+from ..ops import call
 
 dropout_p = 0.0
 do_seq_dropout = False

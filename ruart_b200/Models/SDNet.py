@@ -25,7 +25,8 @@ import torch.nn as nn
 
 from .. import ops
 from .. import sdnet_ops as K
-from .._lib import call, current_stream, ptr
+from .._lib import current_stream, ptr
+from ..ops import call
 from . import Layers
 from .Bert.Bert import Bert
 from .Layers import (Attention, DeepAttention, GetFinalScores, LinearSelfAttn, RNN_from_opt, dropout,

@@ -90,9 +90,26 @@ def check(rc):
         raise RuntimeError("ruart_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+_KERNELS_PER_CALL = {"ruart_whole_layernorm": 2}
+launch_count = 0
+_timing_hook = None  # set by bench.py: callable(name, args) -> context manager, or None
+
+
+def set_timing_hook(hook):
+    global _timing_hook
+    _timing_hook = hook
+
+
 def call(name, *args):
     """Call a C-ABI function by name and raise on a non-zero return code."""
-    check(getattr(lib(), name)(*args))
+    global launch_count
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
+    if _timing_hook is not None:
+        with _timing_hook(name, args):
+            check(getattr(lib(), name)(*args))
+    else:
+        check(getattr(lib(), name)(*args))
 
 
 def ptr(t):

@@ -20,7 +20,8 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import call, current_stream, ptr
+from ._lib import current_stream, ptr
+from .ops import call
 
 WINDOW = 512  # BERT_MAX_LEN, Models/Bert/Bert.py:18
 

@@ -7,7 +7,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import call, current_stream, ptr
+from ._lib import current_stream, ptr
+
+
+def call(name, *args):
+    return _lib.call(name, *args)
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_RELU_SCALE, EPI_BIAS_RELU = 0, 1, 2, 3, 4
 PHOC_DIM = 604

@@ -7,7 +7,8 @@ fused kernels of csrc/sdnet_kernels.cu / csrc/lstm.cu.  No torch math here: torc
 import torch
 
 from . import ops
-from ._lib import call, current_stream, ptr
+from ._lib import current_stream, ptr
+from .ops import call
 
 _TERMS = {1: 1, 2: 3, 3: 6}
 _wcache = {}
