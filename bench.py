@@ -134,7 +134,7 @@ def run_reference_arm(args, rank, world):
     budget = 150.0 / max(1, args.steps + args.warmup)
     n_q = max(1, min(32, int(budget / 0.8)))
     net, opt = build_net(sample_cfg(args.cfg, n_q), None)
-    sd = net.state_dict()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     batch = synth.make_batch(sample_cfg(args.cfg, n_q), seed=2003)
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -280,7 +280,8 @@ def main():
         n_q = 16
         cnet, copt = build_net(sample_cfg(args.cfg, n_q), None)
         cb = synth.make_batch(sample_cfg(args.cfg, n_q), seed=2003)
-        csd = cnet.state_dict()
+        csd = {k: v.detach().cpu() for k, v in cnet.state_dict().items()}
+        del cnet
         with torch.no_grad():
             t0 = time.perf_counter()
             cpu_port_step(csd, copt, cb)

@@ -190,7 +190,7 @@ __device__ __forceinline__ float2 ld2<__nv_bfloat16>(const __nv_bfloat16* p) {
 template <typename T>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 bert_attention_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu_seqlens, int n_seq,
-                      int n_heads, float scale, int stage_tokens, float* out_f32,
+                      int n_heads, float scale, int stage_tokens, int skip_upto, float* out_f32,
                       __nv_bfloat16* out_b16, int parts) {
   // per warp: K and V [stage_tokens][64] fp32 + the scaled query row [64]
   extern __shared__ float att_smem[];
@@ -205,6 +205,7 @@ bert_attention_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu_
   const int head = static_cast<int>(task - static_cast<long long>(seq) * n_heads);
   const int t0 = cu_seqlens[seq];
   const int len = cu_seqlens[seq + 1] - t0;
+  if (len <= skip_upto) return;  // handled by bert_attention_short_kernel
   const int H = n_heads * 64;
   const long long ld = 3LL * H;
   const T* qbase = qkv + static_cast<long long>(t0) * ld + head * 64;
@@ -292,6 +293,126 @@ bert_attention_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu_
                                            part * H + ocol) = hh;
         r0 -= __bfloat162float(h0);
         r1 -= __bfloat162float(h1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Short-sequence variant (bf16 qkv, len <= SHORT_MAX; RUArt's OCR / object-label items are 3..10
+// wordpieces).  One warp per SEQUENCE, all heads: K and V of the sequence are staged once in
+// shared memory (bf16, each 128-byte head row padded to 144 B so that heads fall into different
+// bank groups), and every lane owns (query i, head h) pairs p = lane, lane+32, ... — with len*heads
+// pairs per sequence all 32 lanes work even for 3-token items, where "lane = key" would idle 90 %.
+// Per pair: q row in registers (fp32, pre-scaled), keys streamed in chunks of 8 with an online
+// softmax, output row [64] accumulated in registers and written as one 128-byte run.
+constexpr int SHORT_MAX = 16;
+constexpr int SHORT_WARPS = 4;
+constexpr int HEAD_ROW_B = 144;  // bytes per (token, head) row in smem: 128 B data + 16 B pad
+
+__global__ void __launch_bounds__(SHORT_WARPS * 32)
+bert_attention_short_kernel(const __nv_bfloat16* __restrict__ qkv,
+                            const int32_t* __restrict__ cu_seqlens, int n_seq, int n_heads,
+                            float scale, int stage_tokens, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t sh_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok_b = n_heads * HEAD_ROW_B;  // bytes per token for K (same for V)
+  uint8_t* sK = sh_raw + static_cast<size_t>(warp) * 2 * stage_tokens * tok_b;
+  uint8_t* sV = sK + static_cast<size_t>(stage_tokens) * tok_b;
+  const int H = n_heads * 64;
+  const long long ld = 3LL * H;
+  const int chunks_per_tok = n_heads * 8;  // 16-byte chunks of one token's K (or V)
+  for (int seq = blockIdx.x * SHORT_WARPS + warp; seq < n_seq; seq += gridDim.x * SHORT_WARPS) {
+    const int t0 = cu_seqlens[seq];
+    const int len = cu_seqlens[seq + 1] - t0;
+    if (len <= 0 || len > stage_tokens) continue;  // long sequences: bert_attention_kernel
+    __syncwarp();
+    // stage K and V: 16-byte chunk c of token j -> head c/8, chunk c%8
+    for (int idx = lane; idx < len * chunks_per_tok; idx += 32) {
+      const int j = idx / chunks_per_tok;
+      const int c = idx - j * chunks_per_tok;
+      const __nv_bfloat16* row = qkv + (static_cast<long long>(t0 + j)) * ld;
+      const uint4 kk = __ldg(reinterpret_cast<const uint4*>(row + H) + c);
+      const uint4 vv = __ldg(reinterpret_cast<const uint4*>(row + 2 * H) + c);
+      const int off = j * tok_b + (c >> 3) * HEAD_ROW_B + (c & 7) * 16;
+      *reinterpret_cast<uint4*>(sK + off) = kk;
+      *reinterpret_cast<uint4*>(sV + off) = vv;
+    }
+    __syncwarp();
+    const int n_pairs = len * n_heads;
+    for (int p = lane; p < n_pairs; p += 32) {
+      const int i = p / n_heads;
+      const int h = p - i * n_heads;
+      float q[64];
+      {
+        const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(t0 + i)) * ld + h * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = __ldg(qp + c);
+          q[c * 8 + 0] = bf16_lo(u.x) * scale; q[c * 8 + 1] = bf16_hi(u.x) * scale;
+          q[c * 8 + 2] = bf16_lo(u.y) * scale; q[c * 8 + 3] = bf16_hi(u.y) * scale;
+          q[c * 8 + 4] = bf16_lo(u.z) * scale; q[c * 8 + 5] = bf16_hi(u.z) * scale;
+          q[c * 8 + 6] = bf16_lo(u.w) * scale; q[c * 8 + 7] = bf16_hi(u.w) * scale;
+        }
+      }
+      float o[64];
+#pragma unroll
+      for (int d = 0; d < 64; ++d) o[d] = 0.f;
+      float m = -INFINITY, l = 0.f;
+      const uint8_t* kh = sK + h * HEAD_ROW_B;
+      const uint8_t* vh = sV + h * HEAD_ROW_B;
+      for (int j0 = 0; j0 < len; j0 += 8) {
+        float sc[8];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          sc[jj] = -INFINITY;
+          if (j0 + jj < len) {
+            const uint4* kp = reinterpret_cast<const uint4*>(kh + (j0 + jj) * tok_b);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 u = kp[c];
+              a0 = fmaf(q[c * 8 + 0], bf16_lo(u.x), a0); a1 = fmaf(q[c * 8 + 1], bf16_hi(u.x), a1);
+              a2 = fmaf(q[c * 8 + 2], bf16_lo(u.y), a2); a3 = fmaf(q[c * 8 + 3], bf16_hi(u.y), a3);
+              a0 = fmaf(q[c * 8 + 4], bf16_lo(u.z), a0); a1 = fmaf(q[c * 8 + 5], bf16_hi(u.z), a1);
+              a2 = fmaf(q[c * 8 + 6], bf16_lo(u.w), a2); a3 = fmaf(q[c * 8 + 7], bf16_hi(u.w), a3);
+            }
+            sc[jj] = (a0 + a1) + (a2 + a3);
+            cmax = fmaxf(cmax, sc[jj]);
+          }
+        }
+        const float m_new = fmaxf(m, cmax);
+        const float corr = __expf(m - m_new);  // 0 on the first chunk (m = -inf)
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) o[d] *= corr;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          if (j0 + jj < len) {
+            const float pj = __expf(sc[jj] - m_new);
+            l += pj;
+            const uint4* vp = reinterpret_cast<const uint4*>(vh + (j0 + jj) * tok_b);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 u = vp[c];
+              o[c * 8 + 0] = fmaf(pj, bf16_lo(u.x), o[c * 8 + 0]); o[c * 8 + 1] = fmaf(pj, bf16_hi(u.x), o[c * 8 + 1]);
+              o[c * 8 + 2] = fmaf(pj, bf16_lo(u.y), o[c * 8 + 2]); o[c * 8 + 3] = fmaf(pj, bf16_hi(u.y), o[c * 8 + 3]);
+              o[c * 8 + 4] = fmaf(pj, bf16_lo(u.z), o[c * 8 + 4]); o[c * 8 + 5] = fmaf(pj, bf16_hi(u.z), o[c * 8 + 5]);
+              o[c * 8 + 6] = fmaf(pj, bf16_lo(u.w), o[c * 8 + 6]); o[c * 8 + 7] = fmaf(pj, bf16_hi(u.w), o[c * 8 + 7]);
+            }
+          }
+        }
+        m = m_new;
+      }
+      const float inv = 1.0f / l;
+      uint4* op = reinterpret_cast<uint4*>(out + (static_cast<long long>(t0 + i)) * H + h * 64);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        op[c] = make_uint4(pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv),
+                           pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv),
+                           pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv),
+                           pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv));
       }
     }
   }
@@ -448,15 +569,9 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
   RUART_ARG_CHECK(n_heads > 0);
   if (n_seq == 0) return RUART_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int stage_tokens = max_len < 1 ? 1 : (max_len > ATT_MAX_STAGE ? ATT_MAX_STAGE : max_len);
-  stage_tokens = (stage_tokens + 7) / 8 * 8;
-  if (stage_tokens > 24) stage_tokens = (stage_tokens > 48) ? 64 : 48;
-  const int warps = stage_tokens <= 24 ? ATT_WARPS : 4;
-  const size_t smem = warps * (2 * stage_tokens * 64 + 64) * sizeof(float);
-  const size_t smem_max = 4 * (2 * ATT_MAX_STAGE * 64 + 64) * sizeof(float);
-  const long long tasks = static_cast<long long>(n_seq) * n_heads;
-  const unsigned grid = static_cast<unsigned>((tasks + warps - 1) / warps);
   static bool attr_set = false;
+  const size_t smem_max = 4 * (2 * ATT_MAX_STAGE * 64 + 64) * sizeof(float);
+  const size_t short_max = 227 * 1024;
   if (!attr_set) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<float>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -464,16 +579,43 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<__nv_bfloat16>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_max));
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_short_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)short_max));
     attr_set = true;
   }
+  // bf16 in, plain bf16 out: sequences of <= SHORT_MAX tokens go to the warp-per-sequence kernel
+  int skip_upto = 0;
+  if (qkv_bf16 != nullptr && out_f32 == nullptr && out_parts == 1 && n_heads <= 16) {
+    const int stage = max_len < SHORT_MAX ? (max_len < 1 ? 1 : max_len) : SHORT_MAX;
+    int stage_fit = stage;
+    while (static_cast<size_t>(SHORT_WARPS) * 2 * stage_fit * n_heads * HEAD_ROW_B > short_max) --stage_fit;
+    const size_t smem = static_cast<size_t>(SHORT_WARPS) * 2 * stage_fit * n_heads * HEAD_ROW_B;
+    long long ctas = (n_seq + SHORT_WARPS - 1) / SHORT_WARPS;
+    const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
+    if (ctas > cap) ctas = cap;
+    bert_attention_short_kernel<<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, smem, st>>>(
+        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, stage_fit,
+        (__nv_bfloat16*)out_bf16);
+    RUART_LAUNCH_CHECK();
+    if (max_len <= stage_fit) return RUART_OK;
+    skip_upto = stage_fit;
+  }
+  int stage_tokens = max_len < 1 ? 1 : (max_len > ATT_MAX_STAGE ? ATT_MAX_STAGE : max_len);
+  stage_tokens = (stage_tokens + 7) / 8 * 8;
+  if (stage_tokens > 24) stage_tokens = (stage_tokens > 48) ? 64 : 48;
+  const int warps = stage_tokens <= 24 ? ATT_WARPS : 4;
+  const size_t smem = warps * (2 * stage_tokens * 64 + 64) * sizeof(float);
+  const long long tasks = static_cast<long long>(n_seq) * n_heads;
+  const unsigned grid = static_cast<unsigned>((tasks + warps - 1) / warps);
   if (qkv_f32 != nullptr)
     bert_attention_kernel<float><<<grid, warps * 32, smem, st>>>(
-        qkv_f32, cu_seqlens, n_seq, n_heads, scale, stage_tokens, out_f32, (__nv_bfloat16*)out_bf16,
-        out_parts);
+        qkv_f32, cu_seqlens, n_seq, n_heads, scale, stage_tokens, skip_upto, out_f32,
+        (__nv_bfloat16*)out_bf16, out_parts);
   else
     bert_attention_kernel<__nv_bfloat16><<<grid, warps * 32, smem, st>>>(
-        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, stage_tokens, out_f32,
-        (__nv_bfloat16*)out_bf16, out_parts);
+        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, stage_tokens, skip_upto,
+        out_f32, (__nv_bfloat16*)out_bf16, out_parts);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
