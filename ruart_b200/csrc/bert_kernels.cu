@@ -299,120 +299,147 @@ bert_attention_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu_
 }
 
 // ---------------------------------------------------------------------------------------
-// Short-sequence variant (bf16 qkv, len <= SHORT_MAX; RUArt's OCR / object-label items are 3..10
-// wordpieces).  One warp per SEQUENCE, all heads: K and V of the sequence are staged once in
-// shared memory (bf16, each 128-byte head row padded to 144 B so that heads fall into different
-// bank groups), and every lane owns (query i, head h) pairs p = lane, lane+32, ... — with len*heads
-// pairs per sequence all 32 lanes work even for 3-token items, where "lane = key" would idle 90 %.
-// Per pair: q row in registers (fp32, pre-scaled), keys streamed in chunks of 8 with an online
-// softmax, output row [64] accumulated in registers and written as one 128-byte run.
+// Short-sequence variant (bf16 qkv, len <= SHORT_MAX = 16; RUArt's OCR / object-label items are
+// 3..10 wordpieces).  One warp per sequence, looping over heads; per head the [len x 64] Q, K, V
+// slices are staged in shared memory (16-byte chunks XOR-swizzled by row, rows >= len zeroed) and
+// the two small products run on the warp-level tensor-core path (mma.sync m16n8k16, bf16 in, fp32
+// accumulate) in the FlashAttention-2 register layout:
+//     S[16 x 16] = Q K^T   (4 k-steps x 2 key tiles)   -> masked softmax in registers (quad shuffles)
+//     O[16 x 64] = P V     (8 dim tiles, P re-used from the S accumulators as the A fragment)
+// tcgen05 cannot help here (its smallest M is 64 and operands must sit in 1024-byte swizzle
+// atoms); these tiles are 5x64.  O is staged back through the Q tile and leaves as 16-byte rows.
 constexpr int SHORT_MAX = 16;
-constexpr int SHORT_WARPS = 4;
-constexpr int HEAD_ROW_B = 144;  // bytes per (token, head) row in smem: 128 B data + 16 B pad
+constexpr int SHORT_WARPS = 8;
+constexpr int TILE_B = 16 * 128;  // one [16 x 64] bf16 tile
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                          uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                               uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// byte offset of 16-byte chunk c of row r inside a swizzled [16 x 64] bf16 tile
+__device__ __forceinline__ int tile_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
 __global__ void __launch_bounds__(SHORT_WARPS * 32)
 bert_attention_short_kernel(const __nv_bfloat16* __restrict__ qkv,
                             const int32_t* __restrict__ cu_seqlens, int n_seq, int n_heads,
-                            float scale, int stage_tokens, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t sh_raw[];
+                            float scale, int max_short, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(128) uint8_t sh[SHORT_WARPS][3 * TILE_B];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tok_b = n_heads * HEAD_ROW_B;  // bytes per token for K (same for V)
-  uint8_t* sK = sh_raw + static_cast<size_t>(warp) * 2 * stage_tokens * tok_b;
-  uint8_t* sV = sK + static_cast<size_t>(stage_tokens) * tok_b;
+  uint8_t* sQ = sh[warp];
+  uint8_t* sK = sQ + TILE_B;
+  uint8_t* sV = sK + TILE_B;
+  const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
   const int H = n_heads * 64;
   const long long ld = 3LL * H;
-  const int chunks_per_tok = n_heads * 8;  // 16-byte chunks of one token's K (or V)
+  const int g = lane >> 2, t = lane & 3;
+  // ldmatrix row/chunk roles of this lane
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;  // A (Q) and V^T: rows 0..15
+  const int a_chk = lane >> 4;                           // + 2*ks  (Q) / + dim-tile pair (V)
+  const int b_row = lane & 7;                            // K: key inside the 8-key tile
+  const int b_chk = lane >> 3;                           // + 4*half (two k-steps per x4)
   for (int seq = blockIdx.x * SHORT_WARPS + warp; seq < n_seq; seq += gridDim.x * SHORT_WARPS) {
     const int t0 = cu_seqlens[seq];
     const int len = cu_seqlens[seq + 1] - t0;
-    if (len <= 0 || len > stage_tokens) continue;  // long sequences: bert_attention_kernel
-    __syncwarp();
-    // stage K and V: 16-byte chunk c of token j -> head c/8, chunk c%8
-    for (int idx = lane; idx < len * chunks_per_tok; idx += 32) {
-      const int j = idx / chunks_per_tok;
-      const int c = idx - j * chunks_per_tok;
-      const __nv_bfloat16* row = qkv + (static_cast<long long>(t0 + j)) * ld;
-      const uint4 kk = __ldg(reinterpret_cast<const uint4*>(row + H) + c);
-      const uint4 vv = __ldg(reinterpret_cast<const uint4*>(row + 2 * H) + c);
-      const int off = j * tok_b + (c >> 3) * HEAD_ROW_B + (c & 7) * 16;
-      *reinterpret_cast<uint4*>(sK + off) = kk;
-      *reinterpret_cast<uint4*>(sV + off) = vv;
-    }
-    __syncwarp();
-    const int n_pairs = len * n_heads;
-    for (int p = lane; p < n_pairs; p += 32) {
-      const int i = p / n_heads;
-      const int h = p - i * n_heads;
-      float q[64];
-      {
-        const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(t0 + i)) * ld + h * 64);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = __ldg(qp + c);
-          q[c * 8 + 0] = bf16_lo(u.x) * scale; q[c * 8 + 1] = bf16_hi(u.x) * scale;
-          q[c * 8 + 2] = bf16_lo(u.y) * scale; q[c * 8 + 3] = bf16_hi(u.y) * scale;
-          q[c * 8 + 4] = bf16_lo(u.z) * scale; q[c * 8 + 5] = bf16_hi(u.z) * scale;
-          q[c * 8 + 6] = bf16_lo(u.w) * scale; q[c * 8 + 7] = bf16_hi(u.w) * scale;
+    if (len <= 0 || len > max_short) continue;  // long sequences: bert_attention_kernel
+    const int n_chunks = len * 8;
+    for (int h = 0; h < n_heads; ++h) {
+      __syncwarp();
+      // stage Q, K, V head slices; zero the pad rows
+      for (int idx = lane; idx < 16 * 8; idx += 32) {
+        const int r = idx >> 3, c = idx & 7;
+        uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+        if (idx < n_chunks) {
+          const uint4* row = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(t0 + r)) * ld + h * 64);
+          q4 = __ldg(row + c);
+          k4 = __ldg(row + (H >> 3) + c);
+          v4 = __ldg(row + 2 * (H >> 3) + c);
         }
+        const int off = tile_off(r, c);
+        *reinterpret_cast<uint4*>(sQ + off) = q4;
+        *reinterpret_cast<uint4*>(sK + off) = k4;
+        *reinterpret_cast<uint4*>(sV + off) = v4;
       }
-      float o[64];
-#pragma unroll
-      for (int d = 0; d < 64; ++d) o[d] = 0.f;
-      float m = -INFINITY, l = 0.f;
-      const uint8_t* kh = sK + h * HEAD_ROW_B;
-      const uint8_t* vh = sV + h * HEAD_ROW_B;
-      for (int j0 = 0; j0 < len; j0 += 8) {
-        float sc[8];
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          sc[jj] = -INFINITY;
-          if (j0 + jj < len) {
-            const uint4* kp = reinterpret_cast<const uint4*>(kh + (j0 + jj) * tok_b);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 u = kp[c];
-              a0 = fmaf(q[c * 8 + 0], bf16_lo(u.x), a0); a1 = fmaf(q[c * 8 + 1], bf16_hi(u.x), a1);
-              a2 = fmaf(q[c * 8 + 2], bf16_lo(u.y), a2); a3 = fmaf(q[c * 8 + 3], bf16_hi(u.y), a3);
-              a0 = fmaf(q[c * 8 + 4], bf16_lo(u.z), a0); a1 = fmaf(q[c * 8 + 5], bf16_hi(u.z), a1);
-              a2 = fmaf(q[c * 8 + 6], bf16_lo(u.w), a2); a3 = fmaf(q[c * 8 + 7], bf16_hi(u.w), a3);
-            }
-            sc[jj] = (a0 + a1) + (a2 + a3);
-            cmax = fmaxf(cmax, sc[jj]);
-          }
-        }
-        const float m_new = fmaxf(m, cmax);
-        const float corr = __expf(m - m_new);  // 0 on the first chunk (m = -inf)
-        l *= corr;
-#pragma unroll
-        for (int d = 0; d < 64; ++d) o[d] *= corr;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          if (j0 + jj < len) {
-            const float pj = __expf(sc[jj] - m_new);
-            l += pj;
-            const uint4* vp = reinterpret_cast<const uint4*>(vh + (j0 + jj) * tok_b);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 u = vp[c];
-              o[c * 8 + 0] = fmaf(pj, bf16_lo(u.x), o[c * 8 + 0]); o[c * 8 + 1] = fmaf(pj, bf16_hi(u.x), o[c * 8 + 1]);
-              o[c * 8 + 2] = fmaf(pj, bf16_lo(u.y), o[c * 8 + 2]); o[c * 8 + 3] = fmaf(pj, bf16_hi(u.y), o[c * 8 + 3]);
-              o[c * 8 + 4] = fmaf(pj, bf16_lo(u.z), o[c * 8 + 4]); o[c * 8 + 5] = fmaf(pj, bf16_hi(u.z), o[c * 8 + 5]);
-              o[c * 8 + 6] = fmaf(pj, bf16_lo(u.w), o[c * 8 + 6]); o[c * 8 + 7] = fmaf(pj, bf16_hi(u.w), o[c * 8 + 7]);
-            }
-          }
-        }
-        m = m_new;
+      __syncwarp();
+      // S = Q K^T : two key tiles (keys 0-7, 8-15), four k-steps over the 64 dims
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t kb0[8], kb1[8];  // K fragments: [ks*2 + {0,1}] for key tile 0 / 1
+      ldsm_x4(aK + tile_off(b_row, b_chk), kb0[0], kb0[1], kb0[2], kb0[3]);
+      ldsm_x4(aK + tile_off(b_row, 4 + b_chk), kb0[4], kb0[5], kb0[6], kb0[7]);
+      const bool two = len > 8;
+      if (two) {
+        ldsm_x4(aK + tile_off(8 + b_row, b_chk), kb1[0], kb1[1], kb1[2], kb1[3]);
+        ldsm_x4(aK + tile_off(8 + b_row, 4 + b_chk), kb1[4], kb1[5], kb1[6], kb1[7]);
       }
-      const float inv = 1.0f / l;
-      uint4* op = reinterpret_cast<uint4*>(out + (static_cast<long long>(t0 + i)) * H + h * 64);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        op[c] = make_uint4(pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv),
-                           pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv),
-                           pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv),
-                           pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv));
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(aQ + tile_off(a_row, 2 * ks + a_chk), a0, a1, a2, a3);
+        mma_bf16_16816(s0, a0, a1, a2, a3, kb0[2 * ks], kb0[2 * ks + 1]);
+        if (two) mma_bf16_16816(s1, a0, a1, a2, a3, kb1[2 * ks], kb1[2 * ks + 1]);
+      }
+      // masked softmax over keys; thread holds rows g (c0,c1) and g+8 (c2,c3), keys 2t,2t+1 (+8)
+      const int k0 = 2 * t, k1 = 2 * t + 1;
+      float v[8];
+      v[0] = (k0 < len) ? s0[0] * scale : -INFINITY;
+      v[1] = (k1 < len) ? s0[1] * scale : -INFINITY;
+      v[2] = (k0 < len) ? s0[2] * scale : -INFINITY;
+      v[3] = (k1 < len) ? s0[3] * scale : -INFINITY;
+      v[4] = (8 + k0 < len) ? s1[0] * scale : -INFINITY;
+      v[5] = (8 + k1 < len) ? s1[1] * scale : -INFINITY;
+      v[6] = (8 + k0 < len) ? s1[2] * scale : -INFINITY;
+      v[7] = (8 + k1 < len) ? s1[3] * scale : -INFINITY;
+      float mA = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[4], v[5]));
+      float mB = fmaxf(fmaxf(v[2], v[3]), fmaxf(v[6], v[7]));
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+      float pA0 = __expf(v[0] - mA), pA1 = __expf(v[1] - mA), pA2 = __expf(v[4] - mA), pA3 = __expf(v[5] - mA);
+      float pB0 = __expf(v[2] - mB), pB1 = __expf(v[3] - mB), pB2 = __expf(v[6] - mB), pB3 = __expf(v[7] - mB);
+      float lA = (pA0 + pA1) + (pA2 + pA3), lB = (pB0 + pB1) + (pB2 + pB3);
+      lA += __shfl_xor_sync(0xffffffffu, lA, 1);
+      lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+      lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+      lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+      // P as the A fragment of the second product (rows g / g+8, keys 2t.. / 8+2t..)
+      const uint32_t p0 = pack_bf16x2(pA0, pA1), p1 = pack_bf16x2(pB0, pB1);
+      const uint32_t p2 = pack_bf16x2(pA2, pA3), p3 = pack_bf16x2(pB2, pB3);
+      const float iA = 1.0f / lA, iB = 1.0f / lB;
+      __syncwarp();  // all lanes are done reading sQ: it becomes the O staging tile
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-wide dim tiles
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(aV + tile_off(a_row, 2 * dp + a_chk), b0, b1, b2, b3);
+        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(o0, p0, p1, p2, p3, b0, b1);
+        mma_bf16_16816(o1, p0, p1, p2, p3, b2, b3);
+        // O[g][16dp + 2t..], O[g+8][...]; second tile at +8 dims
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp) + 4 * t) = pack_bf16x2(o0[0] * iA, o0[1] * iA);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp) + 4 * t) = pack_bf16x2(o0[2] * iB, o0[3] * iB);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[0] * iA, o1[1] * iA);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[2] * iB, o1[3] * iB);
+      }
+      __syncwarp();
+      for (int idx = lane; idx < n_chunks; idx += 32) {
+        const int r = idx >> 3, c = idx & 7;
+        const uint4 o4 = *reinterpret_cast<const uint4*>(sQ + tile_off(r, c));
+        *(reinterpret_cast<uint4*>(out + (static_cast<long long>(t0 + r)) * H + h * 64) + c) = o4;
       }
     }
   }
@@ -571,7 +598,6 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   const size_t smem_max = 4 * (2 * ATT_MAX_STAGE * 64 + 64) * sizeof(float);
-  const size_t short_max = 227 * 1024;
   if (!attr_set) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<float>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -579,27 +605,20 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<__nv_bfloat16>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_max));
-    RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_short_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)short_max));
     attr_set = true;
   }
-  // bf16 in, plain bf16 out: sequences of <= SHORT_MAX tokens go to the warp-per-sequence kernel
+  // bf16 in, plain bf16 out: sequences of <= SHORT_MAX tokens go to the warp-per-sequence MMA kernel
   int skip_upto = 0;
-  if (qkv_bf16 != nullptr && out_f32 == nullptr && out_parts == 1 && n_heads <= 16) {
-    const int stage = max_len < SHORT_MAX ? (max_len < 1 ? 1 : max_len) : SHORT_MAX;
-    int stage_fit = stage;
-    while (static_cast<size_t>(SHORT_WARPS) * 2 * stage_fit * n_heads * HEAD_ROW_B > short_max) --stage_fit;
-    const size_t smem = static_cast<size_t>(SHORT_WARPS) * 2 * stage_fit * n_heads * HEAD_ROW_B;
+  if (qkv_bf16 != nullptr && out_f32 == nullptr && out_parts == 1) {
     long long ctas = (n_seq + SHORT_WARPS - 1) / SHORT_WARPS;
-    const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
+    const long long cap = static_cast<long long>(ruart_num_sms()) * 8;
     if (ctas > cap) ctas = cap;
-    bert_attention_short_kernel<<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, smem, st>>>(
-        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, stage_fit,
+    bert_attention_short_kernel<<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, 0, st>>>(
+        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, SHORT_MAX,
         (__nv_bfloat16*)out_bf16);
     RUART_LAUNCH_CHECK();
-    if (max_len <= stage_fit) return RUART_OK;
-    skip_upto = stage_fit;
+    if (max_len <= SHORT_MAX) return RUART_OK;
+    skip_upto = SHORT_MAX;
   }
   int stage_tokens = max_len < 1 ? 1 : (max_len > ATT_MAX_STAGE ? ATT_MAX_STAGE : max_len);
   stage_tokens = (stage_tokens + 7) / 8 * 8;
