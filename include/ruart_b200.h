@@ -105,6 +105,19 @@ RUART_API int ruart_subword_avg_accum(const float* h_f32, const void* h_bf16, co
                                       int W, float* dst, long long dst_stride, const float* alpha,
                                       int n_layers, const float* gamma, int layer, int first,
                                       int hidden, void* stream);
+/* Same for all encoder layers at once: h is [n_layers][T][hidden] (layer_stride elements apart);
+ * dst = sum_l mean(h_l[st..ed)) * softmax(alpha)[l] * gamma, written once, in layer order.    */
+RUART_API int ruart_subword_avg_layers(const float* h_f32, const void* h_bf16,
+                                       long long layer_stride, const int32_t* words, int n_words,
+                                       const int32_t* row_start, const uint8_t* x_mask, int W,
+                                       float* dst, long long dst_stride, const float* alpha,
+                                       int n_layers, const float* gamma, int hidden, void* stream);
+/* Real (mask != 0) wordpieces of ids [N, L] (int64, the collate's dtype) -> packed int32 ids and
+ * position ids (column % window) at out[row_start[r] ...]; replaces the padded [N, L] layout of
+ * BertModel.forward's inputs (modeling.py:585-604).                                            */
+RUART_API int ruart_pack_tokens(const long long* ids, const uint8_t* mask, int N, int L,
+                                const int32_t* row_start, int window, int32_t* out_ids,
+                                int32_t* out_pos, void* stream);
 /* fp32 [*, K] (row pitch ld) -> bf16 split operand [rows, parts*Kp] for ruart_gemm_bf16; output
  * row r reads source row row_idx[r] (NULL = r)                                                 */
 RUART_API int ruart_split_bf16(const float* src, long long ld, const int32_t* row_idx,

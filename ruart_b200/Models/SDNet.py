@@ -189,6 +189,14 @@ class SDNet(nn.Module):
                     word_src=word_src, word_dst=word_dst, mask=mask, total_words=total)
 
     # ------------------------------------------------------------------ forward
+    phase_log = None  # set to a list to collect (label, seconds since forward start) with device syncs
+
+    def _phase(self, label):
+        if self.phase_log is not None:
+            import time
+            torch.cuda.synchronize()
+            self.phase_log.append((label, time.perf_counter()))
+
     def forward(self, q_list, ocr_list, od_list, return_score=False):
         if self.training and (Layers.dropout_p > 0 or self.drop_emb):
             raise NotImplementedError("ruart_b200.SDNet implements inference; call .eval() and set drop_emb=False")
@@ -208,6 +216,40 @@ class SDNet(nn.Module):
         pos_dim, ent_dim = opt['pos_dim'], opt['ent_dim']
         H = opt['hidden_size']
 
+        self._phase('start')
+        # ---- embeddings: [word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) -------------
+        q_in = torch.zeros((B, Wq, QD), **f32)
+        items_in = torch.zeros((N_ocr * Wo + N_od * Wd, XD), **f32)
+        ocr_in = items_in[:N_ocr * Wo].view(N_ocr, Wo, XD)
+        od_in = items_in[N_ocr * Wo:].view(N_od, Wd, XD)
+        q_word = torch.empty((B, Wq, VD), **f32)
+        ocr_word = torch.empty((N_ocr, Wo, VD), **f32)
+        od_word = torch.empty((N_od, Wd, VD), **f32)
+        c_pos, c_ent = VD + BD, VD + BD + pos_dim
+
+        def embed(lst, key, table, buf, raw, n_rows):
+            K.gather_rows(table.weight.detach(), lst[key].reshape(-1), buf, None, n_rows, VD, dst2=raw)
+            K.gather_rows(self.pos_embedding.weight.detach(), lst['pos'].reshape(-1), buf[..., c_pos:], None,
+                          n_rows, pos_dim)
+            K.gather_rows(self.ent_embedding.weight.detach(), lst['ent'].reshape(-1), buf[..., c_ent:], None,
+                          n_rows, ent_dim)
+
+        embed(q_list, 'glove', self.glove_embed, q_in, q_word, B * Wq)
+        embed(ocr_list, 'fasttext', self.fast_embed, ocr_in, ocr_word, N_ocr * Wo)
+        embed(od_list, 'fasttext', self.fast_embed, od_in, od_word, N_od * Wd)
+        q_list['glove_emb'] = q_word          # side effect of the reference (SDNet.py:449-450,458-459)
+        ocr_list['fasttext_emb'] = ocr_word
+        od_list['fasttext_emb'] = od_word
+
+        self._phase('embed')
+        # ---- BERT: one packed pass, subword mean + layer sum into the concat buffers ------------
+        self.Bert.encode_into(
+            [(q_list['bert'], q_list['bert_mask'], q_list['bert_offsets'], q_list['glove_mask']),
+             (ocr_list['bert'], ocr_list['bert_mask'], ocr_list['bert_offsets'], ocr_list['fasttext_mask']),
+             (od_list['bert'], od_list['bert_mask'], od_list['bert_offsets'], od_list['fasttext_mask'])],
+            [(q_in, QD, VD), (ocr_in, XD, VD), (od_in, XD, VD)], self.alphaBERT, self.gammaBERT)
+
+        self._phase('bert')
         # ---- host indices (one upload) -------------------------------------------------------
         io = self._item_index(ocr_list['num_cnt'], ocr_list['len_cnt'], Wo, M)
         id_ = self._item_index(od_list['num_cnt'], od_list['len_cnt'], Wd, M_od)
@@ -235,37 +277,7 @@ class SDNet(nn.Module):
         od_mask = masks_d[B * M:].view(B, M_od)
         q_mask = K.as_u8(q_list['glove_mask'])
 
-        # ---- embeddings: [word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) -------------
-        q_in = torch.zeros((B, Wq, QD), **f32)
-        items_in = torch.zeros((N_ocr * Wo + N_od * Wd, XD), **f32)
-        ocr_in = items_in[:N_ocr * Wo].view(N_ocr, Wo, XD)
-        od_in = items_in[N_ocr * Wo:].view(N_od, Wd, XD)
-        q_word = torch.empty((B, Wq, VD), **f32)
-        ocr_word = torch.empty((N_ocr, Wo, VD), **f32)
-        od_word = torch.empty((N_od, Wd, VD), **f32)
-        c_pos, c_ent = VD + BD, VD + BD + pos_dim
-
-        def embed(lst, key, table, buf, raw, n_rows):
-            K.gather_rows(table.weight.detach(), lst[key].reshape(-1), buf, None, n_rows, VD, dst2=raw)
-            K.gather_rows(self.pos_embedding.weight.detach(), lst['pos'].reshape(-1), buf[..., c_pos:], None,
-                          n_rows, pos_dim)
-            K.gather_rows(self.ent_embedding.weight.detach(), lst['ent'].reshape(-1), buf[..., c_ent:], None,
-                          n_rows, ent_dim)
-
-        embed(q_list, 'glove', self.glove_embed, q_in, q_word, B * Wq)
-        embed(ocr_list, 'fasttext', self.fast_embed, ocr_in, ocr_word, N_ocr * Wo)
-        embed(od_list, 'fasttext', self.fast_embed, od_in, od_word, N_od * Wd)
-        q_list['glove_emb'] = q_word          # side effect of the reference (SDNet.py:449-450,458-459)
-        ocr_list['fasttext_emb'] = ocr_word
-        od_list['fasttext_emb'] = od_word
-
-        # ---- BERT: one packed pass, subword mean + layer sum into the concat buffers ------------
-        self.Bert.encode_into(
-            [(q_list['bert'], q_list['bert_mask'], q_list['bert_offsets'], q_list['glove_mask']),
-             (ocr_list['bert'], ocr_list['bert_mask'], ocr_list['bert_offsets'], ocr_list['fasttext_mask']),
-             (od_list['bert'], od_list['bert_mask'], od_list['bert_offsets'], od_list['fasttext_mask'])],
-            [(q_in, QD, VD), (ocr_in, XD, VD), (od_in, XD, VD)], self.alphaBERT, self.gammaBERT)
-
+        self._phase('host_index')
         # ---- word-level pre-alignment (SDNet.py:495-551) --------------------------------------
         c_pre = VD + BD + pos_dim + ent_dim
         p2_cache = {}
@@ -277,6 +289,7 @@ class SDNet(nn.Module):
             att = self.pre_align(packed, q_word, q_mask, p2_cache=p2_cache)
             K.gather_rows(att, wdst, buf[..., c_pre:], wsrc, idx['total_words'], VD)
 
+        self._phase('prealign')
         # ---- multi2one: real word steps only, last step -> slot (SDNet.py:270-271,300-318) ----
         HS = self.multi2one_output_size
         slots = torch.zeros((B * M + B * M_od, HS), **f32)
@@ -303,6 +316,7 @@ class SDNet(nn.Module):
         ocr_x = slots[:B * M].view(B, M, HS)
         od_x = slots[B * M:].view(B, M_od, HS)
 
+        self._phase('multi2one')
         # ---- encoders with whole-tensor LN (SDNet.py:338-350) ----------------------------------
         L_in = opt['in_rnn_layers']
 
@@ -320,6 +334,7 @@ class SDNet(nn.Module):
         q_high = encode(self.high_lvl_ques_rnn, q_cat, opt['question_high_lvl_rnn_layers'])[-1]
         q_layers = q_layers + [q_high]
 
+        self._phase('encoders')
         # ---- deep inter-attention + context self-attention (SDNet.py:376-390) ------------------
         def context_branch(x, layers, mask, Mx):
             after, before = self.deep_attn([x], layers, [q_word], q_layers, mask, q_mask, return_bef_rnn=True)
@@ -333,6 +348,7 @@ class SDNet(nn.Module):
         ocr_high = context_branch(ocr_x, ocr_layers, ocr_mask, M)
         od_high = context_branch(od_x, od_layers, od_mask, M_od)
 
+        self._phase('deep_self_attn')
         # ---- OD <-> OCR + position attention (SDNet.py:393-405) -------------------------------
         CF = ocr_high.shape[2]
         ocr_final = torch.empty((B, M, 2 * CF), **f32)
@@ -342,12 +358,14 @@ class SDNet(nn.Module):
         self.position_attn(ocr_list['position'].float(), od_list['position'].float(), od_mask, x3=od_high,
                            out=x_od_ocr, add_to_out=True)
 
+        self._phase('od_ocr')
         # ---- question summary + answer scores (SDNet.py:411-431) -------------------------------
         q_final = self.ques_self_attn(q_high, q_high, q_mask)
         q_merged = self.ques_merger.pooled(q_final, q_mask)
         nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         score_s = self.get_answer(ocr_final, q_merged, ocr_mask, opt['ES_ocr_len'], mask_flag='mask_score' in opt,
                                   nan_flag=nan_flag, want_logits=bool(opt.get('KEEP_LOGITS', False)))
+        self._phase('scores')
         if self.check_nan and int(nan_flag.item()) != 0:
             raise AssertionError("NaN in answer scores (reference: assert torch.sum(torch.isnan(...)) == 0)")
         return score_s, att_score

@@ -37,6 +37,9 @@ _SIGNATURES = {
                              c_void_p, c_int, c_void_p],
     "ruart_subword_avg_accum": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                 c_ll, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    "ruart_subword_avg_layers": [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "ruart_pack_tokens": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "ruart_split_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p],
     "ruart_gather_rows": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_int,
                           c_int, c_void_p],

@@ -124,12 +124,14 @@ class BertEngine(object):
     # ------------------------------------------------------------------ packing
     @staticmethod
     def pack(segments):
-        """Token packing for a list of Segments (device int ops only; one host sync for T).
+        """Token packing for a list of Segments: a few integer torch ops for the row lengths, ONE
+        host sync (total token count + longest sequence per segment, needed to size buffers and
+        pick kernels), then one pack_tokens kernel per segment.
 
         Returns dict: ids/pos int32 [T]; cu_seqlens int32 [S+1] over 512-token windows; per
-        segment (row_start int32 [N], seq range, max_len)."""
+        segment: row_start int32 [N], its range of sequences, its longest sequence."""
         dev = segments[0].ids.device
-        row_lens, win_lens, meta = [], [], []
+        row_lens, win_lens, nwins = [], [], []
         for sg in segments:
             rl = sg.mask.sum(1, dtype=torch.int32)
             row_lens.append(rl)
@@ -139,37 +141,30 @@ class BertEngine(object):
             else:
                 base = torch.arange(nwin, device=dev, dtype=torch.int32) * WINDOW
                 win_lens.append((rl[:, None] - base[None, :]).clamp_(0, WINDOW).reshape(-1))
-            meta.append(nwin)
+            nwins.append(nwin)
         all_rows = torch.cat(row_lens)
         cu_rows = torch.zeros(all_rows.numel() + 1, dtype=torch.int32, device=dev)
-        cu_rows[1:] = torch.cumsum(all_rows, 0)
+        torch.cumsum(all_rows, 0, out=cu_rows[1:])
         all_win = torch.cat(win_lens)
         cu_seq = torch.zeros(all_win.numel() + 1, dtype=torch.int32, device=dev)
-        cu_seq[1:] = torch.cumsum(all_win, 0)
-        maxes = torch.stack([w.max() if w.numel() else torch.zeros((), dtype=torch.int32, device=dev)
-                             for w in win_lens])
-        host = torch.cat([cu_rows[-1:].to(torch.int64), maxes.to(torch.int64)]).cpu()  # the one sync
+        torch.cumsum(all_win, 0, out=cu_seq[1:])
+        maxes = [w.max() if w.numel() else torch.zeros((), dtype=torch.int32, device=dev) for w in win_lens]
+        host = torch.stack([cu_rows[-1]] + maxes).cpu()  # the one sync
         T = int(host[0])
         ids = torch.empty(T, dtype=torch.int32, device=dev)
         pos = torch.empty(T, dtype=torch.int32, device=dev)
         segs = []
         r0 = s0 = 0
+        st = current_stream()
         for k, sg in enumerate(segments):
-            # valid tokens are a prefix of each row, so row-major order == packed order
-            sel = torch.nonzero(sg.mask.reshape(-1), as_tuple=False).squeeze(1)
-            segs.append({"row_start": cu_rows[r0:r0 + sg.N].contiguous(), "seq0": s0,
-                         "seq1": s0 + sg.N * meta[k], "max_len": int(host[1 + k]), "sel": sel,
-                         "n_tok": sel.numel()})
+            row_start = cu_rows[r0:r0 + sg.N].contiguous()
+            mask8 = sg.mask.contiguous().view(torch.uint8) if sg.mask.dtype == torch.bool else sg.mask.to(torch.uint8).contiguous()
+            call("ruart_pack_tokens", ptr(sg.ids.contiguous()), ptr(mask8), sg.N, sg.L, ptr(row_start), WINDOW,
+                 ptr(ids), ptr(pos), st)
+            segs.append({"row_start": row_start, "seq0": s0, "seq1": s0 + sg.N * nwins[k],
+                         "max_len": int(host[1 + k])})
             r0 += sg.N
-            s0 += sg.N * meta[k]
-        off = 0
-        for k, sg in enumerate(segments):
-            sel = segs[k].pop("sel")
-            n = segs[k]["n_tok"]
-            ids[off:off + n] = sg.ids.reshape(-1)[sel].to(torch.int32)
-            pos[off:off + n] = (sel % sg.L % WINDOW).to(torch.int32)
-            off += n
-        assert off == T
+            s0 += sg.N * nwins[k]
         return {"ids": ids, "pos": pos, "cu_seqlens": cu_seq, "T": T, "segments": segs}
 
     # ------------------------------------------------------------------ forward
@@ -195,25 +190,34 @@ class BertEngine(object):
         or a list of n_layers such triples when alpha is None (per-layer outputs).
 
         With alpha/gamma: dst[item, j, col_off:col_off+H] = sum_l mean_subwords(h_l) * softmax(alpha)_l * gamma.
+
+        All encoder-layer outputs are kept ([n_layers, T, H]) so that the subword averaging runs
+        once at the end; the Python word-offset lists are flattened on the host AFTER the whole
+        encoder has been queued, i.e. while the GPU is busy.
         """
         dev = segments[0].ids.device
         if dev.type != "cuda":
             raise RuntimeError("ruart_b200 BERT runs on CUDA only; there is no CPU fallback")
         W = self.prepare(dev)
         pk = self.pack(segments)
-        T, H, I = pk["T"], self.H, self.I
+        T, H, I, NL = pk["T"], self.H, self.I, self.n_layers
         st = current_stream()
         fp32 = self.mode == "fp32"
         keep32 = fp32 or self.residual_fp32   # fp32 copy of the residual stream
         parts = 3 if fp32 else 1
-        words = []
-        for k, sg in enumerate(segments):
-            wt = flatten_offsets(sg.offsets, sg.N)
-            words.append((torch.from_numpy(wt).to(dev, non_blocking=True), wt.shape[1],
-                          sg.word_mask.to(torch.uint8).contiguous()))
-        # embeddings
-        h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if keep32 else None
-        h_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
+        # per-layer outputs: fp32 [NL, T, H] when an fp32 stream exists, else bf16 [NL, T, H]
+        hs_f = torch.empty((NL + 1, T, H), dtype=torch.float32, device=dev) if keep32 else None
+        if fp32:
+            hs_b = None  # split operands are transient per layer
+        else:
+            hs_b = torch.empty((NL + 1, T, H), dtype=torch.bfloat16, device=dev)
+
+        def layer_bufs(i):
+            f = hs_f[i] if keep32 else None
+            b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev) if fp32 else hs_b[i]
+            return f, b
+
+        h_f, h_b = layer_bufs(0)
         call("ruart_bert_embed_ln", ptr(pk["ids"]), ptr(pk["pos"]), ptr(W["word"]), ptr(W["pos"]),
              ptr(W["type"]), ptr(W["eg"]), ptr(W["eb"]), W["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
         scale = 1.0 / 8.0
@@ -235,20 +239,28 @@ class BertEngine(object):
             _, ff = self._gemm(h1_b, lw["wi"], lw["bi"], I, H, ops.EPI_BIAS_GELU, "split",
                                fast_gelu=not fp32)
             d_f, d_b = self._gemm(ff, lw["wd"], lw["bd"], H, I, ops.EPI_BIAS, "act")
-            h_f = torch.empty((T, H), dtype=torch.float32, device=dev) if keep32 else None
-            h_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
+            h_f, h_b = layer_bufs(li + 1)
             call("ruart_add_layernorm", ptr(d_f), ptr(d_b), ptr(h1_f), ptr(h1_b) if not keep32 else None,
                  ptr(lw["g2"]), ptr(lw["b2"]), lw["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
-            for k, sg in enumerate(segments):
-                wt, nw, wmask = words[k]
-                if alpha is not None:
-                    dst, stride, col = sinks[k]
-                    first = 1 if li == 0 else 0
-                else:
+        # ---- host: flatten the word-offset lists while the encoder runs on the device ----------
+        layer_stride = T * H
+        for k, sg in enumerate(segments):
+            wt_np = flatten_offsets(sg.offsets, sg.N)
+            nw = wt_np.shape[1]
+            wt = torch.from_numpy(wt_np).to(dev, non_blocking=True)
+            wmask = sg.word_mask.contiguous().view(torch.uint8) if sg.word_mask.dtype == torch.bool \
+                else sg.word_mask.to(torch.uint8).contiguous()
+            rs = pk["segments"][k]["row_start"]
+            hf1 = hs_f[1:] if keep32 else None
+            hb1 = None if keep32 else hs_b[1:]
+            if alpha is not None:
+                dst, stride, col = sinks[k]
+                call("ruart_subword_avg_layers", ptr(hf1), ptr(hb1), layer_stride, ptr(wt), nw, ptr(rs), ptr(wmask),
+                     sg.W, dst.data_ptr() + 4 * col, stride, ptr(alpha), NL, ptr(gamma), H, st)
+            else:
+                for li in range(NL):
                     dst, stride, col = sinks[k][li]
-                    first = 1
-                base = dst.data_ptr() + 4 * col
-                call("ruart_subword_avg_accum", ptr(h_f), None if keep32 else ptr(h_b), ptr(wt), nw,
-                     ptr(pk["segments"][k]["row_start"]), ptr(wmask), sg.W, base, stride,
-                     ptr(alpha), self.n_layers, ptr(gamma), li, first, H, st)
+                    call("ruart_subword_avg_accum", ptr(hf1[li]) if keep32 else None,
+                         None if keep32 else ptr(hb1[li]), ptr(wt), nw, ptr(rs), ptr(wmask), sg.W,
+                         dst.data_ptr() + 4 * col, stride, None, NL, None, li, 1, H, st)
         return pk

@@ -513,6 +513,92 @@ subword_avg_accum_kernel(const float* h_f32, const __nv_bfloat16* h_b16,
   }
 }
 
+// All-layers form of the kernel above: the encoder keeps its n_layers outputs ([n_layers][T][H],
+// `layer_stride` elements apart) and ONE pass per word computes
+//     dst[item, j] = sum_l ( mean_{t in [st,ed)} h_l[t] * softmax(alpha)[l] ) * gamma
+// in layer order (res = t_0; res += t_1; ... as SDNet.py:575-580), writing dst once.
+template <int HC>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+subword_avg_layers_kernel(const float* h_f32, const __nv_bfloat16* h_b16, long long layer_stride,
+                          const int32_t* __restrict__ words, int n_words,
+                          const int32_t* __restrict__ row_start, const uint8_t* __restrict__ x_mask,
+                          int W, float* __restrict__ dst, long long dst_stride,
+                          const float* __restrict__ alpha, int n_layers,
+                          const float* __restrict__ gamma_p) {
+  const int lane = threadIdx.x & 31;
+  const long long w = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (w >= n_words) return;
+  const int item = words[w];
+  const int j = words[n_words + w];
+  const int st = words[2LL * n_words + w];
+  const int ed = words[3LL * n_words + w];
+  if (j >= W) return;
+  if (x_mask != nullptr && x_mask[static_cast<long long>(item) * W + j] == 0) return;
+  float mx = -INFINITY;
+  for (int i = 0; i < n_layers; ++i) mx = fmaxf(mx, alpha[i]);
+  float den = 0.f;
+  for (int i = 0; i < n_layers; ++i) den += expf(alpha[i] - mx);
+  const float g = gamma_p[0];
+  const int cnt = ed - st;
+  const long long t0 = static_cast<long long>(row_start[item]) + st;
+  const float fc = static_cast<float>(cnt);
+  RowVec<HC> tot;
+#pragma unroll
+  for (int i = 0; i < HC * 8; ++i) tot.v[i] = 0.f;
+  for (int l = 0; l < n_layers; ++l) {
+    const float a = expf(alpha[l] - mx) / den;
+    const float* hf = h_f32 ? h_f32 + l * layer_stride : nullptr;
+    const __nv_bfloat16* hb = h_b16 ? h_b16 + l * layer_stride : nullptr;
+    RowVec<HC> acc;
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) acc.v[i] = 0.f;
+    for (int t = 0; t < cnt; ++t) {
+      RowVec<HC> r;
+      load_act<HC>(hf, hb, t0 + t, lane, r);
+#pragma unroll
+      for (int i = 0; i < HC * 8; ++i) acc.v[i] += r.v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) {
+      const float mean = (cnt > 1) ? acc.v[i] / fc : acc.v[i];
+      const float term = (mean * a) * g;
+      tot.v[i] = (l == 0) ? term : tot.v[i] + term;
+    }
+  }
+  float* d = dst + (static_cast<long long>(item) * W + j) * dst_stride;
+#pragma unroll
+  for (int c = 0; c < HC; ++c) {
+    *reinterpret_cast<float4*>(d + c * 256 + lane * 8) =
+        make_float4(tot.v[c * 8 + 0], tot.v[c * 8 + 1], tot.v[c * 8 + 2], tot.v[c * 8 + 3]);
+    *reinterpret_cast<float4*>(d + c * 256 + lane * 8 + 4) =
+        make_float4(tot.v[c * 8 + 4], tot.v[c * 8 + 5], tot.v[c * 8 + 6], tot.v[c * 8 + 7]);
+  }
+}
+
+// Token packing: ids [N, L] + mask [N, L] -> the real tokens of every row, in row order, at
+// out[row_start[r] ...]; position id = column index inside its 512-token window (the reference
+// restarts positions per window, Bert.py:96-99,135-138 + modeling.py:186-187).  One warp per row.
+__global__ void __launch_bounds__(256)
+pack_tokens_kernel(const long long* __restrict__ ids, const uint8_t* __restrict__ mask, int N, int L,
+                   const int32_t* __restrict__ row_start, int window, int32_t* __restrict__ out_ids,
+                   int32_t* __restrict__ out_pos) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  int base = row_start[row];
+  for (int c0 = 0; c0 < L; c0 += 32) {
+    const int c = c0 + lane;
+    const bool keep = (c < L) && mask[static_cast<long long>(row) * L + c] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int k = base + __popc(bal & ((1u << lane) - 1u));
+      out_ids[k] = static_cast<int32_t>(ids[static_cast<long long>(row) * L + c]);
+      out_pos[k] = c % window;
+    }
+    base += __popc(bal);
+  }
+}
+
 // fp32 [rows, K] (row stride ld) -> bf16 split [rows, parts*Kp], zero padded to Kp per part.
 __global__ void split_bf16_kernel(const float* __restrict__ src, long long ld,
                                   const int32_t* __restrict__ row_idx, long long rows, int K,
@@ -659,6 +745,40 @@ extern "C" int ruart_subword_avg_accum(const float* h_f32, const void* h_bf16, c
     subword_avg_accum_kernel<4><<<row_grid(n_words), ROWS_PER_CTA * 32, 0, st>>>(
         h_f32, (const __nv_bfloat16*)h_bf16, words, n_words, row_start, x_mask, W, dst, dst_stride,
         alpha, n_layers, gamma, layer, first);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_subword_avg_layers(const float* h_f32, const void* h_bf16,
+                                        long long layer_stride, const int32_t* words, int n_words,
+                                        const int32_t* row_start, const uint8_t* x_mask, int W,
+                                        float* dst, long long dst_stride, const float* alpha,
+                                        int n_layers, const float* gamma, int hidden, void* stream) {
+  RUART_ARG_CHECK(hidden == 768 || hidden == 1024);
+  RUART_ARG_CHECK((h_f32 != nullptr) != (h_bf16 != nullptr));
+  RUART_ARG_CHECK(alpha != nullptr && gamma != nullptr && n_layers >= 1);
+  RUART_ARG_CHECK((dst_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+  if (n_words == 0) return RUART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hidden == 768)
+    subword_avg_layers_kernel<3><<<row_grid(n_words), ROWS_PER_CTA * 32, 0, st>>>(
+        h_f32, (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dst,
+        dst_stride, alpha, n_layers, gamma);
+  else
+    subword_avg_layers_kernel<4><<<row_grid(n_words), ROWS_PER_CTA * 32, 0, st>>>(
+        h_f32, (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dst,
+        dst_stride, alpha, n_layers, gamma);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_pack_tokens(const long long* ids, const uint8_t* mask, int N, int L,
+                                 const int32_t* row_start, int window, int32_t* out_ids,
+                                 int32_t* out_pos, void* stream) {
+  RUART_ARG_CHECK(N >= 0 && L > 0 && window > 0);
+  if (N == 0) return RUART_OK;
+  pack_tokens_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ids, mask, N, L, row_start,
+                                                                    window, out_ids, out_pos);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
