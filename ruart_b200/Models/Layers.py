@@ -101,7 +101,7 @@ class StackedBRNN(nn.Module):
             out = torch.empty((x.shape[0], x.shape[1], self.bidir_coef * H), dtype=torch.float32, device=x.device)
         w_ih, w_hh, b_ih, b_hh = self._dir_params(i)
         if H <= 128:
-            K.lstm_layer(x, (id(self), i), w_ih, w_hh, b_ih, b_hh, H, sdnet_parts, out, whole_ln=bool(LN))
+            K.lstm_layer(self, x, i, w_ih, w_hh, b_ih, b_hh, H, sdnet_parts, out, whole_ln=bool(LN))
         else:
             self._run_layer_stepwise(i, x, out)
             if LN:
@@ -117,9 +117,9 @@ class StackedBRNN(nn.Module):
         w_ih, w_hh, b_ih, b_hh = self._dir_params(i)
         parts = 3  # the cell kernel always emits a 3-part split of h
         a, Kp_in = K.split_act(x, parts)
-        wi, _ = K.prep_weight((id(self), i, "w_ih"), w_ih, parts)
-        wh, Kp_h = K.prep_weight((id(self), i, "w_hh"), w_hh, parts)
-        bias = K.prep_vector((id(self), i, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
+        wi, _ = K.prep_weight(self, (i, "w_ih"), w_ih, parts)
+        wh, Kp_h = K.prep_weight(self, (i, "w_hh"), w_hh, parts)
+        bias = K.prep_vector(self, (i, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
         gx = torch.empty((B * L, 4 * H), dtype=torch.float32, device=x.device)
         K.linear(a, Kp_in, wi, B * L, 4 * H, parts, gx, epi=ops.EPI_BIAS, bias=bias)
         c = torch.zeros((B, H), dtype=torch.float32, device=x.device)
@@ -176,10 +176,10 @@ class AttentionScore(nn.Module):
         if a_split is None:
             a_split = K.split_act(x, sdnet_parts)
         a, Kp = a_split
-        w, _ = K.prep_weight((id(self), "w"), [self.linear.weight], sdnet_parts)
+        w, _ = K.prep_weight(self, ("w"), [self.linear.weight], sdnet_parts)
         out = torch.empty((rows, self.hidden_size), dtype=torch.float32, device=x.device)
         if with_diag:
-            d = K.prep_vector((id(self), "d"), lambda: self.diagonal.reshape(-1), [self.diagonal])
+            d = K.prep_vector(self, ("d"), lambda: self.diagonal.reshape(-1), [self.diagonal])
         else:
             d = K.ones(x.device)
         K.linear(a, Kp, w, rows, self.hidden_size, sdnet_parts, out, epi=ops.EPI_RELU_SCALE, scale=d)
@@ -287,9 +287,9 @@ class GetFinalScores(nn.Module):
                                       "no yes/no heads) is implemented")
         B, M, X = x.shape
         parts = sdnet_parts
-        w, _ = K.prep_weight((id(self), "w3"), [self.attn.linear.weight, self.attn2.linear.weight,
+        w, _ = K.prep_weight(self, ("w3"), [self.attn.linear.weight, self.attn2.linear.weight,
                                                  self.noanswer_linear.weight], parts)
-        b3 = K.prep_vector((id(self), "b3"), lambda: torch.cat([self.attn.linear.bias, self.attn2.linear.bias,
+        b3 = K.prep_vector(self, ("b3"), lambda: torch.cat([self.attn.linear.bias, self.attn2.linear.bias,
                                                                  self.noanswer_linear.bias]),
                            [self.attn.linear.bias, self.attn2.linear.bias, self.noanswer_linear.bias])
         a, Kp = K.split_act(h0, parts)

@@ -267,9 +267,9 @@ class SDNet(nn.Module):
         a_rows = np.concatenate([base_all[perm[:n]] + t for t, n in enumerate(n_t)])
         i32 = np.concatenate([io['word_src'], io['word_dst'], id_['word_src'], id_['word_dst'], a_rows,
                               lens_all[perm] - 1]).astype(np.int32)
-        i32_d = torch.from_numpy(i32).to(dev, non_blocking=True)
-        i64_d = torch.from_numpy((slot_all[perm] * self.multi2one_output_size).astype(np.int64)).to(dev, non_blocking=True)
-        masks_d = torch.from_numpy(np.concatenate([io['mask'].reshape(-1), id_['mask'].reshape(-1)])).to(dev, non_blocking=True)
+        i32_d = K.upload(i32, dev)
+        i64_d = K.upload((slot_all[perm] * self.multi2one_output_size).astype(np.int64), dev)
+        masks_d = K.upload(np.concatenate([io['mask'].reshape(-1), id_['mask'].reshape(-1)]), dev)
         cuts = np.cumsum([0, io['total_words'], io['total_words'], id_['total_words'], id_['total_words'],
                           a_rows.size, lens_all.size])
         ocr_wsrc, ocr_wdst, od_wsrc, od_wdst, a_rows_d, last_d = [i32_d[cuts[i]:cuts[i + 1]] for i in range(6)]
@@ -296,9 +296,9 @@ class SDNet(nn.Module):
         m2o = self.multi2one
         w_ih, w_hh, b_ih, b_hh = m2o._dir_params(0)
         a_sp, Kp_in = K.split_act(items_in, 3, row_idx=a_rows_d, n_rows=int(a_rows.size))
-        wi, _ = K.prep_weight((id(m2o), 0, "w_ih"), w_ih, 3)
-        wh, Kp_h = K.prep_weight((id(m2o), 0, "w_hh"), w_hh, 3)
-        bias = K.prep_vector((id(m2o), 0, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
+        wi, _ = K.prep_weight(m2o, (0, "w_ih"), w_ih, 3)
+        wh, Kp_h = K.prep_weight(m2o, (0, "w_hh"), w_hh, 3)
+        bias = K.prep_vector(m2o, (0, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
         gx = torch.empty((int(a_rows.size), 4 * HS), **f32)
         K.linear(a_sp, Kp_in, wi, int(a_rows.size), 4 * HS, 3, gx, epi=ops.EPI_BIAS, bias=bias)
         n_all = lens_all.size

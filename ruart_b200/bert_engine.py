@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .sdnet_ops import upload
 from ._lib import current_stream, ptr
 from .ops import call
 
@@ -247,7 +248,7 @@ class BertEngine(object):
         for k, sg in enumerate(segments):
             wt_np = flatten_offsets(sg.offsets, sg.N)
             nw = wt_np.shape[1]
-            wt = torch.from_numpy(wt_np).to(dev, non_blocking=True)
+            wt = upload(wt_np, dev)
             wmask = sg.word_mask.contiguous().view(torch.uint8) if sg.word_mask.dtype == torch.bool \
                 else sg.word_mask.to(torch.uint8).contiguous()
             rs = pk["segments"][k]["row_start"]

@@ -11,6 +11,7 @@
 //
 // One warp owns one 768- (or 1024-) wide row: lane l holds columns c*256 + l*8 .. +7 of chunk c,
 // i.e. 16-byte vector accesses for bf16 and 2 x 16 bytes for fp32, fully coalesced.
+#include <cstdlib>
 #include "common.cuh"
 #include "ruart_b200.h"
 
@@ -695,7 +696,8 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
   }
   // bf16 in, plain bf16 out: sequences of <= SHORT_MAX tokens go to the warp-per-sequence MMA kernel
   int skip_upto = 0;
-  if (qkv_bf16 != nullptr && out_f32 == nullptr && out_parts == 1) {
+  static const bool no_short = getenv("RUART_NO_SHORT_ATTN") != nullptr;  // debugging aid
+  if (!no_short && qkv_bf16 != nullptr && out_f32 == nullptr && out_parts == 1) {
     long long ctas = (n_seq + SHORT_WARPS - 1) / SHORT_WARPS;
     const long long cap = static_cast<long long>(ruart_num_sms()) * 8;
     if (ctas > cap) ctas = cap;

@@ -11,8 +11,32 @@ from ._lib import current_stream, ptr
 from .ops import call
 
 _TERMS = {1: 1, 2: 3, 3: 6}
-_wcache = {}
 _consts = {}
+
+
+_copy_streams = {}
+
+
+def upload(arr, dev):
+    """numpy array -> device tensor through pinned memory on a side stream: the copy neither waits
+    for the kernels already queued on the compute stream nor blocks the host until they finish
+    (a pageable cudaMemcpyAsync would do both)."""
+    src = torch.from_numpy(arr)
+    pinned = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    pinned.copy_(src)
+    key = str(dev)
+    cs = _copy_streams.get(key)
+    if cs is None:
+        cs = torch.cuda.Stream(device=dev)
+        _copy_streams[key] = cs
+    main = torch.cuda.current_stream(dev)
+    with torch.cuda.stream(cs):
+        d = pinned.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+    main.wait_event(ev)
+    d.record_stream(main)
+    return d
 
 
 def rows2d(t):
@@ -55,8 +79,19 @@ def split_act(x, parts, row_idx=None, n_rows=None):
     return out, Kp
 
 
-def prep_weight(key, tensors, parts):
+def _cache_of(owner):
+    """Per-module cache (dies with the module: a global cache keyed by id() could be hit by a
+    different module that re-uses the id and the freed CUDA addresses)."""
+    c = owner.__dict__.get("_ruart_cache")
+    if c is None:
+        c = {}
+        owner.__dict__["_ruart_cache"] = c
+    return c
+
+
+def prep_weight(owner, key, tensors, parts):
     """Cache the split-bf16 form of a weight matrix (concatenation of `tensors` along dim 0)."""
+    _wcache = _cache_of(owner)
     ver = tuple((t.data_ptr(), t._version) for t in tensors) + (parts,)
     hit = _wcache.get(key)
     if hit is not None and hit[0] == ver:
@@ -68,7 +103,8 @@ def prep_weight(key, tensors, parts):
     return out, Kp
 
 
-def prep_vector(key, fn, tensors):
+def prep_vector(owner, key, fn, tensors):
+    _wcache = _cache_of(owner)
     ver = tuple((t.data_ptr(), t._version) for t in tensors)
     hit = _wcache.get(key)
     if hit is not None and hit[0] == ver:
@@ -121,15 +157,15 @@ def as_u8(mask):
     return mask.to(torch.uint8).contiguous()
 
 
-def lstm_layer(x, key, w_ih, w_hh, b_ih, b_hh, H, parts, out, whole_ln=False):
+def lstm_layer(owner, x, key, w_ih, w_hh, b_ih, b_hh, H, parts, out, whole_ln=False):
     """One (Bi)LSTM layer of StackedBRNN (Layers.py:156-170) for H <= 128 on [B, L, in] input.
     w_ih/w_hh/b_ih/b_hh are lists over directions.  `out` [B, L, ndir*H] may be a strided view."""
     B, L = x.shape[0], x.shape[1]
     ndir = len(w_ih)
     a, Kp = split_act(x, parts)
-    w, _ = prep_weight((key, "w_ih"), w_ih, parts)
-    bias = prep_vector((key, "bias"), lambda: torch.cat([bi + bh for bi, bh in zip(b_ih, b_hh)], 0), b_ih + b_hh)
-    whh = prep_vector((key, "w_hh"), lambda: torch.stack(w_hh, 0), w_hh)
+    w, _ = prep_weight(owner, (key, "w_ih"), w_ih, parts)
+    bias = prep_vector(owner, (key, "bias"), lambda: torch.cat([bi + bh for bi, bh in zip(b_ih, b_hh)], 0), b_ih + b_hh)
+    whh = prep_vector(owner, (key, "w_hh"), lambda: torch.stack(w_hh, 0), w_hh)
     xg = torch.empty((B * L, ndir * 4 * H), dtype=torch.float32, device=x.device)
     linear(a, Kp, w, B * L, ndir * 4 * H, parts, xg, epi=ops.EPI_BIAS, bias=bias)
     _, _, op = rows2d(out)
