@@ -311,7 +311,6 @@ bert_attention_kernel(const T* __restrict__ qkv, const int32_t* __restrict__ cu_
 // atoms); these tiles are 5x64.  O is staged back through the Q tile and leaves as 16-byte rows.
 constexpr int SHORT_MAX = 16;
 constexpr int SHORT_WARPS = 8;
-constexpr int TILE_B = 16 * 128;  // one [16 x 64] bf16 tile
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
                                         uint32_t& r3) {
@@ -336,112 +335,139 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 // byte offset of 16-byte chunk c of row r inside a swizzled [16 x 64] bf16 tile
 __device__ __forceinline__ int tile_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
+// MAXT = 16 or 64: rows of the staged Q/K/V tiles.  One warp per (sequence, head) task with
+// lo < len <= MAXT; other lengths are left to the other instantiation / the streaming kernel.
+template <int MAXT>
 __global__ void __launch_bounds__(SHORT_WARPS * 32)
-bert_attention_short_kernel(const __nv_bfloat16* __restrict__ qkv,
-                            const int32_t* __restrict__ cu_seqlens, int n_seq, int n_heads,
-                            float scale, int max_short, __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(128) uint8_t sh[SHORT_WARPS][3 * TILE_B];
+bert_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                          const int32_t* __restrict__ cu_seqlens, int n_seq, int n_heads,
+                          float scale, int lo, __nv_bfloat16* __restrict__ out) {
+  constexpr int TB = MAXT * 128;        // bytes of one [MAXT x 64] bf16 tile
+  constexpr int NKT = MAXT / 8;         // 8-key tiles
+  constexpr int NQT = MAXT / 16;        // 16-query tiles
+  extern __shared__ __align__(128) uint8_t sh_dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* sQ = sh[warp];
-  uint8_t* sK = sQ + TILE_B;
-  uint8_t* sV = sK + TILE_B;
+  uint8_t* sQ = sh_dyn + static_cast<size_t>(warp) * 3 * TB;
+  uint8_t* sK = sQ + TB;
+  uint8_t* sV = sK + TB;
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
   const int H = n_heads * 64;
   const long long ld = 3LL * H;
   const int g = lane >> 2, t = lane & 3;
-  // ldmatrix row/chunk roles of this lane
-  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;  // A (Q) and V^T: rows 0..15
-  const int a_chk = lane >> 4;                           // + 2*ks  (Q) / + dim-tile pair (V)
-  const int b_row = lane & 7;                            // K: key inside the 8-key tile
-  const int b_chk = lane >> 3;                           // + 4*half (two k-steps per x4)
-  for (int seq = blockIdx.x * SHORT_WARPS + warp; seq < n_seq; seq += gridDim.x * SHORT_WARPS) {
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int a_chk = lane >> 4;
+  const int b_row = lane & 7;
+  const int b_chk = lane >> 3;
+  const long long n_tasks = static_cast<long long>(n_seq) * n_heads;
+  for (long long task = static_cast<long long>(blockIdx.x) * SHORT_WARPS + warp; task < n_tasks;
+       task += static_cast<long long>(gridDim.x) * SHORT_WARPS) {
+    const int seq = static_cast<int>(task / n_heads);
+    const int h = static_cast<int>(task - static_cast<long long>(seq) * n_heads);
     const int t0 = cu_seqlens[seq];
     const int len = cu_seqlens[seq + 1] - t0;
-    if (len <= 0 || len > max_short) continue;  // long sequences: bert_attention_kernel
+    if (len <= lo || len > MAXT) continue;
     const int n_chunks = len * 8;
-    for (int h = 0; h < n_heads; ++h) {
-      __syncwarp();
-      // stage Q, K, V head slices; zero the pad rows
-      for (int idx = lane; idx < 16 * 8; idx += 32) {
-        const int r = idx >> 3, c = idx & 7;
-        uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
-        if (idx < n_chunks) {
-          const uint4* row = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(t0 + r)) * ld + h * 64);
-          q4 = __ldg(row + c);
-          k4 = __ldg(row + (H >> 3) + c);
-          v4 = __ldg(row + 2 * (H >> 3) + c);
-        }
-        const int off = tile_off(r, c);
-        *reinterpret_cast<uint4*>(sQ + off) = q4;
-        *reinterpret_cast<uint4*>(sK + off) = k4;
-        *reinterpret_cast<uint4*>(sV + off) = v4;
+    const int n_qt = (len + 15) >> 4, n_kt = (len + 7) >> 3, n_kk = (len + 15) >> 4;
+    const int rows_used = n_qt * 16;  // rows touched by the MMAs (pad rows zeroed)
+    __syncwarp();
+    for (int idx = lane; idx < rows_used * 8; idx += 32) {
+      const int r = idx >> 3, c = idx & 7;
+      uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+      if (idx < n_chunks) {
+        const uint4* row = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(t0 + r)) * ld + h * 64);
+        q4 = __ldg(row + c);
+        k4 = __ldg(row + (H >> 3) + c);
+        v4 = __ldg(row + 2 * (H >> 3) + c);
       }
-      __syncwarp();
-      // S = Q K^T : two key tiles (keys 0-7, 8-15), four k-steps over the 64 dims
-      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t kb0[8], kb1[8];  // K fragments: [ks*2 + {0,1}] for key tile 0 / 1
-      ldsm_x4(aK + tile_off(b_row, b_chk), kb0[0], kb0[1], kb0[2], kb0[3]);
-      ldsm_x4(aK + tile_off(b_row, 4 + b_chk), kb0[4], kb0[5], kb0[6], kb0[7]);
-      const bool two = len > 8;
-      if (two) {
-        ldsm_x4(aK + tile_off(8 + b_row, b_chk), kb1[0], kb1[1], kb1[2], kb1[3]);
-        ldsm_x4(aK + tile_off(8 + b_row, 4 + b_chk), kb1[4], kb1[5], kb1[6], kb1[7]);
-      }
+      const int off = tile_off(r, c);
+      *reinterpret_cast<uint4*>(sQ + off) = q4;
+      *reinterpret_cast<uint4*>(sK + off) = k4;
+      *reinterpret_cast<uint4*>(sV + off) = v4;
+    }
+    __syncwarp();
+    for (int qt = 0; qt < n_qt; ++qt) {
+      uint32_t qa[4][4];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t a0, a1, a2, a3;
-        ldsm_x4(aQ + tile_off(a_row, 2 * ks + a_chk), a0, a1, a2, a3);
-        mma_bf16_16816(s0, a0, a1, a2, a3, kb0[2 * ks], kb0[2 * ks + 1]);
-        if (two) mma_bf16_16816(s1, a0, a1, a2, a3, kb1[2 * ks], kb1[2 * ks + 1]);
+      for (int ks = 0; ks < 4; ++ks)
+        ldsm_x4(aQ + tile_off(qt * 16 + a_row, 2 * ks + a_chk), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      float s[NKT][4];
+#pragma unroll
+      for (int nt = 0; nt < NKT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        if (nt < n_kt) {
+          uint32_t kb[8];
+          ldsm_x4(aK + tile_off(nt * 8 + b_row, b_chk), kb[0], kb[1], kb[2], kb[3]);
+          ldsm_x4(aK + tile_off(nt * 8 + b_row, 4 + b_chk), kb[4], kb[5], kb[6], kb[7]);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16_16816(s[nt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], kb[2 * ks], kb[2 * ks + 1]);
+        }
       }
-      // masked softmax over keys; thread holds rows g (c0,c1) and g+8 (c2,c3), keys 2t,2t+1 (+8)
-      const int k0 = 2 * t, k1 = 2 * t + 1;
-      float v[8];
-      v[0] = (k0 < len) ? s0[0] * scale : -INFINITY;
-      v[1] = (k1 < len) ? s0[1] * scale : -INFINITY;
-      v[2] = (k0 < len) ? s0[2] * scale : -INFINITY;
-      v[3] = (k1 < len) ? s0[3] * scale : -INFINITY;
-      v[4] = (8 + k0 < len) ? s1[0] * scale : -INFINITY;
-      v[5] = (8 + k1 < len) ? s1[1] * scale : -INFINITY;
-      v[6] = (8 + k0 < len) ? s1[2] * scale : -INFINITY;
-      v[7] = (8 + k1 < len) ? s1[3] * scale : -INFINITY;
-      float mA = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[4], v[5]));
-      float mB = fmaxf(fmaxf(v[2], v[3]), fmaxf(v[6], v[7]));
+      // masked softmax: rows g (regs 0,1) and g+8 (regs 2,3); keys nt*8 + 2t, +1
+      float mA = -INFINITY, mB = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NKT; ++nt) {
+        const int k0 = nt * 8 + 2 * t;
+        s[nt][0] = (k0 < len) ? s[nt][0] * scale : -INFINITY;
+        s[nt][1] = (k0 + 1 < len) ? s[nt][1] * scale : -INFINITY;
+        s[nt][2] = (k0 < len) ? s[nt][2] * scale : -INFINITY;
+        s[nt][3] = (k0 + 1 < len) ? s[nt][3] * scale : -INFINITY;
+        mA = fmaxf(mA, fmaxf(s[nt][0], s[nt][1]));
+        mB = fmaxf(mB, fmaxf(s[nt][2], s[nt][3]));
+      }
       mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
       mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
       mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
       mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
-      float pA0 = __expf(v[0] - mA), pA1 = __expf(v[1] - mA), pA2 = __expf(v[4] - mA), pA3 = __expf(v[5] - mA);
-      float pB0 = __expf(v[2] - mB), pB1 = __expf(v[3] - mB), pB2 = __expf(v[6] - mB), pB3 = __expf(v[7] - mB);
-      float lA = (pA0 + pA1) + (pA2 + pA3), lB = (pB0 + pB1) + (pB2 + pB3);
+      float lA = 0.f, lB = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NKT; ++nt) {
+        s[nt][0] = __expf(s[nt][0] - mA);
+        s[nt][1] = __expf(s[nt][1] - mA);
+        s[nt][2] = __expf(s[nt][2] - mB);
+        s[nt][3] = __expf(s[nt][3] - mB);
+        lA += s[nt][0] + s[nt][1];
+        lB += s[nt][2] + s[nt][3];
+      }
       lA += __shfl_xor_sync(0xffffffffu, lA, 1);
       lA += __shfl_xor_sync(0xffffffffu, lA, 2);
       lB += __shfl_xor_sync(0xffffffffu, lB, 1);
       lB += __shfl_xor_sync(0xffffffffu, lB, 2);
-      // P as the A fragment of the second product (rows g / g+8, keys 2t.. / 8+2t..)
-      const uint32_t p0 = pack_bf16x2(pA0, pA1), p1 = pack_bf16x2(pB0, pB1);
-      const uint32_t p2 = pack_bf16x2(pA2, pA3), p3 = pack_bf16x2(pB2, pB3);
       const float iA = 1.0f / lA, iB = 1.0f / lB;
-      __syncwarp();  // all lanes are done reading sQ: it becomes the O staging tile
+      // P fragments per 16-key step
+      uint32_t pa[NQT][4];
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {  // pairs of 8-wide dim tiles
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(aV + tile_off(a_row, 2 * dp + a_chk), b0, b1, b2, b3);
+      for (int kk = 0; kk < NQT; ++kk) {
+        pa[kk][0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[kk][1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[kk][2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      }
+      __syncwarp();  // Q fragments of this query tile are in registers: its rows become O staging
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
         float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_bf16_16816(o0, p0, p1, p2, p3, b0, b1);
-        mma_bf16_16816(o1, p0, p1, p2, p3, b2, b3);
-        // O[g][16dp + 2t..], O[g+8][...]; second tile at +8 dims
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp) + 4 * t) = pack_bf16x2(o0[0] * iA, o0[1] * iA);
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp) + 4 * t) = pack_bf16x2(o0[2] * iB, o0[3] * iB);
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[0] * iA, o1[1] * iA);
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[2] * iB, o1[3] * iB);
+#pragma unroll
+        for (int kk = 0; kk < NQT; ++kk) {
+          if (kk < n_kk) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(aV + tile_off(kk * 16 + a_row, 2 * dp + a_chk), b0, b1, b2, b3);
+            mma_bf16_16816(o0, pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
+            mma_bf16_16816(o1, pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b2, b3);
+          }
+        }
+        const int rA = qt * 16 + g, rB = rA + 8;
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(rA, 2 * dp) + 4 * t) = pack_bf16x2(o0[0] * iA, o0[1] * iA);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(rB, 2 * dp) + 4 * t) = pack_bf16x2(o0[2] * iB, o0[3] * iB);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(rA, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[0] * iA, o1[1] * iA);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(rB, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[2] * iB, o1[3] * iB);
       }
-      __syncwarp();
-      for (int idx = lane; idx < n_chunks; idx += 32) {
-        const int r = idx >> 3, c = idx & 7;
-        const uint4 o4 = *reinterpret_cast<const uint4*>(sQ + tile_off(r, c));
-        *(reinterpret_cast<uint4*>(out + (static_cast<long long>(t0 + r)) * H + h * 64) + c) = o4;
-      }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < n_chunks; idx += 32) {
+      const int r = idx >> 3, c = idx & 7;
+      const uint4 o4 = *reinterpret_cast<const uint4*>(sQ + tile_off(r, c));
+      *(reinterpret_cast<uint4*>(out + (static_cast<long long>(t0 + r)) * H + h * 64) + c) = o4;
     }
   }
 }
@@ -692,21 +718,32 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<__nv_bfloat16>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_max));
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_mma_kernel<64>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SHORT_WARPS * 3 * 64 * 128));
     attr_set = true;
   }
-  // bf16 in, plain bf16 out: sequences of <= SHORT_MAX tokens go to the warp-per-sequence MMA kernel
+  // bf16 in, plain bf16 out: sequences of <= 64 tokens run on the warp-level MMA kernels
   int skip_upto = 0;
   static const bool no_short = getenv("RUART_NO_SHORT_ATTN") != nullptr;  // debugging aid
   if (!no_short && qkv_bf16 != nullptr && out_f32 == nullptr && out_parts == 1) {
-    long long ctas = (n_seq + SHORT_WARPS - 1) / SHORT_WARPS;
-    const long long cap = static_cast<long long>(ruart_num_sms()) * 8;
+    const long long n_tasks = static_cast<long long>(n_seq) * n_heads;
+    long long ctas = (n_tasks + SHORT_WARPS - 1) / SHORT_WARPS;
+    const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
     if (ctas > cap) ctas = cap;
-    bert_attention_short_kernel<<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, 0, st>>>(
-        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, SHORT_MAX,
+    const size_t smem16 = static_cast<size_t>(SHORT_WARPS) * 3 * 16 * 128;
+    bert_attention_mma_kernel<16><<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, smem16, st>>>(
+        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, 0,
         (__nv_bfloat16*)out_bf16);
     RUART_LAUNCH_CHECK();
-    if (max_len <= SHORT_MAX) return RUART_OK;
-    skip_upto = SHORT_MAX;
+    if (max_len <= 16) return RUART_OK;
+    const size_t smem64 = static_cast<size_t>(SHORT_WARPS) * 3 * 64 * 128;
+    bert_attention_mma_kernel<64><<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, smem64, st>>>(
+        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, 16,
+        (__nv_bfloat16*)out_bf16);
+    RUART_LAUNCH_CHECK();
+    if (max_len <= 64) return RUART_OK;
+    skip_upto = 64;
   }
   int stage_tokens = max_len < 1 ? 1 : (max_len > ATT_MAX_STAGE ? ATT_MAX_STAGE : max_len);
   stage_tokens = (stage_tokens + 7) / 8 * 8;
