@@ -76,8 +76,12 @@ class SDNet(nn.Module):
         self.drop_emb = False
         set_dropout_prob(0.0 if 'DROPOUT' not in opt else float(opt['DROPOUT']))
         set_seq_dropout('VARIATIONAL_DROPOUT' in opt)
-        if 'SDNET_precision' in opt:
-            Layers.set_sdnet_precision({'fp32': 3, 'bf16x2': 2, 'bf16': 1}[opt['SDNET_precision']])
+        # split parts of the SDNet-stack GEMM operands: fp32-grade (3 parts, 6 products) when BERT runs
+        # in fp32 mode, 2 parts (3 products, ~2^-16 relative) next to a bf16 BERT whose own error is
+        # 1e-4..1e-2; override with opt['SDNET_precision'].
+        default_prec = 'fp32' if opt.get('BERT_precision', 'bf16') == 'fp32' else 'bf16x2'
+        self.sdnet_parts = {'fp32': 3, 'bf16x2': 2, 'bf16': 1}[opt.get('SDNET_precision', default_prec)]
+        Layers.set_sdnet_precision(self.sdnet_parts)
 
         self.vocab_size = int(opt['vocab_size'])
         self.fast_dim = int(opt['fast_dim'])
@@ -207,6 +211,7 @@ class SDNet(nn.Module):
                                "there is no CPU fallback")
         opt = self.opt
         st = current_stream()
+        Layers.set_sdnet_precision(self.sdnet_parts)
         f32 = dict(dtype=torch.float32, device=dev)
         B = len(ocr_list['num_cnt'])
         M, M_od = ocr_list['position'].size(1), od_list['position'].size(1)
