@@ -161,6 +161,9 @@ class SDNet(nn.Module):
         ocr_final_size = context_final_size * 2
         self.get_answer = GetFinalScores(ocr_final_size, ques_final_size, yesno=False, no_answer=True, useES=True)
         self.check_nan = bool(opt.get('CHECK_NAN', True))
+        self.use_streams = bool(opt.get('USE_STREAMS', True))
+        self._side = None
+        self._warm_version = None
         log.debug('Network build successes')
 
     # ------------------------------------------------------------------ host-side index building
@@ -322,8 +325,25 @@ class SDNet(nn.Module):
         od_x = slots[B * M:].view(B, M_od, HS)
 
         self._phase('multi2one')
-        # ---- encoders with whole-tensor LN (SDNet.py:338-350) ----------------------------------
+        # ---- the OCR, OD and question branches are independent until they meet: they run on three
+        # streams (main = OCR, side = OD, question).  Temporaries are allocated and consumed inside
+        # their branch's stream; tensors that cross branches live until the joins below.  A forward
+        # whose weight caches are cold (first call / weights changed) runs serially on the main
+        # stream so that no branch reads a prepared weight another branch is still writing.
         L_in = opt['in_rnn_layers']
+        main = torch.cuda.current_stream(dev)
+        ver = sum(p._version for p in self.parameters())
+        concurrent = self.use_streams and self.phase_log is None and self._warm_version == ver
+        if concurrent:
+            if self._side is None:
+                self._side = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            s_od, s_q = self._side
+            fork = torch.cuda.Event()
+            fork.record(main)
+            s_od.wait_event(fork)
+            s_q.wait_event(fork)
+        else:
+            s_od = s_q = main
 
         def encode(rnn, x, n_layers):
             outs, cur = [], x
@@ -332,16 +352,8 @@ class SDNet(nn.Module):
                 outs.append(cur)
             return outs
 
-        ocr_layers = encode(self.context_rnn, ocr_x, L_in)
-        q_layers = encode(self.ques_rnn, q_in, L_in)
-        od_layers = encode(self.context_rnn, od_x, L_in)
-        q_cat = torch.cat(q_layers, 2)
-        q_high = encode(self.high_lvl_ques_rnn, q_cat, opt['question_high_lvl_rnn_layers'])[-1]
-        q_layers = q_layers + [q_high]
-
-        self._phase('encoders')
-        # ---- deep inter-attention + context self-attention (SDNet.py:376-390) ------------------
         def context_branch(x, layers, mask, Mx):
+            # deep inter-attention + context self-attention (SDNet.py:376-390)
             after, before = self.deep_attn([x], layers, [q_word], q_layers, mask, q_mask, return_bef_rnn=True)
             s_in = torch.cat([after, before, x], 2)
             DA = self.deep_attn_output_size
@@ -350,10 +362,33 @@ class SDNet(nn.Module):
             self.highlvl_self_att(s_in, s_in, mask, x3=after, out=hl_in[:, :, DA:])
             return self.high_lvl_context_rnn.run_layer(0, hl_in, LN=True)
 
+        # encoders with whole-tensor LN (SDNet.py:338-350)
+        with torch.cuda.stream(s_q):
+            q_layers = encode(self.ques_rnn, q_in, L_in)
+            q_cat = torch.cat(q_layers, 2)
+            q_high = encode(self.high_lvl_ques_rnn, q_cat, opt['question_high_lvl_rnn_layers'])[-1]
+            q_layers = q_layers + [q_high]
+            ev_q = torch.cuda.Event()
+            ev_q.record(s_q)
+        with torch.cuda.stream(s_od):
+            od_layers = encode(self.context_rnn, od_x, L_in)
+        ocr_layers = encode(self.context_rnn, ocr_x, L_in)
+        self._phase('encoders')
+        main.wait_event(ev_q)
+        s_od.wait_event(ev_q)
+        with torch.cuda.stream(s_od):
+            od_high = context_branch(od_x, od_layers, od_mask, M_od)
+            ev_od = torch.cuda.Event()
+            ev_od.record(s_od)
+        with torch.cuda.stream(s_q):
+            # question summary (SDNet.py:411-415)
+            q_final = self.ques_self_attn(q_high, q_high, q_mask)
+            q_merged = self.ques_merger.pooled(q_final, q_mask)
+            ev_q2 = torch.cuda.Event()
+            ev_q2.record(s_q)
         ocr_high = context_branch(ocr_x, ocr_layers, ocr_mask, M)
-        od_high = context_branch(od_x, od_layers, od_mask, M_od)
-
         self._phase('deep_self_attn')
+        main.wait_event(ev_od)
         # ---- OD <-> OCR + position attention (SDNet.py:393-405) -------------------------------
         CF = ocr_high.shape[2]
         ocr_final = torch.empty((B, M, 2 * CF), **f32)
@@ -362,14 +397,13 @@ class SDNet(nn.Module):
         self.od_ocr_attn(ocr_high, od_high, od_mask, out=x_od_ocr)
         self.position_attn(ocr_list['position'].float(), od_list['position'].float(), od_mask, x3=od_high,
                            out=x_od_ocr, add_to_out=True)
-
         self._phase('od_ocr')
-        # ---- question summary + answer scores (SDNet.py:411-431) -------------------------------
-        q_final = self.ques_self_attn(q_high, q_high, q_mask)
-        q_merged = self.ques_merger.pooled(q_final, q_mask)
+        main.wait_event(ev_q2)
+        # ---- answer scores (SDNet.py:428-431) -------------------------------------------------
         nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         score_s = self.get_answer(ocr_final, q_merged, ocr_mask, opt['ES_ocr_len'], mask_flag='mask_score' in opt,
                                   nan_flag=nan_flag, want_logits=bool(opt.get('KEEP_LOGITS', False)))
+        self._warm_version = ver
         self._phase('scores')
         if self.check_nan and int(nan_flag.item()) != 0:
             raise AssertionError("NaN in answer scores (reference: assert torch.sum(torch.isnan(...)) == 0)")

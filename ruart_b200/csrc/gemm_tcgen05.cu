@@ -31,10 +31,10 @@ constexpr int C_STAGE_BYTES = BM * 64 * 2;      // 16 KB: 128 rows x 64 bf16, TM
 constexpr int OFF_B = STAGES * A_STAGE_BYTES;
 constexpr int OFF_C = OFF_B + STAGES * B_STAGE_BYTES;
 constexpr int OFF_VEC = OFF_C + 2 * C_STAGE_BYTES;
-constexpr int OFF_BAR = OFF_VEC + MAX_BN * 4;
-constexpr int BAR_BYTES = 256;
-constexpr int GEMM_SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
-constexpr int GEMM_THREADS = 256;
+constexpr int OFF_BAR = OFF_VEC + 2 * MAX_BN * 4;  // bias / scale slice, double-buffered per tile
+constexpr int BAR_BYTES = 128;
+constexpr int GEMM_SMEM_BYTES = OFF_BAR + BAR_BYTES;
+constexpr int GEMM_THREADS = 384;  // TMA, MMA, TMEM-alloc, spare + 2 x 4 epilogue warps
 constexpr int TMEM_COLS = 512;
 static_assert(GEMM_SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -68,6 +68,11 @@ __device__ __forceinline__ float epi_fn(float acc, float v) {
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// epilogue group barrier (group 0 -> id 1, group 1 -> id 2), 128 threads each
+__device__ __forceinline__ void grp_bar_sync(int grp) {
+  asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+}
+__device__ __forceinline__ void epi_all_bar_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    tmap),
@@ -92,9 +97,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + OFF_B;
   uint8_t* smem_c = smem + OFF_C;
@@ -121,7 +125,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], TMA_OUT ? 256 : 128);
     }
     fence_mbar_init();
   }
@@ -199,45 +203,54 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may touch
-    const int et = threadIdx.x - 128;
+  } else if (warp >= 4 && (TMA_OUT || warp < 8)) {
+    // ------------------------------------------------------------------ epilogue
+    // TMA_OUT: two groups of 4 warps (warps 4-7 / 8-11, i.e. two warps per SM sub-partition so that
+    // the MUFU/ALU latency of the GELU is hidden); group g converts the 64-column chunks
+    // g, g+2, ... of the tile, each through its own staging buffer and TMA store.
+    // Direct-store path: group 0 only.
+    const int grp = (warp - 4) >> 2;
+    const int ew = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int et = threadIdx.x - 128 - grp * 128;  // thread index inside the group
     const int r_local = ew * 32 + lane;
     const bool issuer = (et == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t tile_ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
       const int tile_col0 = n_blk * p.block_n;
-      // stage this tile's bias / scale slice (previous tile's readers are past their last barrier)
+      float* vec = s_vec + (TMA_OUT ? (tile_ctr & 1u) * MAX_BN : 0);
+      // stage this tile's bias / scale slice
       if (EPI != K_NONE) {
-        for (int i = et; i < p.block_n; i += 128) {
+        const int stride = TMA_OUT ? 256 : 128;
+        for (int i = et + grp * 128; i < p.block_n; i += stride) {
           const int col = tile_col0 + i;
-          s_vec[i] = (col < p.N) ? __ldg(p.vec + static_cast<long long>(col) * p.vec_stride) : 0.0f;
+          vec[i] = (col < p.N) ? __ldg(p.vec + static_cast<long long>(col) * p.vec_stride) : 0.0f;
         }
       }
-      if (!TMA_OUT) epi_bar_sync();
+      if (TMA_OUT) epi_all_bar_sync(); else epi_bar_sync();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                                 static_cast<uint32_t>(acc * MAX_BN);
       if constexpr (TMA_OUT) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 64) {
-          uint8_t* cbuf = smem_c + (chunk_ctr & 1u) * C_STAGE_BYTES;
-          if (issuer) bulk_wait_read<1>();  // the store that last used this buffer has read it
-          epi_bar_sync();                   // ... and everybody knows (also publishes s_vec)
+        uint8_t* cbuf = smem_c + grp * C_STAGE_BYTES;
+        if (grp * 64 >= p.block_n) {  // this group has no chunk in such a narrow tile
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        for (int c0 = grp * 64; c0 < p.block_n; c0 += 128) {
           uint32_t v0[32], v1[32];
           tmem_ld_32x32b_x32(tmem_acc + c0, v0);
           tmem_ld_32x32b_x32(tmem_acc + c0 + 32, v1);
           tmem_ld_wait();
-          if (c0 + 64 >= p.block_n) {  // last TMEM read of this tile: hand the accumulator back
+          if (c0 + 128 >= p.block_n) {  // the group's last TMEM read of this tile
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[acc]);
           }
-          uint8_t* row_ptr = cbuf + r_local * 128;
+          uint4 pk4[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint32_t pk[4];
@@ -252,19 +265,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 x0 = __uint_as_float(v1[j - 32]);
                 x1 = __uint_as_float(v1[j - 31]);
               }
-              const float2 bv = *reinterpret_cast<const float2*>(s_vec + c0 + j);
+              const float2 bv = *reinterpret_cast<const float2*>(vec + c0 + j);
               pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x), epi_fn<EPI>(x1, bv.y));
             }
-            *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4)) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            pk4[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
+          if (issuer) bulk_wait_read<0>();  // the group's previous store has finished reading cbuf
+          grp_bar_sync(grp);
+          uint8_t* row_ptr = cbuf + r_local * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4)) = pk4[c];
           fence_proxy_async();
-          epi_bar_sync();
+          grp_bar_sync(grp);
           if (issuer) {
             tma_store_2d(&tmap_c, cbuf, tile_col0 + c0, m_blk * BM);
             bulk_commit();
           }
-          ++chunk_ctr;
         }
       } else {
         const int row = m_blk * BM + r_local;
@@ -279,7 +296,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const bool full_chunk = (col0 + 32 <= p.N);
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = epi_fn<EPI>(__uint_as_float(v[j]), s_vec[c0 + j]);
+          for (int j = 0; j < 32; ++j) f[j] = epi_fn<EPI>(__uint_as_float(v[j]), vec[c0 + j]);
           if (row_ok && p.out_f32 != nullptr) {
             float* dst = p.out_f32 + static_cast<long long>(row) * p.ldo_f32 + col0;
             if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
