@@ -298,7 +298,7 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_desc(args.cfg), "per_gpu_batch": B, "global_batch": B * world,
                        "parallelism": "batch-sharded x%d, no collective" % world,
-                       "precision": "BERT bf16 operands / fp32 accumulate; SDNet stack fp32-grade (3-part bf16 split)",
+                       "precision": "BERT bf16 operands / fp32 accumulate; SDNet stack fp32 activations, GEMM operands as 2-part bf16 splits (~2^-16)",
                        "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_host.numel() * 4,

@@ -157,8 +157,9 @@ RUART_API int ruart_final_scores(const float* x, long long x_pitch, int B, int M
                                  float* logits, int* nan_flag, void* stream);
 /* One step of the step-synchronous uni-LSTM `multi2one` (SDNet.py:137,270-271,304,310).        */
 RUART_API int ruart_lstm_cell(const float* gx, const int32_t* row_gx, const float* gh, float* c,
-                              void* h_split, int Kp, int H, int n_rows, const int32_t* last_step,
-                              int step, const long long* slot_off, float* slots, void* stream);
+                              void* h_split, int parts, int Kp, int H, int n_rows,
+                              const int32_t* last_step, int step, const long long* slot_off,
+                              float* slots, void* stream);
 /* Persistent (Bi)LSTM recurrence of StackedBRNN (Layers.py:137,166): xg = x W_ih^T + b_ih + b_hh
  * [B*L, ndir*4H] -> out[:, dir*H + j]; w_hh [ndir][4H][H]; H <= 128; pads are processed.      */
 RUART_API int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const float* w_hh,

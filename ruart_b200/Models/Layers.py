@@ -115,7 +115,7 @@ class StackedBRNN(nn.Module):
         H = self.hidden_size
         B, L, _ = x.shape
         w_ih, w_hh, b_ih, b_hh = self._dir_params(i)
-        parts = 3  # the cell kernel always emits a 3-part split of h
+        parts = sdnet_parts
         a, Kp_in = K.split_act(x, parts)
         wi, _ = K.prep_weight(self, (i, "w_ih"), w_ih, parts)
         wh, Kp_h = K.prep_weight(self, (i, "w_hh"), w_hh, parts)
@@ -123,7 +123,7 @@ class StackedBRNN(nn.Module):
         gx = torch.empty((B * L, 4 * H), dtype=torch.float32, device=x.device)
         K.linear(a, Kp_in, wi, B * L, 4 * H, parts, gx, epi=ops.EPI_BIAS, bias=bias)
         c = torch.zeros((B, H), dtype=torch.float32, device=x.device)
-        hs = torch.zeros((B, 3 * Kp_h), dtype=torch.bfloat16, device=x.device)
+        hs = torch.zeros((B, parts * Kp_h), dtype=torch.bfloat16, device=x.device)
         gh = torch.empty((B, 4 * H), dtype=torch.float32, device=x.device)
         last = torch.zeros(B, dtype=torch.int32, device=x.device)
         op = K.rows2d(out)[2]
@@ -133,8 +133,11 @@ class StackedBRNN(nn.Module):
             if t > 0:
                 K.linear(hs, Kp_h, wh, B, 4 * H, parts, gh)
             last.fill_(t)
-            call("ruart_lstm_cell", ptr(gx), ptr(rows_b + t), ptr(gh) if t > 0 else None, ptr(c), ptr(hs), Kp_h, H,
-                 B, ptr(last), t, ptr(offs_b + t * op), ptr(out), current_stream())
+            # keep both index tensors alive across the call: two unnamed temporaries would share
+            # one freed allocator block
+            rg, so = rows_b + t, offs_b + t * op
+            call("ruart_lstm_cell", ptr(gx), ptr(rg), ptr(gh) if t > 0 else None, ptr(c), ptr(hs), parts, Kp_h, H,
+                 B, ptr(last), t, ptr(so), ptr(out), current_stream())
 
     def forward(self, x, x_mask, return_list=False, x_additional=None, LN=None):
         _need_cuda(x)
@@ -243,9 +246,10 @@ class LinearSelfAttn(nn.Module):
         _need_cuda(x)
         B, L, D = x.shape
         out = torch.empty((B, D), dtype=torch.float32, device=x.device)
-        call("ruart_self_attn_pool", ptr(x), K.rows2d(x)[2], B, L, D, ptr(K.as_u8(x_mask)),
-             ptr(self.linear.weight.detach().reshape(-1).contiguous()), ptr(self.linear.bias.detach()),
-             ptr(out), D, current_stream())
+        mask8 = K.as_u8(x_mask)  # named: must outlive the launch
+        w = self.linear.weight.detach().reshape(-1).contiguous()
+        call("ruart_self_attn_pool", ptr(x), K.rows2d(x)[2], B, L, D, ptr(mask8), ptr(w),
+             ptr(self.linear.bias.detach()), ptr(out), D, current_stream())
         return out
 
     def forward(self, x, x_mask):
@@ -297,9 +301,10 @@ class GetFinalScores(nn.Module):
         K.linear(a, Kp, w, B, 3 * X, parts, wy, epi=ops.EPI_BIAS, bias=b3)
         probs = torch.empty((B, M + 1), dtype=torch.float32, device=x.device)
         logits = torch.empty((B, M + 1), dtype=torch.float32, device=x.device) if want_logits else None
-        call("ruart_final_scores", ptr(x), K.rows2d(x)[2], B, M, X, ptr(wy), ptr(K.as_u8(x_mask)), int(ES_len),
-             ptr(self.noanswer_w.weight.detach().reshape(-1).contiguous()), ptr(self.noanswer_w.bias.detach()),
-             ptr(probs), ptr(logits), ptr(nan_flag), current_stream())
+        mask8 = K.as_u8(x_mask)  # named: must outlive the launch
+        nw = self.noanswer_w.weight.detach().reshape(-1).contiguous()
+        call("ruart_final_scores", ptr(x), K.rows2d(x)[2], B, M, X, ptr(wy), ptr(mask8), int(ES_len),
+             ptr(nw), ptr(self.noanswer_w.bias.detach()), ptr(probs), ptr(logits), ptr(nan_flag), current_stream())
         self.last_logits = logits
         return probs
 

@@ -303,23 +303,24 @@ class SDNet(nn.Module):
         slots = torch.zeros((B * M + B * M_od, HS), **f32)
         m2o = self.multi2one
         w_ih, w_hh, b_ih, b_hh = m2o._dir_params(0)
-        a_sp, Kp_in = K.split_act(items_in, 3, row_idx=a_rows_d, n_rows=int(a_rows.size))
-        wi, _ = K.prep_weight(m2o, (0, "w_ih"), w_ih, 3)
-        wh, Kp_h = K.prep_weight(m2o, (0, "w_hh"), w_hh, 3)
+        mp = self.sdnet_parts
+        a_sp, Kp_in = K.split_act(items_in, mp, row_idx=a_rows_d, n_rows=int(a_rows.size))
+        wi, _ = K.prep_weight(m2o, (0, "w_ih"), w_ih, mp)
+        wh, Kp_h = K.prep_weight(m2o, (0, "w_hh"), w_hh, mp)
         bias = K.prep_vector(m2o, (0, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
         gx = torch.empty((int(a_rows.size), 4 * HS), **f32)
-        K.linear(a_sp, Kp_in, wi, int(a_rows.size), 4 * HS, 3, gx, epi=ops.EPI_BIAS, bias=bias)
+        K.linear(a_sp, Kp_in, wi, int(a_rows.size), 4 * HS, mp, gx, epi=ops.EPI_BIAS, bias=bias)
         n_all = lens_all.size
         c_state = torch.zeros((n_all, HS), **f32)
-        h_split = torch.zeros((n_all, 3 * Kp_h), dtype=torch.bfloat16, device=dev)
+        h_split = torch.zeros((n_all, mp * Kp_h), dtype=torch.bfloat16, device=dev)
         gh = torch.empty((n_all, 4 * HS), **f32)
         row0 = 0
         for t, n in enumerate(n_t):
             n = int(n)
             if t > 0:
-                K.linear(h_split, Kp_h, wh, n, 4 * HS, 3, gh)
+                K.linear(h_split, Kp_h, wh, n, 4 * HS, mp, gh)
             call("ruart_lstm_cell", gx.data_ptr() + row0 * 4 * HS * 4, None, ptr(gh) if t > 0 else None,
-                 ptr(c_state), ptr(h_split), Kp_h, HS, n, ptr(last_d), t, ptr(i64_d), ptr(slots), st)
+                 ptr(c_state), ptr(h_split), mp, Kp_h, HS, n, ptr(last_d), t, ptr(i64_d), ptr(slots), st)
             row0 += n
         ocr_x = slots[:B * M].view(B, M, HS)
         od_x = slots[B * M:].view(B, M_od, HS)

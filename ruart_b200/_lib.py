@@ -50,7 +50,7 @@ _SIGNATURES = {
                              c_ll, c_void_p],
     "ruart_final_scores": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    "ruart_lstm_cell": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+    "ruart_lstm_cell": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                         c_int, c_void_p, c_void_p, c_void_p],
     "ruart_lstm_recurrence": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p],
 }

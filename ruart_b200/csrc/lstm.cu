@@ -18,11 +18,20 @@ namespace {
 using namespace ruart;
 
 constexpr int LSTM_THREADS = 512;
-constexpr int KR = 64;        // weights per row kept in registers
-constexpr int HP = 128;       // padded hidden size (h rows in smem)
-constexpr int ROWP = 512;     // padded gate-row count (smem weight pitch)
+constexpr int KR = 64;     // weights per row kept in registers (as 32 float2)
+constexpr int HP = 128;    // padded hidden size (h rows in smem, zero padded)
+constexpr int ROWP = 512;  // padded gate-row count (threads)
+constexpr int NQ = (HP - KR) / 4;  // float4 weight quads per row kept in smem
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  // packed fp32x2 FMA (Blackwell FFMA2): d.x = a.x*b.x + c.x, d.y = a.y*b.y + c.y
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
 
 template <int BT>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
@@ -30,9 +39,9 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
                        const float* __restrict__ w_hh,                    // [ndir][4H][H]
                        float* __restrict__ out, long long out_pitch,      // [B*L, >= ndir*H]
                        int B, int L, int H) {
-  extern __shared__ float smem[];
-  float* s_w = smem;                               // [(H-KR)][ROWP]
-  float* s_h = smem + (HP - KR) * ROWP;            // [2][BT][HP]
+  extern __shared__ __align__(16) float smem[];
+  float4* s_w = reinterpret_cast<float4*>(smem);   // [NQ][ROWP] quads: k = KR + 4q .. +3 of row t
+  float* s_h = smem + NQ * ROWP * 4;               // [2][BT][HP]
   const int t = threadIdx.x;
   const int dir = blockIdx.y;
   const int b0 = blockIdx.x * BT;
@@ -42,13 +51,27 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
   const int wrow = g * H + j;  // row of W_hh / column of xg for this thread
   const float* W = w_hh + static_cast<long long>(dir) * rows * H;
 
-  float wreg[KR];
+  float2 wreg[KR / 2];
 #pragma unroll
-  for (int k = 0; k < KR; ++k) wreg[k] = (active && k < H) ? W[static_cast<long long>(wrow) * H + k] : 0.f;
-  for (int k = KR; k < H; ++k)
-    if (active) s_w[(k - KR) * ROWP + t] = W[static_cast<long long>(wrow) * H + k];
+  for (int k = 0; k < KR; k += 2) {
+    wreg[k / 2].x = (active && k < H) ? W[static_cast<long long>(wrow) * H + k] : 0.f;
+    wreg[k / 2].y = (active && k + 1 < H) ? W[static_cast<long long>(wrow) * H + k + 1] : 0.f;
+  }
+  for (int q = 0; q < NQ; ++q) {
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k = KR + 4 * q;
+    if (active) {
+      const float* wr = W + static_cast<long long>(wrow) * H;
+      if (k < H) w4.x = wr[k];
+      if (k + 1 < H) w4.y = wr[k + 1];
+      if (k + 2 < H) w4.z = wr[k + 2];
+      if (k + 3 < H) w4.w = wr[k + 3];
+    }
+    s_w[q * ROWP + t] = w4;
+  }
   for (int i = t; i < 2 * BT * HP; i += LSTM_THREADS) s_h[i] = 0.f;
   __syncthreads();
+  const int nq = (H > KR) ? (H - KR + 3) / 4 : 0;
 
   float c[BT];
   float nxt[BT];
@@ -56,7 +79,6 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
   for (int b = 0; b < BT; ++b) c[b] = 0.f;
   const long long xcol = static_cast<long long>(dir) * rows + wrow;
   auto step_time = [&](int s) { return dir == 0 ? s : (L - 1 - s); };
-  // prefetch step 0
 #pragma unroll
   for (int b = 0; b < BT; ++b) {
     const int bb = b0 + b;
@@ -66,9 +88,9 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
   }
   int cur = 0;
   for (int s = 0; s < L; ++s) {
-    float acc[BT];
+    float2 acc[BT];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = nxt[b];
+    for (int b = 0; b < BT; ++b) acc[b] = make_float2(nxt[b], 0.f);
     if (s + 1 < L) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
@@ -80,32 +102,37 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
     }
     const float* hc = s_h + cur * BT * HP;
 #pragma unroll
-    for (int k = 0; k < KR; k += 4) {
+    for (int k4 = 0; k4 < KR / 4; ++k4) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
-        const float4 hv = *reinterpret_cast<const float4*>(hc + b * HP + k);
-        acc[b] = fmaf(wreg[k], hv.x, acc[b]);
-        acc[b] = fmaf(wreg[k + 1], hv.y, acc[b]);
-        acc[b] = fmaf(wreg[k + 2], hv.z, acc[b]);
-        acc[b] = fmaf(wreg[k + 3], hv.w, acc[b]);
+        const float4 hv = *reinterpret_cast<const float4*>(hc + b * HP + 4 * k4);
+        acc[b] = ffma2(wreg[2 * k4], make_float2(hv.x, hv.y), acc[b]);
+        acc[b] = ffma2(wreg[2 * k4 + 1], make_float2(hv.z, hv.w), acc[b]);
       }
     }
-    for (int k = KR; k < H; ++k) {
-      const float wv = s_w[(k - KR) * ROWP + t];
+    for (int q = 0; q < nq; ++q) {
+      const float4 wv = s_w[q * ROWP + t];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc[b] = fmaf(wv, hc[b * HP + k], acc[b]);
+      for (int b = 0; b < BT; ++b) {
+        const float4 hv = *reinterpret_cast<const float4*>(hc + b * HP + KR + 4 * q);
+        acc[b] = ffma2(make_float2(wv.x, wv.y), make_float2(hv.x, hv.y), acc[b]);
+        acc[b] = ffma2(make_float2(wv.z, wv.w), make_float2(hv.z, hv.w), acc[b]);
+      }
     }
     float* hn = s_h + (cur ^ 1) * BT * HP;
     const int tt = step_time(s);
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
-      const float vi = acc[b];
-      const float vf = __shfl_down_sync(0xffffffffu, acc[b], 1);
-      const float vg = __shfl_down_sync(0xffffffffu, acc[b], 2);
-      const float vo = __shfl_down_sync(0xffffffffu, acc[b], 3);
+      // every lane activates its own gate: i, f, o -> sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 ; g -> tanh
+      const float pre = acc[b].x + acc[b].y;
+      const float th = tanhf(g == 2 ? pre : 0.5f * pre);
+      const float av = (g == 2) ? th : fmaf(0.5f, th, 0.5f);
+      const float a_f = __shfl_down_sync(0xffffffffu, av, 1);
+      const float a_g = __shfl_down_sync(0xffffffffu, av, 2);
+      const float a_o = __shfl_down_sync(0xffffffffu, av, 3);
       if (g == 0 && active) {
-        const float cn = sigmoidf_(vf) * c[b] + sigmoidf_(vi) * tanhf(vg);
-        const float hv = sigmoidf_(vo) * tanhf(cn);
+        const float cn = fmaf(a_f, c[b], av * a_g);
+        const float hv = a_o * tanhf(cn);
         c[b] = cn;
         hn[b * HP + j] = hv;
         const int bb = b0 + b;
@@ -120,7 +147,7 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
 template <int BT>
 int launch(const float* xg, long long xg_pitch, const float* w_hh, float* out, long long out_pitch,
            int B, int L, int H, int ndir, cudaStream_t st) {
-  const size_t smem = (static_cast<size_t>(HP - KR) * ROWP + 2 * BT * HP) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(NQ) * ROWP * 4 + 2 * BT * HP) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(lstm_recurrence_kernel<BT>,

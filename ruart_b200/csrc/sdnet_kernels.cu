@@ -348,7 +348,7 @@ final_scores_kernel(const float* __restrict__ x, long long x_pitch, int M, int X
 // when this is an item's last word (last_step[r] == step), into its slot row (SDNet.py:304,310).
 __global__ void lstm_cell_kernel(const float* __restrict__ gx, const int32_t* __restrict__ row_gx,
                                  const float* __restrict__ gh, float* __restrict__ c,
-                                 __nv_bfloat16* __restrict__ h_split, int Kp, int H, int n_rows,
+                                 __nv_bfloat16* __restrict__ h_split, int parts, int Kp, int H, int n_rows,
                                  const int32_t* __restrict__ last_step, int step,
                                  const long long* __restrict__ slot_off, float* __restrict__ slots) {
   const long long total = static_cast<long long>(n_rows) * H;
@@ -371,9 +371,9 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gx, const int32_t* __
     const float hn = so * tanhf(cn);
     c[i] = cn;
     float rem = hn;
-    for (int p = 0; p < 3; ++p) {
+    for (int p = 0; p < parts; ++p) {
       const __nv_bfloat16 hb = __float2bfloat16_rn(rem);
-      h_split[static_cast<long long>(r) * 3 * Kp + static_cast<long long>(p) * Kp + j] = hb;
+      h_split[static_cast<long long>(r) * parts * Kp + static_cast<long long>(p) * Kp + j] = hb;
       rem -= __bfloat162float(hb);
     }
     if (last_step[r] == step) slots[slot_off[r] + j] = hn;
@@ -474,13 +474,14 @@ extern "C" int ruart_final_scores(const float* x, long long x_pitch, int B, int 
 }
 
 extern "C" int ruart_lstm_cell(const float* gx, const int32_t* row_gx, const float* gh, float* c,
-                               void* h_split, int Kp, int H, int n_rows, const int32_t* last_step,
-                               int step, const long long* slot_off, float* slots, void* stream) {
-  RUART_ARG_CHECK(H > 0 && Kp >= H && (Kp % 64) == 0);
+                               void* h_split, int parts, int Kp, int H, int n_rows,
+                               const int32_t* last_step, int step, const long long* slot_off,
+                               float* slots, void* stream) {
+  RUART_ARG_CHECK(H > 0 && Kp >= H && (Kp % 64) == 0 && parts >= 1 && parts <= 3);
   if (n_rows == 0) return RUART_OK;
   lstm_cell_kernel<<<cap_grid(static_cast<long long>(n_rows) * H, 256), 256, 0,
-                     (cudaStream_t)stream>>>(gx, row_gx, gh, c, (__nv_bfloat16*)h_split, Kp, H,
-                                             n_rows, last_step, step, slot_off, slots);
+                     (cudaStream_t)stream>>>(gx, row_gx, gh, c, (__nv_bfloat16*)h_split, parts,
+                                             Kp, H, n_rows, last_step, step, slot_off, slots);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
