@@ -33,6 +33,11 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&d);
 }
 
+// 1 / (1 + e^-x) = rcp(1 + ex2(-x log2 e)); saturates cleanly (ex2 -> inf -> rcp -> 0).
+__device__ __forceinline__ float logistic(float x) {
+  return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+}
+
 template <int BT>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*L, ndir*4H]
@@ -123,16 +128,17 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
     const int tt = step_time(s);
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
-      // every lane activates its own gate: i, f, o -> sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 ; g -> tanh
+      // every lane activates its own gate with one logistic evaluation on the MUFU ex2/rcp
+      // approximations (<= 2 ulp each): i, f, o -> s(x) ; g -> tanh(x) = 2 s(2x) - 1
       const float pre = acc[b].x + acc[b].y;
-      const float th = tanhf(g == 2 ? pre : 0.5f * pre);
-      const float av = (g == 2) ? th : fmaf(0.5f, th, 0.5f);
+      const float sg = logistic(g == 2 ? 2.0f * pre : pre);
+      const float av = (g == 2) ? fmaf(2.0f, sg, -1.0f) : sg;
       const float a_f = __shfl_down_sync(0xffffffffu, av, 1);
       const float a_g = __shfl_down_sync(0xffffffffu, av, 2);
       const float a_o = __shfl_down_sync(0xffffffffu, av, 3);
       if (g == 0 && active) {
         const float cn = fmaf(a_f, c[b], av * a_g);
-        const float hv = a_o * tanhf(cn);
+        const float hv = a_o * fmaf(2.0f, logistic(2.0f * cn), -1.0f);
         c[b] = cn;
         hn[b * HP + j] = hv;
         const int bb = b0 + b;
