@@ -335,6 +335,163 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
 // byte offset of 16-byte chunk c of row r inside a swizzled [16 x 64] bf16 tile
 __device__ __forceinline__ int tile_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
+// Item sequences (<= 8 wordpieces, the bulk of RUArt's rows) go two at a time: consecutive
+// sequences A and B are also consecutive token rows, so A fills rows 0-7 and B rows 8-15 of ONE
+// 16-row MMA tile; the cross blocks of S are masked to -inf, which makes P block-diagonal and
+// O = P V exact for both.  A sequence of 9..16 tokens takes the tile alone.  One warp per
+// (sequence pair, head).
+__global__ void __launch_bounds__(SHORT_WARPS * 32)
+bert_attention_mma16_kernel(const __nv_bfloat16* __restrict__ qkv,
+                            const int32_t* __restrict__ cu_seqlens, int n_seq, int n_heads,
+                            float scale, __nv_bfloat16* __restrict__ out) {
+  constexpr int TB = 16 * 128;
+  __shared__ __align__(128) uint8_t sh16[SHORT_WARPS][3 * TB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sQ = sh16[warp];
+  uint8_t* sK = sQ + TB;
+  uint8_t* sV = sK + TB;
+  const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+  const int H = n_heads * 64;
+  const long long ld = 3LL * H;
+  const int g = lane >> 2, t = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int a_chk = lane >> 4;
+  const int b_row = lane & 7;
+  const int b_chk = lane >> 3;
+  const int n_pairs = (n_seq + 1) >> 1;
+  const long long n_tasks = static_cast<long long>(n_pairs) * n_heads;
+  for (long long task = static_cast<long long>(blockIdx.x) * SHORT_WARPS + warp; task < n_tasks;
+       task += static_cast<long long>(gridDim.x) * SHORT_WARPS) {
+    const int pair = static_cast<int>(task / n_heads);
+    const int h = static_cast<int>(task - static_cast<long long>(pair) * n_heads);
+    const int sA = 2 * pair, sB = sA + 1;
+    const int tA = cu_seqlens[sA];
+    const int tB = cu_seqlens[sA + 1];
+    const int lenA = tB - tA;
+    const int lenB = (sB < n_seq) ? cu_seqlens[sB + 1] - tB : 0;
+    // passes: paired (both <= 8), or each sequence of <= 16 tokens on its own
+    const bool paired = lenA <= 8 && lenB <= 8;
+    const int n_pass = paired ? 1 : 2;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      int t0, l0, l1;  // rows 0.. : l0 tokens from t0 ; rows 8.. : l1 tokens from t0 + l0 (paired)
+      if (paired) {
+        t0 = tA; l0 = lenA; l1 = lenB;
+      } else {
+        t0 = pass == 0 ? tA : tB;
+        l0 = pass == 0 ? lenA : lenB;
+        l1 = 0;
+        if (l0 <= 0 || l0 > 16) continue;  // longer sequences belong to the other kernels
+      }
+      if (l0 + l1 == 0) continue;
+      // row r of the tile <-> token t0 + tok(r); rows without a token are zero
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i;
+        const int r = idx >> 3, c = idx & 7;
+        int tok = -1;
+        if (paired) {
+          if (r < 8) { if (r < l0) tok = r; }
+          else if (r - 8 < l1) tok = l0 + (r - 8);
+        } else if (r < l0) {
+          tok = r;
+        }
+        uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+        if (tok >= 0) {
+          const uint4* row = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(t0 + tok)) * ld + h * 64);
+          q4 = __ldg(row + c);
+          k4 = __ldg(row + (H >> 3) + c);
+          v4 = __ldg(row + 2 * (H >> 3) + c);
+        }
+        const int off = tile_off(r, c);
+        *reinterpret_cast<uint4*>(sQ + off) = q4;
+        *reinterpret_cast<uint4*>(sK + off) = k4;
+        *reinterpret_cast<uint4*>(sV + off) = v4;
+      }
+      __syncwarp();
+      const bool two = paired ? (l1 > 0) : (l0 > 8);  // is the second key tile in use?
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t kb0[8], kb1[8];
+      ldsm_x4(aK + tile_off(b_row, b_chk), kb0[0], kb0[1], kb0[2], kb0[3]);
+      ldsm_x4(aK + tile_off(b_row, 4 + b_chk), kb0[4], kb0[5], kb0[6], kb0[7]);
+      if (two) {
+        ldsm_x4(aK + tile_off(8 + b_row, b_chk), kb1[0], kb1[1], kb1[2], kb1[3]);
+        ldsm_x4(aK + tile_off(8 + b_row, 4 + b_chk), kb1[4], kb1[5], kb1[6], kb1[7]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(aQ + tile_off(a_row, 2 * ks + a_chk), a0, a1, a2, a3);
+        mma_bf16_16816(s0, a0, a1, a2, a3, kb0[2 * ks], kb0[2 * ks + 1]);
+        if (two) mma_bf16_16816(s1, a0, a1, a2, a3, kb1[2 * ks], kb1[2 * ks + 1]);
+      }
+      // validity of (row, key): thread holds rows g and g+8, keys 2t, 2t+1 of tile 0 and of tile 1
+      const int k0 = 2 * t, k1 = 2 * t + 1;
+      bool vA0, vA1, vA2, vA3, vB0, vB1, vB2, vB3;  // A: row g ; B: row g+8 ; 0,1: tile 0 ; 2,3: tile 1
+      if (paired) {
+        vA0 = k0 < l0; vA1 = k1 < l0; vA2 = false; vA3 = false;
+        vB0 = false; vB1 = false; vB2 = k0 < l1; vB3 = k1 < l1;
+      } else {
+        vA0 = vB0 = k0 < l0; vA1 = vB1 = k1 < l0;
+        vA2 = vB2 = 8 + k0 < l0; vA3 = vB3 = 8 + k1 < l0;
+      }
+      const float xA0 = vA0 ? s0[0] * scale : -INFINITY, xA1 = vA1 ? s0[1] * scale : -INFINITY;
+      const float xA2 = vA2 ? s1[0] * scale : -INFINITY, xA3 = vA3 ? s1[1] * scale : -INFINITY;
+      const float xB0 = vB0 ? s0[2] * scale : -INFINITY, xB1 = vB1 ? s0[3] * scale : -INFINITY;
+      const float xB2 = vB2 ? s1[2] * scale : -INFINITY, xB3 = vB3 ? s1[3] * scale : -INFINITY;
+      float mA = fmaxf(fmaxf(xA0, xA1), fmaxf(xA2, xA3));
+      float mB = fmaxf(fmaxf(xB0, xB1), fmaxf(xB2, xB3));
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+      // rows without any valid key (pad rows of the tile) would give exp(-inf + inf): clamp the max
+      mA = (mA == -INFINITY) ? 0.f : mA;
+      mB = (mB == -INFINITY) ? 0.f : mB;
+      const float pA0 = __expf(xA0 - mA), pA1 = __expf(xA1 - mA), pA2 = __expf(xA2 - mA), pA3 = __expf(xA3 - mA);
+      const float pB0 = __expf(xB0 - mB), pB1 = __expf(xB1 - mB), pB2 = __expf(xB2 - mB), pB3 = __expf(xB3 - mB);
+      float lA = (pA0 + pA1) + (pA2 + pA3), lB = (pB0 + pB1) + (pB2 + pB3);
+      lA += __shfl_xor_sync(0xffffffffu, lA, 1);
+      lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+      lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+      lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+      const uint32_t p0 = pack_bf16x2(pA0, pA1), p1 = pack_bf16x2(pB0, pB1);
+      const uint32_t p2 = pack_bf16x2(pA2, pA3), p3 = pack_bf16x2(pB2, pB3);
+      const float iA = lA > 0.f ? 1.0f / lA : 0.f, iB = lB > 0.f ? 1.0f / lB : 0.f;
+      __syncwarp();  // all lanes are done reading sQ: it becomes the O staging tile
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(aV + tile_off(a_row, 2 * dp + a_chk), b0, b1, b2, b3);
+        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(o0, p0, p1, p2, p3, b0, b1);
+        mma_bf16_16816(o1, p0, p1, p2, p3, b2, b3);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp) + 4 * t) = pack_bf16x2(o0[0] * iA, o0[1] * iA);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp) + 4 * t) = pack_bf16x2(o0[2] * iB, o0[3] * iB);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[0] * iA, o1[1] * iA);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[2] * iB, o1[3] * iB);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i;
+        const int r = idx >> 3, c = idx & 7;
+        int tok = -1;
+        if (paired) {
+          if (r < 8) { if (r < l0) tok = r; }
+          else if (r - 8 < l1) tok = l0 + (r - 8);
+        } else if (r < l0) {
+          tok = r;
+        }
+        if (tok >= 0) {
+          const uint4 o4 = *reinterpret_cast<const uint4*>(sQ + tile_off(r, c));
+          *(reinterpret_cast<uint4*>(out + (static_cast<long long>(t0 + tok)) * H + h * 64) + c) = o4;
+        }
+      }
+    }
+  }
+}
+
 // MAXT = 16 or 64: rows of the staged Q/K/V tiles.  One warp per (sequence, head) task with
 // lo < len <= MAXT; other lengths are left to the other instantiation / the streaming kernel.
 template <int MAXT>
@@ -731,11 +888,14 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     long long ctas = (n_tasks + SHORT_WARPS - 1) / SHORT_WARPS;
     const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
     if (ctas > cap) ctas = cap;
-    const size_t smem16 = static_cast<size_t>(SHORT_WARPS) * 3 * 16 * 128;
-    bert_attention_mma_kernel<16><<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, smem16, st>>>(
-        (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, 0,
-        (__nv_bfloat16*)out_bf16);
-    RUART_LAUNCH_CHECK();
+    {
+      const long long pair_tasks = static_cast<long long>((n_seq + 1) / 2) * n_heads;
+      long long ctas16 = (pair_tasks + SHORT_WARPS - 1) / SHORT_WARPS;
+      if (ctas16 > cap) ctas16 = cap;
+      bert_attention_mma16_kernel<<<static_cast<unsigned>(ctas16), SHORT_WARPS * 32, 0, st>>>(
+          (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, (__nv_bfloat16*)out_bf16);
+      RUART_LAUNCH_CHECK();
+    }
     if (max_len <= 16) return RUART_OK;
     const size_t smem64 = static_cast<size_t>(SHORT_WARPS) * 3 * 64 * 128;
     bert_attention_mma_kernel<64><<<static_cast<unsigned>(ctas), SHORT_WARPS * 32, smem64, st>>>(
