@@ -66,12 +66,14 @@ RUART_API int ruart_phoc_batch_host(const char* chars_host, const int32_t* offse
  * n_terms: 1 (plain bf16), 3 (two-part split, ~2^-16 rel) or 6 (three-part split, ~fp32).
  * Outputs: fp32 (out_f32, ldo_f32) and/or bf16 (out_bf16, ldo_bf16); the bf16 output may itself
  * be written as out_parts split parts, part p at column offset p*out_part_stride.
+ * residual_bf16 (optional, plain-bf16-output mode with N % 64 == 0): a [M, N] bf16 matrix added in
+ * fp32 before the output is rounded (dense(x) + input_tensor, modeling.py:263,302).
  * Replaces nn.Linear at modeling.py:225-227,261,287,300 and Layers.py:226-227,166 (W_ih).    */
 RUART_API int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const void* W, long long ldw,
                     int w_parts, int M, int N, int Kp, int n_terms, int epi, const float* bias,
                     const float* scale, int scale_len, float* out_f32, long long ldo_f32,
                     void* out_bf16, long long ldo_bf16, int out_parts, long long out_part_stride,
-                    int fast_gelu, void* stream);
+                    int fast_gelu, const void* residual_bf16, long long ld_res, void* stream);
 
 /* ---------------------------------------------------------------- BERT (packed, pad-free rows)
  * Activations are [T, hidden] row-major over the T real wordpieces of all sequences; every
@@ -83,7 +85,8 @@ RUART_API int ruart_bert_embed_ln(const int32_t* ids, const int32_t* pos, const 
                                   const float* pos_emb, const float* type_emb, const float* gamma,
                                   const float* beta, float eps, int T, int hidden, float* out_f32,
                                   void* out_bf16, int out_parts, void* stream);
-/* BertSelfOutput / BertOutput tail, modeling.py:260-264,299-303: LN(x + residual)           */
+/* BertSelfOutput / BertOutput tail, modeling.py:260-264,299-303: LN(x + residual); both residual
+ * pointers NULL = x already contains the residual (fused into the GEMM epilogue)             */
 RUART_API int ruart_add_layernorm(const float* x_f32, const void* x_bf16, const float* res_f32,
                                   const void* res_bf16, const float* gamma, const float* beta,
                                   float eps, int T, int hidden, float* out_f32, void* out_bf16,

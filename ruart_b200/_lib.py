@@ -30,7 +30,7 @@ _SIGNATURES = {
                               ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int32)],
     "ruart_gemm_bf16": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
                         c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
-                        c_ll, c_int, c_void_p],
+                        c_ll, c_int, c_void_p, c_ll, c_void_p],
     "ruart_bert_embed_ln": [c_void_p] * 7 + [c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ruart_add_layernorm": [c_void_p] * 6 + [c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ruart_bert_attention": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p,

@@ -169,13 +169,14 @@ class BertEngine(object):
         return {"ids": ids, "pos": pos, "cu_seqlens": cu_seq, "T": T, "segments": segs}
 
     # ------------------------------------------------------------------ forward
-    def _gemm(self, a, w, bias, N, K, epi, out_kind, fast_gelu=False):
-        """a: activation GEMM operand; returns (f32, bf16) outputs according to mode/out_kind."""
+    def _gemm(self, a, w, bias, N, K, epi, out_kind, fast_gelu=False, residual=None):
+        """a: activation GEMM operand; returns (f32, bf16) outputs according to mode/out_kind.
+        residual (bf16 mode): added in the GEMM epilogue before the output is rounded."""
         T = a.shape[0]
         dev = a.device
         if self.mode == "bf16":
             out = torch.empty((T, N), dtype=torch.bfloat16, device=dev)
-            ops.gemm(a, w, T, N, K, epi=epi, bias=bias, out_bf16=out, fast_gelu=fast_gelu)
+            ops.gemm(a, w, T, N, K, epi=epi, bias=bias, out_bf16=out, fast_gelu=fast_gelu, residual=residual)
             return None, out
         if out_kind == "split":  # consumer is another GEMM only
             out = torch.empty((T, 3 * N), dtype=torch.bfloat16, device=dev)
@@ -232,16 +233,19 @@ class BertEngine(object):
                 cu = pk["cu_seqlens"][sgm["seq0"]:sgm["seq1"] + 1]
                 call("ruart_bert_attention", ptr(q_f), ptr(q_b), ptr(cu), n_seq, self.heads, scale,
                      sgm["max_len"], None, ptr(ctx), parts, st)
-            a_f, a_b = self._gemm(ctx, lw["wo"], lw["bo"], H, H, ops.EPI_BIAS, "act")
+            fuse_res = not keep32  # bf16 residual stream: the GEMM epilogue adds it
+            a_f, a_b = self._gemm(ctx, lw["wo"], lw["bo"], H, H, ops.EPI_BIAS, "act",
+                                  residual=h_b if fuse_res else None)
             h1_f = torch.empty((T, H), dtype=torch.float32, device=dev) if keep32 else None
             h1_b = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
-            call("ruart_add_layernorm", ptr(a_f), ptr(a_b), ptr(h_f), ptr(h_b) if not keep32 else None,
+            call("ruart_add_layernorm", ptr(a_f), ptr(a_b), ptr(h_f), None,
                  ptr(lw["g1"]), ptr(lw["b1"]), lw["eps"], T, H, ptr(h1_f), ptr(h1_b), parts, st)
             _, ff = self._gemm(h1_b, lw["wi"], lw["bi"], I, H, ops.EPI_BIAS_GELU, "split",
                                fast_gelu=not fp32)
-            d_f, d_b = self._gemm(ff, lw["wd"], lw["bd"], H, I, ops.EPI_BIAS, "act")
+            d_f, d_b = self._gemm(ff, lw["wd"], lw["bd"], H, I, ops.EPI_BIAS, "act",
+                                  residual=h1_b if fuse_res else None)
             h_f, h_b = layer_bufs(li + 1)
-            call("ruart_add_layernorm", ptr(d_f), ptr(d_b), ptr(h1_f), ptr(h1_b) if not keep32 else None,
+            call("ruart_add_layernorm", ptr(d_f), ptr(d_b), ptr(h1_f), None,
                  ptr(lw["g2"]), ptr(lw["b2"]), lw["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
         # ---- host: flatten the word-offset lists while the encoder runs on the device ----------
         layer_stride = T * H

@@ -158,11 +158,14 @@ add_ln_kernel(const float* x_f32, const __nv_bfloat16* x_b16, const float* res_f
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
   if (row >= T) return;
-  RowVec<HC> x, r;
+  RowVec<HC> x;
   load_act<HC>(x_f32, x_b16, row, lane, x);
-  load_act<HC>(res_f32, res_b16, row, lane, r);
+  if (res_f32 != nullptr || res_b16 != nullptr) {  // absent: the GEMM epilogue already added it
+    RowVec<HC> r;
+    load_act<HC>(res_f32, res_b16, row, lane, r);
 #pragma unroll
-  for (int i = 0; i < HC * 8; ++i) x.v[i] += r.v[i];
+    for (int i = 0; i < HC * 8; ++i) x.v[i] += r.v[i];
+  }
   layer_norm_row<HC>(x, gamma, beta, eps, lane);
   store_act<HC>(out_f32, out_b16, parts, row, lane, x);
 }
@@ -841,7 +844,7 @@ extern "C" int ruart_add_layernorm(const float* x_f32, const void* x_bf16, const
                                    int out_parts, void* stream) {
   RUART_ARG_CHECK(hidden == 768 || hidden == 1024);
   RUART_ARG_CHECK((x_f32 != nullptr) != (x_bf16 != nullptr));
-  RUART_ARG_CHECK((res_f32 != nullptr) != (res_bf16 != nullptr));
+  RUART_ARG_CHECK(!(res_f32 != nullptr && res_bf16 != nullptr));
   RUART_ARG_CHECK(out_f32 != nullptr || out_bf16 != nullptr);
   if (T == 0) return RUART_OK;
   cudaStream_t st = (cudaStream_t)stream;

@@ -54,6 +54,8 @@ struct GemmParams {
   long long ldo_bf16;
   int out_parts;              // 1: plain bf16; 2/3: hi|mid|lo split parts
   long long out_part_stride;  // elements between parts inside one row
+  const __nv_bfloat16* residual;  // TMA_OUT only: added (fp32) before rounding, or nullptr
+  long long ld_res;
 };
 
 template <int EPI>
@@ -251,8 +253,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_arrive(&tmem_empty_bar[acc]);
           }
           uint4 pk4[8];
+          // optional residual row slice (BertSelfOutput / BertOutput: dense(x) + input_tensor,
+          // modeling.py:263,302), added in fp32 before the single rounding to bf16
+          const int grow = m_blk * BM + r_local;
+          const bool has_res = p.residual != nullptr && grow < p.M && tile_col0 + c0 + 64 <= p.N;
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              p.residual + static_cast<long long>(grow) * p.ld_res + tile_col0 + c0);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
+            uint4 r4 = make_uint4(0, 0, 0, 0);
+            if (has_res) r4 = __ldg(rp + c);
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
             uint32_t pk[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -266,7 +277,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 x1 = __uint_as_float(v1[j - 31]);
               }
               const float2 bv = *reinterpret_cast<const float2*>(vec + c0 + j);
-              pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x), epi_fn<EPI>(x1, bv.y));
+              pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x) + bf16_lo(rw[q]),
+                                  epi_fn<EPI>(x1, bv.y) + bf16_hi(rw[q]));
             }
             pk4[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
@@ -445,7 +457,8 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
                                int epi, const float* bias, const float* scale, int scale_len,
                                float* out_f32, long long ldo_f32, void* out_bf16,
                                long long ldo_bf16, int out_parts, long long out_part_stride,
-                               int fast_gelu, void* stream) {
+                               int fast_gelu, const void* residual_bf16, long long ld_res,
+                               void* stream) {
   RUART_ARG_CHECK(M >= 0 && N > 0 && Kp > 0 && (Kp % BK) == 0);
   RUART_ARG_CHECK(a_parts >= 1 && a_parts <= 3 && w_parts >= 1 && w_parts <= 3);
   RUART_ARG_CHECK(n_terms == 1 || n_terms == 3 || n_terms == 6);
@@ -505,6 +518,13 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   p.ldo_bf16 = ldo_bf16;
   p.out_parts = out_parts;
   p.out_part_stride = out_part_stride;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16);
+  p.ld_res = ld_res;
+  if (residual_bf16 != nullptr) {
+    // fused residual: staged TMA-store epilogue only, whole 64-column chunks, 16-byte aligned rows
+    RUART_ARG_CHECK(tma_out && (N % 64) == 0 && (ld_res % 8) == 0 &&
+                    (reinterpret_cast<uintptr_t>(residual_bf16) & 15u) == 0);
+  }
 
   CUtensorMap tma, tmb, tmc;
   int rc = make_tmap_bf16(&tma, A, M, (long long)a_parts * Kp, lda, BM);

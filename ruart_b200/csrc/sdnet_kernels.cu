@@ -206,6 +206,144 @@ attention_tail_kernel(const float* __restrict__ p1, long long p1_pitch, const fl
   }
 }
 
+// Register-tiled version for L2 <= 128 (every attention of the shipped conf): one CTA per
+// (batch, 32 query rows), 256 threads = 8 query groups (4 rows each) x 32 lanes.
+//   phase 1  S[32 x L2]: k-chunks of 32 of p1 / p2 staged in smem (row pitch 36 floats: 16-byte
+//            aligned, conflict-free); thread tile 4 queries x 4 keys (keys lane, lane+32, ...)
+//   phase 2  masked softmax per row (4 rows per warp), in smem
+//   phase 3  O[32 x D3] = A x3: x3 staged in [32 keys x 128 dims] chunks; thread tile 4 queries x
+//            4 consecutive dims (float4)
+constexpr int AT_Q = 32, AT_KC = 32, AT_L2 = 128, AT_P = 36, AT_SP = 132, AT_DC = 128;
+
+__global__ void __launch_bounds__(256)
+attention_tail_tiled_kernel(const float* __restrict__ p1, long long p1_pitch,
+                            const float* __restrict__ p2, long long p2_pitch, int Hd,
+                            const uint8_t* __restrict__ mask, const float* __restrict__ x3,
+                            long long x3_pitch, int D3, float* __restrict__ out,
+                            long long out_pitch, int L1, int L2, int add_to_out) {
+  __shared__ __align__(16) float s_a[AT_Q * AT_P];       // p1 chunk [32 q][32 k]
+  __shared__ __align__(16) float s_b[AT_L2 * AT_P];      // p2 chunk [128 keys][32 k]; later x3 chunk
+  __shared__ __align__(16) float s_s[AT_Q * AT_SP];      // scores / probabilities [32 q][L2]
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * AT_Q;
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  const float* p1b = p1 + (static_cast<long long>(b) * L1 + q0) * p1_pitch;
+  const float* p2b = p2 + static_cast<long long>(b) * L2 * p2_pitch;
+  const int nq = min(AT_Q, L1 - q0);
+  const int nj = (L2 + 31) >> 5;  // 32-key groups actually present (warp-uniform)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < Hd; k0 += AT_KC) {
+    __syncthreads();
+    // stage p1 chunk: 32 rows x 32 k (one float per thread x 4)
+    for (int i = tid; i < AT_Q * AT_KC; i += 256) {
+      const int r = i >> 5, k = i & 31;
+      s_a[r * AT_P + k] = (r < nq && k0 + k < Hd) ? p1b[r * p1_pitch + k0 + k] : 0.f;
+    }
+    for (int i = tid; i < nj * 32 * AT_KC; i += 256) {
+      const int r = i >> 5, k = i & 31;
+      s_b[r * AT_P + k] = (r < L2 && k0 + k < Hd) ? p2b[r * p2_pitch + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < AT_KC; k += 4) {
+      float4 av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(s_a + (4 * ty + i) * AT_P + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nj) bv[j] = *reinterpret_cast<const float4*>(s_b + (tx + 32 * j) * AT_P + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nj) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+            acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+            acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+            acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+          }
+        }
+      }
+    }
+  }
+  // scores -> smem, masked
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int key = tx + 32 * j;
+    if (key < L2) {
+      const bool keep = mask[static_cast<long long>(b) * L2 + key] != 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_s[(4 * ty + i) * AT_SP + key] = keep ? acc[i][j] : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // softmax over keys: warp ty owns rows 4ty .. 4ty+3
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* row = s_s + (4 * ty + i) * AT_SP;
+    float m = -INFINITY;
+    for (int k = tx; k < L2; k += 32) m = fmaxf(m, row[k]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = tx; k < L2; k += 32) {
+      const float e = expf(row[k] - m);
+      row[k] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int k = tx; k < L2; k += 32) row[k] *= inv;
+  }
+  // out = A @ x3, 128 dims per pass, keys in chunks of 32 staged through s_b ([32][AT_SP])
+  const float* x3b = x3 + static_cast<long long>(b) * L2 * x3_pitch;
+  float* ob = out + (static_cast<long long>(b) * L1 + q0) * out_pitch;
+  for (int d0 = 0; d0 < D3; d0 += AT_DC) {
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    for (int kk = 0; kk < L2; kk += 32) {
+      __syncthreads();
+      for (int i = tid; i < 32 * AT_DC; i += 256) {
+        const int r = i >> 7, d = i & 127;
+        s_b[r * AT_SP + d] = (kk + r < L2 && d0 + d < D3) ? x3b[(kk + r) * x3_pitch + d0 + d] : 0.f;
+      }
+      __syncthreads();
+      const int kmax = min(32, L2 - kk);
+      for (int k = 0; k < kmax; ++k) {
+        const float4 xv = *reinterpret_cast<const float4*>(s_b + k * AT_SP + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = s_s[(4 * ty + i) * AT_SP + kk + k];
+          o[i][0] = fmaf(a, xv.x, o[i][0]);
+          o[i][1] = fmaf(a, xv.y, o[i][1]);
+          o[i][2] = fmaf(a, xv.z, o[i][2]);
+          o[i][3] = fmaf(a, xv.w, o[i][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = 4 * ty + i;
+      if (q < nq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int d = d0 + 4 * tx + j;
+          if (d < D3) {
+            float* op = ob + q * out_pitch + d;
+            *op = add_to_out ? (*op + o[i][j]) : o[i][j];
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // LinearSelfAttn + weighted_avg (Layers.py:328-341,529-534; SDNet.py:414-415):
 //   alpha = softmax(mask(x w + b)) over the sequence ; out[b] = sum_l alpha_l x[b, l]
@@ -432,6 +570,14 @@ extern "C" int ruart_attention_tail(const float* p1, long long p1_pitch, const f
                                     long long out_pitch, int B, int L1, int L2, int add_to_out,
                                     void* stream) {
   RUART_ARG_CHECK(B > 0 && L1 > 0 && L2 > 0 && hidden > 0 && D3 > 0);
+  if (L2 <= AT_L2) {
+    dim3 grid((L1 + AT_Q - 1) / AT_Q, B);
+    attention_tail_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        p1, p1_pitch, p2, p2_pitch, hidden, mask, x3, x3_pitch, D3, out, out_pitch, L1, L2,
+        add_to_out);
+    RUART_LAUNCH_CHECK();
+    return RUART_OK;
+  }
   const size_t smem = (static_cast<size_t>(ATT_QT) * hidden + static_cast<size_t>(ATT_QT) * L2) *
                       sizeof(float);
   RUART_ARG_CHECK(smem <= 200 * 1024);

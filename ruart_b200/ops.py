@@ -66,7 +66,7 @@ def phoc_strings(strings, device="cuda"):
 
 # ------------------------------------------------------------------------------------ GEMM
 def gemm(a, w, M, N, Kp, *, a_parts=1, w_parts=1, n_terms=1, epi=EPI_NONE, bias=None, scale=None,
-         out_f32=None, out_bf16=None, out_parts=1, out_part_stride=0, fast_gelu=False):
+         out_f32=None, out_bf16=None, out_parts=1, out_part_stride=0, fast_gelu=False, residual=None):
     """out[M,N] = epi(a[M, parts*Kp] @ w[N, parts*Kp]^T); a, w bf16 row-major (last dim contiguous)."""
     _need_cuda(a, w, bias, scale, out_f32, out_bf16)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -77,4 +77,5 @@ def gemm(a, w, M, N, Kp, *, a_parts=1, w_parts=1, n_terms=1, epi=EPI_NONE, bias=
          ptr(bias), ptr(scale), 0 if scale is None else scale.numel(),
          ptr(out_f32), 0 if out_f32 is None else out_f32.stride(-2),
          ptr(out_bf16), 0 if out_bf16 is None else out_bf16.stride(-2), out_parts,
-         out_part_stride, 1 if fast_gelu else 0, current_stream())
+         out_part_stride, 1 if fast_gelu else 0, ptr(residual), 0 if residual is None else residual.stride(-2),
+         current_stream())

@@ -119,7 +119,7 @@ def linear(a_split, Kp, w_split, rows, N, parts, out, epi=ops.EPI_NONE, bias=Non
     _, _, pitch = rows2d(out)
     call("ruart_gemm_bf16", ptr(a_split), a_split.stride(0), parts, ptr(w_split), w_split.stride(0), parts,
          rows, N, Kp, _TERMS[parts], epi, ptr(bias), ptr(scale), 0 if scale is None else scale.numel(),
-         ptr(out), pitch, None, 0, 1, 0, 0, current_stream())
+         ptr(out), pitch, None, 0, 1, 0, 0, None, 0, current_stream())
     return out
 
 

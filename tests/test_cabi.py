@@ -28,6 +28,6 @@ def test_bad_arguments_are_reported_without_a_gpu():
     L = _lib.lib()
     # Kp not a multiple of 64 -> RUART_ERR_ARG before any CUDA call
     rc = L.ruart_gemm_bf16(None, 8, 1, None, 8, 1, 4, 4, 10, 1, 0, None, None, 0, None, 0, None, 0,
-                           1, 0, 0, None)
+                           1, 0, 0, None, 0, None)
     assert rc == 2
     assert b"bad argument" in L.ruart_last_error()

@@ -107,3 +107,16 @@ def test_gemm_split_output_parts():
     recon = out[:, 0:N].float() + out[:, 192:192 + N].float() + out[:, 384:384 + N].float()
     assert (recon - want).abs().max().item() < 2e-5 * want.abs().max().item() + 1e-6
     assert out[:, N:192].abs().max().item() == 0
+
+
+def test_gemm_fused_residual():
+    from ruart_b200 import ops
+    M, N, K = 777, 768, 3072
+    a = (torch.randn(M, K, device="cuda") * 0.3).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, M, N, K, epi=1, bias=bias, out_bf16=out, residual=res)
+    want = a.float() @ w.float().t() + bias + res.float()
+    assert (out.float() - want).abs().max().item() < 1e-2 * want.abs().max().item()
