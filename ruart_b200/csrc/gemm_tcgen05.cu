@@ -94,11 +94,12 @@ __device__ __forceinline__ void bulk_wait_all() {
 
 // EPI: epilogue kind.  TMA_OUT: plain bf16 output written with swizzled smem staging + TMA
 // stores (the BERT path); otherwise generic direct stores (fp32 and/or split bf16 outputs).
-template <int EPI, bool TMA_OUT>
+template <int EPI, bool TMA_OUT, bool HAS_RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_c,
+                         const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_a = smem;
@@ -110,7 +111,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full_bar = bars + 2 * STAGES;
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;  // one per epilogue group: residual tile landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,6 +121,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (TMA_OUT) tma_prefetch_desc(&tmap_c);
+    if (TMA_OUT && HAS_RES) tma_prefetch_desc(&tmap_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -128,6 +131,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], TMA_OUT ? 256 : 128);
+      mbar_init(&res_bar[s], 1);
     }
     fence_mbar_init();
   }
@@ -218,6 +222,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool issuer = (et == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
     uint32_t tile_ctr = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_ctr) {
       const int m_blk = tile / n_tiles;
@@ -239,11 +244,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 static_cast<uint32_t>(acc * MAX_BN);
       if constexpr (TMA_OUT) {
         uint8_t* cbuf = smem_c + grp * C_STAGE_BYTES;
+        constexpr bool has_res = HAS_RES;
         if (grp * 64 >= p.block_n) {  // this group has no chunk in such a narrow tile
           tc_fence_before();
           mbar_arrive(&tmem_empty_bar[acc]);
         }
         for (int c0 = grp * 64; c0 < p.block_n; c0 += 128) {
+          // residual tile (BertSelfOutput / BertOutput: dense(x) + input_tensor, modeling.py:263,302):
+          // TMA-loaded into the group's staging buffer while the accumulators are converted
+          if (has_res && issuer) {
+            bulk_wait_read<0>();  // the group's previous store has finished reading cbuf
+            mbar_arrive_expect_tx(&res_bar[grp], C_STAGE_BYTES);
+            tma_load_2d(&tmap_r, &res_bar[grp], cbuf, tile_col0 + c0, m_blk * BM);
+          }
           uint32_t v0[32], v1[32];
           tmem_ld_32x32b_x32(tmem_acc + c0, v0);
           tmem_ld_32x32b_x32(tmem_acc + c0 + 32, v1);
@@ -252,42 +265,56 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[acc]);
           }
-          uint4 pk4[8];
-          // optional residual row slice (BertSelfOutput / BertOutput: dense(x) + input_tensor,
-          // modeling.py:263,302), added in fp32 before the single rounding to bf16
-          const int grow = m_blk * BM + r_local;
-          const bool has_res = p.residual != nullptr && grow < p.M && tile_col0 + c0 + 64 <= p.N;
-          const uint4* rp = reinterpret_cast<const uint4*>(
-              p.residual + static_cast<long long>(grow) * p.ld_res + tile_col0 + c0);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 r4 = make_uint4(0, 0, 0, 0);
-            if (has_res) r4 = __ldg(rp + c);
-            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-            uint32_t pk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int j = c * 8 + q * 2;  // column inside the 64-wide chunk
-              float x0, x1;
-              if (j < 32) {
-                x0 = __uint_as_float(v0[j]);
-                x1 = __uint_as_float(v0[j + 1]);
-              } else {
-                x0 = __uint_as_float(v1[j - 32]);
-                x1 = __uint_as_float(v1[j - 31]);
-              }
-              const float2 bv = *reinterpret_cast<const float2*>(vec + c0 + j);
-              pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x) + bf16_lo(rw[q]),
-                                  epi_fn<EPI>(x1, bv.y) + bf16_hi(rw[q]));
-            }
-            pk4[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-          if (issuer) bulk_wait_read<0>();  // the group's previous store has finished reading cbuf
-          grp_bar_sync(grp);
           uint8_t* row_ptr = cbuf + r_local * 128;
+          if constexpr (!HAS_RES) {
+            // convert and pack BEFORE waiting for the staging buffer: the math overlaps the wait
+            uint4 pk4[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4)) = pk4[c];
+            for (int c = 0; c < 8; ++c) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int j = c * 8 + q * 2;  // column inside the 64-wide chunk
+                const float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+                const float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
+                const float2 bv = *reinterpret_cast<const float2*>(vec + c0 + j);
+                pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x), epi_fn<EPI>(x1, bv.y));
+              }
+              pk4[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            if (issuer) bulk_wait_read<0>();  // the group's previous store has finished reading cbuf
+            grp_bar_sync(grp);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4)) = pk4[c];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float2 b0 = *reinterpret_cast<const float2*>(vec + c0 + j);
+              const float2 b1 = *reinterpret_cast<const float2*>(vec + c0 + 32 + j);
+              v0[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j]), b0.x));
+              v0[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j + 1]), b0.y));
+              v1[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j]), b1.x));
+              v1[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j + 1]), b1.y));
+            }
+            mbar_wait(&res_bar[grp], res_phase);  // residual tile has landed in cbuf
+            res_phase ^= 1u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              uint4* slot = reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4));
+              const uint4 r4 = *slot;
+              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int j = c * 8 + q * 2;
+                const float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+                const float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
+                pk[q] = pack_bf16x2(x0 + bf16_lo(rw[q]), x1 + bf16_hi(rw[q]));
+              }
+              *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
           fence_proxy_async();
           grp_bar_sync(grp);
           if (issuer) {
@@ -431,14 +458,16 @@ int pick_block_n(int N, int gran) {
 }
 
 typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                           const GemmParams);
+                           const CUtensorMap, const GemmParams);
 
 template <int EPI>
 GemmKernel pick_kernel(bool tma_out) {
-  return tma_out ? gemm_bf16_tcgen05_kernel<EPI, true> : gemm_bf16_tcgen05_kernel<EPI, false>;
+  return tma_out ? gemm_bf16_tcgen05_kernel<EPI, true, false>
+                 : gemm_bf16_tcgen05_kernel<EPI, false, false>;
 }
 
-GemmKernel kernel_for(int kind, bool tma_out) {
+GemmKernel kernel_for(int kind, bool tma_out, bool has_res) {
+  if (has_res) return gemm_bf16_tcgen05_kernel<K_BIAS, true, true>;  // the only fused-residual form
   switch (kind) {
     case K_NONE: return pick_kernel<K_NONE>(tma_out);
     case K_BIAS: return pick_kernel<K_BIAS>(tma_out);
@@ -522,7 +551,7 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   p.ld_res = ld_res;
   if (residual_bf16 != nullptr) {
     // fused residual: staged TMA-store epilogue only, whole 64-column chunks, 16-byte aligned rows
-    RUART_ARG_CHECK(tma_out && (N % 64) == 0 && (ld_res % 8) == 0 &&
+    RUART_ARG_CHECK(tma_out && kind == K_BIAS && (N % 64) == 0 && (ld_res % 8) == 0 &&
                     (reinterpret_cast<uintptr_t>(residual_bf16) & 15u) == 0);
   }
 
@@ -537,19 +566,26 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   } else {
     tmc = tma;
   }
+  CUtensorMap tmr = tmc;
+  if (residual_bf16 != nullptr) {
+    rc = make_tmap_bf16(&tmr, residual_bf16, M, N, ld_res, BM);
+    if (rc != RUART_OK) return rc;
+  }
 
-  GemmKernel kern = kernel_for(kind, tma_out);
-  static bool attr_set[K_NUM][2] = {};
-  if (!attr_set[kind][tma_out ? 1 : 0]) {
+  const bool has_res = residual_bf16 != nullptr;
+  GemmKernel kern = kernel_for(kind, tma_out, has_res);
+  static bool attr_set[K_NUM][3] = {};
+  const int slot = has_res ? 2 : (tma_out ? 1 : 0);
+  if (!attr_set[kind][slot]) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           GEMM_SMEM_BYTES));
-    attr_set[kind][tma_out ? 1 : 0] = true;
+    attr_set[kind][slot] = true;
   }
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + p.block_n - 1) / p.block_n;
   const int total = m_tiles * n_tiles;
   const int grid = total < ruart_num_sms() ? total : ruart_num_sms();
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, p);
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, tmr, p);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
