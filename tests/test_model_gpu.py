@@ -97,3 +97,42 @@ def test_sharded_forward_equals_oracle_per_shard():
         want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(sh))
         probs, logits, _ = run_ours(net, sh)
         assert rel_err(logits, want_l) < 1e-4
+
+
+def test_long_ocr_config5_shape():
+    """BASELINE configs[4] shape at a reduced batch: 200 OCR items per image (max_ocr_num 201), the
+    question row padded to the 512-token BERT window; fp32 mode vs the CPU oracle."""
+    cfg = dict(B=2, n_ocr=200, n_od=36, max_ocr_num=201, max_od_num=37, max_q_bert_len=512)
+    net, opt = build_ours(cfg, seed=3, bert_init="random", device="cuda", BERT_precision="fp32", KEEP_LOGITS=True)
+    batch = synth.make_batch(cfg, seed=2005, opt=opt)
+    assert batch[0]["bert"].shape[1] == 512 and batch[1]["position"].shape[1] == 201
+    cpu_sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch))
+    probs, logits, _ = run_ours(net, batch)
+    assert rel_err(logits, want_l) < 1e-4
+    assert torch.equal(probs.argmax(1), want_p.argmax(1))
+
+
+def test_bert_window_split_long_row():
+    """Rows longer than 512 wordpieces are encoded as independent 512-token windows with positions
+    restarting at 0 (Bert.py:96-99,135-138)."""
+    net, opt = build_ours("tiny", device="cuda", BERT_precision="fp32", BERT_num_layers=2)
+    g = torch.Generator().manual_seed(9)
+    N, L, W = 2, 700, 40
+    ids = torch.zeros(N, L, dtype=torch.long)
+    lens = [700, 530]
+    offsets = []
+    for i, n in enumerate(lens):
+        ids[i, :n] = torch.randint(1000, 30000, (n,), generator=g)
+        offs, p = [], 1
+        for _ in range(W):
+            k = int(torch.randint(1, 4, (1,), generator=g))
+            offs.append([p, p + k])
+            p += k + int(torch.randint(0, 20, (1,), generator=g))
+        offsets.append(offs)
+    mask = ~ids.eq(0)
+    wmask = torch.ones(N, W, dtype=torch.bool)
+    outs = net.Bert(ids.cuda(), mask.cuda(), offsets, wmask.cuda())
+    sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    want = sdnet_oracle.bert_words(sd, opt, ids, mask, offsets, wmask, 2, 12)
+    assert rel_err(outs[-1].cpu(), want[-1]) < 1e-4

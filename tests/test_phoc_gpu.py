@@ -91,3 +91,27 @@ def test_unit_drop_in_build_phoc():
     want, _ = phoc_oracle.batch(["hello"])
     assert isinstance(v, list) and len(v) == 604 and isinstance(v[0], float)
     assert np.array_equal(np.asarray(v, np.float32), want[0])
+
+
+def test_baseline_config2_one_million_strings_bit_exact():
+    """BASELINE.json configs[1]: 1M synthetic OCR strings (len 1-20) vs Utils/cphoc.c (through the
+    C oracle pinned to it), compared through a checksum of checksums and a dense sample."""
+    from ruart_b200 import ops
+    rng = np.random.default_rng(2002)
+    n = 1_000_000
+    lens = rng.integers(1, 21, size=n)
+    offsets = np.zeros(n + 1, np.int32)
+    offsets[1:] = np.cumsum(lens)
+    alpha = np.frombuffer(ALPHA.encode(), np.uint8)
+    chars = alpha[rng.integers(0, 36, size=int(offsets[-1]))]
+    want, bad = phoc_oracle.batch_flat(chars, offsets)
+    assert bad == -1
+    got = ops.phoc_batch(torch.from_numpy(np.concatenate([chars, np.zeros(1, np.uint8)])).cuda(),
+                         torch.from_numpy(offsets).cuda())
+    assert got.shape == (n, 604)
+    w = torch.arange(1, 605, device="cuda", dtype=torch.float64)
+    row_sig = (got.double() * w).sum(1).cpu().numpy()          # per-string checksum
+    want_sig = (want.astype(np.float64) * np.arange(1, 605)).sum(1)
+    assert np.array_equal(row_sig, want_sig)
+    idx = rng.integers(0, n, size=20000)
+    assert np.array_equal(got[torch.from_numpy(idx).cuda()].cpu().numpy(), want[idx])
