@@ -49,6 +49,15 @@ def workload_desc(cfg):
             (cfg, c["B"], c["n_ocr"], c["n_od"], c["max_ocr_num"], c["max_od_num"]))
 
 
+def gemm_traffic():
+    """Mean DRAM bytes per BERT GEMM launch from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            return float(json.load(f)["mean_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -305,7 +314,8 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None,
+                         "frac": (ach / peak) if ach else None, "traffic": gemm_traffic(),
+                         "traffic_unit": "bytes per launch (mean of the 4 BERT GEMM shapes, ncu dram read+write)",
                          "kernel": "gemm_bf16_tcgen05_kernel (all %d BERT GEMM launches of the timed steps)" % n_gemm,
                          "kernel_ms_per_step": g_ms / args.steps, "peak_source": peak_src},
         }

@@ -44,12 +44,87 @@ __device__ __forceinline__ bool overlaps_half(float occ0, float occ1, int region
   return ratio >= 0.5f;
 }
 
+// The region tests depend only on (string length n, character position idx), so for n <= LUT_N
+// they are tabulated ONCE per process by lut_init_kernel — which evaluates exactly the same fp32
+// expressions (overlaps_half) as the direct path, hence bit-identical — and the hot kernel replaces
+// 28 IEEE divisions per character by one shared-memory lookup.
+//   uni[n][idx] : bit (level_base_index + region) for the 14 (level, region) pairs, levels 2..5
+//   bi[n][idx]  : bit region (0/1) for a bigram starting at idx
+constexpr int LUT_N = 32;
+__device__ uint16_t g_lut_uni[(LUT_N + 1) * LUT_N];
+__device__ uint8_t g_lut_bi[(LUT_N + 1) * LUT_N];
+__device__ int8_t g_bigram_lut[36 * 36];  // copy of c_bigram_lut for staging into shared memory
+
+__global__ void lut_init_kernel() {
+  const int n = blockIdx.x;  // 0 .. LUT_N
+  const int idx = threadIdx.x;
+  if (idx >= LUT_N) return;
+  uint32_t m = 0, b = 0;
+  if (n > 0 && idx < n) {
+    const float fn = static_cast<float>(n);
+    const float occ0 = __fdiv_rn(static_cast<float>(idx), fn);
+    const float occ1 = __fdiv_rn(static_cast<float>(idx + 1), fn);
+    int bit = 0;
+    for (int level = 2; level < 6; ++level)
+      for (int region = 0; region < level; ++region, ++bit)
+        if (overlaps_half(occ0, occ1, region, level)) m |= 1u << bit;
+    const float g1 = __fdiv_rn(static_cast<float>(idx + 2), fn);
+    for (int region = 0; region < 2; ++region)
+      if (overlaps_half(occ0, g1, region, 2)) b |= 1u << region;
+  }
+  g_lut_uni[n * LUT_N + idx] = static_cast<uint16_t>(m);
+  g_lut_bi[n * LUT_N + idx] = static_cast<uint8_t>(b);
+}
+
+// feature offset of (level, region) pair number `bit` (levels 2..5 in order): region blocks of 36
+__device__ __forceinline__ int pair_base(int bit) { return bit * 36; }
+
 __device__ __forceinline__ void build_mask(const uint8_t* __restrict__ chars, int begin, int n,
-                                           uint32_t* mask, int lane, int64_t str_idx,
-                                           int32_t* err) {
+                                           uint32_t* mask, int lane, int64_t str_idx, int32_t* err,
+                                           const uint16_t* s_uni, const uint8_t* s_bi,
+                                           const int8_t* s_big, uint32_t c_pref) {
   if (lane < PHOC_WORDS) mask[lane] = 0u;
   __syncwarp();
   bool bad = false;
+  if (n <= LUT_N) {
+    // tabulated path: one lane per character
+    // c_pref: this lane's character, loaded one iteration ahead; the next one comes by shuffle
+    const uint32_t c_next = __shfl_down_sync(0xffffffffu, c_pref, 1);
+    if (lane < n) {
+      const uint8_t c = static_cast<uint8_t>(c_pref);
+      const int ci = unigram_index(c);
+      if (ci < 0) {
+        bad = true;
+        const unsigned long long key = (static_cast<unsigned long long>(str_idx) << 24) |
+                                       (static_cast<unsigned long long>(lane) << 8) | c;
+        atomicMin(reinterpret_cast<unsigned long long*>(err), key);
+      } else {
+        uint32_t m = s_uni[n * LUT_N + lane];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int f = pair_base(bit) + ci;
+          atomicOr(&mask[f >> 5], 1u << (f & 31));
+        }
+        if (lane + 1 < n) {
+          const int cj = unigram_index(static_cast<uint8_t>(c_next));
+          if (cj >= 0) {
+            const int bidx = s_big[ci * 36 + cj];
+            if (bidx >= 0) {
+              const uint32_t b = s_bi[n * LUT_N + lane];
+              if (b & 1u) atomicOr(&mask[(504 + bidx) >> 5], 1u << ((504 + bidx) & 31));
+              if (b & 2u) atomicOr(&mask[(554 + bidx) >> 5], 1u << ((554 + bidx) & 31));
+            }
+          }
+        }
+      }
+    }
+    const bool any_bad_fast = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    if (any_bad_fast && lane < PHOC_WORDS) mask[lane] = 0u;
+    __syncwarp();
+    return;
+  }
   const float fn = static_cast<float>(n);
   for (int idx = lane; idx < n; idx += 32) {
     const uint8_t c = chars[begin + idx];
@@ -107,15 +182,44 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 phoc_kernel(const uint8_t* __restrict__ chars, const int32_t* __restrict__ offsets, int64_t n,
             float* __restrict__ out, uint32_t* __restrict__ out_words, int32_t* err) {
   __shared__ uint32_t s_mask[WARPS_PER_CTA][PHOC_WORDS + 1];
+  __shared__ uint16_t s_uni[(LUT_N + 1) * LUT_N];
+  __shared__ uint8_t s_bi[(LUT_N + 1) * LUT_N];
+  __shared__ int8_t s_big[36 * 36];
+  for (int i = threadIdx.x; i < (LUT_N + 1) * LUT_N; i += blockDim.x) {
+    s_uni[i] = g_lut_uni[i];
+    s_bi[i] = g_lut_bi[i];
+  }
+  for (int i = threadIdx.x; i < 36 * 36; i += blockDim.x) s_big[i] = g_bigram_lut[i];
+  __syncthreads();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint32_t* mask = s_mask[warp];
   const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * WARPS_PER_CTA + warp;
   const int64_t n_warps = static_cast<int64_t>(gridDim.x) * WARPS_PER_CTA;
+  // two-deep software pipeline over this warp's strings: offsets are loaded two iterations ahead,
+  // characters one ahead, so neither dependent global load stalls the in-order instruction stream
+  auto load_off = [&](int64_t s, int& b, int& l) {
+    b = 0;
+    l = 0;
+    if (s < n) {
+      b = offsets[s];
+      l = offsets[s + 1] - b;
+    }
+  };
+  auto load_chr = [&](int b, int l) -> uint32_t {
+    return (l <= LUT_N && lane < l) ? chars[b + lane] : 0u;
+  };
+  int b0, l0, b1, l1, b2, l2;
+  load_off(warp_global, b0, l0);
+  load_off(warp_global + n_warps, b1, l1);
+  uint32_t c0 = load_chr(b0, l0);
   for (int64_t s = warp_global; s < n; s += n_warps) {
-    const int begin = offsets[s];
-    const int len = offsets[s + 1] - begin;
-    build_mask(chars, begin, len, mask, lane, s, err);
+    const int begin = b0, len = l0;
+    const uint32_t c_cur = c0;
+    c0 = load_chr(b1, l1);                  // characters of the next string
+    load_off(s + 2 * n_warps, b2, l2);      // offsets of the one after
+    b0 = b1; l0 = l1; b1 = b2; l1 = l2;
+    build_mask(chars, begin, len, mask, lane, s, err, s_uni, s_bi, s_big, c_cur);
     if (kPacked) {
       if (lane < PHOC_WORDS) out_words[s * PHOC_WORDS + lane] = mask[lane];
     } else {
@@ -147,6 +251,10 @@ int upload_lut() {
     lut[a * 36 + b] = static_cast<int8_t>(k);
   }
   RUART_CUDA_CHECK(cudaMemcpyToSymbol(c_bigram_lut, lut, sizeof(lut)));
+  RUART_CUDA_CHECK(cudaMemcpyToSymbol(g_bigram_lut, lut, sizeof(lut)));
+  lut_init_kernel<<<LUT_N + 1, 32>>>();
+  RUART_CUDA_CHECK(cudaGetLastError());
+  RUART_CUDA_CHECK(cudaDeviceSynchronize());
   done = true;
   return RUART_OK;
 }
@@ -161,7 +269,7 @@ int launch(const uint8_t* chars, const int32_t* offsets, int64_t n, float* out,
   if (n == 0) return RUART_OK;
   // 8 CTAs of 8 warps per SM keeps 64 warps resident; cap by the work available.
   int64_t ctas = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  const int64_t max_ctas = static_cast<int64_t>(ruart_num_sms()) * 8 * 4;
+  const int64_t max_ctas = static_cast<int64_t>(ruart_num_sms()) * 8;
   if (ctas > max_ctas) ctas = max_ctas;
   if (out != nullptr) {
     RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
