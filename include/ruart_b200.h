@@ -169,6 +169,11 @@ RUART_API int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const f
                                     float* out, long long out_pitch, int B, int L, int H,
                                     int ndir, void* stream);
 
+/* Answer-index rule of SDNetTrainer.predict (SDNetTrainer.py:402-412): out_idx[b] = index of the
+ * largest probability among {last column (if label_no_answer)} U {i < num_cnt[b] - 1}.          */
+RUART_API int ruart_select_answers(const float* probs, const int32_t* num_cnt, int B, int M1,
+                                   int label_no_answer, int32_t* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,11 +198,17 @@ class SDNet(nn.Module):
     # ------------------------------------------------------------------ forward
     phase_log = None  # set to a list to collect (label, seconds since forward start) with device syncs
 
+    phase_events = None  # set to a list to collect (label, cuda event) on the main stream, no syncs
+
     def _phase(self, label):
         if self.phase_log is not None:
             import time
             torch.cuda.synchronize()
             self.phase_log.append((label, time.perf_counter()))
+        if self.phase_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_events.append((label, ev))
 
     def forward(self, q_list, ocr_list, od_list, return_score=False):
         if self.training and (Layers.dropout_p > 0 or self.drop_emb):

@@ -518,6 +518,41 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gx, const int32_t* __
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Answer-index rule of SDNetTrainer.predict (SDNetTrainer.py:402-412) on the device: walking the
+// slots by descending probability, the loop stops at the no-answer column (last), skips the
+// `<OCR>` end slot (index num_cnt-1) and every index >= num_cnt, and accepts the first index
+// < num_cnt.  That is: the highest-probability index in {M} U {i < num_cnt - 1}.  Ties (equal
+// probabilities) resolve to the smallest index; torch.sort's order among ties is unspecified.
+__global__ void select_answers_kernel(const float* __restrict__ probs, const int32_t* __restrict__ num_cnt,
+                                      int B, int M1, int no_answer, int32_t* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* p = probs + static_cast<long long>(b) * M1;
+  const int n_ok = num_cnt[b] - 1;  // indices 0 .. n_ok-1 are real OCR items
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = lane; i < M1; i += 32) {
+    const bool ok = (i < n_ok) || (no_answer && i == M1 - 1);
+    const float v = p[i];
+    if (ok && (v > best || (v == best && i < best_i))) {
+      best = v;
+      best_i = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) {
+      best = ov;
+      best_i = oi;
+    }
+  }
+  if (lane == 0) out[b] = (best_i == 0x7fffffff) ? (M1 - 1) : best_i;
+}
+
 inline unsigned cap_grid(long long work_items, int per_cta) {
   long long g = (work_items + per_cta - 1) / per_cta;
   const long long cap = static_cast<long long>(ruart_num_sms()) * 8;
@@ -628,6 +663,15 @@ extern "C" int ruart_lstm_cell(const float* gx, const int32_t* row_gx, const flo
   lstm_cell_kernel<<<cap_grid(static_cast<long long>(n_rows) * H, 256), 256, 0,
                      (cudaStream_t)stream>>>(gx, row_gx, gh, c, (__nv_bfloat16*)h_split, parts,
                                              Kp, H, n_rows, last_step, step, slot_off, slots);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_select_answers(const float* probs, const int32_t* num_cnt, int B, int M1,
+                                    int label_no_answer, int32_t* out_idx, void* stream) {
+  RUART_ARG_CHECK(B > 0 && M1 > 0 && probs != nullptr && num_cnt != nullptr && out_idx != nullptr);
+  select_answers_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(probs, num_cnt, B, M1,
+                                                                      label_no_answer, out_idx);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

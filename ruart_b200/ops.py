@@ -79,3 +79,18 @@ def gemm(a, w, M, N, Kp, *, a_parts=1, w_parts=1, n_terms=1, epi=EPI_NONE, bias=
          ptr(out_bf16), 0 if out_bf16 is None else out_bf16.stride(-2), out_parts,
          out_part_stride, 1 if fast_gelu else 0, ptr(residual), 0 if residual is None else residual.stride(-2),
          current_stream())
+
+
+# ------------------------------------------------------------------------------------ answers
+def select_answers(probs, num_cnt, label_no_answer=True):
+    """Device form of SDNetTrainer.predict's index rule (SDNetTrainer.py:402-412):
+    probs fp32 [B, M+1] (device), num_cnt list/tensor [B] -> int32 [B] answer indices (device)."""
+    _need_cuda(probs)
+    B, M1 = probs.shape
+    if not torch.is_tensor(num_cnt):
+        num_cnt = torch.tensor(list(num_cnt), dtype=torch.int32)
+    num_cnt = num_cnt.to(device=probs.device, dtype=torch.int32)
+    out = torch.empty(B, dtype=torch.int32, device=probs.device)
+    call("ruart_select_answers", ptr(probs.contiguous()), ptr(num_cnt), B, M1, 1 if label_no_answer else 0,
+         ptr(out), current_stream())
+    return out

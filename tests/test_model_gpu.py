@@ -136,3 +136,18 @@ def test_bert_window_split_long_row():
     sd = {k: v.cpu() for k, v in net.state_dict().items()}
     want = sdnet_oracle.bert_words(sd, opt, ids, mask, offsets, wmask, 2, 12)
     assert rel_err(outs[-1].cpu(), want[-1]) < 1e-4
+
+
+def test_device_answer_selection_matches_trainer_rule():
+    from ruart_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, M1 = 64, 101
+    probs = torch.rand(B, M1, generator=g)
+    num_cnt = torch.randint(1, 100, (B,), generator=g).tolist()
+    for i, n in enumerate(num_cnt):
+        probs[i, n:M1 - 1] = 0.0
+    probs[3, M1 - 1] = 2.0      # no-answer wins
+    probs[5, num_cnt[5] - 1] = 3.0   # the <OCR> end slot must be skipped
+    want = synth.select_answers(probs, num_cnt)
+    got = ops.select_answers(probs.cuda(), num_cnt).cpu().tolist()
+    assert got == want

@@ -25,6 +25,26 @@ with torch.no_grad():
     for (a, t0), (b, t1) in zip(log[:-1], log[1:]):
         print("%-16s %8.3f ms" % (b, 1e3 * (t1 - t0)))
     print("%-16s %8.3f ms (with phase syncs)" % ("total", 1e3 * (log[-1][1] - log[0][1])))
+    # GPU-timeline phases (events on the main stream, streams enabled, no host syncs)
+    for _ in range(2):
+        net(*tuple(dict(d) for d in batch))
+    torch.cuda.synchronize()
+    net.phase_events = []
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    net(*tuple(dict(d) for d in batch))
+    e_end = torch.cuda.Event(enable_timing=True)
+    e_end.record()
+    torch.cuda.synchronize()
+    evs = net.phase_events
+    net.phase_events = None
+    prev = e_start
+    print("--- main-stream timeline (no syncs) ---")
+    for lab, ev in evs:
+        print("%-16s %8.3f ms" % (lab, prev.elapsed_time(ev)))
+        prev = ev
+    print("%-16s %8.3f ms" % ("tail", prev.elapsed_time(e_end)))
+    print("%-16s %8.3f ms" % ("total", e_start.elapsed_time(e_end)))
     t0 = time.perf_counter()
     for d in batch:
         flatten_offsets(d["bert_offsets"], d["bert"].shape[0])
