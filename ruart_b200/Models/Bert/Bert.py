@@ -71,9 +71,14 @@ class Bert(nn.Module):
             outs = [o.to(device) for o in outs]
         return outs if self.linear_combine else outs[-1]
 
-    def encode_into(self, segments, sinks, alpha, gamma):
+    def pack_begin(self, segments):
+        """Start the token packing of `segments` on a side stream (see BertEngine.pack_begin)."""
+        segs = [Segment(*s) for s in segments]
+        return self.engine().pack_begin(segs)
+
+    def encode_into(self, segments, sinks, alpha, gamma, pack_handle=None):
         """Fused path: segments = [(ids, mask, offsets, word_mask)], sinks = [(dst, stride, col)].
         dst[item, j, col:col+dim] = sum_l softmax(alpha)_l * gamma * mean_subwords(layer_l)."""
-        segs = [Segment(*s) for s in segments]
+        segs = pack_handle["segments"] if pack_handle is not None else [Segment(*s) for s in segments]
         return self.engine().encode(segs, sinks, alpha=alpha.detach().float().contiguous(),
-                                    gamma=gamma.detach().float().contiguous())
+                                    gamma=gamma.detach().float().contiguous(), pack_handle=pack_handle)

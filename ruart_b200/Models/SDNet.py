@@ -231,6 +231,13 @@ class SDNet(nn.Module):
         H = opt['hidden_size']
 
         self._phase('start')
+        # token-length bookkeeping of the BERT pass starts on a side stream; its one host sync is
+        # taken after the embedding gathers below have been queued
+        bert_segments = [
+            (q_list['bert'], q_list['bert_mask'], q_list['bert_offsets'], q_list['glove_mask']),
+            (ocr_list['bert'], ocr_list['bert_mask'], ocr_list['bert_offsets'], ocr_list['fasttext_mask']),
+            (od_list['bert'], od_list['bert_mask'], od_list['bert_offsets'], od_list['fasttext_mask'])]
+        pack_handle = self.Bert.pack_begin(bert_segments)
         # ---- embeddings: [word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) -------------
         q_in = torch.zeros((B, Wq, QD), **f32)
         items_in = torch.zeros((N_ocr * Wo + N_od * Wd, XD), **f32)
@@ -257,11 +264,8 @@ class SDNet(nn.Module):
 
         self._phase('embed')
         # ---- BERT: one packed pass, subword mean + layer sum into the concat buffers ------------
-        self.Bert.encode_into(
-            [(q_list['bert'], q_list['bert_mask'], q_list['bert_offsets'], q_list['glove_mask']),
-             (ocr_list['bert'], ocr_list['bert_mask'], ocr_list['bert_offsets'], ocr_list['fasttext_mask']),
-             (od_list['bert'], od_list['bert_mask'], od_list['bert_offsets'], od_list['fasttext_mask'])],
-            [(q_in, QD, VD), (ocr_in, XD, VD), (od_in, XD, VD)], self.alphaBERT, self.gammaBERT)
+        self.Bert.encode_into(bert_segments, [(q_in, QD, VD), (ocr_in, XD, VD), (od_in, XD, VD)],
+                              self.alphaBERT, self.gammaBERT, pack_handle=pack_handle)
 
         self._phase('bert')
         # ---- host indices (one upload) -------------------------------------------------------

@@ -123,34 +123,66 @@ class BertEngine(object):
         return W
 
     # ------------------------------------------------------------------ packing
+    _pack_streams = {}
+
+    @classmethod
+    def pack_begin(cls, segments):
+        """First half of the token packing: row / window lengths and their prefix sums, computed
+        with a few integer torch ops on a SIDE stream, and an async copy of the totals into pinned
+        memory.  The caller can queue unrelated work on the compute stream before pack_finish()."""
+        dev = segments[0].ids.device
+        key = str(dev)
+        side = cls._pack_streams.get(key)
+        if side is None:
+            side = torch.cuda.Stream(device=dev)
+            cls._pack_streams[key] = side
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)  # inputs produced on the compute stream are visible
+        with torch.cuda.stream(side):
+            row_lens, win_lens, nwins = [], [], []
+            for sg in segments:
+                rl = sg.mask.sum(1, dtype=torch.int32)
+                row_lens.append(rl)
+                nwin = (sg.L + WINDOW - 1) // WINDOW
+                if nwin == 1:
+                    win_lens.append(rl)
+                else:
+                    base = torch.arange(nwin, device=dev, dtype=torch.int32) * WINDOW
+                    win_lens.append((rl[:, None] - base[None, :]).clamp_(0, WINDOW).reshape(-1))
+                nwins.append(nwin)
+            all_rows = torch.cat(row_lens)
+            cu_rows = torch.zeros(all_rows.numel() + 1, dtype=torch.int32, device=dev)
+            torch.cumsum(all_rows, 0, out=cu_rows[1:])
+            all_win = torch.cat(win_lens)
+            cu_seq = torch.zeros(all_win.numel() + 1, dtype=torch.int32, device=dev)
+            torch.cumsum(all_win, 0, out=cu_seq[1:])
+            maxes = [w.max() if w.numel() else torch.zeros((), dtype=torch.int32, device=dev) for w in win_lens]
+            totals = torch.stack([cu_rows[-1]] + maxes)
+            host = torch.empty(totals.shape, dtype=totals.dtype, pin_memory=True)
+            host.copy_(totals, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        return {"segments": segments, "cu_rows": cu_rows, "cu_seq": cu_seq, "host": host, "done": done,
+                "nwins": nwins, "keep": (row_lens, win_lens, all_rows, all_win, totals)}
+
     @staticmethod
-    def pack(segments):
-        """Token packing for a list of Segments: a few integer torch ops for the row lengths, ONE
-        host sync (total token count + longest sequence per segment, needed to size buffers and
-        pick kernels), then one pack_tokens kernel per segment.
+    def pack_finish(h):
+        """Second half: ONE host wait (for the side stream only: total token count and the longest
+        sequence per segment size the buffers and pick the kernels), then a pack_tokens kernel
+        per segment on the compute stream.
 
         Returns dict: ids/pos int32 [T]; cu_seqlens int32 [S+1] over 512-token windows; per
         segment: row_start int32 [N], its range of sequences, its longest sequence."""
+        segments = h["segments"]
         dev = segments[0].ids.device
-        row_lens, win_lens, nwins = [], [], []
-        for sg in segments:
-            rl = sg.mask.sum(1, dtype=torch.int32)
-            row_lens.append(rl)
-            nwin = (sg.L + WINDOW - 1) // WINDOW
-            if nwin == 1:
-                win_lens.append(rl)
-            else:
-                base = torch.arange(nwin, device=dev, dtype=torch.int32) * WINDOW
-                win_lens.append((rl[:, None] - base[None, :]).clamp_(0, WINDOW).reshape(-1))
-            nwins.append(nwin)
-        all_rows = torch.cat(row_lens)
-        cu_rows = torch.zeros(all_rows.numel() + 1, dtype=torch.int32, device=dev)
-        torch.cumsum(all_rows, 0, out=cu_rows[1:])
-        all_win = torch.cat(win_lens)
-        cu_seq = torch.zeros(all_win.numel() + 1, dtype=torch.int32, device=dev)
-        torch.cumsum(all_win, 0, out=cu_seq[1:])
-        maxes = [w.max() if w.numel() else torch.zeros((), dtype=torch.int32, device=dev) for w in win_lens]
-        host = torch.stack([cu_rows[-1]] + maxes).cpu()  # the one sync
+        main = torch.cuda.current_stream(dev)
+        h["done"].synchronize()
+        main.wait_event(h["done"])
+        cu_rows, cu_seq, host, nwins = h["cu_rows"], h["cu_seq"], h["host"], h["nwins"]
+        cu_rows.record_stream(main)
+        cu_seq.record_stream(main)
         T = int(host[0])
         ids = torch.empty(T, dtype=torch.int32, device=dev)
         pos = torch.empty(T, dtype=torch.int32, device=dev)
@@ -159,14 +191,20 @@ class BertEngine(object):
         st = current_stream()
         for k, sg in enumerate(segments):
             row_start = cu_rows[r0:r0 + sg.N].contiguous()
+            row_start.record_stream(main)
             mask8 = sg.mask.contiguous().view(torch.uint8) if sg.mask.dtype == torch.bool else sg.mask.to(torch.uint8).contiguous()
-            call("ruart_pack_tokens", ptr(sg.ids.contiguous()), ptr(mask8), sg.N, sg.L, ptr(row_start), WINDOW,
+            ids64 = sg.ids.contiguous()
+            call("ruart_pack_tokens", ptr(ids64), ptr(mask8), sg.N, sg.L, ptr(row_start), WINDOW,
                  ptr(ids), ptr(pos), st)
             segs.append({"row_start": row_start, "seq0": s0, "seq1": s0 + sg.N * nwins[k],
                          "max_len": int(host[1 + k])})
             r0 += sg.N
             s0 += sg.N * nwins[k]
         return {"ids": ids, "pos": pos, "cu_seqlens": cu_seq, "T": T, "segments": segs}
+
+    @classmethod
+    def pack(cls, segments):
+        return cls.pack_finish(cls.pack_begin(segments))
 
     # ------------------------------------------------------------------ forward
     def _gemm(self, a, w, bias, N, K, epi, out_kind, fast_gelu=False, residual=None):
@@ -187,7 +225,7 @@ class BertEngine(object):
         ops.gemm(a, w, T, N, K, a_parts=3, w_parts=3, n_terms=6, epi=epi, bias=bias, out_f32=out)
         return out, None
 
-    def encode(self, segments, sinks, alpha=None, gamma=None):
+    def encode(self, segments, sinks, alpha=None, gamma=None, pack_handle=None):
         """segments: list[Segment]; sinks: per segment (dst fp32 tensor, dst_stride floats, col_off)
         or a list of n_layers such triples when alpha is None (per-layer outputs).
 
@@ -201,7 +239,7 @@ class BertEngine(object):
         if dev.type != "cuda":
             raise RuntimeError("ruart_b200 BERT runs on CUDA only; there is no CPU fallback")
         W = self.prepare(dev)
-        pk = self.pack(segments)
+        pk = self.pack_finish(pack_handle) if pack_handle is not None else self.pack(segments)
         T, H, I, NL = pk["T"], self.H, self.I, self.n_layers
         st = current_stream()
         fp32 = self.mode == "fp32"
