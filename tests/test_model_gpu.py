@@ -151,3 +151,43 @@ def test_device_answer_selection_matches_trainer_rule():
     want = synth.select_answers(probs, num_cnt)
     got = ops.select_answers(probs.cuda(), num_cnt).cpu().tolist()
     assert got == want
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    (dict(B=3, n_ocr=99, n_od=29, max_ocr_num=100, max_od_num=30), dict()),          # every slot used
+    (dict(B=2, n_ocr=0, n_od=0, max_ocr_num=100, max_od_num=30), dict()),            # only the end items
+    (dict(B=1, n_ocr=7, n_od=2, max_ocr_num=100, max_od_num=30, max_q_bert_len=128), dict(n_q_words=40)),  # batch of one, 40-word question
+    (dict(B=5, n_ocr=3, n_od=1, max_ocr_num=100, max_od_num=30), dict(n_q_words=1)),  # one-word questions
+])
+def test_edge_shapes_match_oracle(cfg, kw):
+    net, opt = build_ours(cfg, seed=21, bert_init="random", device="cuda", BERT_precision="fp32", KEEP_LOGITS=True)
+    batch = synth.make_batch(cfg, seed=77, opt=opt, **kw)
+    cpu_sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch))
+    probs, logits, _ = run_ours(net, batch)
+    assert rel_err(logits, want_l) < 1e-4
+    assert (probs - want_p).abs().max().item() < 1e-4
+
+
+def test_many_word_items_and_repeated_forward_are_deterministic():
+    # items with up to 20 words x 1 piece (max_ocr_len), and bit-identical results across calls
+    cfg = dict(B=2, n_ocr=6, n_od=2, max_ocr_num=100, max_od_num=30)
+    net, opt = build_ours(cfg, seed=8, device="cuda", BERT_precision="fp32", KEEP_LOGITS=True)
+    q, ocr, od = synth.make_batch(cfg, seed=5, opt=opt)
+    g = torch.Generator().manual_seed(1)
+    # rewrite OCR item 0 of image 0 into a 20-word item, one wordpiece per word
+    ocr["fasttext"][0, :20] = torch.randint(5, 5000, (20,), generator=g)
+    ocr["pos"][0, :20] = 1
+    ocr["ent"][0, :20] = 1
+    ocr["bert"][0, :22] = torch.cat([torch.tensor([101]), torch.randint(1000, 30000, (20,), generator=g), torch.tensor([102])])
+    ocr["bert_offsets"][0] = [[1 + k, 2 + k] for k in range(20)]
+    ocr["len_cnt"][0][0] = 20
+    ocr["fasttext_mask"] = ~ocr["fasttext"].eq(0)
+    ocr["bert_mask"] = ~ocr["bert"].eq(0)
+    batch = (q, ocr, od)
+    cpu_sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch))
+    p1, l1, _ = run_ours(net, batch)
+    p2, l2, _ = run_ours(net, batch)
+    assert rel_err(l1, want_l) < 1e-4
+    assert torch.equal(p1, p2) and torch.equal(l1, l2)
