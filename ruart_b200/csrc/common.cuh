@@ -276,18 +276,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // instructions + 2 MUFU per element; erff() costs ~40 with a slow path.  (The 7/5-term rational fit
 // of Eigen/XLA needs one MUFU but 20 FMA-pipe instructions and measured slower in the epilogue.)
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
+  // gelu(x) = x Phi(x), Phi(x) = 1 - 0.5 p(t) e^{-x^2/2} for x >= 0 and 0.5 p(t) e^{-x^2/2} for x < 0,
+  // t = 1 / (1 + 0.3275911 |x| / sqrt2).  With r = 0.5 p(t) e^{-x^2/2}:  gelu = max(x, 0) - |x| r.
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
   p *= t;
-  const float e = ex2_approx(z * z * -1.4426950408889634f);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  const float hx = 0.5f * x;
-  return fmaf(hx, erf_v, hx);
+  const float e = ex2_approx((x * x) * (-0.5f * 1.4426950408889634f));
+  const float r = p * e;
+  return fmaf(-ax, r, fmaxf(x, 0.0f));
 }
 
 }  // namespace ruart
