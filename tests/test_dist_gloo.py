@@ -31,6 +31,13 @@ def _worker(rank, world, port, q):
     picks = synth.select_answers(probs, shard[1]["num_cnt"])
     all_picks = dist_utils.gather_picks(picks)
     ms = dist_utils.max_over_ranks([10.0 + rank, 5.0 - rank])
+    # gradient all-reduce (mean) of the optional training step on a toy parameter set
+    lin = torch.nn.Linear(3, 2)
+    frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    for p_ in lin.parameters():
+        p_.grad = torch.full_like(p_, float(rank + 1))
+    n_red = dist_utils.allreduce_mean_grads(list(lin.parameters()) + [frozen])
+    assert n_red == 8 and all(torch.allclose(p_.grad, torch.full_like(p_, 1.5)) for p_ in lin.parameters())
     q.put((rank, picks, all_picks, ms, float(probs.sum())))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
