@@ -344,29 +344,55 @@ class DeepAttention(nn.Module):
         self.rnn, self.output_size = RNN_from_opt(rnn_input_size, opt['highlvl_hidden_size'], num_layers=1)
         self.opt = opt
 
+    def _fused_weights(self):
+        """The abstr_list_cnt+1 attention heads share their inputs, so their projections run as ONE
+        GEMM per side with the weights stacked along N (and the trainable diagonals concatenated)."""
+        lins = [a.scoring.linear.weight for a in self.int_attn_list]
+        diags = [a.scoring.diagonal for a in self.int_attn_list]
+        w, _ = K.prep_weight(self, ("w_all",), lins, sdnet_parts)
+        hid = self.int_attn_list[0].scoring.hidden_size
+        d = K.prep_vector(self, ("d_all",), lambda: torch.cat([
+            x.reshape(-1) if x.numel() > 1 else x.reshape(-1).expand(hid) for x in diags]), diags)
+        return w, d, hid
+
+    def project_x2(self, x2_word, x2_abstr):
+        """relu(x2_att W_i^T) for every head i: [B*L2, heads*hid] (shared by every x1 it is paired with)."""
+        x2_att = torch.cat(x2_word + x2_abstr[:-1], 2)
+        w, _, hid = self._fused_weights()
+        n = len(self.int_attn_list) * hid
+        a, Kp = K.split_act(x2_att, sdnet_parts)
+        rows = x2_att.shape[0] * x2_att.shape[1]
+        p2 = torch.empty((rows, n), dtype=torch.float32, device=x2_att.device)
+        K.linear(a, Kp, w, rows, n, sdnet_parts, p2, epi=ops.EPI_RELU_SCALE, scale=K.ones(x2_att.device))
+        return p2
+
     def forward(self, x1_word, x1_abstr, x2_word, x2_abstr, x1_mask, x2_mask, return_bef_rnn=False,
-                return_score=False):
-        """History-of-word multi-level inter-attention (Layers.py:493-524)."""
+                return_score=False, x2_proj=None):
+        """History-of-word multi-level inter-attention (Layers.py:493-524).  x2_proj: optional
+        result of project_x2 (the question side is the same for the OCR and the OD call)."""
+        _need_cuda(*x1_abstr)
+        _no_training(self, dropout_p)
         if return_score or 'no_DeepAttention' in self.opt:
             raise NotImplementedError("return_score / no_DeepAttention are not on the shipped conf's path")
         x1_att = torch.cat(x1_word + x1_abstr, 2)
-        x2_att = torch.cat(x2_word + x2_abstr[:-1], 2)
-        B, L1 = x1_att.shape[0], x1_att.shape[1]
+        B, L1, L2 = x1_att.shape[0], x1_att.shape[1], x2_abstr[0].shape[1]
         widths = [t.shape[2] for t in x1_abstr] + [t.shape[2] for t in x2_abstr]
         x1 = torch.empty((B, L1, sum(widths)), dtype=torch.float32, device=x1_att.device)
         col = 0
         for t in x1_abstr:
             x1[:, :, col:col + t.shape[2]] = t
             col += t.shape[2]
-        sp1 = K.split_act(x1_att, sdnet_parts)
-        sp2 = K.split_act(x2_att, sdnet_parts)
+        w, d, hid = self._fused_weights()
+        n = len(self.int_attn_list) * hid
+        a1, Kp = K.split_act(x1_att, sdnet_parts)
+        p1 = torch.empty((B * L1, n), dtype=torch.float32, device=x1_att.device)
+        K.linear(a1, Kp, w, B * L1, n, sdnet_parts, p1, epi=ops.EPI_RELU_SCALE, scale=d)
+        p2 = x2_proj if x2_proj is not None else self.project_x2(x2_word, x2_abstr)
         mask = K.as_u8(x2_mask)
         for i in range(len(x2_abstr)):
-            sc = self.int_attn_list[i].scoring
-            p1, _ = sc.project(x1_att, True, a_split=sp1)
-            p2, _ = sc.project(x2_att, False, a_split=sp2)
             x3 = x2_abstr[i]
-            K.attention_tail(p1, p2, mask, x3, x1[:, :, col:col + x3.shape[2]], B, L1, x2_att.shape[1])
+            K.attention_tail(p1[:, i * hid:(i + 1) * hid], p2[:, i * hid:(i + 1) * hid], mask, x3,
+                             x1[:, :, col:col + x3.shape[2]], B, L1, L2)
             col += x3.shape[2]
         x1_hiddens = self.rnn(x1, x1_mask)
         if return_bef_rnn:

@@ -347,7 +347,8 @@ class SDNet(nn.Module):
         concurrent = self.use_streams and self.phase_log is None and self._warm_version == ver
         if concurrent:
             if self._side is None:
-                self._side = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+                # the question branch gates both context branches: high priority
+                self._side = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1))
             s_od, s_q = self._side
             fork = torch.cuda.Event()
             fork.record(main)
@@ -365,7 +366,8 @@ class SDNet(nn.Module):
 
         def context_branch(x, layers, mask, Mx):
             # deep inter-attention + context self-attention (SDNet.py:376-390)
-            after, before = self.deep_attn([x], layers, [q_word], q_layers, mask, q_mask, return_bef_rnn=True)
+            after, before = self.deep_attn([x], layers, [q_word], q_layers, mask, q_mask, return_bef_rnn=True,
+                                           x2_proj=q_proj)
             s_in = torch.cat([after, before, x], 2)
             DA = self.deep_attn_output_size
             hl_in = torch.empty((B, Mx, 2 * DA), **f32)
@@ -379,14 +381,16 @@ class SDNet(nn.Module):
             q_cat = torch.cat(q_layers, 2)
             q_high = encode(self.high_lvl_ques_rnn, q_cat, opt['question_high_lvl_rnn_layers'])[-1]
             q_layers = q_layers + [q_high]
+            q_proj = self.deep_attn.project_x2([q_word], q_layers)  # shared by the OCR and OD branches
             ev_q = torch.cuda.Event()
             ev_q.record(s_q)
+        ocr_layers = encode(self.context_rnn, ocr_x, L_in)   # critical path: queued before the OD branch
         with torch.cuda.stream(s_od):
             od_layers = encode(self.context_rnn, od_x, L_in)
-        ocr_layers = encode(self.context_rnn, ocr_x, L_in)
         self._phase('encoders')
         main.wait_event(ev_q)
         s_od.wait_event(ev_q)
+        ocr_high = context_branch(ocr_x, ocr_layers, ocr_mask, M)
         with torch.cuda.stream(s_od):
             od_high = context_branch(od_x, od_layers, od_mask, M_od)
             ev_od = torch.cuda.Event()
@@ -397,7 +401,6 @@ class SDNet(nn.Module):
             q_merged = self.ques_merger.pooled(q_final, q_mask)
             ev_q2 = torch.cuda.Event()
             ev_q2.record(s_q)
-        ocr_high = context_branch(ocr_x, ocr_layers, ocr_mask, M)
         self._phase('deep_self_attn')
         main.wait_event(ev_od)
         # ---- OD <-> OCR + position attention (SDNet.py:393-405) -------------------------------

@@ -362,16 +362,19 @@ bert_attention_mma16_kernel(const __nv_bfloat16* __restrict__ qkv,
   const int b_row = lane & 7;
   const int b_chk = lane >> 3;
   const int n_pairs = (n_seq + 1) >> 1;
-  const long long n_tasks = static_cast<long long>(n_pairs) * n_heads;
-  for (long long task = static_cast<long long>(blockIdx.x) * SHORT_WARPS + warp; task < n_tasks;
-       task += static_cast<long long>(gridDim.x) * SHORT_WARPS) {
-    const int pair = static_cast<int>(task / n_heads);
-    const int h = static_cast<int>(task - static_cast<long long>(pair) * n_heads);
+  // one warp per sequence pair, looping over the heads: the sequence bookkeeping (three dependent
+  // cu_seqlens loads) is paid once per pair instead of once per (pair, head)
+  const int h_split = (n_heads % 2 == 0) ? 2 : 1;  // two warps share a pair's heads (finer tasks)
+  const int h_per = n_heads / h_split;
+  for (int task = blockIdx.x * SHORT_WARPS + warp; task < n_pairs * h_split; task += gridDim.x * SHORT_WARPS) {
+    const int pair = task / h_split;
+    const int h_lo = (task - pair * h_split) * h_per;
     const int sA = 2 * pair, sB = sA + 1;
     const int tA = cu_seqlens[sA];
     const int tB = cu_seqlens[sA + 1];
     const int lenA = tB - tA;
     const int lenB = (sB < n_seq) ? cu_seqlens[sB + 1] - tB : 0;
+   for (int h = h_lo; h < h_lo + h_per; ++h) {
     // passes: paired (both <= 8), or each sequence of <= 16 tokens on its own
     const bool paired = lenA <= 8 && lenB <= 8;
     const int n_pass = paired ? 1 : 2;
@@ -492,6 +495,7 @@ bert_attention_mma16_kernel(const __nv_bfloat16* __restrict__ qkv,
         }
       }
     }
+   }
   }
 }
 
@@ -892,7 +896,7 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
     if (ctas > cap) ctas = cap;
     {
-      const long long pair_tasks = static_cast<long long>((n_seq + 1) / 2) * n_heads;
+      const long long pair_tasks = static_cast<long long>((n_seq + 1) / 2) * ((n_heads % 2 == 0) ? 2 : 1);
       long long ctas16 = (pair_tasks + SHORT_WARPS - 1) / SHORT_WARPS;
       if (ctas16 > cap) ctas16 = cap;
       bert_attention_mma16_kernel<<<static_cast<unsigned>(ctas16), SHORT_WARPS * 32, 0, st>>>(
