@@ -240,7 +240,10 @@ class SDNet(nn.Module):
         pack_handle = self.Bert.pack_begin(bert_segments)
         # ---- embeddings: [word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) -------------
         q_in = torch.zeros((B, Wq, QD), **f32)
-        items_in = torch.zeros((N_ocr * Wo + N_od * Wd, XD), **f32)
+        # no zero-fill (2 GB at cfg-3): every column of every REAL word row is written below (word / pos /
+        # ent gathers, BERT sink incl. explicit zeros for masked words, pre-align); pad-word rows of an
+        # item are never read (multi2one consumes real word steps only)
+        items_in = torch.empty((N_ocr * Wo + N_od * Wd, XD), **f32)
         ocr_in = items_in[:N_ocr * Wo].view(N_ocr, Wo, XD)
         od_in = items_in[N_ocr * Wo:].view(N_od, Wd, XD)
         q_word = torch.empty((B, Wq, VD), **f32)

@@ -724,7 +724,17 @@ subword_avg_layers_kernel(const float* h_f32, const __nv_bfloat16* h_b16, long l
   const int st = words[2LL * n_words + w];
   const int ed = words[3LL * n_words + w];
   if (j >= W) return;
-  if (x_mask != nullptr && x_mask[static_cast<long long>(item) * W + j] == 0) return;
+  if (x_mask != nullptr && x_mask[static_cast<long long>(item) * W + j] == 0) {
+    // masked word: the reference leaves zeros (Bert.py:155-156); written explicitly so that the
+    // destination buffer needs no zero-fill
+    float* dz = dst + (static_cast<long long>(item) * W + j) * dst_stride;
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+      *reinterpret_cast<float4*>(dz + c * 256 + lane * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(dz + c * 256 + lane * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
   float mx = -INFINITY;
   for (int i = 0; i < n_layers; ++i) mx = fmaxf(mx, alpha[i]);
   float den = 0.f;
