@@ -115,6 +115,16 @@ RUART_API int ruart_subword_avg_layers(const float* h_f32, const void* h_bf16,
                                        const int32_t* row_start, const uint8_t* x_mask, int W,
                                        float* dst, long long dst_stride, const float* alpha,
                                        int n_layers, const float* gamma, int hidden, void* stream);
+/* Sequence bookkeeping of the packed layout.  ruart_seq_lengths: per row of mask [N, L] the number of
+ * real tokens (row_len[N]) and of each window of `window` columns (win_len[N * n_win]).
+ * ruart_seq_scan (one CTA): exclusive prefix sums cu_rows[R+1], cu_seq[S+1] over all segments'
+ * rows / windows, totals[0] = token count, totals[1+k] = longest window of segment k;
+ * seg_row0 / seg_seq0 are HOST arrays of n_seg+1 boundaries (n_seg <= 8).                       */
+RUART_API int ruart_seq_lengths(const uint8_t* mask, int N, int L, int window, int32_t* row_len,
+                                int32_t* win_len, void* stream);
+RUART_API int ruart_seq_scan(const int32_t* row_len, int R, const int32_t* win_len, int S, int n_seg,
+                             const int32_t* seg_row0_host, const int32_t* seg_seq0_host,
+                             int32_t* cu_rows, int32_t* cu_seq, int32_t* totals, void* stream);
 /* Real (mask != 0) wordpieces of ids [N, L] (int64, the collate's dtype) -> packed int32 ids and
  * position ids (column % window) at out[row_start[r] ...]; replaces the padded [N, L] layout of
  * BertModel.forward's inputs (modeling.py:585-604).                                            */

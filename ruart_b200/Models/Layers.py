@@ -146,9 +146,9 @@ class StackedBRNN(nn.Module):
         for i in range(self.num_layers):
             rnn_input = hiddens[-1]
             if i == 1 and x_additional is not None:
-                rnn_input = torch.cat((rnn_input, x_additional), 2)
+                rnn_input = K.concat_cols([rnn_input, x_additional])
             hiddens.append(self.run_layer(i, rnn_input.contiguous(), LN=LN))
-        output = torch.cat(hiddens[1:], 2) if self.concat_layers else hiddens[-1]
+        output = K.concat_cols(hiddens[1:]) if self.concat_layers else hiddens[-1]
         if return_list:
             return output, hiddens[1:]
         return output
@@ -357,7 +357,7 @@ class DeepAttention(nn.Module):
 
     def project_x2(self, x2_word, x2_abstr):
         """relu(x2_att W_i^T) for every head i: [B*L2, heads*hid] (shared by every x1 it is paired with)."""
-        x2_att = torch.cat(x2_word + x2_abstr[:-1], 2)
+        x2_att = K.concat_cols(x2_word + x2_abstr[:-1])
         w, _, hid = self._fused_weights()
         n = len(self.int_attn_list) * hid
         a, Kp = K.split_act(x2_att, sdnet_parts)
@@ -374,13 +374,13 @@ class DeepAttention(nn.Module):
         _no_training(self, dropout_p)
         if return_score or 'no_DeepAttention' in self.opt:
             raise NotImplementedError("return_score / no_DeepAttention are not on the shipped conf's path")
-        x1_att = torch.cat(x1_word + x1_abstr, 2)
+        x1_att = K.concat_cols(x1_word + x1_abstr)
         B, L1, L2 = x1_att.shape[0], x1_att.shape[1], x2_abstr[0].shape[1]
         widths = [t.shape[2] for t in x1_abstr] + [t.shape[2] for t in x2_abstr]
         x1 = torch.empty((B, L1, sum(widths)), dtype=torch.float32, device=x1_att.device)
         col = 0
         for t in x1_abstr:
-            x1[:, :, col:col + t.shape[2]] = t
+            K.copy_cols(t, x1[:, :, col:col + t.shape[2]])
             col += t.shape[2]
         w, d, hid = self._fused_weights()
         n = len(self.int_attn_list) * hid

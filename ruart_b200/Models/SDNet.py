@@ -371,17 +371,17 @@ class SDNet(nn.Module):
             # deep inter-attention + context self-attention (SDNet.py:376-390)
             after, before = self.deep_attn([x], layers, [q_word], q_layers, mask, q_mask, return_bef_rnn=True,
                                            x2_proj=q_proj)
-            s_in = torch.cat([after, before, x], 2)
+            s_in = K.concat_cols([after, before, x])
             DA = self.deep_attn_output_size
             hl_in = torch.empty((B, Mx, 2 * DA), **f32)
-            hl_in[:, :, :DA] = after
+            K.copy_cols(after, hl_in[:, :, :DA])
             self.highlvl_self_att(s_in, s_in, mask, x3=after, out=hl_in[:, :, DA:])
             return self.high_lvl_context_rnn.run_layer(0, hl_in, LN=True)
 
         # encoders with whole-tensor LN (SDNet.py:338-350)
         with torch.cuda.stream(s_q):
             q_layers = encode(self.ques_rnn, q_in, L_in)
-            q_cat = torch.cat(q_layers, 2)
+            q_cat = K.concat_cols(q_layers)
             q_high = encode(self.high_lvl_ques_rnn, q_cat, opt['question_high_lvl_rnn_layers'])[-1]
             q_layers = q_layers + [q_high]
             q_proj = self.deep_attn.project_x2([q_word], q_layers)  # shared by the OCR and OD branches
@@ -409,7 +409,7 @@ class SDNet(nn.Module):
         # ---- OD <-> OCR + position attention (SDNet.py:393-405) -------------------------------
         CF = ocr_high.shape[2]
         ocr_final = torch.empty((B, M, 2 * CF), **f32)
-        ocr_final[:, :, :CF] = ocr_high
+        K.copy_cols(ocr_high, ocr_final[:, :, :CF])
         x_od_ocr = ocr_final[:, :, CF:]
         self.od_ocr_attn(ocr_high, od_high, od_mask, out=x_od_ocr)
         self.position_attn(ocr_list['position'].float(), od_list['position'].float(), od_mask, x3=od_high,

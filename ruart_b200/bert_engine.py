@@ -127,8 +127,8 @@ class BertEngine(object):
 
     @classmethod
     def pack_begin(cls, segments):
-        """First half of the token packing: row / window lengths and their prefix sums, computed
-        with a few integer torch ops on a SIDE stream, and an async copy of the totals into pinned
+        """First half of the token packing: row / window lengths (ruart_seq_lengths) and their prefix
+        sums + totals (ruart_seq_scan) on a SIDE stream, and an async copy of the totals into pinned
         memory.  The caller can queue unrelated work on the compute stream before pack_finish()."""
         dev = segments[0].ids.device
         key = str(dev)
@@ -141,31 +141,35 @@ class BertEngine(object):
         ready.record(main)
         side.wait_event(ready)  # inputs produced on the compute stream are visible
         with torch.cuda.stream(side):
-            row_lens, win_lens, nwins = [], [], []
-            for sg in segments:
-                rl = sg.mask.sum(1, dtype=torch.int32)
-                row_lens.append(rl)
-                nwin = (sg.L + WINDOW - 1) // WINDOW
-                if nwin == 1:
-                    win_lens.append(rl)
-                else:
-                    base = torch.arange(nwin, device=dev, dtype=torch.int32) * WINDOW
-                    win_lens.append((rl[:, None] - base[None, :]).clamp_(0, WINDOW).reshape(-1))
-                nwins.append(nwin)
-            all_rows = torch.cat(row_lens)
-            cu_rows = torch.zeros(all_rows.numel() + 1, dtype=torch.int32, device=dev)
-            torch.cumsum(all_rows, 0, out=cu_rows[1:])
-            all_win = torch.cat(win_lens)
-            cu_seq = torch.zeros(all_win.numel() + 1, dtype=torch.int32, device=dev)
-            torch.cumsum(all_win, 0, out=cu_seq[1:])
-            maxes = [w.max() if w.numel() else torch.zeros((), dtype=torch.int32, device=dev) for w in win_lens]
-            totals = torch.stack([cu_rows[-1]] + maxes)
+            nwins = [(sg.L + WINDOW - 1) // WINDOW for sg in segments]
+            row0 = np.zeros(len(segments) + 1, dtype=np.int32)
+            seq0 = np.zeros(len(segments) + 1, dtype=np.int32)
+            for k, sg in enumerate(segments):
+                row0[k + 1] = row0[k] + sg.N
+                seq0[k + 1] = seq0[k] + sg.N * nwins[k]
+            R, S = int(row0[-1]), int(seq0[-1])
+            row_len = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
+            win_len = torch.empty(max(S, 1), dtype=torch.int32, device=dev)
+            cu_rows = torch.empty(R + 1, dtype=torch.int32, device=dev)
+            cu_seq = torch.empty(S + 1, dtype=torch.int32, device=dev)
+            totals = torch.empty(1 + len(segments), dtype=torch.int32, device=dev)
+            st = current_stream()
+            masks = []
+            for k, sg in enumerate(segments):
+                m8 = sg.mask.contiguous().view(torch.uint8) if sg.mask.dtype == torch.bool \
+                    else sg.mask.to(torch.uint8).contiguous()
+                masks.append(m8)
+                call("ruart_seq_lengths", ptr(m8), sg.N, sg.L, WINDOW, row_len.data_ptr() + 4 * int(row0[k]),
+                     win_len.data_ptr() + 4 * int(seq0[k]), st)
+            call("ruart_seq_scan", ptr(row_len), R, ptr(win_len), S, len(segments), row0.ctypes.data,
+                 seq0.ctypes.data, ptr(cu_rows), ptr(cu_seq), ptr(totals), st)
             host = torch.empty(totals.shape, dtype=totals.dtype, pin_memory=True)
             host.copy_(totals, non_blocking=True)
             done = torch.cuda.Event()
             done.record(side)
+            keep = (row_len, win_len, totals, masks, row0, seq0)
         return {"segments": segments, "cu_rows": cu_rows, "cu_seq": cu_seq, "host": host, "done": done,
-                "nwins": nwins, "keep": (row_lens, win_lens, all_rows, all_win, totals)}
+                "nwins": nwins, "keep": keep}
 
     @staticmethod
     def pack_finish(h):

@@ -776,6 +776,83 @@ subword_avg_layers_kernel(const float* h_f32, const __nv_bfloat16* h_b16, long l
   }
 }
 
+// Sequence bookkeeping of the packed layout, on the device (replaces a handful of torch integer ops):
+//   seq_lengths_kernel : one warp per row -> number of real tokens of the row and of each of its
+//                        512-token windows (written at the row's / windows' global slots)
+//   seq_scan_kernel    : ONE CTA: exclusive prefix sums cu_rows[R+1], cu_seq[S+1] and the totals the
+//                        host needs to size buffers: totals[0] = T, totals[1 + k] = longest window of
+//                        segment k
+constexpr int MAX_SEGMENTS = 8;
+struct SegTable {
+  int n_seg;
+  int row0[MAX_SEGMENTS + 1];  // first global row of segment k (row0[n_seg] = R)
+  int seq0[MAX_SEGMENTS + 1];  // first global window-sequence of segment k
+};
+
+__global__ void __launch_bounds__(256)
+seq_lengths_kernel(const uint8_t* __restrict__ mask, int N, int L, int window, int n_win,
+                   int32_t* __restrict__ row_len, int32_t* __restrict__ win_len) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  int total = 0;
+  for (int w = 0; w < n_win; ++w) {
+    int cnt = 0;
+    const int c_end = min(L, (w + 1) * window);
+    for (int c = w * window + lane; c < c_end; c += 32)
+      cnt += mask[static_cast<long long>(row) * L + c] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) win_len[static_cast<long long>(row) * n_win + w] = cnt;
+    total += cnt;
+  }
+  if (lane == 0) row_len[row] = total;
+}
+
+__device__ void block_exclusive_scan(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out) {
+  // out[0] = 0, out[i+1] = in[0] + ... + in[i]; one CTA of 1024 threads, chunked
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int per = (n + nt - 1) / nt;
+  const int lo = min(n, t * per), hi = min(n, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += in[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < nt; off <<= 1) {  // Hillis-Steele inclusive scan of the partials
+    const int v = (t >= off) ? s_part[t - off] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int run = (t == 0) ? 0 : s_part[t - 1];
+  if (t == 0) out[0] = 0;
+  for (int i = lo; i < hi; ++i) {
+    run += in[i];
+    out[i + 1] = run;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+seq_scan_kernel(const int32_t* __restrict__ row_len, int R, const int32_t* __restrict__ win_len, int S,
+                const SegTable seg, int32_t* __restrict__ cu_rows, int32_t* __restrict__ cu_seq,
+                int32_t* __restrict__ totals) {
+  block_exclusive_scan(row_len, R, cu_rows);
+  block_exclusive_scan(win_len, S, cu_seq);
+  __shared__ int s_max[MAX_SEGMENTS];
+  if (threadIdx.x < MAX_SEGMENTS) s_max[threadIdx.x] = 0;
+  __syncthreads();
+  for (int k = 0; k < seg.n_seg; ++k) {
+    int m = 0;
+    for (int i = seg.seq0[k] + threadIdx.x; i < seg.seq0[k + 1]; i += blockDim.x) m = max(m, win_len[i]);
+    atomicMax(&s_max[k], m);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) totals[0] = cu_rows[R];
+  if (threadIdx.x < seg.n_seg) totals[1 + threadIdx.x] = s_max[threadIdx.x];
+}
+
 // Token packing: ids [N, L] + mask [N, L] -> the real tokens of every row, in row order, at
 // out[row_start[r] ...]; position id = column index inside its 512-token window (the reference
 // restarts positions per window, Bert.py:96-99,135-138 + modeling.py:186-187).  One warp per row.
@@ -984,6 +1061,33 @@ extern "C" int ruart_subword_avg_layers(const float* h_f32, const void* h_bf16,
     subword_avg_layers_kernel<4><<<row_grid(n_words), ROWS_PER_CTA * 32, 0, st>>>(
         h_f32, (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dst,
         dst_stride, alpha, n_layers, gamma);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_seq_lengths(const uint8_t* mask, int N, int L, int window, int32_t* row_len,
+                                 int32_t* win_len, void* stream) {
+  RUART_ARG_CHECK(N >= 0 && L > 0 && window > 0);
+  if (N == 0) return RUART_OK;
+  const int n_win = (L + window - 1) / window;
+  seq_lengths_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(mask, N, L, window, n_win,
+                                                                    row_len, win_len);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_seq_scan(const int32_t* row_len, int R, const int32_t* win_len, int S, int n_seg,
+                              const int32_t* seg_row0, const int32_t* seg_seq0, int32_t* cu_rows,
+                              int32_t* cu_seq, int32_t* totals, void* stream) {
+  RUART_ARG_CHECK(n_seg >= 1 && n_seg <= MAX_SEGMENTS && R >= 0 && S >= 0);
+  SegTable seg;
+  seg.n_seg = n_seg;
+  for (int k = 0; k <= n_seg; ++k) {  // host arrays of n_seg + 1 entries
+    seg.row0[k] = seg_row0[k];
+    seg.seq0[k] = seg_seq0[k];
+  }
+  seq_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_len, R, win_len, S, seg, cu_rows, cu_seq,
+                                                        totals);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

@@ -135,6 +135,26 @@ def gather_rows(src, src_idx, dst, dst_idx, n, D, dst2=None):
          is64, current_stream())
 
 
+def copy_cols(src, dst):
+    """dst[..., :D] = src (row-wise copy between differently pitched fp32 buffers)."""
+    rows, D, _ = rows2d(src)
+    gather_rows(src, None, dst, None, rows, D)
+    return dst
+
+
+def concat_cols(tensors):
+    """torch.cat(tensors, -1) for fp32 [.., D_i] tensors with equal leading dims, done by the row
+    copy kernel (keeps the hot path free of library kernels)."""
+    lead = tensors[0].shape[:-1]
+    widths = [t.shape[-1] for t in tensors]
+    out = torch.empty(tuple(lead) + (sum(widths),), dtype=torch.float32, device=tensors[0].device)
+    col = 0
+    for t, w in zip(tensors, widths):
+        copy_cols(t, out[..., col:col + w])
+        col += w
+    return out
+
+
 def whole_layernorm_(x, eps=1e-5):
     rows, cols, pitch = rows2d(x)
     call("ruart_whole_layernorm", ptr(x), rows, cols, pitch, eps, ptr(ln_workspace(x.device)), current_stream())
