@@ -193,3 +193,23 @@ def test_many_word_items_and_repeated_forward_are_deterministic():
     p2, l2, _ = run_ours(net, batch)
     assert rel_err(l1, want_l) < 1e-4
     assert torch.equal(p1, p2) and torch.equal(l1, l2)
+
+
+def test_baseline_config1_full_size_both_modes():
+    """BASELINE.json configs[0] at full size: 32 questions x 20 q-tokens x 50 OCR tokens (+10 OD),
+    reference-style random init; one CPU-oracle run checks fp32 mode (1e-4) and bf16 mode (2e-2)
+    and answer agreement >= 99.5 % (here: all 32)."""
+    net, opt = build_ours("cfg1", seed=1033, bert_init="random", device="cuda", BERT_precision="fp32",
+                          KEEP_LOGITS=True)
+    batch = synth.make_batch("cfg1")
+    cpu_sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch))
+    want_pick = synth.select_answers(want_p, batch[1]["num_cnt"])
+    for mode, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        net.Bert.precision = mode
+        net.sdnet_parts = 3 if mode == "fp32" else 2
+        probs, logits, _ = run_ours(net, batch)
+        assert rel_err(logits, want_l) < tol, mode
+        picks = synth.select_answers(probs, batch[1]["num_cnt"])
+        agree = sum(int(a == b) for a, b in zip(picks, want_pick)) / len(picks)
+        assert agree >= 0.995, (mode, agree)
