@@ -346,7 +346,8 @@ class SDNet(nn.Module):
         # stream so that no branch reads a prepared weight another branch is still writing.
         L_in = opt['in_rnn_layers']
         main = torch.cuda.current_stream(dev)
-        ver = sum(p._version for p in self.parameters())
+        # anything that invalidates the prepared-weight caches: parameter versions and the split width
+        ver = (sum(p._version for p in self.parameters()), self.sdnet_parts)
         concurrent = self.use_streams and self.phase_log is None and self._warm_version == ver
         if concurrent:
             if self._side is None:
