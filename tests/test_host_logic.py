@@ -1,0 +1,79 @@
+"""CPU: the host-side index logic that replaces the reference's Python loops — checked against
+straightforward loop restatements of Models/SDNet.py:300-318,498-550 and Models/Bert/Bert.py:153-165."""
+import numpy as np
+import torch
+
+from ruart_b200 import synth
+from ruart_b200.bert_engine import flatten_offsets
+from ruart_b200.Models.SDNet import SDNet
+
+
+def test_flatten_offsets_matches_nested_loops():
+    _, ocr, _ = synth.make_batch("small", ragged=True)
+    offs = ocr["bert_offsets"]
+    w = flatten_offsets(offs, len(offs))
+    k = 0
+    for i, item in enumerate(offs):
+        for j, (st, ed) in enumerate(item):
+            assert tuple(w[:, k]) == (i, j, st, ed)
+            k += 1
+    assert k == w.shape[1]
+    # bertify's flat [1, 1] for an item without words (VQA_Dataset.py:426-427)
+    w2 = flatten_offsets([[[1, 2], [2, 4]], [1, 1], [[1, 3]]], 3)
+    assert w2.T.tolist() == [[0, 0, 1, 2], [0, 1, 2, 4], [1, 0, 1, 1], [2, 0, 1, 3]]
+
+
+def test_item_index_matches_reference_loops():
+    W, M = 20, 100
+    _, ocr, _ = synth.make_batch("small", ragged=True)
+    num_cnt, len_cnt = ocr["num_cnt"], ocr["len_cnt"]
+    idx = SDNet._item_index(num_cnt, len_cnt, W, M)
+    B = len(num_cnt)
+    # slot scatter + mask (SDNet.py:300-318)
+    it = 0
+    for b in range(B):
+        for k, n in enumerate(len_cnt[b]):
+            assert idx["item_img"][it] == b and idx["item_slot"][it] == k and idx["lens"][it] == n
+            it += 1
+        assert idx["mask"][b].tolist() == [1] * num_cnt[b] + [0] * (M - num_cnt[b])
+    assert it == idx["n_items"]
+    # pre-align pack / unpack (SDNet.py:498-520,540-550)
+    T_max = max(sum(l) for l in len_cnt)
+    assert idx["T_max"] == T_max
+    src, dst = [], []
+    it = 0
+    for b in range(B):
+        t = 0
+        for n in len_cnt[b]:
+            for w in range(n):
+                src.append(it * W + w)
+                dst.append(b * T_max + t + w)
+            t += n
+            it += 1
+    assert idx["word_src"].tolist() == src and idx["word_dst"].tolist() == dst
+    assert idx["total_words"] == len(src)
+
+
+def test_make_batch_layout_matches_collate_contract():
+    q, ocr, od = synth.make_batch("tiny", ragged=True)
+    B = q["glove"].shape[0]
+    assert q["glove"].shape == (B, 40) and q["bert"].shape == (B, 50) and q["glove"].dtype == torch.int64
+    assert ocr["fasttext"].shape[1] == 20 and ocr["bert"].shape[1] == 30 and ocr["position"].shape == (B, 100, 8)
+    assert od["fasttext"].shape[1] == 10 and od["bert"].shape[1] == 10 and od["position"].shape == (B, 30, 8)
+    assert sum(ocr["num_cnt"]) == ocr["fasttext"].shape[0] == len(ocr["bert_offsets"])
+    # every image ends with the <OCR> / <OD> end item (VQA_Dataset.py:336-349)
+    last = np.cumsum(ocr["num_cnt"]) - 1
+    assert (ocr["fasttext"][last, 0] == 3).all() and (od["fasttext"][np.cumsum(od["num_cnt"]) - 1, 0] == 4).all()
+    assert torch.equal(ocr["fasttext_mask"], ~ocr["fasttext"].eq(0)) and torch.equal(q["bert_mask"], ~q["bert"].eq(0))
+
+
+def test_unsupported_options_are_rejected_loudly():
+    import pytest
+    opt = synth.make_opt("tiny")
+    opt["PHOC"] = True
+    with pytest.raises(NotImplementedError):
+        SDNet(opt, synth.make_embedding())
+    opt = synth.make_opt("tiny")
+    opt["position_mod"] = "cat"
+    with pytest.raises(NotImplementedError):
+        SDNet(opt, synth.make_embedding())
