@@ -52,6 +52,11 @@ RUART_API int ruart_num_sms(void);
  * (string_index << 24 | char_position << 8 | char) over all offending characters.           */
 RUART_API int ruart_phoc_batch(const uint8_t* chars, const int32_t* offsets, int64_t n, float* out,
                      int32_t* err, void* stream);
+/* Same, writing row i at out + i*out_pitch floats (out_pitch >= 604, multiple of 4; out 16-byte
+ * aligned): the PHOC channel of an item embedding `[phoc604 | word300 | bert768 | ...]`
+ * (Models/SDNet.py:441-446) computed from the strings in place of the `[V,604]` table lookup.   */
+RUART_API int ruart_phoc_batch_pitched(const uint8_t* chars, const int32_t* offsets, int64_t n,
+                             float* out, int64_t out_pitch, int32_t* err, void* stream);
 /* Same, bit-packed: 19 uint32 words per string (bit b of word w = feature 32*w+b). */
 RUART_API int ruart_phoc_batch_packed(const uint8_t* chars, const int32_t* offsets, int64_t n,
                             uint32_t* out_words, int32_t* err, void* stream);

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE — golden vectors for the model path, made by running the UNMODIFIED
 reference (oracle/ref_harness.py) on seeded synthetic inputs.  Build-container only:
 
-    python -m oracle.gen_model_golden
+    python -m oracle.gen_model_golden [case ...]
 
 Writes tests/golden/model_<case>.npz with the reference's probabilities, pre-softmax logits,
 selected answer indices (SDNetTrainer.py:402-412 rule) and a few slices of intermediate tensors.
@@ -15,7 +15,7 @@ import torch
 
 from ruart_b200 import synth
 
-from . import ref_harness
+from . import phoc_oracle, ref_harness
 
 CASES = {
     # name: (config, ragged, bert_init, weight seed)
@@ -23,7 +23,10 @@ CASES = {
     "tiny_ragged_pretrained": ("tiny", True, "pretrained_like", 1033),
     "small_ragged_random": ("small", True, "random", 77),
     "small_uniform_pretrained": ("small", False, "pretrained_like", 5),
+    # PHOC channel on the OCR / OD side (opt PHOC, ocr_embedding phoc,...: SDNet.py:51-55,441-446)
+    "tiny_ragged_phoc": ("tiny", True, "random", 1033),
 }
+PHOC_CASES = ("tiny_ragged_phoc",)
 CAPTURE = ("Bert", "multi2one", "context_rnn", "ques_rnn", "deep_attn", "high_lvl_context_rnn", "ques_self_attn")
 
 
@@ -31,15 +34,26 @@ def first(x):
     return x[0] if isinstance(x, (tuple, list)) else x
 
 
-def main():
+def main(only=()):
     if not ref_harness.available():
         raise SystemExit("needs the reference tree (build container only)")
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     for name, (cfg, ragged, init, seed) in CASES.items():
         torch.manual_seed(0)
-        opt = synth.make_opt(cfg)
-        net = ref_harness.build_reference(opt, seed=seed, bert_init=init)
-        batch = synth.make_batch(cfg, ragged=ragged)
+        if only and name not in only:
+            continue
+        embedding = None
+        if name in PHOC_CASES:
+            # the table is built by the reference's own cphoc (oracle/_ref) over the synthetic vocabulary
+            opt = synth.make_opt(cfg, **synth.PHOC_OPT)
+            embedding = synth.make_embedding(seed)
+            embedding["phoc_embedding"] = torch.from_numpy(
+                phoc_oracle.vocab_table(synth.make_vocab_words(seed), use_ref=True))
+            batch = synth.add_phoc(synth.make_batch(cfg, ragged=ragged))
+        else:
+            opt = synth.make_opt(cfg)
+            batch = synth.make_batch(cfg, ragged=ragged)
+        net = ref_harness.build_reference(opt, embedding=embedding, seed=seed, bert_init=init)
         probs, logits, cap = ref_harness.run_reference(net, batch, capture=CAPTURE)
         picks = synth.select_answers(probs, batch[1]["num_cnt"])
         bert_calls = cap["Bert"]  # q, ocr, od: each a list of 12 [N, W, 768]
@@ -61,4 +75,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(only=tuple(sys.argv[1:]))

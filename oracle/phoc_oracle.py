@@ -65,3 +65,19 @@ def ref_module():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+_ALPHABET = set("abcdefghijklmnopqrstuvwxyz0123456789")
+
+
+def vocab_table(words, use_ref=True):
+    """[len(words), 604] float32: what CoQAUtils.build_phoc_embedding (CoQAUtils.py:75-87) intends —
+    row i = build_phoc(word i) with the wrapper's normalisation (Utils/phoc.py:8-13).  Uses the
+    reference's own cphoc (oracle/_ref) when it was built, else the C restatement (bit-identical)."""
+    norm = ["".join(c for c in w.lower().strip() if c in _ALPHABET) for w in words]
+    ref = ref_module() if use_ref else None
+    if ref is not None:
+        return np.asarray([ref.build_phoc(w) for w in norm], dtype=np.float32)
+    out, bad = batch(norm)
+    assert bad < 0, "unknown unigram after normalisation"
+    return out

@@ -36,7 +36,7 @@ log = logging.getLogger(__name__)
 
 _REQUIRED = ("PRE_ALIGN", "PRE_ALIGN_befor_rnn", "BERT", "BERT_LINEAR_COMBINE", "useES", "label_no_answer",
              "mask_score", "position_dim", "GLOVE", "FastText")
-_UNSUPPORTED = ("PHOC", "img_feature", "fixed_answers", "ModelParallel", "label_yesno", "no_Context_Self_Attention",
+_UNSUPPORTED = ("img_feature", "fixed_answers", "ModelParallel", "label_yesno", "no_Context_Self_Attention",
                 "no_DeepAttention", "PRE_ALIGN_after_rnn", "BERT_LARGE_only")
 
 
@@ -65,8 +65,13 @@ class SDNet(nn.Module):
                 raise NotImplementedError("ruart_b200.SDNet: option %s is outside the implemented path" % k)
         if opt['position_mod'] != 'qk+' or opt['pos_att_merge_mod'] != 'cat' or opt.get('ES_using_way') != 'as_ocr':
             raise NotImplementedError("only position_mod qk+, pos_att_merge_mod cat, ES_using_way as_ocr")
-        if opt['q_embedding'] != 'glove,pos,ent,bert' or opt['ocr_embedding'] != 'fasttext,pos,ent,bert':
-            raise NotImplementedError("only q_embedding glove,pos,ent,bert / ocr_embedding fasttext,pos,ent,bert")
+        q_names, ocr_names = set(opt['q_embedding'].split(',')), set(opt['ocr_embedding'].split(','))
+        if q_names - {'phoc'} != {'glove', 'pos', 'ent', 'bert'} or \
+                ocr_names - {'phoc'} != {'fasttext', 'pos', 'ent', 'bert'}:
+            raise NotImplementedError("only q_embedding glove,pos,ent,bert / ocr_embedding fasttext,pos,ent,bert "
+                                      "(each optionally with phoc)")
+        if 'phoc' in (q_names | ocr_names) and 'PHOC' not in opt:
+            raise KeyError("'phoc' in q_embedding / ocr_embedding needs the PHOC option (SDNet.py:51-55)")
         self.vocab_dim = 300
         self.use_cuda = (opt['cuda'] == True)
         self.q_embedding = opt['q_embedding'].split(',')
@@ -84,6 +89,14 @@ class SDNet(nn.Module):
         Layers.set_sdnet_precision(self.sdnet_parts)
 
         self.vocab_size = int(opt['vocab_size'])
+        if 'PHOC' in opt:  # registered first, like the reference (SDNet.py:51-55), so state_dict order matches
+            self.phoc_dim = int(opt['phoc_dim'])
+            if self.phoc_dim != ops.PHOC_DIM:
+                raise NotImplementedError("phoc_dim must be %d" % ops.PHOC_DIM)
+            self.phoc_embed = nn.Embedding(self.vocab_size, self.phoc_dim, padding_idx=1)
+            self.phoc_embed.weight.data = embedding['phoc_embedding']
+        self.phoc_q = self.phoc_dim if 'phoc' in self.q_embedding else 0
+        self.phoc_x = self.phoc_dim if 'phoc' in self.ocr_embedding else 0
         self.fast_dim = int(opt['fast_dim'])
         self.glove_dim = int(opt['glove_dim'])
         self.fast_embed = nn.Embedding(self.vocab_size, self.fast_dim, padding_idx=1)
@@ -114,8 +127,8 @@ class SDNet(nn.Module):
 
         pos_dim, ent_dim = opt['pos_dim'], opt['ent_dim']
         n_pos, n_ent = _pos_ent_sizes(opt)
-        x_input_size = self.fast_dim + bert_dim + self.vocab_dim + pos_dim + ent_dim
-        ques_input_size = self.glove_dim + bert_dim + pos_dim + ent_dim
+        x_input_size = self.phoc_x + self.fast_dim + bert_dim + self.vocab_dim + pos_dim + ent_dim
+        ques_input_size = self.phoc_q + self.glove_dim + bert_dim + pos_dim + ent_dim
         self.pre_align = Attention(self.vocab_dim, opt['prealign_hidden'], correlation_func=3, do_similarity=True)
         self.pos_embedding = nn.Embedding(n_pos, pos_dim)
         self.ent_embedding = nn.Embedding(n_ent, ent_dim)
@@ -195,6 +208,22 @@ class SDNet(nn.Module):
         return dict(B=B, n_items=n_items, lens=lens, item_img=item_img, item_slot=item_slot, T_max=T_max,
                     word_src=word_src, word_dst=word_dst, mask=mask, total_words=total)
 
+    def _phoc_channel(self, lst, dst, n_rows, errs):
+        """PHOC columns of one item list (SDNet.py:441-446).  With `lst['phoc']` word ids: the
+        reference's `[V, 604]` table lookup.  With `lst['phoc_chars']` (uint8) / `lst['phoc_offsets']`
+        (int32 [n_rows+1]; see Utils.phoc.encode_tokens) the PHOC kernel writes the vectors of the
+        word strings straight into the embedding buffer — no table, no out-of-vocabulary loss
+        (SURVEY.md §8f-3).  Word slots with an empty string get zeros."""
+        if 'phoc_chars' in lst:
+            offs = lst['phoc_offsets']
+            if offs.numel() != n_rows + 1 or offs.dtype != torch.int32:
+                raise ValueError("phoc_offsets must be int32 [word slots + 1]")
+            _, err = ops.phoc_batch(lst['phoc_chars'], offs, out=dst, check=False)
+            errs.append(err)
+        else:
+            K.gather_rows(self.phoc_embed.weight.detach(), lst['phoc'].reshape(-1), dst, None, n_rows,
+                          self.phoc_dim)
+
     # ------------------------------------------------------------------ forward
     phase_log = None  # set to a list to collect (label, seconds since forward start) with device syncs
 
@@ -238,7 +267,7 @@ class SDNet(nn.Module):
             (ocr_list['bert'], ocr_list['bert_mask'], ocr_list['bert_offsets'], ocr_list['fasttext_mask']),
             (od_list['bert'], od_list['bert_mask'], od_list['bert_offsets'], od_list['fasttext_mask'])]
         pack_handle = self.Bert.pack_begin(bert_segments)
-        # ---- embeddings: [word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) -------------
+        # ---- embeddings: [(phoc |) word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) ----
         q_in = torch.zeros((B, Wq, QD), **f32)
         # no zero-fill (2 GB at cfg-3): every column of every REAL word row is written below (word / pos /
         # ent gathers, BERT sink incl. explicit zeros for masked words, pre-align); pad-word rows of an
@@ -249,25 +278,29 @@ class SDNet(nn.Module):
         q_word = torch.empty((B, Wq, VD), **f32)
         ocr_word = torch.empty((N_ocr, Wo, VD), **f32)
         od_word = torch.empty((N_od, Wd, VD), **f32)
-        c_pos, c_ent = VD + BD, VD + BD + pos_dim
+        PQ, PX = self.phoc_q, self.phoc_x   # width of the leading PHOC channel (0 without it)
+        phoc_errs = []
 
-        def embed(lst, key, table, buf, raw, n_rows):
-            K.gather_rows(table.weight.detach(), lst[key].reshape(-1), buf, None, n_rows, VD, dst2=raw)
+        def embed(lst, key, table, buf, raw, n_rows, P):
+            if P:
+                self._phoc_channel(lst, buf.view(n_rows, -1)[:, :P], n_rows, phoc_errs)
+            c_pos, c_ent = P + VD + BD, P + VD + BD + pos_dim
+            K.gather_rows(table.weight.detach(), lst[key].reshape(-1), buf[..., P:], None, n_rows, VD, dst2=raw)
             K.gather_rows(self.pos_embedding.weight.detach(), lst['pos'].reshape(-1), buf[..., c_pos:], None,
                           n_rows, pos_dim)
             K.gather_rows(self.ent_embedding.weight.detach(), lst['ent'].reshape(-1), buf[..., c_ent:], None,
                           n_rows, ent_dim)
 
-        embed(q_list, 'glove', self.glove_embed, q_in, q_word, B * Wq)
-        embed(ocr_list, 'fasttext', self.fast_embed, ocr_in, ocr_word, N_ocr * Wo)
-        embed(od_list, 'fasttext', self.fast_embed, od_in, od_word, N_od * Wd)
+        embed(q_list, 'glove', self.glove_embed, q_in, q_word, B * Wq, PQ)
+        embed(ocr_list, 'fasttext', self.fast_embed, ocr_in, ocr_word, N_ocr * Wo, PX)
+        embed(od_list, 'fasttext', self.fast_embed, od_in, od_word, N_od * Wd, PX)
         q_list['glove_emb'] = q_word          # side effect of the reference (SDNet.py:449-450,458-459)
         ocr_list['fasttext_emb'] = ocr_word
         od_list['fasttext_emb'] = od_word
 
         self._phase('embed')
         # ---- BERT: one packed pass, subword mean + layer sum into the concat buffers ------------
-        self.Bert.encode_into(bert_segments, [(q_in, QD, VD), (ocr_in, XD, VD), (od_in, XD, VD)],
+        self.Bert.encode_into(bert_segments, [(q_in, QD, PQ + VD), (ocr_in, XD, PX + VD), (od_in, XD, PX + VD)],
                               self.alphaBERT, self.gammaBERT, pack_handle=pack_handle)
 
         self._phase('bert')
@@ -300,7 +333,7 @@ class SDNet(nn.Module):
 
         self._phase('host_index')
         # ---- word-level pre-alignment (SDNet.py:495-551) --------------------------------------
-        c_pre = VD + BD + pos_dim + ent_dim
+        c_pre = PX + VD + BD + pos_dim + ent_dim
         p2_cache = {}
         for idx, word, wsrc, wdst, buf in ((io, ocr_word, ocr_wsrc, ocr_wdst, ocr_in),
                                            (id_, od_word, od_wsrc, od_wdst, od_in)):
@@ -425,6 +458,10 @@ class SDNet(nn.Module):
         self._phase('scores')
         if self.check_nan and int(nan_flag.item()) != 0:
             raise AssertionError("NaN in answer scores (reference: assert torch.sum(torch.isnan(...)) == 0)")
+        for err in phoc_errs:  # table-free PHOC channel: unknown unigram, like Utils/cphoc.c:45-50
+            key = int(err.item())
+            if key != -1:
+                raise RuntimeError("Error: unigram %s is unknown" % chr(key & 0xFF))
         return score_s, att_score
 
     def linear_sum(self, output, alpha, gamma):

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "ruart_version": [],
     "ruart_num_sms": [],
     "ruart_phoc_batch": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p],
+    "ruart_phoc_batch_pitched": [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p],
     "ruart_phoc_batch_packed": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p],
     "ruart_phoc_batch_host": [ctypes.c_char_p, c_void_p, c_i64, c_void_p,
                               ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_int32)],

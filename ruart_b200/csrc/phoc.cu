@@ -180,7 +180,7 @@ __device__ __forceinline__ void build_mask(const uint8_t* __restrict__ chars, in
 template <bool kPacked>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 phoc_kernel(const uint8_t* __restrict__ chars, const int32_t* __restrict__ offsets, int64_t n,
-            float* __restrict__ out, uint32_t* __restrict__ out_words, int32_t* err) {
+            float* __restrict__ out, int64_t out_pitch, uint32_t* __restrict__ out_words, int32_t* err) {
   __shared__ uint32_t s_mask[WARPS_PER_CTA][PHOC_WORDS + 1];
   __shared__ uint16_t s_uni[(LUT_N + 1) * LUT_N];
   __shared__ uint8_t s_bi[(LUT_N + 1) * LUT_N];
@@ -223,7 +223,7 @@ phoc_kernel(const uint8_t* __restrict__ chars, const int32_t* __restrict__ offse
     if (kPacked) {
       if (lane < PHOC_WORDS) out_words[s * PHOC_WORDS + lane] = mask[lane];
     } else {
-      float4* row = reinterpret_cast<float4*>(out + s * RUART_PHOC_DIM);
+      float4* row = reinterpret_cast<float4*>(out + s * out_pitch);
 #pragma unroll
       for (int q = lane; q < RUART_PHOC_DIM / 4; q += 32) {
         const int f = q * 4;
@@ -259,7 +259,7 @@ int upload_lut() {
   return RUART_OK;
 }
 
-int launch(const uint8_t* chars, const int32_t* offsets, int64_t n, float* out,
+int launch(const uint8_t* chars, const int32_t* offsets, int64_t n, float* out, int64_t out_pitch,
            uint32_t* out_words, int32_t* err, cudaStream_t st) {
   RUART_ARG_CHECK(n >= 0 && offsets != nullptr && err != nullptr);
   RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(err) & 7u) == 0);
@@ -273,12 +273,13 @@ int launch(const uint8_t* chars, const int32_t* offsets, int64_t n, float* out,
   if (ctas > max_ctas) ctas = max_ctas;
   if (out != nullptr) {
     RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    RUART_ARG_CHECK(out_pitch >= RUART_PHOC_DIM && (out_pitch & 3) == 0);
     phoc_kernel<false><<<static_cast<unsigned>(ctas), WARPS_PER_CTA * 32, 0, st>>>(
-        chars, offsets, n, out, nullptr, err);
+        chars, offsets, n, out, out_pitch, nullptr, err);
   } else {
     RUART_ARG_CHECK(out_words != nullptr);
     phoc_kernel<true><<<static_cast<unsigned>(ctas), WARPS_PER_CTA * 32, 0, st>>>(
-        chars, offsets, n, nullptr, out_words, err);
+        chars, offsets, n, nullptr, 0, out_words, err);
   }
   RUART_LAUNCH_CHECK();
   return RUART_OK;
@@ -289,13 +290,19 @@ int launch(const uint8_t* chars, const int32_t* offsets, int64_t n, float* out,
 extern "C" int ruart_phoc_batch(const uint8_t* chars, const int32_t* offsets, int64_t n, float* out,
                                 int32_t* err, void* stream) {
   RUART_ARG_CHECK(out != nullptr || n == 0);
-  return launch(chars, offsets, n, out, nullptr, err, (cudaStream_t)stream);
+  return launch(chars, offsets, n, out, RUART_PHOC_DIM, nullptr, err, (cudaStream_t)stream);
+}
+
+extern "C" int ruart_phoc_batch_pitched(const uint8_t* chars, const int32_t* offsets, int64_t n,
+                                        float* out, int64_t out_pitch, int32_t* err, void* stream) {
+  RUART_ARG_CHECK(out != nullptr || n == 0);
+  return launch(chars, offsets, n, out, out_pitch, nullptr, err, (cudaStream_t)stream);
 }
 
 extern "C" int ruart_phoc_batch_packed(const uint8_t* chars, const int32_t* offsets, int64_t n,
                                        uint32_t* out_words, int32_t* err, void* stream) {
   RUART_ARG_CHECK(out_words != nullptr || n == 0);
-  return launch(chars, offsets, n, nullptr, out_words, err, (cudaStream_t)stream);
+  return launch(chars, offsets, n, nullptr, 0, out_words, err, (cudaStream_t)stream);
 }
 
 extern "C" int ruart_phoc_batch_host(const char* chars_host, const int32_t* offsets_host, int64_t n,
@@ -323,7 +330,7 @@ extern "C" int ruart_phoc_batch_host(const char* chars_host, const int32_t* offs
   PH_CHECK(cudaMalloc(&d_err, 8));
   if (total_chars > 0) PH_CHECK(cudaMemcpy(d_chars, chars_host, total_chars, cudaMemcpyHostToDevice));
   PH_CHECK(cudaMemcpy(d_off, offsets_host, (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
-  rc = launch(d_chars, d_off, n, d_out, nullptr, d_err, 0);
+  rc = launch(d_chars, d_off, n, d_out, RUART_PHOC_DIM, nullptr, d_err, 0);
   if (rc != RUART_OK) goto done;
   PH_CHECK(cudaMemcpy(out_host, d_out, n * RUART_PHOC_DIM * sizeof(float), cudaMemcpyDeviceToHost));
   {

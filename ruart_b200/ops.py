@@ -28,16 +28,23 @@ def round_up(x, m):
 
 
 # ------------------------------------------------------------------------------------ PHOC
-def phoc_batch(chars, offsets, out=None, packed=False):
+def phoc_batch(chars, offsets, out=None, packed=False, check=True):
     """chars uint8 [total], offsets int32 [n+1] (device) -> float32 [n, 604] (or uint32 [n,19]).
 
-    Raises RuntimeError("Error: unigram X is unknown") like Utils/cphoc.c:45-50.
+    `out` may be a column view [n, 604] of a wider row-major fp32 buffer (row pitch a multiple of
+    4 floats).  Raises RuntimeError("Error: unigram X is unknown") like Utils/cphoc.c:45-50; with
+    check=False the 8-byte device error word is returned instead of being read back (no sync).
     """
     _need_cuda(chars, offsets)
     n = offsets.numel() - 1
     dev = offsets.device
     err = torch.empty(1, dtype=torch.int64, device=dev)
-    if packed:
+    if out is not None and not packed and not out.is_contiguous():
+        if out.dim() != 2 or out.shape != (n, PHOC_DIM) or out.stride(1) != 1 or out.dtype != torch.float32:
+            raise ValueError("phoc_batch: out must be an fp32 [n, 604] view with unit column stride")
+        call("ruart_phoc_batch_pitched", ptr(chars), ptr(offsets), n, ptr(out), out.stride(0), ptr(err),
+             current_stream())
+    elif packed:
         if out is None:
             out = torch.empty((n, 19), dtype=torch.int32, device=dev)
         call("ruart_phoc_batch_packed", ptr(chars), ptr(offsets), n, ptr(out), ptr(err),
@@ -46,6 +53,8 @@ def phoc_batch(chars, offsets, out=None, packed=False):
         if out is None:
             out = torch.empty((n, PHOC_DIM), dtype=torch.float32, device=dev)
         call("ruart_phoc_batch", ptr(chars), ptr(offsets), n, ptr(out), ptr(err), current_stream())
+    if not check:
+        return out, err
     key = int(err.item())
     if key != -1:
         raise RuntimeError("Error: unigram %s is unknown" % chr(key & 0xFF))

@@ -83,6 +83,43 @@ def make_embedding(seed=1033, vocab=VOCAB_SIZE, dim=300):
     return out
 
 
+def make_vocab_words(seed=1033, vocab=VOCAB_SIZE):
+    """Synthetic vocabulary strings: the five specials (CoQAPreprocess.py:531-535) then random
+    tokens over [a-z0-9] with some upper case / punctuation for the PHOC wrapper to normalise."""
+    rng = np.random.default_rng(seed * 13 + 5)
+    alphabet = np.array(list("abcdefghijklmnopqrstuvwxyz0123456789"))
+    words = ["<PAD>", "<UNK>", "<Q>", "<OCR>", "<OD>"]
+    while len(words) < vocab:
+        w = "".join(rng.choice(alphabet, size=int(rng.integers(1, 15))))
+        r = rng.random()
+        if r < 0.1:
+            w = w.upper()
+        elif r < 0.2:
+            w = w[:1] + "-" + w[1:] + "."
+        words.append(w)
+    return words
+
+
+PHOC_OPT = {"PHOC": True, "phoc_dim": 604, "ocr_embedding": "phoc,fasttext,pos,ent,bert"}
+
+
+def add_phoc(batch, vocab_words=None, q_side=False):
+    """Add the PHOC channel inputs to a batch: `phoc` = the word ids (VQA_Dataset.py:359-360).
+    With `vocab_words` also the table-free form: `phoc_chars` / `phoc_offsets` holding the string
+    of every word slot (see ruart_b200.Utils.phoc.encode_tokens)."""
+    from .Utils.phoc import encode_tokens
+    q, ocr, od = batch
+    for d, key in ((q, "glove"), (ocr, "fasttext"), (od, "fasttext")):
+        if d is q and not q_side:
+            continue
+        d["phoc"] = d[key].clone()
+        if vocab_words is not None:
+            chars, offsets = encode_tokens([vocab_words[i] for i in d[key].reshape(-1).tolist()])
+            d["phoc_chars"] = torch.from_numpy(chars)
+            d["phoc_offsets"] = torch.from_numpy(offsets)
+    return batch
+
+
 def _seed_for(name, seed):
     return (zlib.crc32(name.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF
 
@@ -112,6 +149,8 @@ def fill_state_dict(module, seed=1033, bert_init="random"):
                 v = torch.randn(shape, generator=g) * 0.02
             else:
                 v = torch.randn(shape, generator=g) * (0.02 if bert_init == "random" else 0.04)
+        elif name == "phoc_embed.weight":
+            continue  # the PHOC table is data (CoQAUtils.py:75-87), not a random weight
         elif name in ("glove_embed.weight", "fast_embed.weight"):
             v = torch.randn(shape, generator=g)
             v[0] = 0
@@ -261,6 +300,8 @@ def shard_batch(batch, rank, world):
     lo, hi = min(rank * per, B), min((rank + 1) * per, B)
 
     def cut_items(d):
+        if "phoc_chars" in d:
+            raise ValueError("shard first, then add_phoc(..., vocab_words): the string buffers are per shard")
         start = sum(d["num_cnt"][:lo])
         stop = start + sum(d["num_cnt"][lo:hi])
         r = {}

@@ -18,12 +18,17 @@ CASES = {
 }
 
 
-def build_ours(cfg, seed=1033, bert_init="random", device=None, **opt_over):
-    """Our SDNet with weights from synth.fill_state_dict (identical to what the reference got)."""
+def build_ours(cfg, seed=1033, bert_init="random", device=None, phoc_table=None, **opt_over):
+    """Our SDNet with weights from synth.fill_state_dict (identical to what the reference got).
+    phoc_table: [V, 604] array -> the PHOC option of the reference (SDNet.py:51-55) on the OCR/OD side."""
     from ruart_b200.Models.SDNet import SDNet
+    embedding = synth.make_embedding(seed)
+    if phoc_table is not None:
+        opt_over = dict(synth.PHOC_OPT, **opt_over)
+        embedding["phoc_embedding"] = torch.as_tensor(phoc_table).clone()
     opt = synth.make_opt(cfg, **opt_over)
     with contextlib.redirect_stdout(io.StringIO()):
-        net = SDNet(opt, synth.make_embedding(seed))
+        net = SDNet(opt, embedding)
     synth.fill_state_dict(net, seed=seed, bert_init=bert_init)
     net.eval()
     net.drop_emb = False

@@ -70,8 +70,11 @@ def test_make_batch_layout_matches_collate_contract():
 def test_unsupported_options_are_rejected_loudly():
     import pytest
     opt = synth.make_opt("tiny")
-    opt["PHOC"] = True
+    opt["img_feature"] = True
     with pytest.raises(NotImplementedError):
+        SDNet(opt, synth.make_embedding())
+    opt = synth.make_opt("tiny", ocr_embedding="phoc,fasttext,pos,ent,bert")   # 'phoc' without the PHOC option
+    with pytest.raises(KeyError):
         SDNet(opt, synth.make_embedding())
     opt = synth.make_opt("tiny")
     opt["position_mod"] = "cat"

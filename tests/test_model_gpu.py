@@ -213,3 +213,37 @@ def test_baseline_config1_full_size_both_modes():
         picks = synth.select_answers(probs, batch[1]["num_cnt"])
         agree = sum(int(a == b) for a, b in zip(picks, want_pick)) / len(picks)
         assert agree >= 0.995, (mode, agree)
+
+
+def test_phoc_channel_matches_reference_and_table_free_form_is_identical():
+    # opt PHOC + 'phoc' in ocr_embedding (SDNet.py:51-55,441-446).  The [V,604] table
+    # comes from the PHOC kernel (Utils.phoc.build_phoc_embedding = CoQAUtils.py:75-87) and must be
+    # bit-identical to the CPU oracle's; the forward must match the reference's golden; and the
+    # table-free form (PHOC computed from the word strings inside the forward) must give the very
+    # same numbers as the table lookup.
+    from oracle import phoc_oracle
+    from ruart_b200.Utils.phoc import build_phoc_embedding
+    words = synth.make_vocab_words(1033)
+    table = build_phoc_embedding(words, 604)
+    assert np.array_equal(table, phoc_oracle.vocab_table(words, use_ref=False))
+    g = load_golden("tiny_ragged_phoc")
+    for mode, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        net, opt = build_ours("tiny", device="cuda", phoc_table=table, BERT_precision=mode, KEEP_LOGITS=True)
+        batch = synth.add_phoc(synth.make_batch("tiny", ragged=True))
+        probs, logits, _ = run_ours(net, batch)
+        assert rel_err(logits, g["logits"]) < tol
+        assert synth.select_answers(probs, batch[1]["num_cnt"]) == g["picks"].tolist()
+        live = synth.add_phoc(synth.make_batch("tiny", ragged=True), vocab_words=words)
+        for d in live[1:]:
+            del d["phoc"]          # no ids, no table: strings only
+        probs2, logits2, _ = run_ours(net, live)
+        assert torch.equal(logits2, logits) and torch.equal(probs2, probs)
+
+
+def test_phoc_channel_reports_unknown_unigram_like_cphoc():
+    words = synth.make_vocab_words(1033)
+    net, opt = build_ours("tiny", device="cuda", phoc_table=np.zeros((synth.VOCAB_SIZE, 604), np.float32))
+    live = synth.add_phoc(synth.make_batch("tiny"), vocab_words=words)
+    live[1]["phoc_chars"][1] = ord("#")   # a raw, un-normalised string reaches the kernel
+    with pytest.raises(RuntimeError, match="unigram # is unknown"):
+        run_ours(net, live)

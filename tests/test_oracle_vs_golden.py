@@ -38,6 +38,22 @@ def test_oracle_reproduces_reference(name):
     assert rel_err(inter["q_final"][:, :8, :16], g["ques_self_attn"]) < 1e-4
 
 
+def test_oracle_phoc_channel_reproduces_reference():
+    # opt PHOC + 'phoc' in ocr_embedding (SDNet.py:51-55,441-446); the golden's table came from the
+    # reference's own cphoc, here it comes from the C restatement
+    from oracle import phoc_oracle
+    g = load_golden("tiny_ragged_phoc")
+    table = phoc_oracle.vocab_table(synth.make_vocab_words(1033), use_ref=False)
+    assert table.shape == (synth.VOCAB_SIZE, 604) and table[0].sum() > 0   # <PAD> row = PHOC("pad")
+    net, opt = build_ours("tiny", phoc_table=table)
+    assert list(net.state_dict())[:3] == ["alphaBERT", "gammaBERT", "phoc_embed.weight"]
+    assert net.multi2one.rnns[0].weight_ih_l0.shape == (1200, 1992)
+    batch = synth.add_phoc(synth.make_batch("tiny", ragged=True))
+    probs, logits, _ = sdnet_oracle.sdnet_forward(net.state_dict(), opt, *batch)
+    assert rel_err(logits, g["logits"]) < 2e-5
+    assert synth.select_answers(probs, batch[1]["num_cnt"]) == g["picks"].tolist()
+
+
 def test_answer_selection_rule():
     # SDNetTrainer.py:402-412: skip the <OCR> end slot, stop at no-answer, accept idx < num_cnt
     p = torch.tensor([[0.1, 0.5, 0.3, 0.0, 0.1], [0.1, 0.2, 0.6, 0.0, 0.1], [0.0, 0.1, 0.2, 0.0, 0.7]])
