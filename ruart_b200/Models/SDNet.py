@@ -12,18 +12,18 @@ How it differs from the reference's forward (same results, different schedule):
     layer sum (Bert.py:149-165, SDNet.py:573-583) are accumulated layer by layer straight into
     the [word300 | bert768 | pos12 | ent8 | prealign300] concat buffers;
   * the host loops of SDNet.py:300-318 and :498-550 become index tensors built once per batch
-    with numpy from `num_cnt` / `len_cnt`, consumed by gather kernels;
+    with numpy from `num_cnt` / `len_cnt` (ruart_b200/host_index.py; optionally already in the
+    collate function, Utils/collate.py), consumed by gather kernels;
   * `multi2one` only runs the real word steps (the LSTM is causal and only step len-1 is read,
     SDNet.py:304,310) and scatters straight into the slot tensors;
   * the NaN asserts (Layers.py:169,290,430,462,467) are one device flag checked once per forward.
 """
 import logging
 
-import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import host_index, ops
 from .. import sdnet_ops as K
 from .._lib import current_stream, ptr
 from ..ops import call
@@ -179,34 +179,8 @@ class SDNet(nn.Module):
         self._warm_version = None
         log.debug('Network build successes')
 
-    # ------------------------------------------------------------------ host-side index building
-    @staticmethod
-    def _item_index(num_cnt, len_cnt, W, M):
-        """numpy indices replacing the loops of SDNet.py:300-318 and :498-550 for one item list."""
-        B = len(num_cnt)
-        num = np.asarray(num_cnt, dtype=np.int64)
-        lens = np.fromiter((l for img in len_cnt for l in img), dtype=np.int64, count=int(num.sum()))
-        if lens.size and lens.min() < 1:
-            raise ValueError("every item must have at least one word (len_cnt >= 1)")
-        if int(num.max()) > M:
-            raise ValueError("num_cnt exceeds the slot count of `position`")
-        n_items = lens.size
-        item_img = np.repeat(np.arange(B, dtype=np.int64), num)
-        first_item = np.cumsum(num) - num
-        item_slot = np.arange(n_items, dtype=np.int64) - first_item[item_img]
-        word_off = np.cumsum(lens) - lens                      # first word of each item, global
-        img_words = np.add.reduceat(lens, first_item) if n_items else np.zeros(B, np.int64)
-        img_first_word = word_off[first_item]
-        t0_item = word_off - img_first_word[item_img]          # word offset of the item inside its image
-        T_max = int(img_words.max())
-        total = int(lens.sum())
-        item_of_word = np.repeat(np.arange(n_items, dtype=np.int64), lens)
-        w = np.arange(total, dtype=np.int64) - np.repeat(word_off, lens)
-        word_src = item_of_word * W + w                        # row in the [items*W] word layout
-        word_dst = item_img[item_of_word] * T_max + t0_item[item_of_word] + w   # row in [B*T_max]
-        mask = (np.arange(M)[None, :] < num[:, None]).astype(np.uint8)
-        return dict(B=B, n_items=n_items, lens=lens, item_img=item_img, item_slot=item_slot, T_max=T_max,
-                    word_src=word_src, word_dst=word_dst, mask=mask, total_words=total)
+    # host-side index building lives in ruart_b200/host_index.py (shared with Utils/collate.py)
+    _item_index = staticmethod(host_index.item_index)
 
     def _phoc_channel(self, lst, dst, n_rows, errs):
         """PHOC columns of one item list (SDNet.py:441-446).  With `lst['phoc']` word ids: the
@@ -262,10 +236,12 @@ class SDNet(nn.Module):
         self._phase('start')
         # token-length bookkeeping of the BERT pass starts on a side stream; its one host sync is
         # taken after the embedding gathers below have been queued
+        def word_offsets(lst):  # the reference's nested list, or its CSR form from Utils.collate
+            return lst['bert_offsets_csr'] if 'bert_offsets_csr' in lst else lst['bert_offsets']
+
         bert_segments = [
-            (q_list['bert'], q_list['bert_mask'], q_list['bert_offsets'], q_list['glove_mask']),
-            (ocr_list['bert'], ocr_list['bert_mask'], ocr_list['bert_offsets'], ocr_list['fasttext_mask']),
-            (od_list['bert'], od_list['bert_mask'], od_list['bert_offsets'], od_list['fasttext_mask'])]
+            (lst['bert'], lst['bert_mask'], word_offsets(lst), lst[wmask])
+            for lst, wmask in ((q_list, 'glove_mask'), (ocr_list, 'fasttext_mask'), (od_list, 'fasttext_mask'))]
         pack_handle = self.Bert.pack_begin(bert_segments)
         # ---- embeddings: [(phoc |) word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) ----
         q_in = torch.zeros((B, Wq, QD), **f32)
@@ -305,27 +281,17 @@ class SDNet(nn.Module):
 
         self._phase('bert')
         # ---- host indices (one upload) -------------------------------------------------------
-        io = self._item_index(ocr_list['num_cnt'], ocr_list['len_cnt'], Wo, M)
-        id_ = self._item_index(od_list['num_cnt'], od_list['len_cnt'], Wd, M_od)
-        if io['n_items'] != N_ocr or id_['n_items'] != N_od:
-            raise ValueError("num_cnt does not match the number of item rows")
-        # multi2one over OCR and OD items together (shared weights, SDNet.py:270-271)
-        lens_all = np.concatenate([io['lens'], id_['lens']])
-        base_all = np.concatenate([np.arange(N_ocr, dtype=np.int64) * Wo,
-                                   N_ocr * Wo + np.arange(N_od, dtype=np.int64) * Wd])
-        slot_all = np.concatenate([io['item_img'] * M + io['item_slot'],
-                                   B * M + id_['item_img'] * M_od + id_['item_slot']])
-        perm = np.argsort(-lens_all, kind='stable')
-        max_len = int(lens_all.max())
-        n_t = [(lens_all > t).sum() for t in range(max_len)]
-        a_rows = np.concatenate([base_all[perm[:n]] + t for t, n in enumerate(n_t)])
-        i32 = np.concatenate([io['word_src'], io['word_dst'], id_['word_src'], id_['word_dst'], a_rows,
-                              lens_all[perm] - 1]).astype(np.int32)
-        i32_d = K.upload(i32, dev)
-        i64_d = K.upload((slot_all[perm] * self.multi2one_output_size).astype(np.int64), dev)
-        masks_d = K.upload(np.concatenate([io['mask'].reshape(-1), id_['mask'].reshape(-1)]), dev)
-        cuts = np.cumsum([0, io['total_words'], io['total_words'], id_['total_words'], id_['total_words'],
-                          a_rows.size, lens_all.size])
+        plan = ocr_list.get('ruart_plan')   # precomputed by Utils.collate.attach_index_tensors, else here
+        if plan is None:
+            plan = host_index.forward_plan(ocr_list['num_cnt'], ocr_list['len_cnt'], od_list['num_cnt'],
+                                           od_list['len_cnt'], Wo, Wd, M, M_od)
+        if plan['key'] != (B, N_ocr, N_od, Wo, Wd, M, M_od):
+            raise ValueError("num_cnt / len_cnt do not match the item rows of this batch")
+        n_t, n_step_rows, n_all = plan['n_t'], plan['n_step_rows'], plan['n_items']
+        i32_d = K.upload(plan['i32'], dev)
+        i64_d = K.upload(plan['slots'] * self.multi2one_output_size, dev)
+        masks_d = K.upload(plan['masks'], dev)
+        cuts = plan['cuts']
         ocr_wsrc, ocr_wdst, od_wsrc, od_wdst, a_rows_d, last_d = [i32_d[cuts[i]:cuts[i + 1]] for i in range(6)]
         ocr_mask = masks_d[:B * M].view(B, M)
         od_mask = masks_d[B * M:].view(B, M_od)
@@ -335,13 +301,13 @@ class SDNet(nn.Module):
         # ---- word-level pre-alignment (SDNet.py:495-551) --------------------------------------
         c_pre = PX + VD + BD + pos_dim + ent_dim
         p2_cache = {}
-        for idx, word, wsrc, wdst, buf in ((io, ocr_word, ocr_wsrc, ocr_wdst, ocr_in),
-                                           (id_, od_word, od_wsrc, od_wdst, od_in)):
-            T_max = idx['T_max']
+        for k, word, wsrc, wdst, buf in ((0, ocr_word, ocr_wsrc, ocr_wdst, ocr_in),
+                                         (1, od_word, od_wsrc, od_wdst, od_in)):
+            T_max, n_words = plan['T_max'][k], plan['total_words'][k]
             packed = torch.zeros((B, T_max, VD), **f32)
-            K.gather_rows(word, wsrc, packed, wdst, idx['total_words'], VD)
+            K.gather_rows(word, wsrc, packed, wdst, n_words, VD)
             att = self.pre_align(packed, q_word, q_mask, p2_cache=p2_cache)
-            K.gather_rows(att, wdst, buf[..., c_pre:], wsrc, idx['total_words'], VD)
+            K.gather_rows(att, wdst, buf[..., c_pre:], wsrc, n_words, VD)
 
         self._phase('prealign')
         # ---- multi2one: real word steps only, last step -> slot (SDNet.py:270-271,300-318) ----
@@ -350,13 +316,12 @@ class SDNet(nn.Module):
         m2o = self.multi2one
         w_ih, w_hh, b_ih, b_hh = m2o._dir_params(0)
         mp = self.sdnet_parts
-        a_sp, Kp_in = K.split_act(items_in, mp, row_idx=a_rows_d, n_rows=int(a_rows.size))
+        a_sp, Kp_in = K.split_act(items_in, mp, row_idx=a_rows_d, n_rows=n_step_rows)
         wi, _ = K.prep_weight(m2o, (0, "w_ih"), w_ih, mp)
         wh, Kp_h = K.prep_weight(m2o, (0, "w_hh"), w_hh, mp)
         bias = K.prep_vector(m2o, (0, "bias"), lambda: b_ih[0] + b_hh[0], b_ih + b_hh)
-        gx = torch.empty((int(a_rows.size), 4 * HS), **f32)
-        K.linear(a_sp, Kp_in, wi, int(a_rows.size), 4 * HS, mp, gx, epi=ops.EPI_BIAS, bias=bias)
-        n_all = lens_all.size
+        gx = torch.empty((n_step_rows, 4 * HS), **f32)
+        K.linear(a_sp, Kp_in, wi, n_step_rows, 4 * HS, mp, gx, epi=ops.EPI_BIAS, bias=bias)
         c_state = torch.zeros((n_all, HS), **f32)
         h_split = torch.zeros((n_all, mp * Kp_h), dtype=torch.bfloat16, device=dev)
         gh = torch.empty((n_all, 4 * HS), **f32)

@@ -37,7 +37,16 @@ class Segment(object):
 
 
 def flatten_offsets(offsets, n_rows):
-    """list[N][n_words][2] -> int32 [4, n_words_total] rows (item, j, st, ed)."""
+    """list[N][n_words][2] -> int32 [4, n_words_total] rows (item, j, st, ed).  An int32 [4, n] array
+    (or CPU tensor) — the CSR form Utils.collate.attach_index_tensors precomputes — passes through."""
+    if torch.is_tensor(offsets):
+        offsets = offsets.numpy()
+    if isinstance(offsets, np.ndarray):
+        if offsets.ndim != 2 or offsets.shape[0] != 4 or offsets.dtype != np.int32:
+            raise ValueError("precomputed word offsets must be int32 [4, n_words]")
+        if offsets.shape[1] and not (0 <= int(offsets[0].min()) and int(offsets[0].max()) < n_rows):
+            raise ValueError("precomputed word offsets name rows outside the batch")
+        return np.ascontiguousarray(offsets)
     try:
         counts = np.fromiter(map(len, offsets), dtype=np.int64, count=n_rows)
         total = int(counts.sum())

@@ -10,6 +10,14 @@
 // memory, transposed ([k][row], conflict-free).  h_{t-1} of the BT sequences sits in shared memory
 // and is read as broadcast float4.  The four gates of a unit are in adjacent lanes and meet through
 // warp shuffles; the g == 0 lane keeps c in registers and publishes h.
+//
+// lstm_recurrence2_kernel (used whenever BT <= 4 fits one wave) register-blocks two gate rows per
+// thread: 256 threads, thread = (unit j, half); half 0 owns gates (i, g), half 1 owns (f, o).  Every
+// broadcast h load now feeds four FFMA2 instead of two, and 88 weights of each row sit in
+// registers, so the shared-memory loads per FMA halve: 3.75 -> 2.61 us per time step at B = 256,
+// H = 125 (profiles/r01_lstm_microbench.txt).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ruart_b200.h"
 
@@ -23,8 +31,12 @@ constexpr int HP = 128;    // padded hidden size (h rows in smem, zero padded)
 constexpr int ROWP = 512;  // padded gate-row count (threads)
 constexpr int NQ = (HP - KR) / 4;  // float4 weight quads per row kept in smem
 
+// Packed fp32x2 FMA (Blackwell FFMA2): d.x = a.x*b.x + c.x, d.y = a.y*b.y + c.y.  Measured on B200
+// (profiles/r01_lstm_microbench.txt): FFMA2 issues every 3.7 clk per sub-partition (69 FMA/clk/SM)
+// and scalar FFMA every 1.0 clk (128 FMA/clk/SM), yet this kernel is faster with FFMA2 (261 vs
+// 290 us for 100 steps): with two warps per scheduler it is bound by issue slots and by the
+// LDS.128 broadcasts of h, not by the FMA pipe, and FFMA2 halves the issued instructions.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  // packed fp32x2 FMA (Blackwell FFMA2): d.x = a.x*b.x + c.x, d.y = a.y*b.y + c.y
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;"
       : "=l"(d)
@@ -150,6 +162,153 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Two gate rows per thread (see the header).  KR2 weights of each row in registers, the remaining
+// HP-KR2 columns as float4 quads in shared memory: s_w[(q*2 + r) * 256 + t].
+constexpr int LSTM2_THREADS = 256;
+template <int BT, int KR2>
+__global__ void __launch_bounds__(LSTM2_THREADS, 1)
+lstm_recurrence2_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*L, ndir*4H]
+                        const float* __restrict__ w_hh,                    // [ndir][4H][H]
+                        float* __restrict__ out, long long out_pitch,      // [B*L, >= ndir*H]
+                        int B, int L, int H) {
+  constexpr int NQ2 = (HP - KR2) / 4;
+  extern __shared__ __align__(16) float smem[];
+  float4* s_w = reinterpret_cast<float4*>(smem);        // [NQ2][2][256] quads
+  float* s_h = smem + NQ2 * 2 * LSTM2_THREADS * 4;      // [2][BT][HP]
+  const int t = threadIdx.x;
+  const int dir = blockIdx.y;
+  const int b0 = blockIdx.x * BT;
+  const int rows = 4 * H;
+  const int j = t >> 1, half = t & 1;
+  const bool active = j < H;
+  // torch gate order i, f, g, o: half 0 -> (i, g), half 1 -> (f, o)
+  const int wrow0 = half * H + j;          // i or f
+  const int wrow1 = (2 + half) * H + j;    // g or o
+  const float* W = w_hh + static_cast<long long>(dir) * rows * H;
+  const float* wr0 = W + static_cast<long long>(wrow0) * H;
+  const float* wr1 = W + static_cast<long long>(wrow1) * H;
+
+  float2 w0[KR2 / 2], w1[KR2 / 2];
+#pragma unroll
+  for (int k = 0; k < KR2; k += 2) {
+    w0[k / 2].x = (active && k < H) ? wr0[k] : 0.f;
+    w0[k / 2].y = (active && k + 1 < H) ? wr0[k + 1] : 0.f;
+    w1[k / 2].x = (active && k < H) ? wr1[k] : 0.f;
+    w1[k / 2].y = (active && k + 1 < H) ? wr1[k + 1] : 0.f;
+  }
+  for (int q = 0; q < NQ2; ++q) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c4 = a;
+    const int k = KR2 + 4 * q;
+    if (active) {
+      if (k < H) { a.x = wr0[k]; c4.x = wr1[k]; }
+      if (k + 1 < H) { a.y = wr0[k + 1]; c4.y = wr1[k + 1]; }
+      if (k + 2 < H) { a.z = wr0[k + 2]; c4.z = wr1[k + 2]; }
+      if (k + 3 < H) { a.w = wr0[k + 3]; c4.w = wr1[k + 3]; }
+    }
+    s_w[(q * 2 + 0) * LSTM2_THREADS + t] = a;
+    s_w[(q * 2 + 1) * LSTM2_THREADS + t] = c4;
+  }
+  for (int i = t; i < 2 * BT * HP; i += LSTM2_THREADS) s_h[i] = 0.f;
+  __syncthreads();
+  const int nq = (H > KR2) ? (H - KR2 + 3) / 4 : 0;
+
+  float c[BT], nx0[BT], nx1[BT];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) c[b] = 0.f;
+  const long long xc0 = static_cast<long long>(dir) * rows + wrow0;
+  const long long xc1 = static_cast<long long>(dir) * rows + wrow1;
+  auto step_time = [&](int s) { return dir == 0 ? s : (L - 1 - s); };
+  auto fetch = [&](int s) {
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      const int bb = b0 + b;
+      const bool ok = active && bb < B;
+      const float* row = xg + (static_cast<long long>(bb) * L + step_time(s)) * xg_pitch;
+      nx0[b] = ok ? __ldg(row + xc0) : 0.f;
+      nx1[b] = ok ? __ldg(row + xc1) : 0.f;
+    }
+  };
+  fetch(0);
+  int cur = 0;
+  for (int s = 0; s < L; ++s) {
+    float2 a0[BT], a1[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      a0[b] = make_float2(nx0[b], 0.f);
+      a1[b] = make_float2(nx1[b], 0.f);
+    }
+    if (s + 1 < L) fetch(s + 1);
+    const float* hc = s_h + cur * BT * HP;
+#pragma unroll
+    for (int k4 = 0; k4 < KR2 / 4; ++k4) {
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 hv = *reinterpret_cast<const float4*>(hc + b * HP + 4 * k4);
+        const float2 hlo = make_float2(hv.x, hv.y), hhi = make_float2(hv.z, hv.w);
+        a0[b] = ffma2(w0[2 * k4], hlo, a0[b]);
+        a1[b] = ffma2(w1[2 * k4], hlo, a1[b]);
+        a0[b] = ffma2(w0[2 * k4 + 1], hhi, a0[b]);
+        a1[b] = ffma2(w1[2 * k4 + 1], hhi, a1[b]);
+      }
+    }
+    for (int q = 0; q < nq; ++q) {
+      const float4 wa = s_w[(q * 2 + 0) * LSTM2_THREADS + t];
+      const float4 wb = s_w[(q * 2 + 1) * LSTM2_THREADS + t];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 hv = *reinterpret_cast<const float4*>(hc + b * HP + KR2 + 4 * q);
+        const float2 hlo = make_float2(hv.x, hv.y), hhi = make_float2(hv.z, hv.w);
+        a0[b] = ffma2(make_float2(wa.x, wa.y), hlo, a0[b]);
+        a1[b] = ffma2(make_float2(wb.x, wb.y), hlo, a1[b]);
+        a0[b] = ffma2(make_float2(wa.z, wa.w), hhi, a0[b]);
+        a1[b] = ffma2(make_float2(wb.z, wb.w), hhi, a1[b]);
+      }
+    }
+    float* hn = s_h + (cur ^ 1) * BT * HP;
+    const int tt = step_time(s);
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      // half 0: s(i) * tanh(g) ; half 1: s(f), s(o).  tanh(x) = 2 s(2x) - 1 on the MUFU ex2/rcp path
+      const float p0 = a0[b].x + a0[b].y;
+      const float p1 = a1[b].x + a1[b].y;
+      const float g0 = logistic(p0);
+      const float s1 = logistic(half ? p1 : 2.0f * p1);
+      const float g1 = half ? s1 : fmaf(2.0f, s1, -1.0f);
+      const float ig = __shfl_xor_sync(0xffffffffu, g0 * g1, 1);  // half 1 receives i*g
+      if (half && active) {
+        const float cn = fmaf(g0, c[b], ig);
+        const float hv = g1 * fmaf(2.0f, logistic(2.0f * cn), -1.0f);
+        c[b] = cn;
+        hn[b * HP + j] = hv;
+        const int bb = b0 + b;
+        if (bb < B) out[(static_cast<long long>(bb) * L + tt) * out_pitch + dir * H + j] = hv;
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+template <int BT, int KR2>
+int launch2(const float* xg, long long xg_pitch, const float* w_hh, float* out, long long out_pitch,
+            int B, int L, int H, int ndir, cudaStream_t st) {
+  constexpr int NQ2 = (HP - KR2) / 4;
+  const size_t smem = (static_cast<size_t>(NQ2) * 2 * LSTM2_THREADS * 4 + 2 * BT * HP) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(lstm_recurrence2_kernel<BT, KR2>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid((B + BT - 1) / BT, ndir);
+  lstm_recurrence2_kernel<BT, KR2><<<grid, LSTM2_THREADS, smem, st>>>(xg, xg_pitch, w_hh, out, out_pitch,
+                                                                 B, L, H);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
 template <int BT>
 int launch(const float* xg, long long xg_pitch, const float* w_hh, float* out, long long out_pitch,
            int B, int L, int H, int ndir, cudaStream_t st) {
@@ -176,7 +335,12 @@ extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const 
   cudaStream_t st = (cudaStream_t)stream;
   // fewest sequences per CTA that still fits one wave of CTAs on the device
   const int sms = ruart_num_sms();
-  if (((B + 1) / 2) * ndir <= sms) return launch<2>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
-  if (((B + 3) / 4) * ndir <= sms) return launch<4>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+  static const bool one_row = getenv("RUART_LSTM_ONE_ROW") != nullptr;  // A/B aid: the 512-thread kernel
+  if (one_row) {
+    if (((B + 1) / 2) * ndir <= sms) return launch<2>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+    if (((B + 3) / 4) * ndir <= sms) return launch<4>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+  }
+  if (((B + 1) / 2) * ndir <= sms) return launch2<2, 88>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+  if (((B + 3) / 4) * ndir <= sms) return launch2<4, 88>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
   return launch<8>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
 }

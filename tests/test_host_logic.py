@@ -80,3 +80,31 @@ def test_unsupported_options_are_rejected_loudly():
     opt["position_mod"] = "cat"
     with pytest.raises(NotImplementedError):
         SDNet(opt, synth.make_embedding())
+
+
+def test_collate_index_tensors_equal_the_per_forward_ones():
+    # the collate-side CSR / plan are what the forward would build itself
+    from ruart_b200 import host_index
+    from ruart_b200.Utils import collate
+    q, ocr, od = synth.make_batch("small", ragged=True)
+    keys = [set(d) for d in (q, ocr, od)]
+    q2, ocr2, od2 = collate.attach_index_tensors(q, ocr, od)
+    for d, k in zip((q2, ocr2, od2), keys):
+        assert k <= set(d)                                   # every original key is kept
+        csr = d[collate.CSR_KEY]
+        assert csr.dtype == np.int32 and np.array_equal(csr, flatten_offsets(d["bert_offsets"], len(d["bert_offsets"])))
+        assert flatten_offsets(csr, len(d["bert_offsets"])) is not None   # the array form passes through
+    plan = ocr2[collate.PLAN_KEY]
+    want = host_index.forward_plan(ocr["num_cnt"], ocr["len_cnt"], od["num_cnt"], od["len_cnt"], 20, 10, 100, 30)
+    assert plan["key"] == want["key"] == (8, sum(ocr["num_cnt"]), sum(od["num_cnt"]), 20, 10, 100, 30)
+    for k in ("i32", "slots", "masks"):
+        assert np.array_equal(plan[k], want[k])
+    # multi2one schedule: step t holds the items with more than t words, longest first
+    lens = np.array([l for img in ocr["len_cnt"] for l in img] + [l for img in od["len_cnt"] for l in img])
+    assert plan["n_t"] == [int((lens > t).sum()) for t in range(lens.max())]
+    assert plan["n_step_rows"] == int(lens.sum()) and plan["n_items"] == lens.size
+    last = plan["i32"][plan["cuts"][5]:plan["cuts"][6]]
+    assert np.array_equal(np.sort(last)[::-1], last) and np.array_equal(np.sort(last), np.sort(lens - 1))
+    import pytest
+    with pytest.raises(ValueError):
+        flatten_offsets(np.zeros((3, 5), np.int32), 4)

@@ -247,3 +247,19 @@ def test_phoc_channel_reports_unknown_unigram_like_cphoc():
     live[1]["phoc_chars"][1] = ord("#")   # a raw, un-normalised string reaches the kernel
     with pytest.raises(RuntimeError, match="unigram # is unknown"):
         run_ours(net, live)
+
+
+def test_collate_side_index_tensors_give_identical_forward():
+    # CSR word offsets + the forward plan precomputed by Utils.collate, batch staged in
+    # pinned memory -> bit-identical scores to the list-driven forward
+    from ruart_b200.Utils import collate
+    net, opt = build_ours("small", seed=77, device="cuda", KEEP_LOGITS=True)
+    batch = synth.make_batch("small", ragged=True)
+    probs, logits, _ = run_ours(net, batch)
+    pre = collate.to_cuda(collate.pin(collate.attach_index_tensors(*copy.deepcopy(batch))))
+    for d in pre:
+        del d["bert_offsets"]                     # only the CSR form is left
+    with torch.no_grad():
+        probs2, _ = net(*pre)
+    torch.cuda.synchronize()
+    assert torch.equal(probs2.cpu(), probs) and torch.equal(net.get_answer.last_logits.cpu(), logits)

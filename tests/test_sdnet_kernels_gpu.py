@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("B,L,I,H,bidir", [(5, 7, 40, 125, True), (1, 1, 300, 125, True), (33, 20, 64, 128, True),
-                                           (9, 13, 50, 64, False), (130, 3, 16, 17, True), (4, 6, 30, 300, False)])
+                                           (9, 13, 50, 64, False), (130, 3, 16, 17, True), (4, 6, 30, 300, False),
+                                           (256, 9, 32, 125, True), (200, 5, 24, 89, False), (600, 3, 16, 125, True)])
 def test_stacked_brnn_layer_matches_oracle(B, L, I, H, bidir):
     from ruart_b200.Models import Layers
     Layers.set_dropout_prob(0.0)

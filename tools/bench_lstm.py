@@ -1,0 +1,40 @@
+"""Time the persistent BiLSTM recurrence kernel on the shapes of the SDNet stack (GPU).
+
+    python tools/bench_lstm.py            # B=256, H=125: L=100 (OCR), 37 (OD), 40 (question)
+"""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from ruart_b200._lib import current_stream, ptr  # noqa: E402
+from ruart_b200.ops import call  # noqa: E402
+
+
+def main():
+    dev = "cuda"
+    H, B = 125, 256
+    res = []
+    for L in (100, 37, 40):
+        xg = torch.randn(B * L, 8 * H, device=dev) * 0.5
+        w = (torch.rand(2, 4 * H, H, device=dev) * 2 - 1) / H ** 0.5
+        out = torch.empty(B * L, 2 * H, device=dev)
+        st = current_stream()
+        run = lambda: call("ruart_lstm_recurrence", ptr(xg), 8 * H, ptr(w), ptr(out), 2 * H, B, L, H, 2, st)
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        res.append({"B": B, "L": L, "H": H, "us": round(us, 1), "us_per_step": round(us / L, 3)})
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
