@@ -343,7 +343,7 @@ __device__ __forceinline__ int tile_off(int r, int c) { return r * 128 + ((c ^ (
 // 16-row MMA tile; the cross blocks of S are masked to -inf, which makes P block-diagonal and
 // O = P V exact for both.  A sequence of 9..16 tokens takes the tile alone.  One warp per
 // (sequence pair, head).
-__global__ void __launch_bounds__(SHORT_WARPS * 32)
+__global__ void __launch_bounds__(SHORT_WARPS * 32, 4)
 bert_attention_mma16_kernel(const __nv_bfloat16* __restrict__ qkv,
                             const int32_t* __restrict__ cu_seqlens, int n_seq, int n_heads,
                             float scale, __nv_bfloat16* __restrict__ out) {
@@ -496,6 +496,170 @@ bert_attention_mma16_kernel(const __nv_bfloat16* __restrict__ qkv,
       }
     }
    }
+  }
+}
+
+// Same tiles and math, but the Q/K/V slices of head h+1 are fetched with cp.async (LDGSTS, 16 bytes
+// per lane, zero-filled for rows without a token) into a second set of tiles while head h is being
+// computed: the kernel is bound by the DRAM round trip of each (pair, head) stage, not by bytes or
+// issue slots, so the prefetch hides one of the two phases.  2 x 6 KB of tiles per warp.
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(SHORT_WARPS * 32, 2)
+bert_attention_mma16_async_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                  const int32_t* __restrict__ cu_seqlens, int n_seq, int n_heads,
+                                  float scale, int h_split, __nv_bfloat16* __restrict__ out) {
+  constexpr int TB = 16 * 128;
+  extern __shared__ __align__(128) uint8_t sh_dyn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sbase = sh_dyn + static_cast<size_t>(warp) * 6 * TB;  // [2 stages][Q | K | V]
+  const uint32_t abase = smem_u32(sbase);
+  const int H = n_heads * 64;
+  const long long ld = 3LL * H;
+  const int g = lane >> 2, t = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int a_chk = lane >> 4;
+  const int b_row = lane & 7;
+  const int b_chk = lane >> 3;
+  const int n_pairs = (n_seq + 1) >> 1;
+  const int h_per = n_heads / h_split;
+  const int cch = lane & 7;
+  for (int task = blockIdx.x * SHORT_WARPS + warp; task < n_pairs * h_split; task += gridDim.x * SHORT_WARPS) {
+    const int pair = task / h_split;
+    const int h_lo = (task - pair * h_split) * h_per;
+    const int sA = 2 * pair, sB = sA + 1;
+    const int tA = cu_seqlens[sA];
+    const int tB = cu_seqlens[sA + 1];
+    const int lenA = tB - tA;
+    const int lenB = (sB < n_seq) ? cu_seqlens[sB + 1] - tB : 0;
+    const bool paired = lenA <= 8 && lenB <= 8;
+    const int n_pass = paired ? 1 : 2;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      int t0, l0, l1;  // rows 0.. : l0 tokens from t0 ; rows 8.. : l1 tokens from t0 + l0 (paired)
+      if (paired) {
+        t0 = tA; l0 = lenA; l1 = lenB;
+      } else {
+        t0 = pass == 0 ? tA : tB;
+        l0 = pass == 0 ? lenA : lenB;
+        l1 = 0;
+        if (l0 <= 0 || l0 > 16) continue;
+      }
+      if (l0 + l1 == 0) continue;
+      auto tok_of = [&](int r) {
+        if (paired) {
+          if (r < 8) return r < l0 ? r : -1;
+          return (r - 8 < l1) ? l0 + (r - 8) : -1;
+        }
+        return r < l0 ? r : -1;
+      };
+      auto issue = [&](int h, int stage) {
+        const uint32_t st_base = abase + stage * 3 * TB;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (lane >> 3) + 4 * i;
+          const int tok = tok_of(r);
+          const __nv_bfloat16* row = qkv + static_cast<long long>(t0 + (tok >= 0 ? tok : 0)) * ld + h * 64 + cch * 8;
+          const uint32_t off = st_base + tile_off(r, cch);
+          cp_async16_zfill(off, row, tok >= 0);
+          cp_async16_zfill(off + TB, row + H, tok >= 0);
+          cp_async16_zfill(off + 2 * TB, row + 2 * H, tok >= 0);
+        }
+        cp_async_commit();
+      };
+      const bool two = paired ? (l1 > 0) : (l0 > 8);
+      const int k0 = 2 * t, k1 = 2 * t + 1;
+      bool vA0, vA1, vA2, vA3, vB0, vB1, vB2, vB3;
+      if (paired) {
+        vA0 = k0 < l0; vA1 = k1 < l0; vA2 = false; vA3 = false;
+        vB0 = false; vB1 = false; vB2 = k0 < l1; vB3 = k1 < l1;
+      } else {
+        vA0 = vB0 = k0 < l0; vA1 = vB1 = k1 < l0;
+        vA2 = vB2 = 8 + k0 < l0; vA3 = vB3 = 8 + k1 < l0;
+      }
+      __syncwarp();  // the previous task's tiles are no longer read
+      issue(h_lo, 0);
+      int stage = 0;
+      for (int h = h_lo; h < h_lo + h_per; ++h, stage ^= 1) {
+        if (h + 1 < h_lo + h_per) {
+          issue(h + 1, stage ^ 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncwarp();
+        uint8_t* sQ = sbase + stage * 3 * TB;
+        const uint32_t aQ = abase + stage * 3 * TB, aK = aQ + TB, aV = aK + TB;
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t kb0[8], kb1[8];
+        ldsm_x4(aK + tile_off(b_row, b_chk), kb0[0], kb0[1], kb0[2], kb0[3]);
+        ldsm_x4(aK + tile_off(b_row, 4 + b_chk), kb0[4], kb0[5], kb0[6], kb0[7]);
+        if (two) {
+          ldsm_x4(aK + tile_off(8 + b_row, b_chk), kb1[0], kb1[1], kb1[2], kb1[3]);
+          ldsm_x4(aK + tile_off(8 + b_row, 4 + b_chk), kb1[4], kb1[5], kb1[6], kb1[7]);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t a0, a1, a2, a3;
+          ldsm_x4(aQ + tile_off(a_row, 2 * ks + a_chk), a0, a1, a2, a3);
+          mma_bf16_16816(s0, a0, a1, a2, a3, kb0[2 * ks], kb0[2 * ks + 1]);
+          if (two) mma_bf16_16816(s1, a0, a1, a2, a3, kb1[2 * ks], kb1[2 * ks + 1]);
+        }
+        const float xA0 = vA0 ? s0[0] * scale : -INFINITY, xA1 = vA1 ? s0[1] * scale : -INFINITY;
+        const float xA2 = vA2 ? s1[0] * scale : -INFINITY, xA3 = vA3 ? s1[1] * scale : -INFINITY;
+        const float xB0 = vB0 ? s0[2] * scale : -INFINITY, xB1 = vB1 ? s0[3] * scale : -INFINITY;
+        const float xB2 = vB2 ? s1[2] * scale : -INFINITY, xB3 = vB3 ? s1[3] * scale : -INFINITY;
+        float mA = fmaxf(fmaxf(xA0, xA1), fmaxf(xA2, xA3));
+        float mB = fmaxf(fmaxf(xB0, xB1), fmaxf(xB2, xB3));
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+        mA = (mA == -INFINITY) ? 0.f : mA;
+        mB = (mB == -INFINITY) ? 0.f : mB;
+        const float pA0 = __expf(xA0 - mA), pA1 = __expf(xA1 - mA), pA2 = __expf(xA2 - mA), pA3 = __expf(xA3 - mA);
+        const float pB0 = __expf(xB0 - mB), pB1 = __expf(xB1 - mB), pB2 = __expf(xB2 - mB), pB3 = __expf(xB3 - mB);
+        float lA = (pA0 + pA1) + (pA2 + pA3), lB = (pB0 + pB1) + (pB2 + pB3);
+        lA += __shfl_xor_sync(0xffffffffu, lA, 1);
+        lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+        lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+        lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+        const uint32_t p0 = pack_bf16x2(pA0, pA1), p1 = pack_bf16x2(pB0, pB1);
+        const uint32_t p2 = pack_bf16x2(pA2, pA3), p3 = pack_bf16x2(pB2, pB3);
+        const float iA = lA > 0.f ? 1.0f / lA : 0.f, iB = lB > 0.f ? 1.0f / lB : 0.f;
+        __syncwarp();  // all lanes are done reading sQ: it becomes the O staging tile
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(aV + tile_off(a_row, 2 * dp + a_chk), b0, b1, b2, b3);
+          float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(o0, p0, p1, p2, p3, b0, b1);
+          mma_bf16_16816(o1, p0, p1, p2, p3, b2, b3);
+          *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp) + 4 * t) = pack_bf16x2(o0[0] * iA, o0[1] * iA);
+          *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp) + 4 * t) = pack_bf16x2(o0[2] * iB, o0[3] * iB);
+          *reinterpret_cast<uint32_t*>(sQ + tile_off(g, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[0] * iA, o1[1] * iA);
+          *reinterpret_cast<uint32_t*>(sQ + tile_off(g + 8, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[2] * iB, o1[3] * iB);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (lane >> 3) + 4 * i;
+          const int tok = tok_of(r);
+          if (tok >= 0) {
+            const uint4 o4 = *reinterpret_cast<const uint4*>(sQ + tile_off(r, cch));
+            *(reinterpret_cast<uint4*>(out + (static_cast<long long>(t0 + tok)) * H + h * 64) + cch) = o4;
+          }
+        }
+        __syncwarp();  // the tiles of this stage are free for the prefetch issued next iteration
+      }
+    }
   }
 }
 
@@ -972,6 +1136,9 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_mma_kernel<64>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SHORT_WARPS * 3 * 64 * 128));
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_mma16_async_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SHORT_WARPS * 6 * 16 * 128));
     attr_set = true;
   }
   // bf16 in, plain bf16 out: sequences of <= 64 tokens run on the warp-level MMA kernels
@@ -986,8 +1153,18 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
       const long long pair_tasks = static_cast<long long>((n_seq + 1) / 2) * ((n_heads % 2 == 0) ? 2 : 1);
       long long ctas16 = (pair_tasks + SHORT_WARPS - 1) / SHORT_WARPS;
       if (ctas16 > cap) ctas16 = cap;
-      bert_attention_mma16_kernel<<<static_cast<unsigned>(ctas16), SHORT_WARPS * 32, 0, st>>>(
-          (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, (__nv_bfloat16*)out_bf16);
+      static const bool sync16 = getenv("RUART_ATTN16_SYNC") != nullptr;  // A/B aid: no cp.async prefetch
+      if (sync16)
+        bert_attention_mma16_kernel<<<static_cast<unsigned>(ctas16), SHORT_WARPS * 32, 0, st>>>(
+            (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, (__nv_bfloat16*)out_bf16);
+      else {
+        const int hs = (n_heads % 2 == 0) ? 2 : 1;  // two warps share a pair's heads (finer tasks)
+        long long c16 = (static_cast<long long>((n_seq + 1) / 2) * hs + SHORT_WARPS - 1) / SHORT_WARPS;
+        if (c16 > cap) c16 = cap;
+        bert_attention_mma16_async_kernel<<<static_cast<unsigned>(c16), SHORT_WARPS * 32,
+                                            SHORT_WARPS * 6 * 16 * 128, st>>>(
+            (const __nv_bfloat16*)qkv_bf16, cu_seqlens, n_seq, n_heads, scale, hs, (__nv_bfloat16*)out_bf16);
+      }
       RUART_LAUNCH_CHECK();
     }
     if (max_len <= 16) return RUART_OK;
