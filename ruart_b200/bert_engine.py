@@ -131,15 +131,6 @@ class BertEngine(object):
         self._key, self._w = key, W
         return W
 
-    _att_streams = {}
-
-    @classmethod
-    def _side_stream(cls, dev):
-        key = str(dev)
-        if key not in cls._att_streams:
-            cls._att_streams[key] = torch.cuda.Stream(device=dev)
-        return cls._att_streams[key]
-
     # ------------------------------------------------------------------ packing
     _pack_streams = {}
 
@@ -284,8 +275,8 @@ class BertEngine(object):
              ptr(W["type"]), ptr(W["eg"]), ptr(W["eb"]), W["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
         scale = 1.0 / 8.0
         # attention launches: adjacent segments of short sequences (<= 16 tokens: the paired-MMA
-        # kernel) are merged into one call; a segment of longer sequences (the questions) runs on a
-        # side stream next to them — the kernels touch disjoint sequences
+        # kernel) are merged into one call.  (Running the question segment on a side stream next to
+        # them was measured: no gain, its 192 KB CTAs and the item kernel's CTAs exclude each other.)
         att_groups = []
         for sgm in pk["segments"]:
             if sgm["seq1"] == sgm["seq0"]:
@@ -293,38 +284,16 @@ class BertEngine(object):
             short = sgm["max_len"] <= 16
             if att_groups and short and att_groups[-1][2] <= 16 and att_groups[-1][1] == sgm["seq0"]:
                 g = att_groups[-1]
-                att_groups[-1] = (g[0], sgm["seq1"], max(g[2], sgm["max_len"]), False)
+                att_groups[-1] = (g[0], sgm["seq1"], max(g[2], sgm["max_len"]))
             else:
-                att_groups.append((sgm["seq0"], sgm["seq1"], sgm["max_len"], False))
-        side = None
-        if not fp32 and len(att_groups) > 1:
-            longest = max(range(len(att_groups)), key=lambda i: att_groups[i][2])
-            if att_groups[longest][2] > 16:
-                g = att_groups[longest]
-                att_groups[longest] = (g[0], g[1], g[2], True)
-                att_groups.sort(key=lambda g: not g[3])   # queue the side-stream group first
-                side = self._side_stream(dev)
-        main = torch.cuda.current_stream(dev)
+                att_groups.append((sgm["seq0"], sgm["seq1"], sgm["max_len"]))
         for li, lw in enumerate(W["layers"]):
             q_f, q_b = self._gemm(h_b, lw["wqkv"], lw["bqkv"], 3 * H, H, ops.EPI_BIAS, "act")
             ctx = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)
-            if side is not None:
-                fork = torch.cuda.Event()
-                fork.record(main)
-                side.wait_event(fork)
-            for s0, s1, mlen, on_side in att_groups:
+            for s0, s1, mlen in att_groups:
                 cu = pk["cu_seqlens"][s0:s1 + 1]
-                if on_side:
-                    with torch.cuda.stream(side):
-                        call("ruart_bert_attention", ptr(q_f), ptr(q_b), ptr(cu), s1 - s0, self.heads, scale,
-                             mlen, None, ptr(ctx), parts, current_stream())
-                else:
-                    call("ruart_bert_attention", ptr(q_f), ptr(q_b), ptr(cu), s1 - s0, self.heads, scale,
-                         mlen, None, ptr(ctx), parts, st)
-            if side is not None:
-                join = torch.cuda.Event()
-                join.record(side)
-                main.wait_event(join)
+                call("ruart_bert_attention", ptr(q_f), ptr(q_b), ptr(cu), s1 - s0, self.heads, scale,
+                     mlen, None, ptr(ctx), parts, st)
             fuse_res = not keep32  # bf16 residual stream: the GEMM epilogue adds it
             a_f, a_b = self._gemm(ctx, lw["wo"], lw["bo"], H, H, ops.EPI_BIAS, "act",
                                   residual=h_b if fuse_res else None)

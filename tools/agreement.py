@@ -24,9 +24,9 @@ want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch
 t_cpu = time.perf_counter() - t0
 want_pick = synth.select_answers(want_p, batch[1]["num_cnt"])
 res = {"cfg": cfg, "questions": len(want_pick), "cpu_oracle_seconds": t_cpu, "weights": "reference-style random init, seed 1033"}
-for mode in ("bf16", "fp32"):
-    net.Bert.precision = mode
-    net.sdnet_parts = 3 if mode == "fp32" else 2
+for mode in ("bf16", "fp32", "bf16_sdnet1"):
+    net.Bert.precision = "fp32" if mode == "fp32" else "bf16"
+    net.sdnet_parts = {"bf16": 2, "fp32": 3, "bf16_sdnet1": 1}[mode]   # bf16_sdnet1: plain bf16 SDNet GEMM operands
     with torch.no_grad():
         probs, _ = net(*synth.batch_to(copy.deepcopy(batch), "cuda"))
     lg = net.get_answer.last_logits.cpu()
