@@ -698,37 +698,44 @@ bert_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
     const int n_qt = (len + 15) >> 4, n_kt = (len + 7) >> 3, n_kk = (len + 15) >> 4;
     const int rows_used = n_qt * 16;  // rows touched by the MMAs (pad rows zeroed)
     __syncwarp();
+    // all chunks of the three tiles are requested at once with cp.async (zero-filled past the last
+    // token): one DRAM round trip per task instead of one per 32-chunk loop iteration
     for (int idx = lane; idx < rows_used * 8; idx += 32) {
       const int r = idx >> 3, c = idx & 7;
-      uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
-      if (idx < n_chunks) {
-        const uint4* row = reinterpret_cast<const uint4*>(qkv + (static_cast<long long>(t0 + r)) * ld + h * 64);
-        q4 = __ldg(row + c);
-        k4 = __ldg(row + (H >> 3) + c);
-        v4 = __ldg(row + 2 * (H >> 3) + c);
-      }
-      const int off = tile_off(r, c);
-      *reinterpret_cast<uint4*>(sQ + off) = q4;
-      *reinterpret_cast<uint4*>(sK + off) = k4;
-      *reinterpret_cast<uint4*>(sV + off) = v4;
+      const bool valid = idx < n_chunks;
+      const __nv_bfloat16* row = qkv + (static_cast<long long>(t0 + (valid ? r : 0))) * ld + h * 64 + c * 8;
+      const uint32_t off = tile_off(r, c);
+      cp_async16_zfill(aQ + off, row, valid);
+      cp_async16_zfill(aK + off, row + H, valid);
+      cp_async16_zfill(aV + off, row + 2 * H, valid);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncwarp();
     for (int qt = 0; qt < n_qt; ++qt) {
       uint32_t qa[4][4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         ldsm_x4(aQ + tile_off(qt * 16 + a_row, 2 * ks + a_chk), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      // k-step outermost: the NKT accumulator chains are independent, so consecutive mma.sync
+      // never wait on each other (the in-order issue would otherwise stall ~30 clk per MMA)
       float s[NKT][4];
 #pragma unroll
-      for (int nt = 0; nt < NKT; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        if (nt < n_kt) {
-          uint32_t kb[8];
-          ldsm_x4(aK + tile_off(nt * 8 + b_row, b_chk), kb[0], kb[1], kb[2], kb[3]);
-          ldsm_x4(aK + tile_off(nt * 8 + b_row, 4 + b_chk), kb[4], kb[5], kb[6], kb[7]);
+      for (int nt = 0; nt < NKT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_bf16_16816(s[nt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], kb[2 * ks], kb[2 * ks + 1]);
+      for (int kh = 0; kh < 2; ++kh) {  // dims 0-31 / 32-63: one ldmatrix.x4 per key tile
+        uint32_t kb[NKT][4];
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt)
+          if (nt < n_kt)
+            ldsm_x4(aK + tile_off(nt * 8 + b_row, 4 * kh + b_chk), kb[nt][0], kb[nt][1], kb[nt][2], kb[nt][3]);
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int ks = 2 * kh + k2;
+#pragma unroll
+          for (int nt = 0; nt < NKT; ++nt)
+            if (nt < n_kt)
+              mma_bf16_16816(s[nt], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], kb[nt][2 * k2], kb[nt][2 * k2 + 1]);
         }
       }
       // masked softmax: rows g (regs 0,1) and g+8 (regs 2,3); keys nt*8 + 2t, +1
@@ -772,23 +779,26 @@ bert_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
         pa[kk][3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
       }
       __syncwarp();  // Q fragments of this query tile are in registers: its rows become O staging
+      float o[8][4];  // eight 8-wide dim tiles: independent accumulator chains, key step outermost
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < NQT; ++kk) {
-          if (kk < n_kk) {
+      for (int kk = 0; kk < NQT; ++kk) {
+        if (kk < n_kk) {
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
             uint32_t b0, b1, b2, b3;
             ldsm_x4_t(aV + tile_off(kk * 16 + a_row, 2 * dp + a_chk), b0, b1, b2, b3);
-            mma_bf16_16816(o0, pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
-            mma_bf16_16816(o1, pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b2, b3);
+            mma_bf16_16816(o[2 * dp], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
+            mma_bf16_16816(o[2 * dp + 1], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b2, b3);
           }
         }
-        const int rA = qt * 16 + g, rB = rA + 8;
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(rA, 2 * dp) + 4 * t) = pack_bf16x2(o0[0] * iA, o0[1] * iA);
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(rB, 2 * dp) + 4 * t) = pack_bf16x2(o0[2] * iB, o0[3] * iB);
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(rA, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[0] * iA, o1[1] * iA);
-        *reinterpret_cast<uint32_t*>(sQ + tile_off(rB, 2 * dp + 1) + 4 * t) = pack_bf16x2(o1[2] * iB, o1[3] * iB);
+      }
+      const int rA = qt * 16 + g, rB = rA + 8;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(rA, d) + 4 * t) = pack_bf16x2(o[d][0] * iA, o[d][1] * iA);
+        *reinterpret_cast<uint32_t*>(sQ + tile_off(rB, d) + 4 * t) = pack_bf16x2(o[d][2] * iB, o[d][3] * iB);
       }
     }
     __syncwarp();
