@@ -71,6 +71,8 @@ RUART_API int ruart_phoc_batch_host(const char* chars_host, const int32_t* offse
  * n_terms: 1 (plain bf16), 3 (two-part split, ~2^-16 rel) or 6 (three-part split, ~fp32).
  * Outputs: fp32 (out_f32, ldo_f32) and/or bf16 (out_bf16, ldo_bf16); the bf16 output may itself
  * be written as out_parts split parts, part p at column offset p*out_part_stride.
+ * fast_gelu (RUART_EPI_BIAS_GELU): 0 = erff(); 1 = erf by Abramowitz-Stegun 7.1.26 on MUFU rcp/ex2
+ * (|gelu error| < 1e-5); 2 = erf matched by a fitted tanh form on one MUFU.TANH (< 4e-5).
  * residual_bf16 (optional, plain-bf16-output mode with N % 64 == 0): a [M, N] bf16 matrix added in
  * fp32 before the output is rounded (dense(x) + input_tensor, modeling.py:263,302).
  * Replaces nn.Linear at modeling.py:225-227,261,287,300 and Layers.py:226-227,166 (W_ih).    */

@@ -290,6 +290,24 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-ax, r, fmaxf(x, 0.0f));
 }
 
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf-GELU through ONE MUFU op: Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is matched by
+// 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with the coefficients fitted to the erf form (not the
+// usual "tanh GELU" constants): max |gelu error| 2.5e-5 over all x before the MUFU.TANH rounding
+// (<= 2^-11 relative).  6 FMA-pipe + 2 ALU + 1 MUFU instructions; used for bf16 outputs only.
+__device__ __forceinline__ float gelu_erf_tanhfit(float x) {
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);  // the quartic turns over beyond |x| ~ 11
+  const float x2 = xc * xc;
+  const float u = xc * fmaf(fmaf(-0.00035151681f, x2, 0.0370056462f), x2, 0.797507884f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(u), hx);
+}
+
 }  // namespace ruart
 
 #endif  // __CUDACC__

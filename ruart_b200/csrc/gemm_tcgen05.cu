@@ -14,6 +14,8 @@
 // up to three bf16 parts X = X0 + X1 + X2 laid side by side ([rows, nparts*Kp]); the K loop then
 // walks a list of (part_a, part_b) terms (1 term: plain bf16; 3 terms: ~2^-16; 6 terms: ~2^-24).
 #include <cuda.h>
+
+#include <cstdlib>
 #include "common.cuh"
 #include "ruart_b200.h"
 
@@ -37,9 +39,20 @@ constexpr int GEMM_SMEM_BYTES = OFF_BAR + BAR_BYTES;
 constexpr int GEMM_THREADS = 384;  // TMA, MMA, TMEM-alloc, spare + 2 x 4 epilogue warps
 constexpr int TMEM_COLS = 512;
 static_assert(GEMM_SMEM_BYTES <= 232448, "shared memory budget");
+// CTA-pair (cta_group::2) variant: pair tile 256 x 256; each CTA stages its 128 rows of A and HALF
+// of the W tile, so a stage is 32 KB and the ring is 6 deep in the same shared memory
+constexpr int STAGES2 = 6;
+constexpr int B2_ROWS = MAX_BN / 2;
+constexpr int B2_STAGE_BYTES = B2_ROWS * BK * 2;  // 16 KB
+constexpr int OFF2_B = STAGES2 * A_STAGE_BYTES;
+constexpr int OFF2_C = OFF2_B + STAGES2 * B2_STAGE_BYTES;
+constexpr int OFF2_VEC = OFF2_C + 2 * C_STAGE_BYTES;
+constexpr int OFF2_BAR = OFF2_VEC + 2 * MAX_BN * 4;
+constexpr int GEMM2_SMEM_BYTES = OFF2_BAR + 256;
+static_assert(GEMM2_SMEM_BYTES <= 232448, "shared memory budget (2-CTA)");
 
 // epilogue kinds as compiled (the ABI's RUART_EPI_BIAS_GELU maps to one of the two GELUs)
-enum : int { K_NONE = 0, K_BIAS, K_GELU_FAST, K_GELU_EXACT, K_RELU_SCALE, K_BIAS_RELU, K_NUM };
+enum : int { K_NONE = 0, K_BIAS, K_GELU_FAST, K_GELU_EXACT, K_RELU_SCALE, K_BIAS_RELU, K_GELU_TANHFIT, K_NUM };
 
 struct GemmParams {
   int M, N, Kp;
@@ -64,6 +77,7 @@ __device__ __forceinline__ float epi_fn(float acc, float v) {
   if constexpr (EPI == K_BIAS) return acc + v;
   if constexpr (EPI == K_GELU_FAST) return gelu_erf_fast(acc + v);
   if constexpr (EPI == K_GELU_EXACT) return gelu_erf(acc + v);
+  if constexpr (EPI == K_GELU_TANHFIT) return gelu_erf_tanhfit(acc + v);
   if constexpr (EPI == K_RELU_SCALE) return fmaxf(acc, 0.0f) * v;
   if constexpr (EPI == K_BIAS_RELU) return fmaxf(acc + v, 0.0f);
   return acc;
@@ -397,6 +411,254 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2) for the plain-bf16-output GEMMs of the BERT encoder.
+// Two CTAs of a cluster (one TPC) own a 256 x 256 tile: CTA r stages rows [128 r, 128 r + 128) of the
+// A tile and rows [128 r, 128 r + 128) of the W tile; the leader's single MMA thread issues
+// M = 256, N = 256 instructions that read both CTAs' shared memory and write each CTA's 128 x 256
+// half of the accumulator into that CTA's own TMEM.  Per CTA a stage shrinks from 48 KB to 32 KB, so
+// the TMA ring is 6 deep instead of 4 (the 1-CTA kernel loses 6-9 % with 3 stages: it is bound by
+// load latency) and the W traffic from L2 halves.  Barrier protocol:
+//   full[s]   (leader's)  1 arrival: the leader's arrive.expect_tx(64 KB); both CTAs' TMA loads
+//                         complete_tx on it
+//   empty[s]  (each CTA)  tcgen05.commit multicast to both CTAs when the MMAs of stage s retire
+//   tmem_full (each CTA)  commit multicast after the last k-block of a tile
+//   tmem_empty (leader's) 4 arrivals: one elected thread per epilogue group of each CTA (the peer's
+//                         arrive remotely)
+// The epilogue is the TMA-store epilogue of the kernel above, per CTA on its own 128 rows.
+template <int EPI, bool HAS_RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                      const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_c,
+                      const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + OFF2_B;
+  uint8_t* smem_c = smem + OFF2_C;
+  float* s_vec = reinterpret_cast<float*>(smem + OFF2_VEC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF2_BAR);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES2;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES2;
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES2 + 2;
+  uint64_t* res_bar = bars + 2 * STAGES2 + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+    if (HAS_RES) tma_prefetch_desc(&tmap_r);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);  // one elected thread per epilogue group per CTA
+      mbar_init(&res_bar[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = p.N / MAX_BN;
+  const int total_tiles = m_pairs * n_tiles;
+  const int k_blocks = p.Kp / BK;
+  const int tile0 = blockIdx.x >> 1;
+  const int tile_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int m_pair = tile / n_tiles;
+        const int n_blk = tile - m_pair * n_tiles;
+        const int row_a = (2 * m_pair + static_cast<int>(rank)) * BM;
+        const int row_b = n_blk * MAX_BN + static_cast<int>(rank) * B2_ROWS;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint32_t full_leader;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                       : "=r"(full_leader)
+                       : "r"(smem_u32(&full_bar[stage])), "r"(0));
+          // the leader alone arrives (expecting the bytes of BOTH CTAs); the peer's loads only
+          // complete_tx on the leader's barrier.  (A remote arrive.release.cluster per stage from
+          // the peer's producer serialised it behind its own TMA loads: 0.73 us per stage.)
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B2_STAGE_BYTES));
+          tma_load_2d_2sm(&tmap_a, full_leader, smem_a + stage * A_STAGE_BYTES, kb * BK, row_a);
+          tma_load_2d_2sm(&tmap_b, full_leader, smem_b + stage * B2_STAGE_BYTES, kb * BK, row_b);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(2 * BM, MAX_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * MAX_BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * B2_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2sm(&tmem_full_bar[acc], 0x3);  // both CTAs' epilogues
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int grp = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int et = threadIdx.x - 128 - grp * 128;
+    const int r_local = ew * 32 + lane;
+    const bool issuer = (et == 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
+    uint32_t tile_ctr = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tile_ctr) {
+      const int m_pair = tile / n_tiles;
+      const int n_blk = tile - m_pair * n_tiles;
+      const int m_blk = 2 * m_pair + static_cast<int>(rank);
+      const int tile_col0 = n_blk * MAX_BN;
+      float* vec = s_vec + (tile_ctr & 1u) * MAX_BN;
+      if (EPI != K_NONE) {
+        for (int i = et + grp * 128; i < MAX_BN; i += 256)
+          vec[i] = __ldg(p.vec + static_cast<long long>(tile_col0 + i) * p.vec_stride);
+      }
+      epi_all_bar_sync();
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                                static_cast<uint32_t>(acc * MAX_BN);
+      uint8_t* cbuf = smem_c + grp * C_STAGE_BYTES;
+      for (int c0 = grp * 64; c0 < MAX_BN; c0 += 128) {
+        if (HAS_RES && issuer) {
+          bulk_wait_read<0>();
+          mbar_arrive_expect_tx(&res_bar[grp], C_STAGE_BYTES);
+          tma_load_2d(&tmap_r, &res_bar[grp], cbuf, tile_col0 + c0, m_blk * BM);
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(tmem_acc + c0, v0);
+        tmem_ld_32x32b_x32(tmem_acc + c0 + 32, v1);
+        tmem_ld_wait();
+        if (c0 + 128 >= MAX_BN) {  // the group's last TMEM read of this tile
+          // one (remote, for the peer) arrive per group instead of 128: every thread's TMEM loads are
+          // ordered before the group barrier, the elected thread then releases the accumulator
+          tc_fence_before();
+          grp_bar_sync(grp);
+          if (issuer) {
+            if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+            else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          }
+        }
+        uint8_t* row_ptr = cbuf + r_local * 128;
+        if constexpr (!HAS_RES) {
+          uint4 pk4[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int j = c * 8 + q * 2;
+              const float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+              const float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
+              const float2 bv = *reinterpret_cast<const float2*>(vec + c0 + j);
+              pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x), epi_fn<EPI>(x1, bv.y));
+            }
+            pk4[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          if (issuer) bulk_wait_read<0>();
+          grp_bar_sync(grp);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4)) = pk4[c];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 b0 = *reinterpret_cast<const float2*>(vec + c0 + j);
+            const float2 b1 = *reinterpret_cast<const float2*>(vec + c0 + 32 + j);
+            v0[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j]), b0.x));
+            v0[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j + 1]), b0.y));
+            v1[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j]), b1.x));
+            v1[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j + 1]), b1.y));
+          }
+          mbar_wait(&res_bar[grp], res_phase);
+          res_phase ^= 1u;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4* slot = reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4));
+            const uint4 r4 = *slot;
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int j = c * 8 + q * 2;
+              const float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+              const float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
+              pk[q] = pack_bf16x2(x0 + bf16_lo(rw[q]), x1 + bf16_hi(rw[q]));
+            }
+            *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_proxy_async();
+        grp_bar_sync(grp);
+        if (issuer) {
+          tma_store_2d(&tmap_c, cbuf, tile_col0 + c0, m_blk * BM);
+          bulk_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (issuer) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's MMAs / multicast commits no longer touch this CTA
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+  }
+}
+
 // --------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -473,6 +735,7 @@ GemmKernel kernel_for(int kind, bool tma_out, bool has_res) {
     case K_BIAS: return pick_kernel<K_BIAS>(tma_out);
     case K_GELU_FAST: return pick_kernel<K_GELU_FAST>(tma_out);
     case K_GELU_EXACT: return pick_kernel<K_GELU_EXACT>(tma_out);
+    case K_GELU_TANHFIT: return pick_kernel<K_GELU_TANHFIT>(tma_out);
     case K_RELU_SCALE: return pick_kernel<K_RELU_SCALE>(tma_out);
     case K_BIAS_RELU: return pick_kernel<K_BIAS_RELU>(tma_out);
   }
@@ -480,6 +743,27 @@ GemmKernel kernel_for(int kind, bool tma_out, bool has_res) {
 }
 
 }  // namespace
+
+// debugging aid: how many CTA pairs of the cta_group::2 kernel the device can hold at once
+extern "C" RUART_API int ruart_debug_gemm2_clusters(void) {
+  auto kern = gemm_bf16_2cta_kernel<K_BIAS, false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ruart_num_sms() & ~1);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = -1;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  return n;
+}
 
 extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const void* W,
                                long long ldw, int w_parts, int M, int N, int Kp, int n_terms,
@@ -502,7 +786,10 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   switch (epi) {
     case RUART_EPI_NONE: kind = K_NONE; break;
     case RUART_EPI_BIAS: kind = K_BIAS; vec = bias; break;
-    case RUART_EPI_BIAS_GELU: kind = fast_gelu ? K_GELU_FAST : K_GELU_EXACT; vec = bias; break;
+    case RUART_EPI_BIAS_GELU:
+      kind = fast_gelu == 2 ? K_GELU_TANHFIT : (fast_gelu ? K_GELU_FAST : K_GELU_EXACT);
+      vec = bias;
+      break;
     case RUART_EPI_BIAS_RELU: kind = K_BIAS_RELU; vec = bias; break;
     case RUART_EPI_RELU_SCALE:
       kind = K_RELU_SCALE;
@@ -573,6 +860,35 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   }
 
   const bool has_res = residual_bf16 != nullptr;
+  // CTA-pair kernel: plain bf16 output, whole 256-column tiles, one MMA term, a full wave of pairs
+  static const bool one_cta = getenv("RUART_GEMM_1CTA") != nullptr;  // A/B aid
+  GemmKernel kern2 = nullptr;
+  if (!one_cta && tma_out && n_terms == 1 && (N % MAX_BN) == 0 && M >= 2 * BM * 8) {
+    if (has_res) kern2 = gemm_bf16_2cta_kernel<K_BIAS, true>;
+    else if (kind == K_BIAS) kern2 = gemm_bf16_2cta_kernel<K_BIAS, false>;
+    else if (kind == K_GELU_FAST) kern2 = gemm_bf16_2cta_kernel<K_GELU_FAST, false>;
+    else if (kind == K_GELU_TANHFIT) kern2 = gemm_bf16_2cta_kernel<K_GELU_TANHFIT, false>;
+  }
+  if (kern2 != nullptr) {
+    CUtensorMap tmb2;
+    rc = make_tmap_bf16(&tmb2, W, N, (long long)w_parts * Kp, ldw, B2_ROWS);
+    if (rc != RUART_OK) return rc;
+    static bool attr2[4] = {};
+    const int slot2 = has_res ? 2 : (kind == K_BIAS ? 0 : (kind == K_GELU_FAST ? 1 : 3));
+    if (!attr2[slot2]) {
+      RUART_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            GEMM2_SMEM_BYTES));
+      attr2[slot2] = true;
+    }
+    const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / MAX_BN);
+    int grid2 = ruart_num_sms() & ~1;
+    static const char* g2 = getenv("RUART_GEMM2_GRID");
+    if (g2 != nullptr) grid2 = atoi(g2);
+    if (grid2 > 2 * pair_tiles) grid2 = 2 * pair_tiles;
+    kern2<<<grid2, GEMM_THREADS, GEMM2_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb2, tmc, tmr, p);
+    RUART_LAUNCH_CHECK();
+    return RUART_OK;
+  }
   GemmKernel kern = kernel_for(kind, tma_out, has_res);
   static bool attr_set[K_NUM][3] = {};
   const int slot = has_res ? 2 : (tma_out ? 1 : 0);
@@ -585,6 +901,23 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   const int n_tiles = (N + p.block_n - 1) / p.block_n;
   const int total = m_tiles * n_tiles;
   const int grid = total < ruart_num_sms() ? total : ruart_num_sms();
+  static const bool dbg_cluster = getenv("RUART_GEMM1_CLUSTER") != nullptr;  // DEBUG: 1-CTA kernel in clusters of 2
+  if (dbg_cluster && (grid % 2) == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RUART_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tma, tmb, tmc, tmr, p));
+    return RUART_OK;
+  }
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, tmr, p);
   RUART_LAUNCH_CHECK();
   return RUART_OK;

@@ -86,7 +86,7 @@ def gemm(a, w, M, N, Kp, *, a_parts=1, w_parts=1, n_terms=1, epi=EPI_NONE, bias=
          ptr(bias), ptr(scale), 0 if scale is None else scale.numel(),
          ptr(out_f32), 0 if out_f32 is None else out_f32.stride(-2),
          ptr(out_bf16), 0 if out_bf16 is None else out_bf16.stride(-2), out_parts,
-         out_part_stride, 1 if fast_gelu else 0, ptr(residual), 0 if residual is None else residual.stride(-2),
+         out_part_stride, int(fast_gelu), ptr(residual), 0 if residual is None else residual.stride(-2),
          current_stream())
 
 

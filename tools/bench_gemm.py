@@ -1,5 +1,6 @@
 """Micro-benchmark of the tcgen05 GEMM at the BERT shapes of BASELINE cfg-3 (valid tokens only).
 Usage (GPU box): python tools/bench_gemm.py [M]"""
+import os
 import sys
 
 import torch
@@ -7,6 +8,7 @@ import torch
 sys.path.insert(0, ".")
 from ruart_b200 import ops  # noqa: E402
 
+GELU = int(os.environ.get("RUART_GELU_MODE", "1"))
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 113664
 shapes = [("qkv", 2304, 768, 1), ("attn_out", 768, 768, 1), ("ffn_up+gelu", 3072, 768, 2), ("ffn_down", 768, 3072, 1)]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -17,14 +19,14 @@ for name, N, K, epi in shapes:
     b = torch.randn(N, device="cuda")
     o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     for _ in range(3):
-        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=True)
+        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=GELU)
     ts = []
     for _ in range(10):
         flush.zero_()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=True)
+        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=GELU)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
