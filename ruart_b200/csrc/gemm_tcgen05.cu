@@ -744,27 +744,6 @@ GemmKernel kernel_for(int kind, bool tma_out, bool has_res) {
 
 }  // namespace
 
-// debugging aid: how many CTA pairs of the cta_group::2 kernel the device can hold at once
-extern "C" RUART_API int ruart_debug_gemm2_clusters(void) {
-  auto kern = gemm_bf16_2cta_kernel<K_BIAS, false>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ruart_num_sms() & ~1);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  int n = -1;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-  if (e != cudaSuccess) return -static_cast<int>(e);
-  return n;
-}
-
 extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const void* W,
                                long long ldw, int w_parts, int M, int N, int Kp, int n_terms,
                                int epi, const float* bias, const float* scale, int scale_len,
@@ -882,8 +861,6 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
     }
     const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / MAX_BN);
     int grid2 = ruart_num_sms() & ~1;
-    static const char* g2 = getenv("RUART_GEMM2_GRID");
-    if (g2 != nullptr) grid2 = atoi(g2);
     if (grid2 > 2 * pair_tiles) grid2 = 2 * pair_tiles;
     kern2<<<grid2, GEMM_THREADS, GEMM2_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb2, tmc, tmr, p);
     RUART_LAUNCH_CHECK();
@@ -901,23 +878,6 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   const int n_tiles = (N + p.block_n - 1) / p.block_n;
   const int total = m_tiles * n_tiles;
   const int grid = total < ruart_num_sms() ? total : ruart_num_sms();
-  static const bool dbg_cluster = getenv("RUART_GEMM1_CLUSTER") != nullptr;  // DEBUG: 1-CTA kernel in clusters of 2
-  if (dbg_cluster && (grid % 2) == 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    RUART_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tma, tmb, tmc, tmr, p));
-    return RUART_OK;
-  }
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, tmr, p);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
