@@ -10,23 +10,26 @@ from ruart_b200 import ops  # noqa: E402
 
 GELU = int(os.environ.get("RUART_GELU_MODE", "1"))
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 113664
-shapes = [("qkv", 2304, 768, 1), ("attn_out", 768, 768, 1), ("ffn_up+gelu", 3072, 768, 2), ("ffn_down", 768, 3072, 1)]
+# (name, N, K, epilogue, fused residual) — as the encoder calls them
+shapes = [("qkv", 2304, 768, 1, False), ("attn_out+res", 768, 768, 1, True), ("ffn_up+gelu", 3072, 768, 2, False),
+          ("ffn_down+res", 768, 3072, 1, True)]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 tot_t = tot_f = 0.0
-for name, N, K, epi in shapes:
+for name, N, K, epi, has_res in shapes:
     a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
     w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
     b = torch.randn(N, device="cuda")
     o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(M, N, device="cuda").bfloat16() if has_res else None
     for _ in range(3):
-        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=GELU)
+        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=GELU, residual=res)
     ts = []
     for _ in range(10):
         flush.zero_()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=GELU)
+        ops.gemm(a, w, M, N, K, epi=epi, bias=b, out_bf16=o, fast_gelu=GELU, residual=res)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
