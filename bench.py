@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cfg", default="cfg3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collate-index", action="store_true",
+                    help="prepare the batch with ruart_b200.Utils.collate.attach_index_tensors (CSR word offsets, "
+                         "forward plan, host-side token counts: no host sync inside the forward)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -195,6 +198,9 @@ def main():
     net, opt = build_net(args.cfg, dev)
     B = synth.CONFIGS[args.cfg]["B"]
     host_batch = synth.make_batch(args.cfg, seed=2003 + rank)
+    if args.collate_index:
+        from ruart_b200.Utils import collate
+        host_batch = collate.attach_index_tensors(*host_batch)
     # pinned host copies for the e2e leg
     pinned = tuple({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in d.items()} for d in host_batch)
     h2d_bytes = sum(v.numel() * v.element_size() for d in pinned for v in d.values() if torch.is_tensor(v))
@@ -308,7 +314,9 @@ def main():
             "config": {"workload": workload_desc(args.cfg), "per_gpu_batch": B, "global_batch": B * world,
                        "parallelism": "batch-sharded x%d, no collective" % world,
                        "precision": "BERT bf16 operands / fp32 accumulate; SDNet stack fp32 activations, GEMM operands as 2-part bf16 splits (~2^-16)",
-                       "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush"},
+                       "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "batch": ("VQA_collate_fun layout + Utils.collate.attach_index_tensors" if args.collate_index
+                                 else "VQA_collate_fun layout (tensors + Python lists), as the reference's collate emits it")},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_host.numel() * 4,
                     "ms_per_step": ms_e2e / args.steps},
@@ -316,7 +324,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                          "frac": (ach / peak) if ach else None, "traffic": gemm_traffic(),
                          "traffic_unit": "bytes per launch (mean of the 4 BERT GEMM shapes, ncu dram read+write)",
-                         "kernel": "gemm_bf16_tcgen05_kernel (all %d BERT GEMM launches of the timed steps)" % n_gemm,
+                         "kernel": "gemm_bf16_2cta_kernel (all %d BERT GEMM launches of the timed steps)" % n_gemm,
                          "kernel_ms_per_step": g_ms / args.steps, "peak_source": peak_src},
         }
         if cpu_base is not None:

@@ -131,13 +131,15 @@ RUART_API int ruart_seq_lengths(const uint8_t* mask, int N, int L, int window, i
                                 int32_t* win_len, void* stream);
 RUART_API int ruart_seq_scan(const int32_t* row_len, int R, const int32_t* win_len, int S, int n_seg,
                              const int32_t* seg_row0_host, const int32_t* seg_seq0_host,
-                             int32_t* cu_rows, int32_t* cu_seq, int32_t* totals, void* stream);
+                             int32_t* cu_rows, int32_t* cu_seq, int32_t* totals, int max_total,
+                             void* stream);
 /* Real (mask != 0) wordpieces of ids [N, L] (int64, the collate's dtype) -> packed int32 ids and
  * position ids (column % window) at out[row_start[r] ...]; replaces the padded [N, L] layout of
- * BertModel.forward's inputs (modeling.py:585-604).                                            */
+ * BertModel.forward's inputs (modeling.py:585-604).  `capacity` = length of out_ids / out_pos:
+ * slots beyond it are not written.                                                            */
 RUART_API int ruart_pack_tokens(const long long* ids, const uint8_t* mask, int N, int L,
                                 const int32_t* row_start, int window, int32_t* out_ids,
-                                int32_t* out_pos, void* stream);
+                                int32_t* out_pos, int capacity, void* stream);
 /* fp32 [*, K] (row pitch ld) -> bf16 split operand [rows, parts*Kp] for ruart_gemm_bf16; output
  * row r reads source row row_idx[r] (NULL = r)                                                 */
 RUART_API int ruart_split_bf16(const float* src, long long ld, const int32_t* row_idx,

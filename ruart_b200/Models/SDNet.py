@@ -28,6 +28,7 @@ from .. import sdnet_ops as K
 from .._lib import current_stream, ptr
 from ..ops import call
 from . import Layers
+from ..bert_engine import BertEngine
 from .Bert.Bert import Bert
 from .Layers import (Attention, DeepAttention, GetFinalScores, LinearSelfAttn, RNN_from_opt, dropout,
                      set_dropout_prob, set_seq_dropout)
@@ -240,7 +241,7 @@ class SDNet(nn.Module):
             return lst['bert_offsets_csr'] if 'bert_offsets_csr' in lst else lst['bert_offsets']
 
         bert_segments = [
-            (lst['bert'], lst['bert_mask'], word_offsets(lst), lst[wmask])
+            (lst['bert'], lst['bert_mask'], word_offsets(lst), lst[wmask], lst.get('bert_totals'))
             for lst, wmask in ((q_list, 'glove_mask'), (ocr_list, 'fasttext_mask'), (od_list, 'fasttext_mask'))]
         pack_handle = self.Bert.pack_begin(bert_segments)
         # ---- embeddings: [(phoc |) word | bert | pos | ent (| prealign)]  (SDNet.py:439-493) ----
@@ -276,8 +277,9 @@ class SDNet(nn.Module):
 
         self._phase('embed')
         # ---- BERT: one packed pass, subword mean + layer sum into the concat buffers ------------
-        self.Bert.encode_into(bert_segments, [(q_in, QD, PQ + VD), (ocr_in, XD, PX + VD), (od_in, XD, PX + VD)],
-                              self.alphaBERT, self.gammaBERT, pack_handle=pack_handle)
+        bert_pack = self.Bert.encode_into(bert_segments,
+                                          [(q_in, QD, PQ + VD), (ocr_in, XD, PX + VD), (od_in, XD, PX + VD)],
+                                          self.alphaBERT, self.gammaBERT, pack_handle=pack_handle)
 
         self._phase('bert')
         # ---- host indices (one upload) -------------------------------------------------------
@@ -423,6 +425,8 @@ class SDNet(nn.Module):
         self._phase('scores')
         if self.check_nan and int(nan_flag.item()) != 0:
             raise AssertionError("NaN in answer scores (reference: assert torch.sum(torch.isnan(...)) == 0)")
+        if self.check_nan:  # (the nan flag read above synchronised the device)
+            BertEngine.check_totals(bert_pack)
         for err in phoc_errs:  # table-free PHOC channel: unknown unigram, like Utils/cphoc.c:45-50
             key = int(err.item())
             if key != -1:

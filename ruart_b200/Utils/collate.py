@@ -18,11 +18,18 @@ from ..host_index import forward_plan
 
 CSR_KEY = "bert_offsets_csr"   # int32 [4, n_words]: (row, word, st, ed) of every word of the list
 PLAN_KEY = "ruart_plan"        # host_index.forward_plan(...) of the batch, stored in ocr_list
+TOTALS_KEY = "bert_totals"     # (real wordpieces of the list, longest 512-token window): lets the token
+                               # packing of the BERT pass skip its one device -> host read-back
+WINDOW = 512                   # Bert.BERT_MAX_LEN (Bert.py:18)
 
 
 def attach_index_tensors(q_list, ocr_list, od_list):
     for d in (q_list, ocr_list, od_list):
         d[CSR_KEY] = flatten_offsets(d["bert_offsets"], len(d["bert_offsets"]))
+        m = d["bert_mask"].cpu() != 0
+        longest = max((int(m[:, p:p + WINDOW].sum(1).max()) for p in range(0, m.shape[1], WINDOW)), default=0) \
+            if m.shape[0] else 0
+        d[TOTALS_KEY] = (int(m.sum()), longest)
     ocr_list[PLAN_KEY] = forward_plan(
         ocr_list["num_cnt"], ocr_list["len_cnt"], od_list["num_cnt"], od_list["len_cnt"],
         ocr_list["fasttext"].size(1), od_list["fasttext"].size(1),

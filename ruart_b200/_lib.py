@@ -42,8 +42,8 @@ _SIGNATURES = {
                                  c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "ruart_seq_lengths": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "ruart_seq_scan": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                       c_void_p],
-    "ruart_pack_tokens": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+                       c_int, c_void_p],
+    "ruart_pack_tokens": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ruart_split_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p],
     "ruart_gather_rows": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_int,
                           c_int, c_void_p],

@@ -30,10 +30,13 @@ WINDOW = 512  # BERT_MAX_LEN, Models/Bert/Bert.py:18
 class Segment(object):
     """One Bert.forward call's worth of input: ids/mask [N, L], word offsets, word mask [N, W]."""
 
-    def __init__(self, ids, mask, offsets, word_mask):
+    def __init__(self, ids, mask, offsets, word_mask, totals=None):
         self.ids, self.mask, self.offsets, self.word_mask = ids, mask, offsets, word_mask
         self.N, self.L = ids.shape
         self.W = word_mask.shape[1]
+        # (real tokens of the list, longest 512-token window) when the collate step already counted
+        # them on the host (Utils.collate.attach_index_tensors): the packing then needs no read-back
+        self.totals = None if totals is None else (int(totals[0]), int(totals[1]))
 
 
 def flatten_offsets(offsets, n_rows):
@@ -174,15 +177,26 @@ class BertEngine(object):
                 masks.append(m8)
                 call("ruart_seq_lengths", ptr(m8), sg.N, sg.L, WINDOW, row_len.data_ptr() + 4 * int(row0[k]),
                      win_len.data_ptr() + 4 * int(seq0[k]), st)
+            host_known = all(sg.totals is not None for sg in segments)
+            # a host-side token count sizes the buffers: the device clamps every offset to it
+            max_total = sum(sg.totals[0] for sg in segments) if host_known else -1
             call("ruart_seq_scan", ptr(row_len), R, ptr(win_len), S, len(segments), row0.ctypes.data,
-                 seq0.ctypes.data, ptr(cu_rows), ptr(cu_seq), ptr(totals), st)
-            host = torch.empty(totals.shape, dtype=totals.dtype, pin_memory=True)
-            host.copy_(totals, non_blocking=True)
+                 seq0.ctypes.data, ptr(cu_rows), ptr(cu_seq), ptr(totals), max_total, st)
+            if host_known:
+                # counted on the host by the collate step: no device -> host read-back, no host wait
+                host = [max_total] + [sg.totals[1] for sg in segments]
+                check = torch.empty(totals.shape, dtype=totals.dtype, pin_memory=True)
+                check.copy_(totals, non_blocking=True)   # compared by check_totals() after the forward
+            else:
+                host = torch.empty(totals.shape, dtype=totals.dtype, pin_memory=True)
+                host.copy_(totals, non_blocking=True)
+                host_known = False
+                check = None
             done = torch.cuda.Event()
             done.record(side)
             keep = (row_len, win_len, totals, masks, row0, seq0)
         return {"segments": segments, "cu_rows": cu_rows, "cu_seq": cu_seq, "host": host, "done": done,
-                "nwins": nwins, "keep": keep}
+                "nwins": nwins, "keep": keep, "host_known": host_known, "check": check}
 
     @staticmethod
     def pack_finish(h):
@@ -195,14 +209,19 @@ class BertEngine(object):
         segments = h["segments"]
         dev = segments[0].ids.device
         main = torch.cuda.current_stream(dev)
-        h["done"].synchronize()
+        if not h["host_known"]:
+            h["done"].synchronize()
         main.wait_event(h["done"])
         cu_rows, cu_seq, host, nwins = h["cu_rows"], h["cu_seq"], h["host"], h["nwins"]
         cu_rows.record_stream(main)
         cu_seq.record_stream(main)
         T = int(host[0])
-        ids = torch.empty(T, dtype=torch.int32, device=dev)
-        pos = torch.empty(T, dtype=torch.int32, device=dev)
+        if h["host_known"]:  # host-supplied count: slots the masks do not fill stay valid ids
+            ids = torch.zeros(T, dtype=torch.int32, device=dev)
+            pos = torch.zeros(T, dtype=torch.int32, device=dev)
+        else:
+            ids = torch.empty(T, dtype=torch.int32, device=dev)
+            pos = torch.empty(T, dtype=torch.int32, device=dev)
         segs = []
         r0 = s0 = 0
         st = current_stream()
@@ -212,12 +231,24 @@ class BertEngine(object):
             mask8 = sg.mask.contiguous().view(torch.uint8) if sg.mask.dtype == torch.bool else sg.mask.to(torch.uint8).contiguous()
             ids64 = sg.ids.contiguous()
             call("ruart_pack_tokens", ptr(ids64), ptr(mask8), sg.N, sg.L, ptr(row_start), WINDOW,
-                 ptr(ids), ptr(pos), st)
+                 ptr(ids), ptr(pos), T, st)
             segs.append({"row_start": row_start, "seq0": s0, "seq1": s0 + sg.N * nwins[k],
                          "max_len": int(host[1 + k])})
             r0 += sg.N
             s0 += sg.N * nwins[k]
-        return {"ids": ids, "pos": pos, "cu_seqlens": cu_seq, "T": T, "segments": segs}
+        return {"ids": ids, "pos": pos, "cu_seqlens": cu_seq, "T": T, "segments": segs,
+                "check": (h["check"], list(host)) if h["host_known"] else None}
+
+    @staticmethod
+    def check_totals(pk):
+        """After a device sync: the host-supplied token counts (collate step) must equal what the device
+        counted from the masks; anything else means the batch dicts were edited after collate."""
+        if pk is None or pk.get("check") is None:
+            return
+        dev_totals, host = pk["check"]
+        if [int(v) for v in dev_totals] != [int(v) for v in host]:
+            raise RuntimeError("bert_totals do not match bert_mask (got %s, masks give %s): rebuild them with "
+                               "Utils.collate.attach_index_tensors" % (host, [int(v) for v in dev_totals]))
 
     @classmethod
     def pack(cls, segments):

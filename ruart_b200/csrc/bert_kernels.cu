@@ -1011,7 +1011,7 @@ __device__ void block_exclusive_scan(const int32_t* __restrict__ in, int n, int3
 __global__ void __launch_bounds__(1024)
 seq_scan_kernel(const int32_t* __restrict__ row_len, int R, const int32_t* __restrict__ win_len, int S,
                 const SegTable seg, int32_t* __restrict__ cu_rows, int32_t* __restrict__ cu_seq,
-                int32_t* __restrict__ totals) {
+                int32_t* __restrict__ totals, int max_total) {
   block_exclusive_scan(row_len, R, cu_rows);
   block_exclusive_scan(win_len, S, cu_seq);
   __shared__ int s_max[MAX_SEGMENTS];
@@ -1023,8 +1023,15 @@ seq_scan_kernel(const int32_t* __restrict__ row_len, int R, const int32_t* __res
     atomicMax(&s_max[k], m);
   }
   __syncthreads();
-  if (threadIdx.x == 0) totals[0] = cu_rows[R];
+  if (threadIdx.x == 0) totals[0] = cu_rows[R];  // the true count, also when clamped below
   if (threadIdx.x < seg.n_seg) totals[1 + threadIdx.x] = s_max[threadIdx.x];
+  if (max_total >= 0) {
+    // the caller sized its buffers from a host-side count: offsets never point past them, whatever
+    // the masks say (a mismatch is reported by the caller from `totals` after the forward)
+    __syncthreads();
+    for (int i = threadIdx.x; i <= R; i += blockDim.x) cu_rows[i] = min(cu_rows[i], max_total);
+    for (int i = threadIdx.x; i <= S; i += blockDim.x) cu_seq[i] = min(cu_seq[i], max_total);
+  }
 }
 
 // Token packing: ids [N, L] + mask [N, L] -> the real tokens of every row, in row order, at
@@ -1033,7 +1040,7 @@ seq_scan_kernel(const int32_t* __restrict__ row_len, int R, const int32_t* __res
 __global__ void __launch_bounds__(256)
 pack_tokens_kernel(const long long* __restrict__ ids, const uint8_t* __restrict__ mask, int N, int L,
                    const int32_t* __restrict__ row_start, int window, int32_t* __restrict__ out_ids,
-                   int32_t* __restrict__ out_pos) {
+                   int32_t* __restrict__ out_pos, int capacity) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -1044,8 +1051,10 @@ pack_tokens_kernel(const long long* __restrict__ ids, const uint8_t* __restrict_
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int k = base + __popc(bal & ((1u << lane) - 1u));
-      out_ids[k] = static_cast<int32_t>(ids[static_cast<long long>(row) * L + c]);
-      out_pos[k] = c % window;
+      if (k < capacity) {  // a host-supplied token count smaller than the masks' never overruns the buffers
+        out_ids[k] = static_cast<int32_t>(ids[static_cast<long long>(row) * L + c]);
+        out_pos[k] = c % window;
+      }
     }
     base += __popc(bal);
   }
@@ -1265,7 +1274,7 @@ extern "C" int ruart_seq_lengths(const uint8_t* mask, int N, int L, int window, 
 
 extern "C" int ruart_seq_scan(const int32_t* row_len, int R, const int32_t* win_len, int S, int n_seg,
                               const int32_t* seg_row0, const int32_t* seg_seq0, int32_t* cu_rows,
-                              int32_t* cu_seq, int32_t* totals, void* stream) {
+                              int32_t* cu_seq, int32_t* totals, int max_total, void* stream) {
   RUART_ARG_CHECK(n_seg >= 1 && n_seg <= MAX_SEGMENTS && R >= 0 && S >= 0);
   SegTable seg;
   seg.n_seg = n_seg;
@@ -1274,18 +1283,18 @@ extern "C" int ruart_seq_scan(const int32_t* row_len, int R, const int32_t* win_
     seg.seq0[k] = seg_seq0[k];
   }
   seq_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_len, R, win_len, S, seg, cu_rows, cu_seq,
-                                                        totals);
+                                                        totals, max_total);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
 
 extern "C" int ruart_pack_tokens(const long long* ids, const uint8_t* mask, int N, int L,
                                  const int32_t* row_start, int window, int32_t* out_ids,
-                                 int32_t* out_pos, void* stream) {
-  RUART_ARG_CHECK(N >= 0 && L > 0 && window > 0);
+                                 int32_t* out_pos, int capacity, void* stream) {
+  RUART_ARG_CHECK(N >= 0 && L > 0 && window > 0 && capacity >= 0);
   if (N == 0) return RUART_OK;
   pack_tokens_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ids, mask, N, L, row_start,
-                                                                    window, out_ids, out_pos);
+                                                                    window, out_ids, out_pos, capacity);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

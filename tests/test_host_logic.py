@@ -94,6 +94,7 @@ def test_collate_index_tensors_equal_the_per_forward_ones():
         csr = d[collate.CSR_KEY]
         assert csr.dtype == np.int32 and np.array_equal(csr, flatten_offsets(d["bert_offsets"], len(d["bert_offsets"])))
         assert flatten_offsets(csr, len(d["bert_offsets"])) is not None   # the array form passes through
+        assert d[collate.TOTALS_KEY] == (int(d["bert_mask"].sum()), int(d["bert_mask"].sum(1).max()))
     plan = ocr2[collate.PLAN_KEY]
     want = host_index.forward_plan(ocr["num_cnt"], ocr["len_cnt"], od["num_cnt"], od["len_cnt"], 20, 10, 100, 30)
     assert plan["key"] == want["key"] == (8, sum(ocr["num_cnt"]), sum(od["num_cnt"]), 20, 10, 100, 30)

@@ -263,3 +263,10 @@ def test_collate_side_index_tensors_give_identical_forward():
         probs2, _ = net(*pre)
     torch.cuda.synchronize()
     assert torch.equal(probs2.cpu(), probs) and torch.equal(net.get_answer.last_logits.cpu(), logits)
+    # the host-side token counts let the BERT packing skip its read-back; stale counts are caught
+    assert pre[1]["bert_totals"][0] == int(batch[1]["bert_mask"].sum())
+    bad = collate.to_cuda(collate.pin(collate.attach_index_tensors(*copy.deepcopy(batch))))
+    bad[2]["bert_mask"] = bad[2]["bert_mask"].clone()
+    bad[2]["bert_mask"][0, 1] = False            # edited after collate: one token fewer than counted
+    with pytest.raises(RuntimeError, match="bert_totals"), torch.no_grad():
+        net(*bad)
