@@ -160,12 +160,15 @@ RUART_API int ruart_gather_rows(const float* src, long long src_pitch, const voi
  * (Layers.py:167-168).  workspace: >= 2048 doubles.                                           */
 RUART_API int ruart_whole_layernorm(float* x, long long rows, int cols, long long pitch, float eps,
                                     double* workspace, void* stream);
-/* Attention.forward after the projections (Layers.py:272-288): out = softmax(mask(p1 p2^T)) x3  */
+/* Attention.forward after the projections (Layers.py:272-288): out = softmax(mask(p1 p2^T)) x3.
+ * split_parts = 2: both products on the tensor cores with every fp32 operand as hi + lo bf16 parts
+ * (three terms per product, ~2^-16 relative, the rule of the 2-part split GEMMs; L2 <= 128);
+ * any other value: fp32 CUDA-core kernel.                                                      */
 RUART_API int ruart_attention_tail(const float* p1, long long p1_pitch, const float* p2,
                                    long long p2_pitch, int hidden, const uint8_t* mask,
                                    const float* x3, long long x3_pitch, int D3, float* out,
                                    long long out_pitch, int B, int L1, int L2, int add_to_out,
-                                   void* stream);
+                                   int split_parts, void* stream);
 /* LinearSelfAttn + weighted_avg (Layers.py:328-341,529-534): out[b] = softmax(mask(x w + b)) x  */
 RUART_API int ruart_self_attn_pool(const float* x, long long x_pitch, int B, int L, int D,
                                    const uint8_t* mask, const float* w, const float* bias,

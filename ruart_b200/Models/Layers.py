@@ -217,7 +217,7 @@ class Attention(nn.Module):
                 p2_cache["p2"] = p2
         if out is None:
             out = torch.empty((B, L1, x3.shape[2]), dtype=torch.float32, device=x1.device)
-        K.attention_tail(p1, p2, K.as_u8(x2_mask), x3, out, B, L1, L2, add=add_to_out)
+        K.attention_tail(p1, p2, K.as_u8(x2_mask), x3, out, B, L1, L2, add=add_to_out, parts=sdnet_parts)
         return out
 
 
@@ -392,7 +392,7 @@ class DeepAttention(nn.Module):
         for i in range(len(x2_abstr)):
             x3 = x2_abstr[i]
             K.attention_tail(p1[:, i * hid:(i + 1) * hid], p2[:, i * hid:(i + 1) * hid], mask, x3,
-                             x1[:, :, col:col + x3.shape[2]], B, L1, L2)
+                             x1[:, :, col:col + x3.shape[2]], B, L1, L2, parts=sdnet_parts)
             col += x3.shape[2]
         x1_hiddens = self.rnn(x1, x1_mask)
         if return_bef_rnn:

@@ -1,6 +1,8 @@
 // fp32 kernels of the SDNet fusion stack (reference Models/Layers.py, Models/SDNet.py) for sm_100a.
 // All of them are small, HBM/L2- or latency-bound; the dense projections that feed them go
 // through the tcgen05 GEMM (gemm_tcgen05.cu) with split-bf16 operands.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ruart_b200.h"
 
@@ -344,6 +346,216 @@ attention_tail_tiled_kernel(const float* __restrict__ p1, long long p1_pitch,
   }
 }
 
+// Tensor-core form of the attention tail for the 2-part-split precision of the SDNet stack
+// (bf16x2: every fp32 operand x is used as hi + lo bf16 parts and a product as the three terms
+// hi*hi + lo*hi + hi*lo, ~2^-16 relative — the same rule the split GEMMs follow).  64 queries per
+// CTA, one warp per 16 queries, mma.sync.m16n8k16 in the FlashAttention-2 register layout:
+//   phase 1  S[16 x L2] = p1 p2^T over 64-wide k chunks; p1 / p2 chunks staged in shared memory as
+//            hi | lo bf16 tiles (128-byte rows, XOR-swizzled 16-byte chunks)
+//   phase 2  mask (-inf), softmax in registers (quad shuffles), P split into hi | lo A-fragments
+//   phase 3  O[16 x D3] = P x3 over 64-wide dim chunks, x3 chunk staged as hi | lo tiles and read with
+//            ldmatrix.trans
+// L2 <= 128 (16 key tiles of accumulators per thread).  The fp32 CUDA-core kernel above stays for
+// the 3-part (fp32-grade) mode and longer key lists.
+constexpr int ATM_Q = 64, ATM_L2 = 128, ATM_THREADS = 128;
+
+__device__ __forceinline__ void split_store4(uint8_t* hi_tile, uint8_t* lo_tile, int r, int col4,
+                                             float4 v) {
+  // four consecutive columns (col4 = first, multiple of 4) of row r -> 8 bytes in each tile
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+  const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+  const uint32_t hi01 = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+  const uint32_t hi23 = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+  const uint32_t lo01 = pack_bf16x2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+  const uint32_t lo23 = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+  const int off = tile_off(r, col4 >> 3) + ((col4 & 4) << 1);
+  *reinterpret_cast<uint2*>(hi_tile + off) = make_uint2(hi01, hi23);
+  *reinterpret_cast<uint2*>(lo_tile + off) = make_uint2(lo01, lo23);
+}
+
+// Stage a [rows x 64] chunk (columns c0 .. c0+63 of `src`, rows >= n_rows and columns >= n_cols zero)
+// as hi | lo bf16 tiles.  `src` rows are `pitch` floats apart.
+__device__ __forceinline__ void stage_split_chunk(const float* __restrict__ src, long long pitch,
+                                                  int n_rows, int n_cols, int c0, int rows,
+                                                  uint8_t* hi_tile, uint8_t* lo_tile, int tid) {
+  for (int i = tid; i < rows * 16; i += ATM_THREADS) {
+    const int r = i >> 4, col4 = (i & 15) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < n_rows) {
+      const float* p = src + static_cast<long long>(r) * pitch + c0 + col4;
+      const int left = n_cols - (c0 + col4);
+      if (left >= 4 && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+        v = *reinterpret_cast<const float4*>(p);
+      } else {
+        if (left > 0) v.x = p[0];
+        if (left > 1) v.y = p[1];
+        if (left > 2) v.z = p[2];
+        if (left > 3) v.w = p[3];
+      }
+    }
+    split_store4(hi_tile, lo_tile, r, col4, v);
+  }
+}
+
+__global__ void __launch_bounds__(ATM_THREADS)
+attention_tail_mma_kernel(const float* __restrict__ p1, long long p1_pitch,
+                          const float* __restrict__ p2, long long p2_pitch, int Hd,
+                          const uint8_t* __restrict__ mask, const float* __restrict__ x3,
+                          long long x3_pitch, int D3, float* __restrict__ out, long long out_pitch,
+                          int L1, int L2, int add_to_out) {
+  // [p1 hi | p1 lo] 2 x 8 KB, [p2 / x3 hi | lo] 2 x 16 KB
+  __shared__ __align__(128) uint8_t s_q[2][ATM_Q * 128];
+  __shared__ __align__(128) uint8_t s_k[2][ATM_L2 * 128];
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * ATM_Q;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int a_chk = lane >> 4;
+  const int b_row = lane & 7;
+  const int b_chk = lane >> 3;
+  const uint32_t aQh = smem_u32(s_q[0]), aQl = smem_u32(s_q[1]);
+  const uint32_t aKh = smem_u32(s_k[0]), aKl = smem_u32(s_k[1]);
+  const float* p1b = p1 + (static_cast<long long>(b) * L1 + q0) * p1_pitch;
+  const float* p2b = p2 + static_cast<long long>(b) * L2 * p2_pitch;
+  const float* x3b = x3 + static_cast<long long>(b) * L2 * x3_pitch;
+  const int nq = min(ATM_Q, L1 - q0);
+  const int n_kt = (L2 + 7) >> 3;    // 8-key tiles in use
+  const int n_kk = (L2 + 15) >> 4;   // 16-key steps in use
+  const int key_rows = n_kk * 16;    // staged key rows (zero padded)
+
+  // ---- phase 1: scores
+  float s[16][4];
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+  for (int k0 = 0; k0 < Hd; k0 += 64) {
+    __syncthreads();
+    stage_split_chunk(p1b, p1_pitch, nq, Hd, k0, ATM_Q, s_q[0], s_q[1], tid);
+    stage_split_chunk(p2b, p2_pitch, L2, Hd, k0, key_rows, s_k[0], s_k[1], tid);
+    __syncthreads();
+    uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int off = tile_off(warp * 16 + a_row, 2 * ks + a_chk);
+      ldsm_x4(aQh + off, qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3]);
+      ldsm_x4(aQl + off, ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      if (nt < n_kt) {
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          uint32_t kb[4], kl[4];
+          const int off = tile_off(nt * 8 + b_row, 4 * kh + b_chk);
+          ldsm_x4(aKh + off, kb[0], kb[1], kb[2], kb[3]);
+          ldsm_x4(aKl + off, kl[0], kl[1], kl[2], kl[3]);
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            const int ks = 2 * kh + k2;
+            mma_bf16_16816(s[nt], ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], kb[2 * k2], kb[2 * k2 + 1]);
+            mma_bf16_16816(s[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], kl[2 * k2], kl[2 * k2 + 1]);
+            mma_bf16_16816(s[nt], qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], kb[2 * k2], kb[2 * k2 + 1]);
+          }
+        }
+      }
+    }
+  }
+  // ---- phase 2: masked softmax over keys; thread holds rows g (regs 0,1) and g+8 (regs 2,3)
+  float mA = -INFINITY, mB = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    const int k0 = nt * 8 + 2 * t;
+    const bool v0 = k0 < L2 && mask[static_cast<long long>(b) * L2 + k0] != 0;
+    const bool v1 = k0 + 1 < L2 && mask[static_cast<long long>(b) * L2 + k0 + 1] != 0;
+    s[nt][0] = v0 ? s[nt][0] : -INFINITY;
+    s[nt][1] = v1 ? s[nt][1] : -INFINITY;
+    s[nt][2] = v0 ? s[nt][2] : -INFINITY;
+    s[nt][3] = v1 ? s[nt][3] : -INFINITY;
+    mA = fmaxf(mA, fmaxf(s[nt][0], s[nt][1]));
+    mB = fmaxf(mB, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+  mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+  mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+  mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+  float lA = 0.f, lB = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    s[nt][0] = expf(s[nt][0] - mA);
+    s[nt][1] = expf(s[nt][1] - mA);
+    s[nt][2] = expf(s[nt][2] - mB);
+    s[nt][3] = expf(s[nt][3] - mB);
+    lA += s[nt][0] + s[nt][1];
+    lB += s[nt][2] + s[nt][3];
+  }
+  lA += __shfl_xor_sync(0xffffffffu, lA, 1);
+  lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+  lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+  lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+  const float iA = 1.0f / lA, iB = 1.0f / lB;
+  // probabilities as hi | lo A-fragments per 16-key step
+  uint32_t ph[8][4], pl[8][4];
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // key tiles 2kk, 2kk+1
+      const float a0 = s[2 * kk + h][0] * iA, a1 = s[2 * kk + h][1] * iA;
+      const float b0 = s[2 * kk + h][2] * iB, b1 = s[2 * kk + h][3] * iB;
+      const __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+      ph[kk][2 * h] = *reinterpret_cast<const uint32_t*>(&ha);
+      ph[kk][2 * h + 1] = *reinterpret_cast<const uint32_t*>(&hb);
+      pl[kk][2 * h] = pack_bf16x2(a0 - __low2float(ha), a1 - __high2float(ha));
+      pl[kk][2 * h + 1] = pack_bf16x2(b0 - __low2float(hb), b1 - __high2float(hb));
+    }
+  }
+  // ---- phase 3: O = P x3, 64 output dims per pass
+  float* ob = out + (static_cast<long long>(b) * L1 + q0) * out_pitch;
+  const int rA = warp * 16 + g, rB = rA + 8;
+  for (int d0 = 0; d0 < D3; d0 += 64) {
+    __syncthreads();
+    stage_split_chunk(x3b, x3_pitch, L2, D3, d0, key_rows, s_k[0], s_k[1], tid);
+    __syncthreads();
+    float o[8][4];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      if (kk < n_kk) {
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t vh[4], vl[4];
+          const int off = tile_off(kk * 16 + a_row, 2 * dp + a_chk);
+          ldsm_x4_t(aKh + off, vh[0], vh[1], vh[2], vh[3]);
+          ldsm_x4_t(aKl + off, vl[0], vl[1], vl[2], vl[3]);
+          mma_bf16_16816(o[2 * dp], pl[kk][0], pl[kk][1], pl[kk][2], pl[kk][3], vh[0], vh[1]);
+          mma_bf16_16816(o[2 * dp], ph[kk][0], ph[kk][1], ph[kk][2], ph[kk][3], vl[0], vl[1]);
+          mma_bf16_16816(o[2 * dp], ph[kk][0], ph[kk][1], ph[kk][2], ph[kk][3], vh[0], vh[1]);
+          mma_bf16_16816(o[2 * dp + 1], pl[kk][0], pl[kk][1], pl[kk][2], pl[kk][3], vh[2], vh[3]);
+          mma_bf16_16816(o[2 * dp + 1], ph[kk][0], ph[kk][1], ph[kk][2], ph[kk][3], vl[2], vl[3]);
+          mma_bf16_16816(o[2 * dp + 1], ph[kk][0], ph[kk][1], ph[kk][2], ph[kk][3], vh[2], vh[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const int col = d0 + d * 8 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = h ? rB : rA;
+        if (r < nq) {
+          float* dst = ob + static_cast<long long>(r) * out_pitch + col;
+          float x0 = o[d][2 * h], x1 = o[d][2 * h + 1];
+          if (col < D3) dst[0] = add_to_out ? dst[0] + x0 : x0;
+          if (col + 1 < D3) dst[1] = add_to_out ? dst[1] + x1 : x1;
+        }
+      }
+    }
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------
 // LinearSelfAttn + weighted_avg (Layers.py:328-341,529-534; SDNet.py:414-415):
 //   alpha = softmax(mask(x w + b)) over the sequence ; out[b] = sum_l alpha_l x[b, l]
@@ -603,8 +815,17 @@ extern "C" int ruart_attention_tail(const float* p1, long long p1_pitch, const f
                                     long long p2_pitch, int hidden, const uint8_t* mask,
                                     const float* x3, long long x3_pitch, int D3, float* out,
                                     long long out_pitch, int B, int L1, int L2, int add_to_out,
-                                    void* stream) {
+                                    int split_parts, void* stream) {
   RUART_ARG_CHECK(B > 0 && L1 > 0 && L2 > 0 && hidden > 0 && D3 > 0);
+  static const bool no_mma = getenv("RUART_TAIL_NO_MMA") != nullptr;  // A/B aid
+  if (split_parts == 2 && L2 <= ATM_L2 && !no_mma) {
+    dim3 grid((L1 + ATM_Q - 1) / ATM_Q, B);
+    attention_tail_mma_kernel<<<grid, ATM_THREADS, 0, (cudaStream_t)stream>>>(
+        p1, p1_pitch, p2, p2_pitch, hidden, mask, x3, x3_pitch, D3, out, out_pitch, L1, L2,
+        add_to_out);
+    RUART_LAUNCH_CHECK();
+    return RUART_OK;
+  }
   if (L2 <= AT_L2) {
     dim3 grid((L1 + AT_Q - 1) / AT_Q, B);
     attention_tail_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(

@@ -161,13 +161,13 @@ def whole_layernorm_(x, eps=1e-5):
     return x
 
 
-def attention_tail(p1, p2, mask_u8, x3, out, B, L1, L2, add=False):
+def attention_tail(p1, p2, mask_u8, x3, out, B, L1, L2, add=False, parts=3):
     _, hid, p1p = rows2d(p1)
     _, _, p2p = rows2d(p2)
     _, D3, x3p = rows2d(x3)
     _, _, op = rows2d(out)
     call("ruart_attention_tail", ptr(p1), p1p, ptr(p2), p2p, hid, ptr(mask_u8), ptr(x3), x3p, D3, ptr(out), op,
-         B, L1, L2, 1 if add else 0, current_stream())
+         B, L1, L2, 1 if add else 0, int(parts), current_stream())
     return out
 
 

@@ -56,3 +56,30 @@ def test_whole_layernorm_on_strided_rows():
     K.whole_layernorm_(view)
     assert (view - want).abs().max().item() < 1e-5
     assert torch.equal(buf[:, :, :5], keep[:, :, :5]) and torch.equal(buf[:, :, 30:], keep[:, :, 30:])
+
+
+@pytest.mark.parametrize("B,L1,L2,Hd,D3", [(3, 100, 100, 250, 250), (2, 37, 40, 250, 250), (4, 70, 128, 300, 300),
+                                           (2, 5, 3, 125, 17), (1, 129, 9, 64, 500)])
+def test_attention_tail_tensor_core_form_matches_fp32_form(B, L1, L2, Hd, D3):
+    # split_parts = 2: mma.sync with hi+lo bf16 operands (3 terms) vs the fp32 CUDA-core kernel,
+    # on strided inputs / outputs like the model's column views
+    from ruart_b200 import sdnet_ops as K
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + L1 + L2)
+    p1 = torch.relu(torch.randn(B * L1, Hd + 6, device="cuda", generator=g))[:, 2:2 + Hd] * 0.3
+    p2 = torch.relu(torch.randn(B * L2, Hd, device="cuda", generator=g)) * 0.3
+    x3 = torch.randn(B, L2, D3 + 2, device="cuda", generator=g)[:, :, 1:1 + D3]
+    mask = (torch.rand(B, L2, device="cuda", generator=g) > 0.3)
+    mask[:, 0] = True
+    m8 = K.as_u8(mask)
+    outs = []
+    for parts in (3, 2):
+        buf = torch.full((B, L1, D3 + 2), 0.5, device="cuda")
+        K.attention_tail(p1, p2, m8, x3, buf[:, :, 2:], B, L1, L2, add=False, parts=parts)
+        K.attention_tail(p1, p2, m8, x3, buf[:, :, 2:], B, L1, L2, add=True, parts=parts)   # accumulate form
+        outs.append(buf)
+    torch.cuda.synchronize()
+    want = torch.softmax((p1.reshape(B, L1, Hd) @ p2.reshape(B, L2, Hd).transpose(1, 2)).masked_fill(~mask[:, None], float("-inf")), -1) @ x3
+    scale = want.abs().max().item()
+    assert (outs[0][:, :, 2:] - 2 * want).abs().max().item() < 1e-4 * scale
+    assert (outs[1][:, :, 2:] - 2 * want).abs().max().item() < 1e-4 * scale
+    assert (outs[1][:, :, :2] == 0.5).all()
