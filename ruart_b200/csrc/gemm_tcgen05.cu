@@ -842,7 +842,8 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   // CTA-pair kernel: plain bf16 output, whole 256-column tiles, one MMA term, a full wave of pairs
   static const bool one_cta = getenv("RUART_GEMM_1CTA") != nullptr;  // A/B aid
   GemmKernel kern2 = nullptr;
-  if (!one_cta && tma_out && n_terms == 1 && (N % MAX_BN) == 0 && M >= 2 * BM * 8) {
+  static bool pair_launch_ok = true;
+  if (!one_cta && pair_launch_ok && tma_out && n_terms == 1 && (N % MAX_BN) == 0 && M >= 2 * BM * 8) {
     if (has_res) kern2 = gemm_bf16_2cta_kernel<K_BIAS, true>;
     else if (kind == K_BIAS) kern2 = gemm_bf16_2cta_kernel<K_BIAS, false>;
     else if (kind == K_GELU_FAST) kern2 = gemm_bf16_2cta_kernel<K_GELU_FAST, false>;
@@ -863,8 +864,16 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
     int grid2 = ruart_num_sms() & ~1;
     if (grid2 > 2 * pair_tiles) grid2 = 2 * pair_tiles;
     kern2<<<grid2, GEMM_THREADS, GEMM2_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb2, tmc, tmr, p);
-    RUART_LAUNCH_CHECK();
-    return RUART_OK;
+    const cudaError_t e2 = cudaGetLastError();
+    if (e2 == cudaSuccess) return RUART_OK;
+    // a device / partition that cannot co-schedule CTA pairs rejects the cluster launch up front
+    // (nothing ran): remember it and use the 1-CTA kernel from now on; anything else is an error
+    if (e2 != cudaErrorInvalidConfiguration && e2 != cudaErrorLaunchOutOfResources &&
+        e2 != cudaErrorNotSupported && e2 != cudaErrorInvalidValue) {
+      ruart_set_error("%s:%d: launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e2));
+      return RUART_ERR_CUDA;
+    }
+    pair_launch_ok = false;
   }
   GemmKernel kern = kernel_for(kind, tma_out, has_res);
   static bool attr_set[K_NUM][3] = {};
