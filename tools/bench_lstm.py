@@ -14,7 +14,8 @@ from ruart_b200.ops import call  # noqa: E402
 
 def main():
     dev = "cuda"
-    H, B = 125, 256
+    H = 125
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     res = []
     for L in (100, 37, 40):
         xg = torch.randn(B * L, 8 * H, device=dev) * 0.5
