@@ -68,17 +68,20 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons while the timed region runs.  The nvidia-smi process is
+    started ahead of time (`start()`, before the warm-up: its start-up can take longer than a short
+    timed region); only rows that arrive inside the `with` window are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -88,11 +91,18 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def __enter__(self):
+        if self.proc is None:
+            self.start()
+        self.t0 = time.perf_counter()
+        return self
 
     def __exit__(self, *a):
+        self.t1 = time.perf_counter()
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.1)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -100,10 +110,11 @@ class ClockSampler(object):
                 self.proc.kill()
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if self.t0 <= t <= self.t1 + 0.06]   # + one sampling period of pipe delay
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -242,6 +253,7 @@ def main():
             return _Timed(2.0 * M_ * N_ * Kp_)
         return null
 
+    clocks = ClockSampler(local_rank).start()   # nvidia-smi is up before the timed region begins
     with torch.no_grad():
         for _ in range(args.warmup):
             probs, _ = net(*fresh(dev_batch))
@@ -250,7 +262,7 @@ def main():
         _lib.set_timing_hook(hook)
         launches0 = _lib.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clocks:
+        with clocks:
             barrier()
             e0.record()
             for _ in range(args.steps):
