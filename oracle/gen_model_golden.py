@@ -25,6 +25,8 @@ CASES = {
     "small_uniform_pretrained": ("small", False, "pretrained_like", 5),
     # PHOC channel on the OCR / OD side (opt PHOC, ocr_embedding phoc,...: SDNet.py:51-55,441-446)
     "tiny_ragged_phoc": ("tiny", True, "random", 1033),
+    # BASELINE.json configs[0] at full size: 32 questions x 20 q-tokens x 50 OCR tokens (+10 OD labels)
+    "cfg1_uniform_random": ("cfg1", False, "random", 1033),
 }
 PHOC_CASES = ("tiny_ragged_phoc",)
 CAPTURE = ("Bert", "multi2one", "context_rnn", "ques_rnn", "deep_attn", "high_lvl_context_rnn", "ques_self_attn")

@@ -207,13 +207,18 @@ def test_baseline_config1_full_size_both_modes():
     cpu_sd = {k: v.cpu() for k, v in net.state_dict().items()}
     want_p, want_l, _ = sdnet_oracle.sdnet_forward(cpu_sd, opt, *copy.deepcopy(batch))
     want_pick = synth.select_answers(want_p, batch[1]["num_cnt"])
+    # ... and the UNMODIFIED reference's own output for this exact case (tests/golden, made by
+    # oracle/gen_model_golden.py in the build container)
+    g = load_golden("cfg1_uniform_random")
+    assert rel_err(want_l, g["logits"]) < 2e-5 and want_pick == g["picks"].tolist()
     for mode, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
         net.Bert.precision = mode
         net.sdnet_parts = 3 if mode == "fp32" else 2
         probs, logits, _ = run_ours(net, batch)
         assert rel_err(logits, want_l) < tol, mode
+        assert rel_err(logits, g["logits"]) < tol, mode
         picks = synth.select_answers(probs, batch[1]["num_cnt"])
-        agree = sum(int(a == b) for a, b in zip(picks, want_pick)) / len(picks)
+        agree = sum(int(a == b) for a, b in zip(picks, g["picks"].tolist())) / len(picks)
         assert agree >= 0.995, (mode, agree)
 
 

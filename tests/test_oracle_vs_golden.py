@@ -38,6 +38,19 @@ def test_oracle_reproduces_reference(name):
     assert rel_err(inter["q_final"][:, :8, :16], g["ques_self_attn"]) < 1e-4
 
 
+def test_oracle_reproduces_reference_at_baseline_config1_size():
+    # BASELINE.json configs[0]: 32 questions x 20 q-tokens x 50 OCR tokens (+10 OD labels), full size
+    from helpers import build_ours as _build
+    g = load_golden("cfg1_uniform_random")
+    net, opt = _build("cfg1", seed=1033, bert_init="random")
+    batch = synth.make_batch("cfg1")
+    probs, logits, _ = sdnet_oracle.sdnet_forward(net.state_dict(), opt, *batch)
+    assert probs.shape == (32, 101)
+    assert rel_err(logits, g["logits"]) < 2e-5
+    assert np.abs(probs.numpy() - g["probs"]).max() < 2e-5
+    assert synth.select_answers(probs, batch[1]["num_cnt"]) == g["picks"].tolist()
+
+
 def test_oracle_phoc_channel_reproduces_reference():
     # opt PHOC + 'phoc' in ocr_embedding (SDNet.py:51-55,441-446); the golden's table came from the
     # reference's own cphoc, here it comes from the C restatement
