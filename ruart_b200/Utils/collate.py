@@ -11,6 +11,7 @@ in the DataLoader worker, and stage the batch in pinned memory so `ToCUDA`
 The added keys are optional: `SDNet.forward` rebuilds them from the lists when they are absent, so a
 batch straight from the reference's collate works unchanged.
 """
+import numpy as np
 import torch
 
 from ..bert_engine import flatten_offsets
@@ -35,6 +36,78 @@ def attach_index_tensors(q_list, ocr_list, od_list):
         ocr_list["fasttext"].size(1), od_list["fasttext"].size(1),
         ocr_list["position"].size(1), od_list["position"].size(1))
     return q_list, ocr_list, od_list
+
+
+class VQA_collate(object):
+    """Drop-in for the reference's collate class (Utils/VQA_Dataset.py:438-542): same constructor,
+    same `VQA_collate_fun(batch) -> (q_list, ocr_list, od_list, gt, extra_info)` and the same dict
+    layout (int64 id tensors padded with 0, `<key>_mask` = ~eq(0), fp32 `position` [B, max_num, 8],
+    `bert_offsets` / `num_cnt` / `len_cnt` lists) — filled through numpy in one pass per key instead of
+    a `torch.cat` per image, and with the index tensors of `attach_index_tensors` already attached
+    (`index=False` gives the reference's keys only; `pinned=True` stages the tensors in pinned memory)."""
+
+    ID_KEYS = ("glove", "fasttext", "phoc", "bert", "bert_only")
+
+    def __init__(self, opt, index=True, pinned=False):
+        self.opt, self.index, self.pinned = opt, index, pinned
+
+    def VQA_collate_fun(self, batch):
+        opt = self.opt
+        q_list = self.que_collate([t["q"] for t in batch], opt["max_q_len"], opt["max_q_bert_len"])
+        ocr_list = self.item_collate([t["ocr"] for t in batch], opt["max_ocr_len"], opt["max_ocr_bert_len"],
+                                     opt["max_ocr_num"])
+        od_list = self.item_collate([t["od"] for t in batch], opt["max_od_len"], opt["max_od_bert_len"],
+                                    opt["max_od_num"])
+        gt = torch.cat([t["gt"] for t in batch], dim=0)
+        if self.index:
+            attach_index_tensors(q_list, ocr_list, od_list)
+        if self.pinned:
+            q_list, ocr_list, od_list = pin((q_list, ocr_list, od_list))
+        return q_list, ocr_list, od_list, gt, [t["extra_info"] for t in batch]
+
+    @staticmethod
+    def _pad_ids(rows, width):
+        out = np.zeros((len(rows), width), dtype=np.int64)
+        for i, r in enumerate(rows):
+            out[i, :len(r)] = r          # a row longer than `width` raises, like the reference's slice assignment
+        return torch.from_numpy(out)
+
+    def _finish(self, res):
+        for k in list(res):
+            if k in self.ID_KEYS:
+                res[k + "_mask"] = ~res[k].eq(0)
+        return res
+
+    def que_collate(self, q_list, max_len, max_bert_len):
+        res = {}
+        for k in q_list[0].keys():
+            if k in ("img_features", "img_spatials"):
+                res[k] = torch.cat([t[k] for t in q_list], dim=0)
+            elif "offset" in k:
+                res[k] = [t[k] for t in q_list]
+            else:
+                res[k] = self._pad_ids([t[k] for t in q_list], max_bert_len if k in ("bert", "bert_only") else max_len)
+        return self._finish(res)
+
+    def item_collate(self, item_list, max_len, max_bert_len, max_num):
+        res = {}
+        flat = [it for items in item_list for it in items]
+        for k in item_list[0][0].keys():
+            if "offset" in k:
+                res[k] = [it[k] for it in flat]
+            elif k == "position":
+                pos = np.zeros((len(item_list), max_num, 8), dtype=np.float32)
+                for b, items in enumerate(item_list):
+                    if items:
+                        pos[b, :len(items)] = np.asarray([it[k] for it in items], dtype=np.float32)
+                res[k] = torch.from_numpy(pos)
+            else:
+                res[k] = self._pad_ids([it[k] for it in flat], max_bert_len if k in ("bert", "bert_only") else max_len)
+        self._finish(res)
+        res["num_cnt"] = [len(items) for items in item_list]
+        word_key = "fasttext" if "FastText" in self.opt else "glove"
+        res["len_cnt"] = [[len(it[word_key]) for it in items] for items in item_list]
+        return res
 
 
 def pin(batch):

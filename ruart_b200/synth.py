@@ -284,6 +284,37 @@ def make_batch(cfg="cfg1", seed=None, ragged=False, opt=None, n_q_words=20):
     return q_list, ocr_list, od_list
 
 
+def uncollate(batch):
+    """Per-sample dicts as VQA_Dataset.__getitem__ hands them to the collate function
+    (Utils/VQA_Dataset.py:448-462: keys 'q', 'ocr', 'od', 'gt', 'extra_info'), recovered from a
+    collated synth batch — the input side of Utils/collate.py's tests."""
+    q, ocr, od = batch
+    B = len(ocr["num_cnt"])
+    samples = []
+    row = {"ocr": 0, "od": 0}
+    for b in range(B):
+        nq = int(q["glove_mask"][b].sum())
+        nb = int(q["bert_mask"][b].sum())
+        qs = {"glove": q["glove"][b, :nq].tolist(), "pos": q["pos"][b, :nq].tolist(), "ent": q["ent"][b, :nq].tolist(),
+              "bert": q["bert"][b, :nb].tolist(), "bert_offsets": q["bert_offsets"][b]}
+        lists = {}
+        for name, d in (("ocr", ocr), ("od", od)):
+            items = []
+            for k in range(d["num_cnt"][b]):
+                r = row[name]
+                nw = d["len_cnt"][b][k]
+                nt = int(d["bert_mask"][r].sum())
+                items.append({"fasttext": d["fasttext"][r, :nw].tolist(), "pos": d["pos"][r, :nw].tolist(),
+                              "ent": d["ent"][r, :nw].tolist(), "bert": d["bert"][r, :nt].tolist(),
+                              "bert_offsets": d["bert_offsets"][r], "position": d["position"][b, k].tolist()})
+                row[name] += 1
+            lists[name] = items
+        gt = torch.zeros(1, ocr["position"].size(1) + 1)
+        gt[0, b % max(1, ocr["num_cnt"][b] - 1)] = 1.0
+        samples.append({"q": qs, "ocr": lists["ocr"], "od": lists["od"], "gt": gt, "extra_info": {"q_id": b}})
+    return samples
+
+
 def batch_to(batch, device):
     """ToCUDA (SDNetTrainer.py:208-230): tensors to `device`, lists stay on the host."""
     out = []

@@ -109,3 +109,28 @@ def test_collate_index_tensors_equal_the_per_forward_ones():
     import pytest
     with pytest.raises(ValueError):
         flatten_offsets(np.zeros((3, 5), np.int32), 4)
+
+
+def test_collate_drop_in_rebuilds_the_reference_layout():
+    # Utils.collate.VQA_collate vs the collated synth batches (oracle/check_collate.py shows, in the build
+    # container, that the unmodified reference's collate emits exactly this layout from the same samples)
+    from ruart_b200.Utils.collate import CSR_KEY, PLAN_KEY, TOTALS_KEY, VQA_collate
+    for cfg, ragged in (("tiny", True), ("small", False)):
+        opt = synth.make_opt(cfg)
+        batch = synth.make_batch(cfg, ragged=ragged)
+        samples = synth.uncollate(batch)
+        assert len(samples) == len(batch[1]["num_cnt"]) and set(samples[0]) == {"q", "ocr", "od", "gt", "extra_info"}
+        q, ocr, od, gt, extra = VQA_collate(opt).VQA_collate_fun(samples)
+        for got, want in ((q, batch[0]), (ocr, batch[1]), (od, batch[2])):
+            assert set(want) <= set(got) and set(got) - set(want) <= {CSR_KEY, PLAN_KEY, TOTALS_KEY}
+            for k, v in want.items():
+                if torch.is_tensor(v):
+                    assert got[k].dtype == v.dtype and torch.equal(got[k], v), k
+                else:
+                    assert got[k] == v, k
+        assert CSR_KEY in q and PLAN_KEY in ocr and ocr[TOTALS_KEY][0] == int(batch[1]["bert_mask"].sum())
+        assert gt.shape == (len(samples), opt["max_ocr_num"] + 1) and [e["q_id"] for e in extra] == list(range(len(samples)))
+    import pytest
+    opt = synth.make_opt("tiny", max_ocr_len=1)          # an item with 2 words no longer fits: error, like the reference
+    with pytest.raises(ValueError):
+        VQA_collate(opt).VQA_collate_fun(synth.uncollate(synth.make_batch("tiny")))
