@@ -31,3 +31,18 @@ def test_bad_arguments_are_reported_without_a_gpu():
                            1, 0, 0, None, 0, None)
     assert rc == 2
     assert b"bad argument" in L.ruart_last_error()
+
+
+def test_ctypes_signatures_have_the_arity_the_header_declares():
+    # every prototype in include/ruart_b200.h: the number of parameters equals the length of the
+    # ctypes argtypes list (catches ABI drift between the header, the library and the binding)
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ruart_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"RUART_API\s+[\w\s\*]+?\b(ruart_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) == len(_lib.declared_symbols())
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        assert n == len(_lib._SIGNATURES[name]), "%s: header %d parameters, binding %d" % (name, n, len(_lib._SIGNATURES[name]))
