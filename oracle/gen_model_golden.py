@@ -27,6 +27,9 @@ CASES = {
     "tiny_ragged_phoc": ("tiny", True, "random", 1033),
     # BASELINE.json configs[0] at full size: 32 questions x 20 q-tokens x 50 OCR tokens (+10 OD labels)
     "cfg1_uniform_random": ("cfg1", False, "random", 1033),
+    # BASELINE.json configs[4] shape (200 OCR tokens per image, question row padded to the 512-token
+    # window) at 4 images
+    "cfg5s_ragged_random": ("cfg5s", True, "random", 1033),
 }
 PHOC_CASES = ("tiny_ragged_phoc",)
 CAPTURE = ("Bert", "multi2one", "context_rnn", "ques_rnn", "deep_attn", "high_lvl_context_rnn", "ques_self_attn")

@@ -52,6 +52,7 @@ CONFIGS = {
     "cfg3": dict(B=256, n_ocr=50, n_od=36, max_ocr_num=100, max_od_num=37),
     "cfg4": dict(B=4096, n_ocr=50, n_od=36, max_ocr_num=100, max_od_num=37),
     "cfg5": dict(B=32, n_ocr=200, n_od=36, max_ocr_num=201, max_od_num=37, max_q_bert_len=512),
+    "cfg5s": dict(B=4, n_ocr=200, n_od=36, max_ocr_num=201, max_od_num=37, max_q_bert_len=512),  # cfg5 shape, 4 images
 }
 
 

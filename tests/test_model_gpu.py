@@ -115,6 +115,18 @@ def test_long_ocr_config5_shape():
     assert torch.equal(probs.argmax(1), want_p.argmax(1))
 
 
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_long_ocr_config5_shape_matches_reference_golden(mode, tol):
+    # the same shape against the UNMODIFIED reference's own output (tests/golden/model_cfg5s_ragged_random.npz)
+    g = load_golden("cfg5s_ragged_random")
+    net, opt = build_ours("cfg5s", seed=1033, bert_init="random", device="cuda", BERT_precision=mode, KEEP_LOGITS=True)
+    batch = synth.make_batch("cfg5s", ragged=True)
+    probs, logits, _ = run_ours(net, batch)
+    assert probs.shape == g["probs"].shape == (4, 202)
+    assert rel_err(logits, g["logits"]) < tol
+    assert synth.select_answers(probs, batch[1]["num_cnt"]) == g["picks"].tolist()
+
+
 def test_bert_window_split_long_row():
     """Rows longer than 512 wordpieces are encoded as independent 512-token windows with positions
     restarting at 0 (Bert.py:96-99,135-138)."""

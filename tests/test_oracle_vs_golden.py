@@ -51,6 +51,20 @@ def test_oracle_reproduces_reference_at_baseline_config1_size():
     assert synth.select_answers(probs, batch[1]["num_cnt"]) == g["picks"].tolist()
 
 
+def test_oracle_reproduces_reference_at_long_ocr_config5_shape():
+    # BASELINE.json configs[4] shape: 200 OCR tokens per image (max_ocr_num 201), question rows padded to
+    # the 512-token BERT window; 4 ragged images
+    from helpers import build_ours as _build
+    g = load_golden("cfg5s_ragged_random")
+    net, opt = _build("cfg5s", seed=1033, bert_init="random")
+    batch = synth.make_batch("cfg5s", ragged=True)
+    assert batch[0]["bert"].shape == (4, 512) and batch[1]["position"].shape == (4, 201, 8)
+    probs, logits, _ = sdnet_oracle.sdnet_forward(net.state_dict(), opt, *batch)
+    assert probs.shape == (4, 202)
+    assert rel_err(logits, g["logits"]) < 2e-5
+    assert synth.select_answers(probs, batch[1]["num_cnt"]) == g["picks"].tolist()
+
+
 def test_oracle_phoc_channel_reproduces_reference():
     # opt PHOC + 'phoc' in ocr_embedding (SDNet.py:51-55,441-446); the golden's table came from the
     # reference's own cphoc, here it comes from the C restatement
