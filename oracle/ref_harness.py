@@ -12,7 +12,9 @@ Shims, all outside the reference tree:
         Models/SDNet.py:288-299, Models/Bert/Bert.py:42,173);
   (iii) a temp dir with bert_config.json + pytorch_model.bin ('bert.'-prefixed BertModel state);
   (iv)  `opt` from ruart_b200.synth.make_opt (the shipped conf restated) ;
-  (v)   net.drop_emb = False, net.eval().
+  (v)   net.drop_emb = False, net.eval();
+  (vi)  training-step goldens only (oracle/gen_train_golden.py): `fixed_embedding_*` cloned, which is what
+        `network.cuda()` does implicitly on a GPU (see the comment there), and all dropout at 0.
 """
 import contextlib
 import json
@@ -83,7 +85,7 @@ def import_reference():
     return ref_sdnet
 
 
-def build_reference(opt, embedding=None, seed=1033, bert_init="random", bert_layers=12):
+def build_reference(opt, embedding=None, seed=1033, bert_init="random", bert_layers=12, bert_dropout=None):
     """Construct the reference SDNet with weights from synth.fill_state_dict (same names as ours)."""
     ref_sdnet = import_reference()
     from Models.Bert.modeling import BertConfig, BertModel
@@ -92,6 +94,8 @@ def build_reference(opt, embedding=None, seed=1033, bert_init="random", bert_lay
     opt = dict(opt)
     with tempfile.TemporaryDirectory() as tmp, _cpu_cuda_identity():
         cfg = BertConfig(synth.BERT_VOCAB, num_hidden_layers=bert_layers)
+        if bert_dropout is not None:  # training-step goldens: deterministic
+            cfg.hidden_dropout_prob = cfg.attention_probs_dropout_prob = float(bert_dropout)
         with open(os.path.join(tmp, "bert_config.json"), "w") as f:
             json.dump(cfg.to_dict(), f)
         bm = BertModel(cfg)
@@ -139,3 +143,30 @@ def run_reference(net, batch, capture=()):
         for h in hooks:
             h.remove()
     return probs.detach(), logits.get("final"), captured
+
+
+
+def run_reference_update(net, opt, batch, targets):
+    """One UNMODIFIED `SDNetTrainer.update` (Models/SDNetTrainer.py:330-376) on `net`, driven through a
+    stand-in trainer object that carries exactly the attributes `update` touches (the real constructor
+    needs the ST-VQA data files).  Returns (loss, {name: grad})."""
+    import types
+
+    import torch.optim as optim
+    import Models.SDNetTrainer as trainer_mod
+
+    class _Meter(object):
+        def update(self, *a, **k):
+            pass
+
+    fake = types.SimpleNamespace(network=net, opt=opt, train_loss=_Meter(), updates=0)
+    fake.instance_bce_with_logits = types.MethodType(trainer_mod.SDNetTrainer.instance_bce_with_logits, fake)
+    fake.loss_func = fake.instance_bce_with_logits
+    params = [p for p in net.parameters() if p.requires_grad]
+    fake.optimizer = optim.Adamax(params, lr=opt["lr"] if "lr" in opt else 2e-3)
+    import copy
+    q, ocr, od = copy.deepcopy(batch)
+    with _cpu_cuda_identity():
+        loss = trainer_mod.SDNetTrainer.update(fake, (q, ocr, od, targets, [{"q_id": i} for i in range(len(targets))]), 0)
+    grads = {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.requires_grad and p.grad is not None}
+    return loss, grads
