@@ -196,6 +196,18 @@ RUART_API int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const f
 RUART_API int ruart_select_answers(const float* probs, const int32_t* num_cnt, int B, int M1,
                                    int label_no_answer, int32_t* out_idx, void* stream);
 
+/* ---------------------------------------------------------------- training step, optimizer side
+ * (SDNetTrainer.update, SDNetTrainer.py:363-365) over ONE flat fp32 buffer of all trainable parameters.
+ * ruart_grad_sqnorm: *out_sq = sum g[i]^2 in double (deterministic; workspace >= 1024 doubles).
+ * ruart_adamax_step: torch.optim.Adamax (no weight decay) on the gradient scaled by
+ * min(1, max_norm / (sqrt(*grad_sq) + 1e-6)) — torch.nn.utils.clip_grad_norm_ — read from device
+ * memory; grad_sq NULL or max_norm <= 0: no clipping.  `step` counts from 1.                    */
+RUART_API int ruart_grad_sqnorm(const float* g, long long n, double* workspace, double* out_sq,
+                                void* stream);
+RUART_API int ruart_adamax_step(float* p, const float* g, float* exp_avg, float* exp_inf, long long n,
+                                float lr, float beta1, float beta2, float eps, int step,
+                                const double* grad_sq, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
