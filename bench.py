@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of RUArt's per-question inference path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg cfg3|cfg4|cfg5]
 
-One "step" = one SDNet.forward over one synthetic ST-VQA-shaped batch (cfg-3: 256 questions x
-20 q-words, 50+1 OCR items, 36+1 OD items, bf16 BERT).  N > 1 is launched with torchrun, one rank
-per GPU; every rank runs its own seeded batch of the same size (weak scaling, no data-path
-collective — SURVEY.md §8e) and rank 0 prints ONE JSON line.
+One "step" = one SDNet.forward over one synthetic ST-VQA-shaped batch.  Workload by default:
+  N = 1   cfg-3 (BASELINE.json configs[2]): 256 questions x 20 q-words, 50+1 OCR items, 36+1 OD items,
+          bf16 BERT, one B200
+  N > 1   cfg-4 (configs[3]): a GLOBAL batch of 4096 such questions split evenly over the N ranks
+          (2048 / 1024 / 512 per GPU), no data-path collective -> "scaling": "strong".
+          `--cfg cfg3` at N > 1 gives the round-1 weak-scaling run (256 questions per GPU).
+N > 1 is launched with torchrun, one rank per GPU; rank 0 prints ONE JSON line.
 
   value      questions/s with the batch's tensors already resident in HBM
   e2e        same through the public API with the batch in pinned HOST memory: H2D of every input
@@ -14,6 +17,11 @@ collective — SURVEY.md §8e) and rank 0 prints ONE JSON line.
   roofline   all tcgen05 GEMM launches of the BERT encoder in the timed steps: algorithmic FLOPs
              (2*T*N*K over the REAL tokens) / CUDA-event time, against the measured sustained bf16
              peak in MEASURED_PEAKS.json
+  roofline_step  whole-step algorithmic work (77.5 GFLOP per question) / step time / peak
+  kernels    live CUDA-event time and algorithmic GB/s of the memory-bound BERT kernels (LayerNorm,
+             attention, subword mean + layer sum) against the measured HBM bandwidth
+  phoc       BASELINE configs[1]: 1 M synthetic strings through the PHOC kernel (strings/s, fraction of
+             HBM bandwidth, bit-exact check against the C oracle on a sample, CPU cphoc baseline)
   cpu_baseline  the CPU oracle port (oracle/sdnet_oracle.py, plain torch fp32 on all host threads)
              on a bounded sample of the same workload (rank 0, N=1 only)
 
@@ -42,11 +50,95 @@ METRIC = "ST-VQA questions/sec"
 UNIT = "questions/s"
 
 
-def workload_desc(cfg):
+def workload_desc(cfg, world=1):
     c = synth.CONFIGS[cfg]
-    return ("%s: B=%d questions x 20 q-words, %d+1 OCR items, %d+1 OD labels per image "
+    split = "" if cfg != "cfg4" else " (global batch, split evenly over %d rank%s)" % (world, "" if world == 1 else "s")
+    return ("%s: B=%d questions%s x 20 q-words, %d+1 OCR items, %d+1 OD labels per image "
             "(max_ocr_num %d, max_od_num %d), synthetic ids, random-init BERT-base + SDNet" %
-            (cfg, c["B"], c["n_ocr"], c["n_od"], c["max_ocr_num"], c["max_od_num"]))
+            (cfg, c["B"], split, c["n_ocr"], c["n_od"], c["max_ocr_num"], c["max_od_num"]))
+
+
+# whole-step algorithmic work per question of the cfg-3 / cfg-4 shape: 19.35 TFLOP of
+# BERT over real tokens + 0.50 TFLOP of SDNet stack per 256 questions
+STEP_GFLOP_PER_QUESTION = 19.85e3 / 256.0
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6500.0, "fallback (B200_PROFILING.md measured copy bandwidth ~6.5 TB/s)"
+
+
+def bert_token_stats(batch):
+    """Host-side counts of one batch for the algorithmic-byte figures: real wordpieces T, words and
+    the wordpieces inside word spans (what the subword mean reads)."""
+    T = words = pieces = 0
+    for d, wkey in zip(batch, ("glove_mask", "fasttext_mask", "fasttext_mask")):
+        T += int(d["bert_mask"].sum())
+        for item in d["bert_offsets"]:
+            if len(item) == 2 and not isinstance(item[0], (list, tuple)):
+                item = [item]
+            for st, ed in item:
+                words += 1
+                pieces += max(0, ed - st)
+    return T, words, pieces
+
+
+def phoc_record(n=1_000_000):
+    """BASELINE configs[1]: n strings, length U[1,20] over [a-z0-9], seed 2002."""
+    import numpy as np
+    from oracle import phoc_oracle
+    from ruart_b200 import ops
+    rng = np.random.default_rng(2002)
+    lens = rng.integers(1, 21, size=n)
+    offsets = np.zeros(n + 1, np.int32)
+    offsets[1:] = np.cumsum(lens)
+    alpha = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789", np.uint8)
+    chars = alpha[rng.integers(0, 36, size=int(offsets[-1]))]
+    d_c = torch.from_numpy(np.concatenate([chars, np.zeros(1, np.uint8)])).cuda()
+    d_o = torch.from_numpy(offsets).cuda()
+    out = torch.empty((n, 604), dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ops.phoc_batch(d_c, d_o, out=out)
+    ts = []
+    for _ in range(10):
+        flush.zero_()   # L2 flush between timed launches (126 MB L2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.phoc_batch(d_c, d_o, out=out, check=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = sorted(ts)[len(ts) // 2]
+    nbytes = int(offsets[-1]) + 4 * (n + 1) + n * 604 * 4
+    peak, src = hbm_peak()
+    # bit-exact check of a bounded sample against the C oracle, and the CPU baselines on that sample
+    m = min(n, 200_000)
+    t0 = time.perf_counter()
+    want, bad = phoc_oracle.batch_flat(chars[:offsets[m]], offsets[:m + 1])
+    dt_port = time.perf_counter() - t0
+    exact = bool(np.array_equal(out[:m].cpu().numpy(), want))
+    rec = {"strings": n, "ms": t, "strings_per_s": n / t * 1e3, "algorithmic_bytes": nbytes,
+           "achieved_GBps": nbytes / t / 1e6, "hbm_peak_GBps": peak, "frac_of_hbm": nbytes / t / 1e6 / peak,
+           "peak_source": src, "bit_exact_vs_oracle": exact, "checked_strings": m,
+           "l2": "256 MB flush between timed launches",
+           "cpu_baseline": {"kind": "port", "cores": 1, "strings_per_s": m / dt_port,
+                            "sample": "%d strings, oracle/phoc_oracle.c (plain C, 1 thread)" % m}}
+    ref = phoc_oracle.ref_module()
+    if ref is not None:   # the reference's own Utils/cphoc.c (built into oracle/_ref in the build container)
+        k = min(m, 100_000)
+        strs = [bytes(chars[offsets[i]:offsets[i + 1]]).decode() for i in range(k)]
+        t0 = time.perf_counter()
+        for x in strs:
+            ref.build_phoc(x)
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline_reference"] = {"kind": "reference", "cores": 1, "strings_per_s": k / dt,
+                                         "sample": "%d strings through the reference's cphoc.build_phoc (CPython call per string)" % k}
+    del out, flush
+    return rec
 
 
 def gemm_traffic():
@@ -145,6 +237,17 @@ def sample_cfg(cfg, n_questions):
     return c
 
 
+def port_vs_reference():
+    """What the UNMODIFIED reference measured next to the port in the build container (the reference tree does
+    not travel to the GPU box): makes the port's bias visible (VERDICT r1 weak #12)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_cpu_port_vs_reference.json")) as f:
+            d = json.load(f)
+        return {"port_vs_reference_in_build_container": d}
+    except Exception:
+        return {}
+
+
 def run_reference_arm(args, rank, world):
     """CPU port on the host cores; each step is a bounded sample of the workload."""
     if rank != 0:
@@ -153,6 +256,7 @@ def run_reference_arm(args, rank, world):
     torch.set_num_threads(threads)
     budget = 150.0 / max(1, args.steps + args.warmup)
     n_q = max(1, min(32, int(budget / 0.8)))
+    args.cfg = args.cfg or ("cfg3" if world == 1 else "cfg4")
     net, opt = build_net(sample_cfg(args.cfg, n_q), None)
     sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     batch = synth.make_batch(sample_cfg(args.cfg, n_q), seed=2003)
@@ -168,8 +272,9 @@ def run_reference_arm(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_desc(args.cfg)},
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_desc(args.cfg, world)},
+        "cpu_baseline": dict({"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                             **port_vs_reference()),
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -180,7 +285,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cfg", default="cfg3")
+    ap.add_argument("--cfg", default=None, help="cfg3 (default at N=1), cfg4 (default at N>1: 4096 questions / N), cfg5")
+    ap.add_argument("--no-phoc", action="store_true", help="skip the cfg-2 PHOC record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collate-index", action="store_true",
                     help="prepare the batch with ruart_b200.Utils.collate.attach_index_tensors (CSR word offsets, "
@@ -206,9 +312,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from ruart_b200 import _lib
+    args.cfg = args.cfg or ("cfg3" if world == 1 else "cfg4")
     net, opt = build_net(args.cfg, dev)
-    B = synth.CONFIGS[args.cfg]["B"]
-    host_batch = synth.make_batch(args.cfg, seed=2003 + rank)
+    B_global = synth.CONFIGS[args.cfg]["B"]
+    strong = args.cfg == "cfg4"
+    if strong:
+        if B_global % world:
+            raise SystemExit("cfg4's 4096 questions do not split evenly over %d ranks" % world)
+        B = B_global // world           # this rank's shard: its own seeded questions, no collective
+        host_batch = synth.make_batch(sample_cfg(args.cfg, B), seed=2004 + rank, opt=opt)
+    else:
+        B = B_global
+        host_batch = synth.make_batch(args.cfg, seed=2000 + list(synth.CONFIGS).index(args.cfg) + rank, opt=opt)
+    n_tok, n_words, n_pieces = bert_token_stats(host_batch)
     if args.collate_index:
         from ruart_b200.Utils import collate
         host_batch = collate.attach_index_tensors(*host_batch)
@@ -228,6 +344,7 @@ def main():
 
     # ---- GEMM timing hook (roofline): CUDA events around every BERT-shaped GEMM launch ----------
     gemm_events = []
+    kern_events = {"add_ln": [], "bert_attention": [], "subword_avg_layers": []}
     H = 768
 
     class _Timed(object):
@@ -245,7 +362,26 @@ def main():
 
     null = contextlib.nullcontext()
 
+    class _TimedK(object):
+        def __init__(self, key):
+            self.key = key
+
+        def __enter__(self):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+        def __exit__(self, *a):
+            self.e1.record()
+            kern_events[self.key].append((self.e0, self.e1))
+
     def hook(name, a):
+        if name == "ruart_add_layernorm":
+            return _TimedK("add_ln")
+        if name == "ruart_bert_attention":
+            return _TimedK("bert_attention")
+        if name == "ruart_subword_avg_layers":
+            return _TimedK("subword_avg_layers")
         if name != "ruart_gemm_bf16":
             return null
         M_, N_, Kp_, terms = a[6], a[7], a[8], a[9]
@@ -275,6 +411,8 @@ def main():
         g_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
         g_fl = sum(f for _, _, f in gemm_events)
         n_gemm = len(gemm_events)
+        k_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in kern_events.items()}
+        k_n = {k: len(v) // args.steps for k, v in kern_events.items()}
         # -------- end to end: pinned host -> device -> forward -> host -------------------------
         out_host = torch.empty((B, probs.shape[1]), dtype=torch.float32).pin_memory()
         for _ in range(2):
@@ -297,6 +435,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
     total_q = B * world * args.steps
+    hbm, hbm_src = hbm_peak()
+    # algorithmic bytes per step of the memory-bound BERT kernels, bf16 activations
+    k_bytes = {"add_ln": 24 * n_tok * 768 * 2 * 2,                 # 24 LayerNorms: read + write [T,768] bf16
+               "bert_attention": 12 * n_tok * (2304 + 768) * 2,    # 12 layers: read qkv, write ctx
+               "subword_avg_layers": 12 * n_pieces * 768 * 2 + n_words * 768 * 4}
+    kernels = {}
+    for k in k_ms:
+        if k_ms[k] > 0:
+            gbs = k_bytes[k] / (k_ms[k] * 1e-3) / 1e9
+            kernels[k] = {"launches_per_step": k_n[k], "ms_per_step": k_ms[k], "algorithmic_bytes_per_step": k_bytes[k],
+                          "achieved_GBps": gbs, "frac_of_hbm": gbs / hbm}
+    phoc = None
+    if rank == 0 and world == 1 and not args.no_phoc:
+        del dev_batch
+        torch.cuda.empty_cache()
+        phoc = phoc_record()
     value = total_q / (ms / 1e3)
     e2e = total_q / (ms_e2e / 1e3)
 
@@ -313,17 +467,18 @@ def main():
             t0 = time.perf_counter()
             cpu_port_step(csd, copt, cb)
             dt = time.perf_counter() - t0
-        cpu_base = {"value": n_q / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": "one forward over %d questions of the %s shape (oracle/sdnet_oracle.py, fp32 torch CPU)" % (n_q, args.cfg)}
+        cpu_base = dict({"value": n_q / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "one forward over %d questions of the %s shape (oracle/sdnet_oracle.py, fp32 torch CPU)" % (n_q, args.cfg)},
+                        **port_vs_reference())
 
     if rank == 0:
         peak, peak_src = peaks()
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_desc(args.cfg), "per_gpu_batch": B, "global_batch": B * world,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_desc(args.cfg, world), "per_gpu_batch": B, "global_batch": B * world,
                        "parallelism": "batch-sharded x%d, no collective" % world,
                        "precision": "BERT bf16 operands / fp32 accumulate; SDNet stack fp32 activations, GEMM operands as 2-part bf16 splits (~2^-16)",
                        "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
@@ -338,7 +493,16 @@ def main():
                          "traffic_unit": "bytes per launch (mean of the 4 BERT GEMM shapes, ncu dram read+write)",
                          "kernel": "gemm_bf16_2cta_kernel (all %d BERT GEMM launches of the timed steps)" % n_gemm,
                          "kernel_ms_per_step": g_ms / args.steps, "peak_source": peak_src},
+            "roofline_step": {"bound": "tensor", "algorithmic_gflop_per_question": STEP_GFLOP_PER_QUESTION,
+                              "achieved": STEP_GFLOP_PER_QUESTION * B / (ms / args.steps) / 1e3 if args.cfg in ("cfg3", "cfg4") else None,
+                              "peak": peak, "unit": "TFLOP/s",
+                              "frac": (STEP_GFLOP_PER_QUESTION * B / (ms / args.steps) / 1e3 / peak) if args.cfg in ("cfg3", "cfg4") else None,
+                              "note": "whole forward (BERT over real tokens + SDNet stack, SURVEY.md §8d) / step time, per GPU"},
+            "kernels": dict(kernels, hbm_peak_GBps=hbm, peak_source=hbm_src,
+                            note="CUDA events around every launch of the timed steps; bytes are algorithmic (DESIGN.md §4)"),
         }
+        if phoc is not None:
+            line["phoc"] = phoc
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))

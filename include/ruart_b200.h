@@ -208,6 +208,90 @@ RUART_API int ruart_adamax_step(float* p, const float* g, float* exp_avg, float*
                                 float lr, float beta1, float beta2, float eps, int step,
                                 const double* grad_sq, float max_norm, void* stream);
 
+
+/* ---------------------------------------------------------------- training step, differentiable path
+ * (SURVEY.md §8 a-19).  The reference differentiates its forward with torch autograd
+ * (SDNetTrainer.update, SDNetTrainer.py:337-362: forward, loss, `loss.backward()`); here every op of the
+ * SDNet stack has a forward and a backward entry point, composed by ruart_b200/autograd_ops.py.  BERT is
+ * locked (SDNet.py:91-94); only alphaBERT / gammaBERT receive a gradient from it.                        */
+
+/* C[b] (+)= alpha * op(A[b]) op(B[b]), fp32 on the CUDA cores; op(A) is [M,K], op(B) is [K,N]; row-major with
+ * leading dimensions ld*, batch strides stride_* (elements; 0 = shared operand).  The per-image products of
+ * Attention.forward (Layers.py:237,244: x1_rep.bmm(x2_rep^T), alpha.bmm(x3)), BilinearSeqAttn (:459) and their
+ * gradients.                                                                                               */
+RUART_API int ruart_bmm_f32(const float* A, long long lda, long long stride_a, int trans_a, const float* B,
+                            long long ldb, long long stride_b, int trans_b, float* C, long long ldc,
+                            long long stride_c, int batch, int M, int N, int K, float alpha, int accumulate,
+                            void* stream);
+/* out = softmax over the last dim of x [B, L1, L2] with keys whose mask[b, j] == 0 set to -inf
+ * (Layers.py:283-288; mask NULL = plain softmax, Layers.py:418); rows without a live key give NaN.  */
+RUART_API int ruart_masked_softmax(const float* x, long long x_pitch, const uint8_t* mask, int B, int L1,
+                                   int L2, float* out, long long out_pitch, void* stream);
+/* dx = p * (dp - sum_j p_j dp_j) per row */
+RUART_API int ruart_softmax_backward(const float* p, long long p_pitch, const float* dp, long long dp_pitch,
+                                     float* dx, long long dx_pitch, long long rows, int cols, void* stream);
+/* Element-wise helpers on pitched fp32 [rows, cols]: op 0 out = a*b; 1 out = a * (b > 0) (ReLU backward);
+ * 2 out = a + b; 3 out = a * v[c] (v_len == 1: scalar) — the diagonal of AttentionScore (Layers.py:229-231);
+ * 4 out = max(a, 0); 5 out = a + v[c].                                                                      */
+RUART_API int ruart_eltwise(int op, const float* a, long long a_pitch, const float* b, long long b_pitch,
+                            const float* v, int v_len, float* out, long long out_pitch, long long rows,
+                            int cols, void* stream);
+/* out[i] = mask[i] ? x[i] : value over n contiguous elements: `scores.data.masked_fill_(x_mask == 0, -inf)`
+ * (Layers.py:283-284,339,426,463).                                                                          */
+RUART_API int ruart_mask_fill(const float* x, const uint8_t* mask, long long n, float value, float* out,
+                              void* stream);
+/* out[c] (+)= sum_r x[r][c] (bias / diagonal gradients), deterministic; workspace >= 64 * cols doubles. */
+RUART_API int ruart_colsum(const float* x, long long pitch, long long rows, int cols, double* workspace,
+                           float* out, int accumulate, void* stream);
+/* fp32 [rows, K] (row pitch ld) -> TRANSPOSED bf16 split operand dst [K, parts * rows_p] (rows_p a multiple
+ * of 64 >= rows, zero padded): the operands of the weight gradient dW = dY^T X and of dX = dY W on
+ * ruart_gemm_bf16.                                                                                        */
+RUART_API int ruart_split_bf16_t(const float* src, long long ld, long long rows, int K, long long rows_p,
+                                 int parts, void* dst, void* stream);
+/* ruart_whole_layernorm that also writes (mean, rstd) to stats_out[2] */
+RUART_API int ruart_whole_layernorm_stats(float* x, long long rows, int cols, long long pitch, float eps,
+                                          double* workspace, float* stats_out, void* stream);
+/* backward of F.layer_norm(x, x.size()) (Layers.py:167-168): y = normalised output, stats from the forward;
+ * workspace >= 2048 doubles.                                                                              */
+RUART_API int ruart_whole_layernorm_backward(const float* y, long long y_pitch, const float* dy,
+                                             long long dy_pitch, long long rows, int cols,
+                                             const float* stats, double* workspace, float* dx,
+                                             long long dx_pitch, void* stream);
+/* nn.Embedding weight gradient (SDNet.py:447-492 lookups): dW[v] (+)= sum_{k: ids[k] == v} dy[k], summed in
+ * ascending k by one warp per vocabulary row (deterministic, no atomics).                                  */
+RUART_API int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
+                                   long long dy_pitch, int D, int V, float* dW, long long dw_pitch,
+                                   int accumulate, void* stream);
+/* Gradient of ruart_subword_avg_layers with respect to alpha [n_layers] and gamma [1] (the encoder itself is
+ * locked): dy is the gradient of dst (same addressing); workspace >= 256 * n_layers doubles.              */
+RUART_API int ruart_subword_layers_backward(const float* h_f32, const void* h_bf16, long long layer_stride,
+                                            const int32_t* words, int n_words, const int32_t* row_start,
+                                            const uint8_t* x_mask, int W, const float* dy,
+                                            long long dy_stride, const float* alpha, int n_layers,
+                                            const float* gamma, int hidden, double* workspace,
+                                            float* dalpha, float* dgamma, int accumulate, void* stream);
+/* ruart_lstm_recurrence that also saves the activated gates and cell state of every step:
+ * gates [B*L, ndir*5*H] (columns dir*5H + {i,f,g,o,c}*H + j).                                            */
+RUART_API int ruart_lstm_recurrence_train(const float* xg, long long xg_pitch, const float* w_hh,
+                                          float* out, long long out_pitch, int B, int L, int H,
+                                          int ndir, float* gates, long long gates_pitch, void* stream);
+/* Back-propagation through time: dout = gradient of `out`; dxg [B*L, ndir*4H] = gradient of the gate
+ * pre-activations (= of xg); dW_hh, dW_ih, db and dx follow from dxg by GEMMs / column sums.             */
+RUART_API int ruart_lstm_recurrence_backward(const float* gates, long long gates_pitch, const float* w_hh,
+                                             const float* dout, long long dout_pitch, float* dxg,
+                                             long long dxg_pitch, int B, int L, int H, int ndir,
+                                             void* stream);
+/* ruart_lstm_cell (gx rows contiguous for the step) that also saves (i,f,g,o,c,h) per row: save [n_rows, 6H] */
+RUART_API int ruart_lstm_cell_train(const float* gx, const float* gh, float* c, void* h_split, int parts,
+                                    int Kp, int H, int n_rows, const int32_t* last_step, int step,
+                                    const long long* slot_off, float* slots, float* save, void* stream);
+/* Backward of one multi2one step: dgates [n_rows, 4H]; dc_carry [n_all, H] carried between steps (zeroed by
+ * the caller); dh_rec [n_rec, H] = dgates(step+1) W_hh, NULL at the last step; save_prev NULL at step 0.  */
+RUART_API int ruart_lstm_cell_backward(const float* save, const float* save_prev, const float* dslots,
+                                       const long long* slot_off, const int32_t* last_step, int step,
+                                       const float* dh_rec, int n_rec, float* dc_carry, float* dgates, int H,
+                                       int n_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,16 @@ CASES = {
     # BASELINE.json configs[4] shape (200 OCR tokens per image, question row padded to the 512-token
     # window) at 4 images
     "cfg5s_ragged_random": ("cfg5s", True, "random", 1033),
+    # ---- the benchmarked configurations at FULL size; BERT_MAX_BatchSize set so the
+    # reference fits in host memory (numerically neutral: BERT rows are independent, Bert.py:65-85);
+    # no intermediate captures (the 12 x [N, W, 768] lists alone are > 9 GB)
+    "cfg3_uniform_random": ("cfg3", False, "random", 1033),        # BASELINE configs[2]: what bench.py times
+    "cfg3_ragged_pretrained": ("cfg3", True, "pretrained_like", 1033),  # B=256, realistic BERT activation scale
+    "cfg4_shard3of8": ("cfg4", False, "random", 1033),             # BASELINE configs[3]: rank 3 of 8 (512 questions)
+    "cfg5_uniform_random": ("cfg5", False, "random", 1033),        # BASELINE configs[4] forward at B=32
 }
+BIG_CASES = ("cfg3_uniform_random", "cfg3_ragged_pretrained", "cfg4_shard3of8", "cfg5_uniform_random")
+SHARDS = {"cfg4_shard3of8": (3, 8)}
 PHOC_CASES = ("tiny_ragged_phoc",)
 CAPTURE = ("Bert", "multi2one", "context_rnn", "ques_rnn", "deep_attn", "high_lvl_context_rnn", "ques_self_attn")
 
@@ -58,9 +67,26 @@ def main(only=()):
         else:
             opt = synth.make_opt(cfg)
             batch = synth.make_batch(cfg, ragged=ragged)
+        if name in SHARDS:
+            batch = synth.shard_batch(batch, *SHARDS[name])
+        big = name in BIG_CASES
+        if big:
+            opt["BERT_MAX_BatchSize"] = 2048
         net = ref_harness.build_reference(opt, embedding=embedding, seed=seed, bert_init=init)
-        probs, logits, cap = ref_harness.run_reference(net, batch, capture=CAPTURE)
-        picks = synth.select_answers(probs, batch[1]["num_cnt"])
+        # the forward runs INSIDE the unmodified SDNetTrainer.predict: `picks` are the reference's own
+        # answer indices (SDNetTrainer.py:402-412), not a restatement
+        probs, logits, picks, cap, _ = ref_harness.run_reference_predict(net, opt, batch,
+                                                                          capture=() if big else CAPTURE)
+        restated = synth.select_answers(probs, batch[1]["num_cnt"])
+        assert restated == picks, "synth.select_answers differs from SDNetTrainer.predict: %s vs %s" % (restated, picks)
+        meta = "cfg=%s ragged=%s bert_init=%s seed=%d torch=%s picks=SDNetTrainer.predict" % (
+            cfg, ragged, init, seed, torch.__version__)
+        if big:
+            np.savez_compressed(os.path.join(out_dir, "model_%s.npz" % name), meta=np.asarray(meta),
+                                probs=probs.numpy(), logits=logits.numpy(), picks=np.asarray(picks, np.int64))
+            print(name, meta, "bytes", os.path.getsize(os.path.join(out_dir, "model_%s.npz" % name)), flush=True)
+            del net
+            continue
         bert_calls = cap["Bert"]  # q, ocr, od: each a list of 12 [N, W, 768]
         data = {
             "probs": probs.numpy(), "logits": logits.numpy(), "picks": np.asarray(picks, np.int64),
@@ -74,9 +100,8 @@ def main(only=()):
             "high_lvl_context_ocr": first(cap["high_lvl_context_rnn"][0])[:, :12, :16].numpy(),
             "ques_self_attn": first(cap["ques_self_attn"][0])[:, :8, :16].numpy(),
         }
-        meta = "cfg=%s ragged=%s bert_init=%s seed=%d torch=%s" % (cfg, ragged, init, seed, torch.__version__)
         np.savez_compressed(os.path.join(out_dir, "model_%s.npz" % name), meta=np.asarray(meta), **data)
-        print(name, meta, "picks", picks, "bytes", os.path.getsize(os.path.join(out_dir, "model_%s.npz" % name)))
+        print(name, meta, "picks", picks, "bytes", os.path.getsize(os.path.join(out_dir, "model_%s.npz" % name)), flush=True)
 
 
 if __name__ == "__main__":

@@ -27,6 +27,22 @@ def make_targets(batch, M):
     return t
 
 
+N_PROJ = 8
+
+
+def grad_projections(name, g):
+    """N_PROJ seeded Rademacher projections <g, r_k> of one gradient tensor: a compact fingerprint of the WHOLE
+    tensor (the full gradients are 49 MB), reproducible from the parameter name alone."""
+    import zlib
+    gen = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    flat = g.detach().double().reshape(-1).cpu()
+    out = []
+    for _ in range(N_PROJ):
+        r = torch.randint(0, 2, (flat.numel(),), generator=gen, dtype=torch.int8).double() * 2 - 1
+        out.append(float((flat * r).sum()))
+    return out
+
+
 def train_opt(cfg):
     return synth.make_opt(cfg, DROPOUT=0.0, dropout_emb=0.0)
 
@@ -55,6 +71,7 @@ def main():
     data = {"loss": np.float64(loss), "names": np.asarray(names),
             "clipped_grad_norm": np.asarray([float(grads[n].norm()) for n in names]),
             "clipped_grad_sum": np.asarray([float(grads[n].double().sum()) for n in names]),
+            "clipped_grad_proj": np.asarray([grad_projections(n, grads[n]) for n in names]),
             "after_sum": np.asarray([float(after[n].double().sum()) for n in names]),
             "delta_norm": np.asarray([float((after[n] - before[n]).norm()) for n in names]),
             "grad_alphaBERT": grads["alphaBERT"].numpy(), "grad_gammaBERT": grads["gammaBERT"].numpy(),

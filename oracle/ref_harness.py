@@ -170,3 +170,83 @@ def run_reference_update(net, opt, batch, targets):
         loss = trainer_mod.SDNetTrainer.update(fake, (q, ocr, od, targets, [{"q_id": i} for i in range(len(targets))]), 0)
     grads = {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.requires_grad and p.grad is not None}
     return loss, grads
+
+
+def stand_in_trainer(net, opt):
+    """An object carrying exactly the attributes the UNMODIFIED `SDNetTrainer.predict` / `load_model` /
+    `save_for_predict` / `update` methods touch (the real constructor needs the ST-VQA data files and
+    spaCy).  The methods themselves are the reference's, bound to this object."""
+    import types
+
+    import Models.SDNetTrainer as trainer_mod
+
+    class _Meter(object):
+        val = avg = sum = count = 0
+
+        def update(self, *a, **k):
+            pass
+
+    T = trainer_mod.SDNetTrainer
+    fake = types.SimpleNamespace(network=net, opt=opt, train_loss=_Meter(), updates=0, fixed_answers_len=0,
+                                 fixed_answers_entry=None)
+    for name in ("instance_bce_with_logits", "predict", "update", "load_model", "save_for_predict", "save"):
+        setattr(fake, name, types.MethodType(getattr(T, name), fake))
+    fake.loss_func = fake.instance_bce_with_logits
+    return fake
+
+
+def predict_extras(batch):
+    """gt_list / extra_info of a synth batch in the form `predict` reads them (SDNetTrainer.py:378-451):
+    extra_info[i]['ocr_list'] = the image's OCR token strings incl. the '<OCR>' end token (its LENGTH
+    is what the index rule uses, :409), answers None (no ANLS), q_id."""
+    q, ocr, od = batch
+    B = len(ocr["num_cnt"])
+    M1 = ocr["position"].size(1) + 1
+    gt = torch.zeros(B, M1)
+    extra = []
+    for i in range(B):
+        n = int(ocr["num_cnt"][i])
+        gt[i, i % max(1, n - 1)] = 1.0
+        extra.append({"q_id": i, "answers": None, "ocr_list": ["tok%d" % k for k in range(n - 1)] + ["<OCR>"]})
+    return gt, extra
+
+
+def run_reference_predict(net, opt, batch, capture=()):
+    """ONE forward of the unmodified reference driven through the unmodified `SDNetTrainer.predict`
+    (Models/SDNetTrainer.py:378-451).  Returns (probs, logits, picks, captured): probs = what
+    `self.network(...)` returned inside predict, logits = the pre-softmax row, picks = `save_res[i]['idx']`,
+    i.e. the reference's own answer-index rule (:402-412) — not a restatement of it."""
+    import copy
+    q, ocr, od = copy.deepcopy(batch)
+    gt, extra = predict_extras(batch)
+    fake = stand_in_trainer(net, opt)
+    captured = {}
+    hooks = []
+    mods = dict(net.named_modules())
+    for name in capture:
+        def _mk(nm):
+            def hook(_m, _inp, out):
+                captured.setdefault(nm, []).append(out)
+            return hook
+        hooks.append(mods[name].register_forward_hook(_mk(name)))
+    seen = {}
+    hooks.append(net.register_forward_hook(lambda _m, _i, out: seen.__setitem__("probs", out[0].detach().clone())))
+    F = torch.nn.functional
+    orig_softmax = F.softmax
+
+    def spy_softmax(x, dim=None, **kw):
+        if x.dim() == 2 and dim == -1:
+            seen["logits"] = x.detach().clone()
+        return orig_softmax(x, dim=dim, **kw)
+
+    F.softmax = spy_softmax
+    try:
+        with torch.no_grad(), _cpu_cuda_identity():
+            _loss, _anls, _acc, res, save_res = fake.predict((q, ocr, od, gt, extra))
+    finally:
+        F.softmax = orig_softmax
+        for h in hooks:
+            h.remove()
+    picks = [int(r["idx"]) for r in save_res]
+    answers = [r["answer"] for r in res]
+    return seen["probs"], seen.get("logits"), picks, captured, answers

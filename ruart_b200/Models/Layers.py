@@ -1,8 +1,18 @@
 """Drop-in for the reference's Models/Layers.py: same classes, constructor signatures, parameter
 names (state_dict compatible) and forward signatures — with the arithmetic done by the sm_100a
-kernels of libruart_b200.so.  Inference only: every forward needs CUDA tensors and raises
-otherwise (no CPU / eager fallback); dropout is the identity in eval mode exactly as in the
-reference (Layers.py:23-39), and training mode is rejected.
+kernels of libruart_b200.so.  Every forward needs CUDA tensors and raises otherwise (no CPU /
+eager fallback).
+
+Two execution forms, same results:
+  * fused inference form (`SDNet.forward` under `torch.no_grad()` / `.eval()`): projections on the
+    tcgen05 GEMM, fused attention tails / scorer / pooling kernels, outputs written into concat buffers;
+  * differentiable form (`grad_mode(module)`: autograd recording and the module in train mode — what
+    `SDNetTrainer.update` does, SDNetTrainer.py:332-337): every op is a torch.autograd.Function of
+    ruart_b200/autograd_ops.py with a hand-written backward kernel.  The `Layers.py`-level forwards
+    that the fused form never calls (`AttentionScore.forward`, `LinearSelfAttn.forward`,
+    `BilinearSeqAttn.forward`, `GetFinalScores.get_single_score`, `weighted_avg`) are always this form.
+Dropout (Layers.py:23-39) is the identity in eval mode; in train mode the masks are drawn with
+torch.bernoulli on the device (the RNG is the only library call) and applied by an own kernel.
 
 Reference map: StackedBRNN Layers.py:124-180 | AttentionScore :182-245 | Attention :247-295 |
 RNN_from_opt :297-317 | LinearSelfAttn :320-341 | GetFinalScores :352-432 |
@@ -12,6 +22,7 @@ import torch
 import torch.nn as nn
 from torch.nn.parameter import Parameter
 
+from .. import autograd_ops as A
 from .. import ops
 from .. import sdnet_ops as K
 from .._lib import current_stream, ptr
@@ -38,22 +49,38 @@ def set_sdnet_precision(parts):
     sdnet_parts = parts
 
 
+train_parts = 3  # split width of the GEMM operands in the differentiable form (3 = fp32 grade)
+
+
+def grad_mode(module=None):
+    """True when the differentiable form must run: autograd is recording and the module trains."""
+    return torch.is_grad_enabled() and (module is None or module.training)
+
+
 def _no_training(module, p):
-    if module.training and p > 0:
-        raise NotImplementedError("ruart_b200 implements the inference path; call .eval() "
-                                  "(training-time dropout/backward is not part of this build)")
+    """The fused inference kernels have no dropout: reaching one in train mode with p > 0 is a bug."""
+    if module.training and p > 0 and not torch.is_grad_enabled():
+        raise NotImplementedError("train-mode dropout needs the differentiable form (autograd enabled); "
+                                  "call .eval() for inference")
 
 
 def seq_dropout(x, p=0, training=False):
+    """Variational dropout: one mask per (batch, feature), shared along the sequence (Layers.py:23-30)."""
     if training == False or p == 0:
         return x
-    raise NotImplementedError("training-time variational dropout is not part of this build")
+    keep = torch.bernoulli(torch.full((x.size(0), x.size(2)), 1.0 - p, dtype=torch.float32, device=x.device))
+    keep = keep * (1.0 / (1.0 - p))
+    return A.mul_const(x, keep.unsqueeze(1).expand_as(x).contiguous())
 
 
 def dropout(x, p=0, training=False):
+    """Layers.py:32-39: seq_dropout for 3-D inputs when do_seq_dropout, else element-wise dropout."""
     if training == False or p == 0:
         return x
-    raise NotImplementedError("training-time dropout is not part of this build")
+    if do_seq_dropout and x.dim() == 3:
+        return seq_dropout(x, p=p, training=training)
+    keep = torch.bernoulli(torch.full(tuple(x.shape), 1.0 - p, dtype=torch.float32, device=x.device))
+    return A.mul_const(x, keep * (1.0 / (1.0 - p)))
 
 
 def _need_cuda(*ts):
@@ -141,6 +168,8 @@ class StackedBRNN(nn.Module):
 
     def forward(self, x, x_mask, return_list=False, x_additional=None, LN=None):
         _need_cuda(x)
+        if grad_mode(self):
+            return self._forward_differentiable(x, return_list, x_additional, LN)
         _no_training(self, dropout_p)
         hiddens = [x]
         for i in range(self.num_layers):
@@ -152,6 +181,32 @@ class StackedBRNN(nn.Module):
         if return_list:
             return output, hiddens[1:]
         return output
+
+
+def _stacked_brnn_differentiable(self, x, return_list=False, x_additional=None, LN=None):
+    """StackedBRNN.forward (Layers.py:156-180) with autograd: per layer dropout -> (Bi)LSTM over the padded
+    tensor -> whole-tensor LayerNorm; hidden sizes <= 128 (the persistent kernel + BPTT kernel)."""
+    if self.hidden_size > 128:
+        raise NotImplementedError("differentiable StackedBRNN needs hidden_size <= 128 (multi2one goes through "
+                                  "autograd_ops.multi2one inside SDNet.forward)")
+    hiddens = [x]
+    for i in range(self.num_layers):
+        rnn_input = hiddens[-1]
+        if i == 1 and x_additional is not None:
+            rnn_input = torch.cat((rnn_input, x_additional), 2)
+        if dropout_p > 0:
+            rnn_input = dropout(rnn_input, p=dropout_p, training=self.training)
+        out = A.lstm_layer(rnn_input, self.rnns[i], parts=train_parts)
+        if LN:
+            out = A.whole_layernorm(out)
+        hiddens.append(out)
+    output = torch.cat(hiddens[1:], 2) if self.concat_layers else hiddens[-1]
+    if return_list:
+        return output, hiddens[1:]
+    return output
+
+
+StackedBRNN._forward_differentiable = _stacked_brnn_differentiable
 
 
 class AttentionScore(nn.Module):
@@ -189,7 +244,17 @@ class AttentionScore(nn.Module):
         return out, a_split
 
     def forward(self, x1, x2):
-        raise NotImplementedError("raw score matrices are never materialised; use Attention.forward")
+        """scores [B, L1, L2] = relu(x1 W^T) D relu(x2 W^T)^T (Layers.py:208-245, correlation_func 3).  The fused
+        inference path never materialises this matrix (Attention.forward); this is the differentiable /
+        `Layers.py`-level form."""
+        _need_cuda(x1, x2)
+        assert self.correlation_func == 3, "only correlation_func=3 is on RUArt's path"
+        x1 = dropout(x1, p=dropout_p, training=self.training)
+        x2 = dropout(x2, p=dropout_p, training=self.training)
+        x1_rep = A.linear(x1, self.linear.weight, None, relu=True, parts=train_parts)
+        x2_rep = A.linear(x2, self.linear.weight, None, relu=True, parts=train_parts)
+        x1_rep = A.scale_cols(x1_rep, self.diagonal)
+        return A.bmm(x1_rep, x2_rep, trans_b=True)
 
 
 class Attention(nn.Module):
@@ -202,11 +267,18 @@ class Attention(nn.Module):
         """attended[b, i] = sum_j softmax_j(score(x1_i, x2_j) | x2_mask) x3_j   (Layers.py:253-295).
         `out` (strided view) / `add_to_out` / `p2_cache` are extensions used by SDNet.forward."""
         _need_cuda(x1, x2, x3)
-        _no_training(self, dropout_p)
         if drop_diagonal or return_score:
             raise NotImplementedError("drop_diagonal / return_score are not used on RUArt's path")
         if x3 is None:
             x3 = x2
+        if grad_mode(self):
+            # differentiable form (Layers.py:272-288): scores -> masked softmax over keys -> alpha.bmm(x3)
+            alpha = A.masked_softmax(self.scoring(x1, x2), x2_mask)
+            res = A.bmm(alpha, x3)
+            if out is not None:
+                raise NotImplementedError("`out=` is an inference-path extension")
+            return res
+        _no_training(self, dropout_p)
         B, L1, L2 = x1.shape[0], x1.shape[1], x2.shape[1]
         p1, sp = self.scoring.project(x1, True)
         if p2_cache is not None and "p2" in p2_cache:
@@ -253,7 +325,13 @@ class LinearSelfAttn(nn.Module):
         return out
 
     def forward(self, x, x_mask):
-        raise NotImplementedError("use LinearSelfAttn.pooled(x, mask) (alpha is fused with weighted_avg)")
+        """alpha [B, L] = softmax(mask(W x_i + b)) (Layers.py:328-341) — the differentiable / API form; the fused
+        inference path uses `pooled` (alpha and weighted_avg in one kernel)."""
+        _need_cuda(x)
+        x = dropout(x, p=dropout_p, training=self.training)
+        B, L, D = x.shape
+        scores = A.linear(x.reshape(B * L, D), self.linear.weight, self.linear.bias, parts=train_parts).view(B, L)
+        return A.masked_softmax(scores, x_mask)
 
 
 def generate_mask(new_data, dropout_p=0.0):
@@ -285,6 +363,8 @@ class GetFinalScores(nn.Module):
     def forward(self, x, h0, x_mask, ES_len, mask_flag=None, nan_flag=None, want_logits=False):
         """softmax([ES scores | OCR scores | no-answer]) (Layers.py:373-419)."""
         _need_cuda(x, h0)
+        if grad_mode(self):
+            return self._forward_differentiable(x, h0, x_mask, ES_len, mask_flag)
         _no_training(self, dropout_p)
         if self.yesno or not self.no_answer or not self.useES or not mask_flag:
             raise NotImplementedError("only the shipped conf's scorer (useES, label_no_answer, mask_score, "
@@ -308,19 +388,53 @@ class GetFinalScores(nn.Module):
         self.last_logits = logits
         return probs
 
+    def _forward_differentiable(self, x, h0, x_mask, ES_len, mask_flag=None):
+        """GetFinalScores.forward (Layers.py:373-419) op by op with autograd.  The GRUCell step of
+        :393-397 does not influence the output (its parameters get no gradient in the reference either)."""
+        if self.yesno:
+            raise NotImplementedError("yes/no heads are outside the shipped conf")
+        if self.useES:
+            x_es, x_es_mask = x[:, :ES_len], x_mask[:, :ES_len]
+            x_ocr, x_ocr_mask = x[:, ES_len:], x_mask[:, ES_len:]
+            score_ocr = self.attn(x_ocr, h0, x_ocr_mask, mask_flag=mask_flag)
+            score_es = self.attn2(x_es, h0, x_es_mask, mask_flag=mask_flag)
+            score_s = torch.cat([score_es, score_ocr], dim=-1)
+        else:
+            score_s = self.attn(x, h0, x_mask, mask_flag=mask_flag)
+        if self.no_answer:
+            h0 = dropout(h0, p=dropout_p, training=self.training)
+            score_noanswer = self.get_single_score(x, h0, x_mask, self.noanswer_linear, self.noanswer_w)
+            score_s = torch.cat([score_s, score_noanswer], dim=-1)
+        self.last_logits = score_s.detach()
+        return A.masked_softmax(score_s, None)
+
     def get_single_score(self, x, h, x_mask, linear, w):
-        raise NotImplementedError("fused into GetFinalScores.forward")
+        """w(softmax(mask(x . linear(h))) . x) -> [B, 1]  (Layers.py:421-432)."""
+        _need_cuda(x, h)
+        Wh = A.linear(h, linear.weight, linear.bias, parts=train_parts)
+        xWh = A.bmm(x, Wh.unsqueeze(2)).squeeze(2)
+        beta = A.masked_softmax(xWh, x_mask)
+        attn_x = A.bmm(beta.unsqueeze(1), x)                      # [B, 1, x_size]
+        return A.linear(attn_x, w.weight, w.bias, parts=train_parts).squeeze(2)
 
 
 class BilinearSeqAttn(nn.Module):
-    """o_i = x_i' (W y + b); parameter holder — evaluated inside GetFinalScores' fused kernel."""
+    """o_i = x_i' (W y + b) (Layers.py:435-468).  The fused inference path evaluates it inside
+    GetFinalScores' kernel; `forward` is the differentiable / API form."""
 
     def __init__(self, x_size, y_size, identity=False):
         super(BilinearSeqAttn, self).__init__()
         self.linear = nn.Linear(y_size, x_size) if not identity else None
 
     def forward(self, x, y, x_mask, mask_flag=True):
-        raise NotImplementedError("fused into GetFinalScores.forward")
+        _need_cuda(x, y)
+        x = dropout(x, p=dropout_p, training=self.training)
+        y = dropout(y, p=dropout_p, training=self.training)
+        Wy = A.linear(y, self.linear.weight, self.linear.bias, parts=train_parts) if self.linear is not None else y
+        xWy = A.bmm(x, Wy.unsqueeze(2)).squeeze(2)                 # [B, len]
+        if mask_flag:
+            xWy = A.mask_fill_neg_inf(xWy, x_mask)
+        return xWy
 
 
 class DeepAttention(nn.Module):
@@ -371,9 +485,18 @@ class DeepAttention(nn.Module):
         """History-of-word multi-level inter-attention (Layers.py:493-524).  x2_proj: optional
         result of project_x2 (the question side is the same for the OCR and the OD call)."""
         _need_cuda(*x1_abstr)
-        _no_training(self, dropout_p)
         if return_score or 'no_DeepAttention' in self.opt:
             raise NotImplementedError("return_score / no_DeepAttention are not on the shipped conf's path")
+        if grad_mode(self):
+            # differentiable form (Layers.py:498-524)
+            x1_att = torch.cat(x1_word + x1_abstr, 2)
+            x2_att = torch.cat(x2_word + x2_abstr[:-1], 2)
+            x1 = torch.cat(x1_abstr, 2)
+            for i in range(len(x2_abstr)):
+                x1 = torch.cat((x1, self.int_attn_list[i](x1_att, x2_att, x2_mask, x3=x2_abstr[i])), 2)
+            x1_hiddens = self.rnn(x1, x1_mask)
+            return (x1_hiddens, x1) if return_bef_rnn else x1_hiddens
+        _no_training(self, dropout_p)
         x1_att = K.concat_cols(x1_word + x1_abstr)
         B, L1, L2 = x1_att.shape[0], x1_att.shape[1], x2_abstr[0].shape[1]
         widths = [t.shape[2] for t in x1_abstr] + [t.shape[2] for t in x2_abstr]
@@ -401,7 +524,8 @@ class DeepAttention(nn.Module):
 
 
 def weighted_avg(x, weights):
-    raise NotImplementedError("fused into LinearSelfAttn.pooled")
+    """x [B, len, d], weights [B, len] -> [B, d]  (Layers.py:529-534)."""
+    return A.bmm(weights.unsqueeze(1), x).squeeze(1)
 
 
 # Present in the reference but never constructed with the shipped conf (SURVEY.md §2 row 2).

@@ -23,6 +23,7 @@ import logging
 import torch
 import torch.nn as nn
 
+from .. import autograd_ops as A
 from .. import host_index, ops
 from .. import sdnet_ops as K
 from .._lib import current_stream, ptr
@@ -215,13 +216,17 @@ class SDNet(nn.Module):
             self.phase_events.append((label, ev))
 
     def forward(self, q_list, ocr_list, od_list, return_score=False):
-        if self.training and (Layers.dropout_p > 0 or self.drop_emb):
-            raise NotImplementedError("ruart_b200.SDNet implements inference; call .eval() and set drop_emb=False")
         att_score = {} if return_score else None
         dev = ocr_list['fasttext'].device
         if dev.type != 'cuda':
             raise RuntimeError("ruart_b200.SDNet.forward needs CUDA inputs (ToCUDA, SDNetTrainer.py:208-230); "
                                "there is no CPU fallback")
+        if Layers.grad_mode(self):
+            # SDNetTrainer.update (SDNetTrainer.py:332-337): network.train(), autograd recording
+            return self._forward_differentiable(q_list, ocr_list, od_list), att_score
+        if self.training and (Layers.dropout_p > 0 or (self.drop_emb and self.opt.get('dropout_emb', 0) > 0)):
+            raise NotImplementedError("train-mode dropout needs autograd enabled (the differentiable form); "
+                                      "for inference call .eval() and set drop_emb=False")
         opt = self.opt
         st = current_stream()
         Layers.set_sdnet_precision(self.sdnet_parts)
@@ -434,4 +439,122 @@ class SDNet(nn.Module):
         return score_s, att_score
 
     def linear_sum(self, output, alpha, gamma):
-        raise NotImplementedError("fused into Bert.encode_into (subword mean + layer sum per layer)")
+        """sum_l output[l] * softmax(alpha)_l * gamma, then dropout_emb (SDNet.py:573-583).  The fused forward
+        never materialises the per-layer tensors (Bert.encode_into); this is the API / differentiable form."""
+        res = A.layer_mix(list(output), alpha, gamma)
+        return dropout(res, p=self.opt['dropout_emb'], training=self.drop_emb)
+
+    # ------------------------------------------------------------------ differentiable forward
+    def _forward_differentiable(self, q_list, ocr_list, od_list):
+        """SDNet.forward (SDNet.py:253-437) op by op on autograd Functions whose forward and backward are
+        kernels of libruart_b200.so (ruart_b200/autograd_ops.py) — what `SDNetTrainer.update` differentiates
+        (SURVEY.md §8 a-19).  BERT is locked (SDNet.py:91-94): the packed encoder runs as in inference and stays
+        in eval mode (the reference's `network.train()` also switches the locked BERT's dropout on,
+        SDNetTrainer.py:332 vs Bert.py:43 — not reproduced: a frozen encoder is kept deterministic); only
+        alphaBERT / gammaBERT receive gradients from it."""
+        opt = self.opt
+        if 'LOCK_BERT' not in opt:
+            raise NotImplementedError("training needs LOCK_BERT (the BERT encoder has no backward kernels)")
+        if self.phoc_q or self.phoc_x:
+            raise NotImplementedError("the PHOC channel is inference-only")
+        P = Layers.train_parts
+        dev = ocr_list['fasttext'].device
+        B = len(ocr_list['num_cnt'])
+        M, M_od = ocr_list['position'].size(1), od_list['position'].size(1)
+        Wo, Wd = ocr_list['fasttext'].size(1), od_list['fasttext'].size(1)
+        N_ocr, N_od = ocr_list['fasttext'].size(0), od_list['fasttext'].size(0)
+        VD = self.vocab_dim
+        p_emb = opt['dropout_emb'] if 'dropout_emb' in opt else 0
+
+        # ---- locked BERT: packed encoder, hidden states kept for the layer-mix gradients --------
+        def word_offsets(lst):
+            return lst['bert_offsets_csr'] if 'bert_offsets_csr' in lst else lst['bert_offsets']
+
+        lists = ((q_list, 'glove_mask'), (ocr_list, 'fasttext_mask'), (od_list, 'fasttext_mask'))
+        with torch.no_grad():
+            from ..bert_engine import Segment
+            segs = [Segment(l['bert'], l['bert_mask'], word_offsets(l), l[m], l.get('bert_totals')) for l, m in lists]
+            eng = self.Bert.engine()
+            pk, hs_f, hs_b = eng.encode_hidden(segs)
+            packs = eng.subword_packs(segs, pk, hs_f, hs_b)
+
+        def embed(lst, key, table, pack):   # get_embedding_from_list, SDNet.py:439-493
+            word = A.embedding(lst[key], table.weight)
+            bert = A.subword_mix(self.alphaBERT, self.gammaBERT, pack)
+            bert = dropout(bert, p=p_emb, training=self.drop_emb)
+            parts = [dropout(word, p=p_emb, training=self.drop_emb), bert,
+                     A.embedding(lst['pos'], self.pos_embedding.weight),
+                     A.embedding(lst['ent'], self.ent_embedding.weight)]
+            return word, torch.cat(parts, -1)
+
+        q_word, q_in = embed(q_list, 'glove', self.glove_embed, packs[0])
+        ocr_word, ocr_in = embed(ocr_list, 'fasttext', self.fast_embed, packs[1])
+        od_word, od_in = embed(od_list, 'fasttext', self.fast_embed, packs[2])
+        q_list['glove_emb'] = q_word
+        ocr_list['fasttext_emb'] = ocr_word
+        od_list['fasttext_emb'] = od_word
+        q_mask = K.as_u8(q_list['glove_mask'])
+
+        plan = ocr_list.get('ruart_plan')
+        if plan is None:
+            plan = host_index.forward_plan(ocr_list['num_cnt'], ocr_list['len_cnt'], od_list['num_cnt'],
+                                           od_list['len_cnt'], Wo, Wd, M, M_od)
+        if plan['key'] != (B, N_ocr, N_od, Wo, Wd, M, M_od):
+            raise ValueError("num_cnt / len_cnt do not match the item rows of this batch")
+        i32_d = K.upload(plan['i32'], dev)
+        i64_d = K.upload(plan['slots'] * self.multi2one_output_size, dev)
+        masks_d = K.upload(plan['masks'], dev)
+        cuts = plan['cuts']
+        ocr_wsrc, ocr_wdst, od_wsrc, od_wdst, a_rows_d, last_d = [i32_d[cuts[i]:cuts[i + 1]] for i in range(6)]
+        ocr_mask = masks_d[:B * M].view(B, M)
+        od_mask = masks_d[B * M:].view(B, M_od)
+
+        # ---- word-level pre-alignment before the item RNN (SDNet.py:265-268,495-551) -------------
+        def prealign(word, wsrc, wdst, k, n_items, W):
+            T_max = plan['T_max'][k]
+            packed = A.permute_rows(word.reshape(-1, VD), wsrc, wdst, B * T_max).view(B, T_max, VD)
+            att = self.pre_align(packed, q_word, q_mask)
+            return A.permute_rows(att.reshape(-1, VD), wdst, wsrc, n_items * W).view(n_items, W, VD)
+
+        ocr_in = torch.cat([ocr_in, prealign(ocr_word, ocr_wsrc, ocr_wdst, 0, N_ocr, Wo)], -1)
+        od_in = torch.cat([od_in, prealign(od_word, od_wsrc, od_wdst, 1, N_od, Wd)], -1)
+
+        # ---- multi2one over the real word steps, last step -> slot (SDNet.py:270-271,300-318) -----
+        XD = ocr_in.shape[-1]
+        if Layers.dropout_p > 0:   # StackedBRNN.forward's input dropout (Layers.py:163-164), one call per list
+            ocr_in = dropout(ocr_in, p=Layers.dropout_p, training=self.training)
+            od_in = dropout(od_in, p=Layers.dropout_p, training=self.training)
+        items_in = torch.cat([ocr_in.reshape(-1, XD), od_in.reshape(-1, XD)], 0)
+        slots = A.multi2one(items_in, self.multi2one.rnns[0],
+                            (a_rows_d, last_d, i64_d, plan['n_t'], B * M + B * M_od), parts=P)
+        HS = self.multi2one_output_size
+        ocr_x = slots[:B * M].view(B, M, HS)
+        od_x = slots[B * M:].view(B, M_od, HS)
+
+        # ---- encoders, deep attention, self attention (SDNet.py:338-390) ----------------------
+        _, ocr_layers = self.context_rnn(ocr_x, ocr_mask, return_list=True, LN=True)
+        _, q_layers = self.ques_rnn(q_in, q_mask, return_list=True, LN=True)
+        _, od_layers = self.context_rnn(od_x, od_mask, return_list=True, LN=True)
+        q_high = self.high_lvl_ques_rnn(torch.cat(q_layers, 2), q_mask, LN=True)
+        q_layers = q_layers + [q_high]
+        ocr_after, ocr_before = self.deep_attn([ocr_x], ocr_layers, [q_word], q_layers, ocr_mask, q_mask,
+                                               return_bef_rnn=True)
+        od_after, od_before = self.deep_attn([od_x], od_layers, [q_word], q_layers, od_mask, q_mask,
+                                             return_bef_rnn=True)
+
+        def self_attend(after, before, x, mask):
+            s_in = torch.cat([after, before, x], 2)
+            s_out = self.highlvl_self_att(s_in, s_in, mask, x3=after)
+            return self.high_lvl_context_rnn(torch.cat([after, s_out], 2), mask, LN=True)
+
+        ocr_high = self_attend(ocr_after, ocr_before, ocr_x, ocr_mask)
+        od_high = self_attend(od_after, od_before, od_x, od_mask)
+        # ---- OD <-> OCR + position attention (SDNet.py:393-405) -------------------------------
+        x_od_ocr = self.od_ocr_attn(ocr_high, od_high, od_mask)
+        pos_att = self.position_attn(ocr_list['position'].float(), od_list['position'].float(), od_mask, x3=od_high)
+        ocr_final = torch.cat([ocr_high, A.add(x_od_ocr, pos_att)], 2)
+        # ---- question summary + scores (SDNet.py:408-431) -------------------------------------
+        q_final = self.ques_self_attn(q_high, q_high, q_mask)
+        q_merged = Layers.weighted_avg(q_final, self.ques_merger(q_final, q_mask))
+        score_s = self.get_answer(ocr_final, q_merged, ocr_mask, opt['ES_ocr_len'], mask_flag='mask_score' in opt)
+        return score_s

@@ -61,6 +61,30 @@ _SIGNATURES = {
     "ruart_adamax_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int,
                           c_void_p, c_float, c_void_p],
     "ruart_select_answers": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    # ---- differentiable path (training step)
+    "ruart_bmm_f32": [c_void_p, c_ll, c_ll, c_int, c_void_p, c_ll, c_ll, c_int, c_void_p, c_ll, c_ll, c_int,
+                      c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "ruart_masked_softmax": [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p],
+    "ruart_softmax_backward": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p],
+    "ruart_eltwise": [c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_ll, c_ll, c_int, c_void_p],
+    "ruart_mask_fill": [c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p],
+    "ruart_colsum": [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "ruart_split_bf16_t": [c_void_p, c_ll, c_ll, c_int, c_ll, c_int, c_void_p, c_void_p],
+    "ruart_whole_layernorm_stats": [c_void_p, c_ll, c_int, c_ll, c_float, c_void_p, c_void_p, c_void_p],
+    "ruart_whole_layernorm_backward": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_ll, c_void_p],
+    "ruart_embedding_grad": [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_int, c_void_p],
+    "ruart_subword_layers_backward": [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_void_p],
+    "ruart_lstm_recurrence_train": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_ll, c_void_p],
+    "ruart_lstm_recurrence_backward": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
+                                       c_int, c_void_p],
+    "ruart_lstm_cell_train": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p],
+    "ruart_lstm_cell_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"ruart_last_error": ctypes.c_char_p}
 
@@ -102,7 +126,8 @@ def check(rc):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_KERNELS_PER_CALL = {"ruart_whole_layernorm": 2}
+_KERNELS_PER_CALL = {"ruart_whole_layernorm": 2, "ruart_whole_layernorm_stats": 2, "ruart_colsum": 2,
+                     "ruart_whole_layernorm_backward": 2, "ruart_subword_layers_backward": 2}
 launch_count = 0
 _timing_hook = None  # set by bench.py: callable(name, args) -> context manager, or None
 

@@ -283,6 +283,51 @@ class BertEngine(object):
         once at the end; the Python word-offset lists are flattened on the host AFTER the whole
         encoder has been queued, i.e. while the GPU is busy.
         """
+        pk, hs_f, hs_b = self.encode_hidden(segments, pack_handle)
+        dev = segments[0].ids.device
+        T, H, NL = pk["T"], self.H, self.n_layers
+        st = current_stream()
+        keep32 = hs_f is not None
+        layer_stride = T * H
+        for k, (sg, (wt, nw, rs, wmask)) in enumerate(zip(segments, self.word_tables(segments, pk))):
+            hf1 = hs_f[1:] if keep32 else None
+            hb1 = None if keep32 else hs_b[1:]
+            if alpha is not None:
+                dst, stride, col = sinks[k]
+                call("ruart_subword_avg_layers", ptr(hf1), ptr(hb1), layer_stride, ptr(wt), nw, ptr(rs), ptr(wmask),
+                     sg.W, dst.data_ptr() + 4 * col, stride, ptr(alpha), NL, ptr(gamma), H, st)
+            else:
+                for li in range(NL):
+                    dst, stride, col = sinks[k][li]
+                    call("ruart_subword_avg_accum", ptr(hf1[li]) if keep32 else None,
+                         None if keep32 else ptr(hb1[li]), ptr(wt), nw, ptr(rs), ptr(wmask), sg.W,
+                         dst.data_ptr() + 4 * col, stride, None, NL, None, li, 1, H, st)
+        return pk
+
+    def word_tables(self, segments, pk):
+        """Per segment: (flattened word offsets int32 [4, n] on the device, n, row_start, uint8 word mask).
+        Host work (flattening the Python lists) — call it after the encoder has been queued."""
+        dev = segments[0].ids.device
+        out = []
+        for k, sg in enumerate(segments):
+            wt_np = flatten_offsets(sg.offsets, sg.N)
+            wt = upload(wt_np, dev)
+            wmask = sg.word_mask.contiguous().view(torch.uint8) if sg.word_mask.dtype == torch.bool \
+                else sg.word_mask.to(torch.uint8).contiguous()
+            out.append((wt, wt_np.shape[1], pk["segments"][k]["row_start"], wmask))
+        return out
+
+    def subword_packs(self, segments, pk, hs_f, hs_b):
+        """What autograd_ops.SubwordMixFn needs per segment (the differentiable form of the layer mix)."""
+        T, H, NL = pk["T"], self.H, self.n_layers
+        hf1 = hs_f[1:] if hs_f is not None else None
+        hb1 = None if hs_f is not None else hs_b[1:]
+        return [(hf1, hb1, T * H, wt, nw, rs, wmask, sg.N, sg.W, NL, H)
+                for sg, (wt, nw, rs, wmask) in zip(segments, self.word_tables(segments, pk))]
+
+    def encode_hidden(self, segments, pack_handle=None):
+        """The encoder alone: returns (pack, hs_f32 or None, hs_bf16 or None) with hs [n_layers + 1, T, H]
+        (index 0 = embedding output, 1.. = encoder layers)."""
         dev = segments[0].ids.device
         if dev.type != "cuda":
             raise RuntimeError("ruart_b200 BERT runs on CUDA only; there is no CPU fallback")
@@ -343,25 +388,4 @@ class BertEngine(object):
             h_f, h_b = layer_bufs(li + 1)
             call("ruart_add_layernorm", ptr(d_f), ptr(d_b), ptr(h1_f), None,
                  ptr(lw["g2"]), ptr(lw["b2"]), lw["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
-        # ---- host: flatten the word-offset lists while the encoder runs on the device ----------
-        layer_stride = T * H
-        for k, sg in enumerate(segments):
-            wt_np = flatten_offsets(sg.offsets, sg.N)
-            nw = wt_np.shape[1]
-            wt = upload(wt_np, dev)
-            wmask = sg.word_mask.contiguous().view(torch.uint8) if sg.word_mask.dtype == torch.bool \
-                else sg.word_mask.to(torch.uint8).contiguous()
-            rs = pk["segments"][k]["row_start"]
-            hf1 = hs_f[1:] if keep32 else None
-            hb1 = None if keep32 else hs_b[1:]
-            if alpha is not None:
-                dst, stride, col = sinks[k]
-                call("ruart_subword_avg_layers", ptr(hf1), ptr(hb1), layer_stride, ptr(wt), nw, ptr(rs), ptr(wmask),
-                     sg.W, dst.data_ptr() + 4 * col, stride, ptr(alpha), NL, ptr(gamma), H, st)
-            else:
-                for li in range(NL):
-                    dst, stride, col = sinks[k][li]
-                    call("ruart_subword_avg_accum", ptr(hf1[li]) if keep32 else None,
-                         None if keep32 else ptr(hb1[li]), ptr(wt), nw, ptr(rs), ptr(wmask), sg.W,
-                         dst.data_ptr() + 4 * col, stride, None, NL, None, li, 1, H, st)
-        return pk
+        return pk, hs_f, hs_b

@@ -18,14 +18,13 @@ extern "C" const char* ruart_last_error(void) { return g_err; }
 extern "C" int ruart_version(void) { return 100; }
 
 extern "C" int ruart_num_sms(void) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    int v = 0;
+  static std::atomic<int> sms[RUART_MAX_DEVICES];
+  const int dev = ruart_current_device();
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
       return 148;
-    sms = v;
+    sms[dev].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
 }

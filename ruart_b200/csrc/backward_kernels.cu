@@ -1,0 +1,790 @@
+// Kernels of the DIFFERENTIABLE form of the SDNet stack (one
+// SDNetTrainer.update, reference Models/SDNetTrainer.py:330-376 — forward with autograd, backward,
+// clip, Adamax).  The inference path keeps its fused kernels; the training path is built from the
+// primitives below, each with an exact backward, wired as torch.autograd.Function objects in
+// ruart_b200/autograd_ops.py.  BERT is locked (LOCK_BERT, SDNet.py:91-94): it needs no backward
+// except the 12 + 1 scalars of the learned layer mix (alphaBERT, gammaBERT).
+//
+//   bmm_f32                  C[b] (+)= alpha * op(A[b]) op(B[b])        per-image score / P.x3 products and
+//                                                                       their gradients (CUDA cores, fp32)
+//   masked_softmax (+ bwd)   Layers.py:237-244,283-288 (masked_fill -inf, softmax over keys)
+//   eltwise                  a*b, relu mask, column scale, a+b          ReLU / diagonal of AttentionScore
+//   colsum                   bias / diagonal gradients (deterministic two-stage column sums)
+//   split_bf16_t             fp32 [rows, K] -> TRANSPOSED split-bf16 operand [K, parts*rows_p]: feeds the
+//                            tcgen05 GEMM for wgrad (dW = dY^T X) and dgrad (dX = dY W)
+//   whole_ln_backward        F.layer_norm(x, x.size()) backward (Layers.py:167-168)
+//   embedding_grad           nn.Embedding weight gradient, one warp per vocabulary row, deterministic
+//   subword_layers_backward  d/d(alphaBERT, gammaBERT) of the subword mean + layer mix
+//                            (Bert.py:149-165, SDNet.py:573-583)
+//   lstm_bptt                back-propagation through time of the persistent (Bi)LSTM (Layers.py:166)
+//   lstm_cell_train/backward the step-synchronous multi2one LSTM (SDNet.py:270-271)
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ruart_b200.h"
+
+namespace {
+
+using namespace ruart;
+
+inline unsigned grid_for(long long work_items, int per_cta) {
+  long long g = (work_items + per_cta - 1) / per_cta;
+  const long long cap = static_cast<long long>(ruart_num_sms()) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+// ------------------------------------------------------------------------------------------ bmm
+constexpr int TB_M = 64, TB_N = 64, TB_K = 16;
+
+__global__ void __launch_bounds__(256)
+bmm_f32_kernel(const float* __restrict__ A, long long lda, long long sa, int transA,
+               const float* __restrict__ Bm, long long ldb, long long sb, int transB,
+               float* __restrict__ C, long long ldc, long long sc, int M, int N, int K, float alpha,
+               int accumulate) {
+  __shared__ float As[TB_K][TB_M + 4];
+  __shared__ float Bs[TB_K][TB_N + 4];
+  const int b = blockIdx.z;
+  A += static_cast<long long>(b) * sa;
+  Bm += static_cast<long long>(b) * sb;
+  C += static_cast<long long>(b) * sc;
+  const int m0 = blockIdx.y * TB_M, n0 = blockIdx.x * TB_N;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += TB_K) {
+    for (int i = threadIdx.x; i < TB_M * TB_K; i += 256) {
+      int m, k;
+      if (transA) { m = i % TB_M; k = i / TB_M; } else { k = i % TB_K; m = i / TB_K; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < K)
+        v = transA ? A[static_cast<long long>(gk) * lda + gm] : A[static_cast<long long>(gm) * lda + gk];
+      As[k][m] = v;
+    }
+    for (int i = threadIdx.x; i < TB_N * TB_K; i += 256) {
+      int n, k;
+      if (transB) { k = i % TB_K; n = i / TB_K; } else { n = i % TB_N; k = i / TB_N; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < K)
+        v = transB ? Bm[static_cast<long long>(gn) * ldb + gk] : Bm[static_cast<long long>(gk) * ldb + gn];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TB_K; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float* p = C + static_cast<long long>(gm) * ldc + gn;
+      const float v = alpha * acc[i][j];
+      *p = accumulate ? (*p + v) : v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ softmax
+// One warp per row r of x [rows = B*L1, L2]; mask [B, L2] (0 = masked -> -inf, Layers.py:283-284),
+// NULL = no mask.  A row without a live key gives NaN, like torch.softmax over all -inf.
+__global__ void __launch_bounds__(256)
+masked_softmax_kernel(const float* __restrict__ x, long long x_pitch, const uint8_t* __restrict__ mask,
+                      int L1, int L2, long long rows, float* __restrict__ out, long long out_pitch) {
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + r * x_pitch;
+  float* orow = out + r * out_pitch;
+  const uint8_t* mr = mask ? mask + (r / L1) * L2 : nullptr;
+  float mx = -INFINITY;
+  for (int j = lane; j < L2; j += 32)
+    if (!mr || mr[j]) mx = fmaxf(mx, xr[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < L2; j += 32)
+    if (!mr || mr[j]) sum += expf(xr[j] - mx);
+  sum = warp_sum(sum);
+  const bool dead = (mx == -INFINITY);   // every key masked (or all -inf): torch gives NaN
+  for (int j = lane; j < L2; j += 32) {
+    float v;
+    if (dead) v = __int_as_float(0x7fc00000);
+    else v = (!mr || mr[j]) ? expf(xr[j] - mx) / sum : 0.f;
+    orow[j] = v;
+  }
+}
+
+// dx = p * (dp - sum_j p_j dp_j)
+__global__ void __launch_bounds__(256)
+softmax_backward_kernel(const float* __restrict__ p, long long p_pitch, const float* __restrict__ dp,
+                        long long dp_pitch, float* __restrict__ dx, long long dx_pitch, long long rows,
+                        int cols) {
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* pr = p + r * p_pitch;
+  const float* dr = dp + r * dp_pitch;
+  float dot = 0.f;
+  for (int j = lane; j < cols; j += 32) dot = fmaf(pr[j], dr[j], dot);
+  dot = warp_sum(dot);
+  float* xr = dx + r * dx_pitch;
+  for (int j = lane; j < cols; j += 32) xr[j] = pr[j] * (dr[j] - dot);
+}
+
+// ------------------------------------------------------------------------------------------ eltwise
+// op 0: out = a * b          op 1: out = a * (b > 0)   (ReLU backward: a = dy, b = relu output)
+// op 2: out = a + b          op 3: out = a * v[c]      (v has v_len entries; v_len == 1: scalar)
+// op 4: out = max(a, 0)      op 5: out = a + v[c]
+template <int OP>
+__global__ void __launch_bounds__(256)
+eltwise_kernel(const float* __restrict__ a, long long a_pitch, const float* __restrict__ b,
+               long long b_pitch, const float* __restrict__ v, int v_len, float* __restrict__ out,
+               long long out_pitch, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float av = a[r * a_pitch + c];
+    float o;
+    if (OP == 0) o = av * b[r * b_pitch + c];
+    else if (OP == 1) o = (b[r * b_pitch + c] > 0.f) ? av : 0.f;
+    else if (OP == 2) o = av + b[r * b_pitch + c];
+    else if (OP == 3) o = av * v[v_len > 1 ? c : 0];
+    else if (OP == 4) o = fmaxf(av, 0.f);
+    else o = av + v[v_len > 1 ? c : 0];
+    out[r * out_pitch + c] = o;
+  }
+}
+
+// out = mask ? x : value   (flat; the reference's scores.data.masked_fill_(mask == 0, -inf))
+__global__ void mask_fill_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, long long n,
+                                 float value, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = mask[i] ? x[i] : value;
+}
+
+// ------------------------------------------------------------------------------------------ colsum
+// out[c] = sum_r x[r][c], deterministic: stage 1 sums row chunk blockIdx.y of column c in double,
+// stage 2 adds the chunk partials in a fixed order.
+constexpr int CS_CHUNKS = 64;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ x, long long pitch, long long rows, int cols,
+                      double* __restrict__ partials) {
+  __shared__ double s[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = per * blockIdx.y, r1 = (r0 + per < rows) ? r0 + per : rows;
+  double acc = 0.0;
+  if (c < cols)
+    for (long long r = r0 + ry; r < r1; r += 8) acc += x[r * pitch + c];
+  s[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x & 31];
+    partials[static_cast<long long>(blockIdx.y) * cols + c] = t;
+  }
+}
+
+__global__ void colsum_final_kernel(const double* __restrict__ partials, int chunks, int cols,
+                                    float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double t = 0.0;
+  for (int i = 0; i < chunks; ++i) t += partials[static_cast<long long>(i) * cols + c];
+  out[c] = accumulate ? out[c] + static_cast<float>(t) : static_cast<float>(t);
+}
+
+// ------------------------------------------------------------------------------------------ split^T
+// dst[k][p * rows_p + r] = part p of src[r][k]   (bf16 hi / mid / lo parts: x = x0 + x1 + x2), zero for
+// r >= rows.  32 x 32 tiles through shared memory; dst row pitch = parts * rows_p.
+__global__ void __launch_bounds__(256)
+split_bf16_t_kernel(const float* __restrict__ src, long long ld, long long rows, int K, long long rows_p,
+                    int parts, __nv_bfloat16* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long r0 = static_cast<long long>(blockIdx.x) * 32;
+  const int k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of threads
+  for (int i = ty; i < 32; i += 8) {
+    const long long r = r0 + i;
+    const int k = k0 + tx;
+    tile[i][tx] = (r < rows && k < K) ? src[r * ld + k] : 0.f;
+  }
+  __syncthreads();
+  const long long dpitch = static_cast<long long>(parts) * rows_p;
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i;
+    const long long r = r0 + tx;
+    if (k >= K || r >= rows_p) continue;
+    float rem = tile[tx][i];
+    for (int p = 0; p < parts; ++p) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(rem);
+      dst[static_cast<long long>(k) * dpitch + static_cast<long long>(p) * rows_p + r] = hb;
+      rem -= __bfloat162float(hb);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ whole LN
+// y = (x - mean) * rstd over ALL elements (Layers.py:167-168); dx = rstd * (dy - mean(dy) - y * mean(dy*y)).
+__global__ void __launch_bounds__(256)
+whole_ln_bwd_stats_kernel(const float* __restrict__ y, long long y_pitch, const float* __restrict__ dy,
+                          long long dy_pitch, long long rows, int cols, double* __restrict__ partials) {
+  __shared__ double s_a[8], s_b[8];
+  const long long total = rows * cols;
+  double a = 0.0, b = 0.0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const float g = dy[r * dy_pitch + c];
+    a += g;
+    b += static_cast<double>(g) * y[r * y_pitch + c];
+  }
+  a = warp_sum_d(a);
+  b = warp_sum_d(b);
+  if ((threadIdx.x & 31) == 0) {
+    s_a[threadIdx.x >> 5] = a;
+    s_b[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      ta += s_a[w];
+      tb += s_b[w];
+    }
+    partials[2 * blockIdx.x] = ta;
+    partials[2 * blockIdx.x + 1] = tb;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+whole_ln_bwd_apply_kernel(const float* __restrict__ y, long long y_pitch, const float* __restrict__ dy,
+                          long long dy_pitch, long long rows, int cols, const double* __restrict__ partials,
+                          int n_parts, const float* __restrict__ stats, float* __restrict__ dx,
+                          long long dx_pitch) {
+  __shared__ float s_m1, s_m2;
+  if (threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n_parts; i += 32) {
+      a += partials[2 * i];
+      b += partials[2 * i + 1];
+    }
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    if (threadIdx.x == 0) {
+      const double n = static_cast<double>(rows) * cols;
+      s_m1 = static_cast<float>(a / n);
+      s_m2 = static_cast<float>(b / n);
+    }
+  }
+  __syncthreads();
+  const float m1 = s_m1, m2 = s_m2, rstd = stats[1];
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    dx[r * dx_pitch + c] = rstd * (dy[r * dy_pitch + c] - m1 - y[r * y_pitch + c] * m2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ embedding
+// dW[v] (+)= sum over k with ids[k] == v of dy[k], in ascending k (deterministic).  One warp per
+// vocabulary row scans the id list 32 entries at a time.
+template <typename I>
+__global__ void __launch_bounds__(256)
+embedding_grad_kernel(const I* __restrict__ ids, long long n, const float* __restrict__ dy,
+                      long long dy_pitch, int D, int V, float* __restrict__ dW, long long dw_pitch,
+                      int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
+    for (int c0 = 0; c0 < D; c0 += 32 * 8) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (long long base = 0; base < n; base += 32) {
+        const long long k = base + lane;
+        const long long id = (k < n) ? static_cast<long long>(ids[k]) : -1;
+        unsigned m = __ballot_sync(0xffffffffu, id == v);
+        while (m) {
+          const int t = __ffs(m) - 1;
+          m &= m - 1;
+          const float* row = dy + (base + t) * dy_pitch;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = c0 + lane + 32 * i;
+            if (c < D) acc[i] += row[c];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + lane + 32 * i;
+        if (c < D) {
+          float* p = dW + static_cast<long long>(v) * dw_pitch + c;
+          *p = accumulate ? *p + acc[i] : acc[i];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ subword
+// s[l] = sum over words of < dy[word], mean_{t in [st,ed)} h_l[row_start[item] + t] >   (Bert.py:149-165):
+// the only quantity the gradients of alphaBERT / gammaBERT need (SDNet.py:573-583).  One warp per word.
+constexpr int SW_MAX_LAYERS = 24;
+template <typename T>
+__global__ void __launch_bounds__(256)
+subword_layers_bwd_kernel(const T* __restrict__ h, long long layer_stride, const int32_t* __restrict__ words,
+                          int n_words, const int32_t* __restrict__ row_start, const uint8_t* __restrict__ x_mask,
+                          int W, const float* __restrict__ dy, long long dy_stride, int n_layers, int hidden,
+                          double* __restrict__ partials) {
+  __shared__ double s_acc[8][SW_MAX_LAYERS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  if (lane < SW_MAX_LAYERS) s_acc[wid][lane] = 0.0;
+  __syncwarp();
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+    const int item = words[w];
+    const int j = words[1LL * n_words + w];
+    const int st = words[2LL * n_words + w];
+    const int ed = words[3LL * n_words + w];
+    if (j >= W || x_mask[static_cast<long long>(item) * W + j] == 0 || ed <= st) continue;
+    const int cnt = ed - st;
+    const float inv = (cnt > 1) ? 1.0f / static_cast<float>(cnt) : 1.0f;
+    const float* g = dy + (static_cast<long long>(item) * W + j) * dy_stride;
+    const long long t0 = static_cast<long long>(row_start[item]) + st;
+#pragma unroll 1
+    for (int l = 0; l < n_layers; ++l) {
+      const T* hl = h + static_cast<long long>(l) * layer_stride + t0 * hidden;
+      float dot = 0.f;
+      for (int c = lane; c < hidden; c += 32) {
+        float sum = 0.f;
+        for (int t = 0; t < cnt; ++t) sum += static_cast<float>(hl[static_cast<long long>(t) * hidden + c]);
+        dot = fmaf(sum * inv, g[c], dot);
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) s_acc[wid][l] += dot;   // per-warp accumulator, words in a fixed order
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_layers) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_acc[w][threadIdx.x];
+    partials[static_cast<long long>(blockIdx.x) * n_layers + threadIdx.x] = t;
+  }
+}
+
+// one thread: s[l] = sum of partials; a = softmax(alpha); out = gamma * sum_l a_l m_l
+//   d gamma = sum_l a_l s_l ; d a_l = gamma s_l ; d alpha_l = a_l (d a_l - sum_k a_k d a_k)
+__global__ void layer_mix_bwd_kernel(const double* __restrict__ partials, int n_blocks, int n_layers,
+                                     const float* __restrict__ alpha, const float* __restrict__ gamma,
+                                     float* __restrict__ dalpha, float* __restrict__ dgamma, int accumulate) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s[SW_MAX_LAYERS], a[SW_MAX_LAYERS];
+  float mx = -INFINITY;
+  for (int l = 0; l < n_layers; ++l) mx = fmaxf(mx, alpha[l]);
+  double den = 0.0;
+  for (int l = 0; l < n_layers; ++l) {
+    a[l] = exp(static_cast<double>(alpha[l] - mx));
+    den += a[l];
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += partials[static_cast<long long>(b) * n_layers + l];
+    s[l] = t;
+  }
+  const double gm = gamma[0];
+  double dg = 0.0, dotda = 0.0;
+  for (int l = 0; l < n_layers; ++l) {
+    a[l] /= den;
+    dg += a[l] * s[l];
+    dotda += a[l] * gm * s[l];
+  }
+  for (int l = 0; l < n_layers; ++l) {
+    const float v = static_cast<float>(a[l] * (gm * s[l] - dotda));
+    dalpha[l] = accumulate ? dalpha[l] + v : v;
+  }
+  dgamma[0] = accumulate ? dgamma[0] + static_cast<float>(dg) : static_cast<float>(dg);
+}
+
+// ------------------------------------------------------------------------------------------ LSTM BPTT
+// Backward of the persistent (Bi)LSTM recurrence (lstm.cu) for H <= 128.  One CTA owns BP_BT sequences
+// of one direction and walks the steps in reverse.  Per step:
+//   phase 1 (thread = (sequence b, unit j)): dh = dout[t] + dh_rec ; gate gradients from the saved
+//           activations (i, f, g, o, c) ; writes d(pre-activation) to dxg[t] and to shared memory
+//   phase 2 (thread = (unit k, gate q)): dh_rec[b][k] = sum_r d_pre[b][r] W_hh[r][k] — W_hh is read through
+//           L1/L2 (250 KB, coalesced along k), partial sums of the four gates meet by warp shuffles.
+// dW_ih, dW_hh, db and dx follow from dxg by GEMMs / column sums outside.
+constexpr int BP_THREADS = 512;
+constexpr int BP_BT = 4;
+constexpr int BP_HP = 128;
+
+__global__ void __launch_bounds__(BP_THREADS, 1)
+lstm_bptt_kernel(const float* __restrict__ gates, long long gates_pitch, const float* __restrict__ w_hh,
+                 const float* __restrict__ dout, long long dout_pitch, float* __restrict__ dxg,
+                 long long dxg_pitch, int B, int L, int H) {
+  __shared__ float s_dg[BP_BT][4 * BP_HP];
+  __shared__ float s_dh[BP_BT][BP_HP];
+  const int t = threadIdx.x;
+  const int dir = blockIdx.y;
+  const int b0 = blockIdx.x * BP_BT;
+  const float* W = w_hh + static_cast<long long>(dir) * 4 * H * H;
+  for (int i = t; i < BP_BT * 4 * BP_HP; i += BP_THREADS) (&s_dg[0][0])[i] = 0.f;
+  for (int i = t; i < BP_BT * BP_HP; i += BP_THREADS) (&s_dh[0][0])[i] = 0.f;
+  __syncthreads();
+  // phase-1 role
+  const int pb = t / H, pj = t - pb * H;
+  const int bb = b0 + pb;
+  const bool p1 = (pb < BP_BT) && (bb < B);
+  float dc_carry = 0.f;
+  // phase-2 role
+  const int k = t >> 2, q = t & 3;
+  const bool p2 = k < H;
+  for (int s = L - 1; s >= 0; --s) {
+    const int tt = dir == 0 ? s : (L - 1 - s);
+    if (p1) {
+      const float* row = gates + (static_cast<long long>(bb) * L + tt) * gates_pitch + dir * 5 * H;
+      const float gi = row[pj], gf = row[H + pj], gg = row[2 * H + pj], go = row[3 * H + pj];
+      const float c = row[4 * H + pj];
+      float c_prev = 0.f;
+      if (s > 0) {
+        const int tp = dir == 0 ? tt - 1 : tt + 1;
+        c_prev = gates[(static_cast<long long>(bb) * L + tp) * gates_pitch + dir * 5 * H + 4 * H + pj];
+      }
+      const float dh = dout[(static_cast<long long>(bb) * L + tt) * dout_pitch + dir * H + pj] + s_dh[pb][pj];
+      const float tc = tanhf(c);
+      const float d_o = dh * tc;
+      const float dc = dc_carry + dh * go * (1.0f - tc * tc);
+      const float dai = dc * gg * gi * (1.0f - gi);
+      const float daf = dc * c_prev * gf * (1.0f - gf);
+      const float dag = dc * gi * (1.0f - gg * gg);
+      const float dao = d_o * go * (1.0f - go);
+      dc_carry = dc * gf;
+      float* xr = dxg + (static_cast<long long>(bb) * L + tt) * dxg_pitch + dir * 4 * H;
+      xr[pj] = dai;
+      xr[H + pj] = daf;
+      xr[2 * H + pj] = dag;
+      xr[3 * H + pj] = dao;
+      s_dg[pb][pj] = dai;
+      s_dg[pb][BP_HP + pj] = daf;
+      s_dg[pb][2 * BP_HP + pj] = dag;
+      s_dg[pb][3 * BP_HP + pj] = dao;
+    }
+    __syncthreads();
+    if (s > 0) {   // the recurrent gradient is not needed before the first step
+      float acc[BP_BT];
+#pragma unroll
+      for (int b = 0; b < BP_BT; ++b) acc[b] = 0.f;
+      if (p2) {
+        const float* wq = W + static_cast<long long>(q) * H * H + k;
+#pragma unroll 5
+        for (int j = 0; j < H; ++j) {
+          const float w = __ldg(wq + static_cast<long long>(j) * H);
+#pragma unroll
+          for (int b = 0; b < BP_BT; ++b) acc[b] = fmaf(s_dg[b][q * BP_HP + j], w, acc[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < BP_BT; ++b) {
+        acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 1);
+        acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], 2);
+      }
+      if (p2 && q == 0) {
+#pragma unroll
+        for (int b = 0; b < BP_BT; ++b) s_dh[b][k] = acc[b];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ multi2one
+// Training form of lstm_cell_kernel (sdnet_kernels.cu): same update with accurate expf / tanhf, also
+// saving (i, f, g, o, c, h) of the step in save[r][6H].
+__global__ void lstm_cell_train_kernel(const float* __restrict__ gx, const float* __restrict__ gh,
+                                       float* __restrict__ c, __nv_bfloat16* __restrict__ h_split, int parts,
+                                       int Kp, int H, int n_rows, const int32_t* __restrict__ last_step,
+                                       int step, const long long* __restrict__ slot_off,
+                                       float* __restrict__ slots, float* __restrict__ save) {
+  const long long total = static_cast<long long>(n_rows) * H;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / H);
+    const int j = static_cast<int>(i - static_cast<long long>(r) * H);
+    const float* g = gx + static_cast<long long>(r) * 4 * H;
+    float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+    float cp = 0.f;
+    if (gh != nullptr) {
+      const float* qh = gh + static_cast<long long>(r) * 4 * H;
+      gi += qh[j]; gf += qh[H + j]; gg += qh[2 * H + j]; go += qh[3 * H + j];
+      cp = c[i];
+    }
+    const float si = 1.0f / (1.0f + expf(-gi));
+    const float sf = 1.0f / (1.0f + expf(-gf));
+    const float so = 1.0f / (1.0f + expf(-go));
+    const float tg = tanhf(gg);
+    const float cn = sf * cp + si * tg;
+    const float hn = so * tanhf(cn);
+    c[i] = cn;
+    float* sv = save + static_cast<long long>(r) * 6 * H;
+    sv[j] = si; sv[H + j] = sf; sv[2 * H + j] = tg; sv[3 * H + j] = so; sv[4 * H + j] = cn; sv[5 * H + j] = hn;
+    float rem = hn;
+    for (int p = 0; p < parts; ++p) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(rem);
+      h_split[static_cast<long long>(r) * parts * Kp + static_cast<long long>(p) * Kp + j] = hb;
+      rem -= __bfloat162float(hb);
+    }
+    if (last_step[r] == step) slots[slot_off[r] + j] = hn;
+  }
+}
+
+// Backward of one step: rows r < n_rows are the items still active at `step`.
+//   dh = (last_step[r] == step ? dslots[slot_off[r] + j] : 0) + (dh_rec ? dh_rec[r][j] : 0)
+//   dc = dc_carry[r][j] (0 for rows that end at this step) + dh * o * (1 - tanh(c)^2)
+// writes d(pre-activations) [n_rows, 4H] and the new dc_carry = dc * f.
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ save, const float* __restrict__ save_prev,
+                                     const float* __restrict__ dslots, const long long* __restrict__ slot_off,
+                                     const int32_t* __restrict__ last_step, int step,
+                                     const float* __restrict__ dh_rec, int n_rec, float* __restrict__ dc_carry,
+                                     float* __restrict__ dgates, int H, int n_rows) {
+  const long long total = static_cast<long long>(n_rows) * H;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / H);
+    const int j = static_cast<int>(i - static_cast<long long>(r) * H);
+    const float* sv = save + static_cast<long long>(r) * 6 * H;
+    const float gi = sv[j], gf = sv[H + j], gg = sv[2 * H + j], go = sv[3 * H + j], c = sv[4 * H + j];
+    const float c_prev = save_prev ? save_prev[static_cast<long long>(r) * 6 * H + 4 * H + j] : 0.f;
+    const bool ends = last_step[r] == step;
+    float dh = ends ? dslots[slot_off[r] + j] : 0.f;
+    if (dh_rec != nullptr && r < n_rec) dh += dh_rec[static_cast<long long>(r) * H + j];
+    const float tc = tanhf(c);
+    const float dc = (ends ? 0.f : dc_carry[i]) + dh * go * (1.0f - tc * tc);
+    float* dg = dgates + static_cast<long long>(r) * 4 * H;
+    dg[j] = dc * gg * gi * (1.0f - gi);
+    dg[H + j] = dc * c_prev * gf * (1.0f - gf);
+    dg[2 * H + j] = dc * gi * (1.0f - gg * gg);
+    dg[3 * H + j] = dh * tc * go * (1.0f - go);
+    dc_carry[i] = dc * gf;
+  }
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+extern "C" int ruart_bmm_f32(const float* A, long long lda, long long stride_a, int trans_a, const float* B,
+                             long long ldb, long long stride_b, int trans_b, float* C, long long ldc,
+                             long long stride_c, int batch, int M, int N, int K, float alpha, int accumulate,
+                             void* stream) {
+  RUART_ARG_CHECK(A != nullptr && B != nullptr && C != nullptr && M >= 0 && N >= 0 && K >= 0 && batch >= 0);
+  RUART_ARG_CHECK(batch <= 65535);
+  if (batch == 0 || M == 0 || N == 0) return RUART_OK;
+  dim3 grid((N + TB_N - 1) / TB_N, (M + TB_M - 1) / TB_M, batch);
+  RUART_ARG_CHECK(grid.y <= 65535);
+  bmm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, stride_a, trans_a, B, ldb, stride_b, trans_b,
+                                                         C, ldc, stride_c, M, N, K, alpha, accumulate);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_masked_softmax(const float* x, long long x_pitch, const uint8_t* mask, int B, int L1,
+                                    int L2, float* out, long long out_pitch, void* stream) {
+  RUART_ARG_CHECK(x != nullptr && out != nullptr && B >= 0 && L1 > 0 && L2 > 0);
+  const long long rows = static_cast<long long>(B) * L1;
+  if (rows == 0) return RUART_OK;
+  masked_softmax_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      x, x_pitch, mask, L1, L2, rows, out, out_pitch);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_softmax_backward(const float* p, long long p_pitch, const float* dp, long long dp_pitch,
+                                      float* dx, long long dx_pitch, long long rows, int cols, void* stream) {
+  RUART_ARG_CHECK(p != nullptr && dp != nullptr && dx != nullptr && rows >= 0 && cols > 0);
+  if (rows == 0) return RUART_OK;
+  softmax_backward_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      p, p_pitch, dp, dp_pitch, dx, dx_pitch, rows, cols);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_eltwise(int op, const float* a, long long a_pitch, const float* b, long long b_pitch,
+                             const float* v, int v_len, float* out, long long out_pitch, long long rows,
+                             int cols, void* stream) {
+  RUART_ARG_CHECK(a != nullptr && out != nullptr && rows >= 0 && cols > 0 && op >= 0 && op <= 5);
+  if (op == 3 || op == 5) RUART_ARG_CHECK(v != nullptr && v_len >= 1 && (v_len == 1 || v_len >= cols));
+  if (op <= 2) RUART_ARG_CHECK(b != nullptr);
+  if (rows == 0) return RUART_OK;
+  const unsigned grid = grid_for(rows * cols, 256 * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (op) {
+    case 0: eltwise_kernel<0><<<grid, 256, 0, st>>>(a, a_pitch, b, b_pitch, v, v_len, out, out_pitch, rows, cols); break;
+    case 1: eltwise_kernel<1><<<grid, 256, 0, st>>>(a, a_pitch, b, b_pitch, v, v_len, out, out_pitch, rows, cols); break;
+    case 2: eltwise_kernel<2><<<grid, 256, 0, st>>>(a, a_pitch, b, b_pitch, v, v_len, out, out_pitch, rows, cols); break;
+    case 3: eltwise_kernel<3><<<grid, 256, 0, st>>>(a, a_pitch, b, b_pitch, v, v_len, out, out_pitch, rows, cols); break;
+    case 4: eltwise_kernel<4><<<grid, 256, 0, st>>>(a, a_pitch, b, b_pitch, v, v_len, out, out_pitch, rows, cols); break;
+    default: eltwise_kernel<5><<<grid, 256, 0, st>>>(a, a_pitch, b, b_pitch, v, v_len, out, out_pitch, rows, cols); break;
+  }
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_mask_fill(const float* x, const uint8_t* mask, long long n, float value, float* out,
+                               void* stream) {
+  RUART_ARG_CHECK(x != nullptr && mask != nullptr && out != nullptr && n >= 0);
+  if (n == 0) return RUART_OK;
+  mask_fill_kernel<<<grid_for(n, 256 * 4), 256, 0, (cudaStream_t)stream>>>(x, mask, n, value, out);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_colsum(const float* x, long long pitch, long long rows, int cols, double* workspace,
+                            float* out, int accumulate, void* stream) {
+  RUART_ARG_CHECK(x != nullptr && out != nullptr && workspace != nullptr && rows >= 0 && cols > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int chunks = static_cast<int>((rows + 255) / 256);
+  if (chunks > CS_CHUNKS) chunks = CS_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  dim3 grid((cols + 31) / 32, chunks);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(x, pitch, rows, cols, workspace);
+  RUART_LAUNCH_CHECK();
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(workspace, chunks, cols, out, accumulate);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_split_bf16_t(const float* src, long long ld, long long rows, int K, long long rows_p,
+                                  int parts, void* dst, void* stream) {
+  RUART_ARG_CHECK(src != nullptr && dst != nullptr && rows >= 0 && K > 0 && rows_p >= rows &&
+                  (rows_p % 64) == 0 && parts >= 1 && parts <= 3);
+  if (rows_p == 0) return RUART_OK;
+  dim3 grid(static_cast<unsigned>(rows_p / 32), (K + 31) / 32);
+  RUART_ARG_CHECK(grid.y <= 65535);
+  split_bf16_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, rows, K, rows_p, parts,
+                                                              (__nv_bfloat16*)dst);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_whole_layernorm_backward(const float* y, long long y_pitch, const float* dy,
+                                              long long dy_pitch, long long rows, int cols,
+                                              const float* stats, double* workspace, float* dx,
+                                              long long dx_pitch, void* stream) {
+  RUART_ARG_CHECK(y != nullptr && dy != nullptr && dx != nullptr && stats != nullptr && workspace != nullptr);
+  RUART_ARG_CHECK(rows > 0 && cols > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  long long g = (rows * cols + 256 * 8 - 1) / (256 * 8);
+  if (g > 1024) g = 1024;
+  if (g < 1) g = 1;
+  whole_ln_bwd_stats_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(y, y_pitch, dy, dy_pitch, rows, cols,
+                                                                     workspace);
+  RUART_LAUNCH_CHECK();
+  whole_ln_bwd_apply_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, st>>>(
+      y, y_pitch, dy, dy_pitch, rows, cols, workspace, static_cast<int>(g), stats, dx, dx_pitch);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
+                                    long long dy_pitch, int D, int V, float* dW, long long dw_pitch,
+                                    int accumulate, void* stream) {
+  RUART_ARG_CHECK(ids != nullptr && dy != nullptr && dW != nullptr && n >= 0 && D > 0 && V > 0);
+  const unsigned grid = grid_for(static_cast<long long>(V) * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (idx_is_64)
+    embedding_grad_kernel<long long><<<grid, 256, 0, st>>>((const long long*)ids, n, dy, dy_pitch, D, V, dW,
+                                                           dw_pitch, accumulate);
+  else
+    embedding_grad_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)ids, n, dy, dy_pitch, D, V, dW,
+                                                         dw_pitch, accumulate);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_subword_layers_backward(const float* h_f32, const void* h_bf16, long long layer_stride,
+                                             const int32_t* words, int n_words, const int32_t* row_start,
+                                             const uint8_t* x_mask, int W, const float* dy,
+                                             long long dy_stride, const float* alpha, int n_layers,
+                                             const float* gamma, int hidden, double* workspace,
+                                             float* dalpha, float* dgamma, int accumulate, void* stream) {
+  RUART_ARG_CHECK((h_f32 != nullptr) != (h_bf16 != nullptr));
+  RUART_ARG_CHECK(n_layers >= 1 && n_layers <= SW_MAX_LAYERS && workspace != nullptr);
+  RUART_ARG_CHECK(alpha != nullptr && gamma != nullptr && dalpha != nullptr && dgamma != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (n_words + 7) / 8;
+  if (blocks > 256) blocks = 256;
+  if (blocks < 1) blocks = 1;
+  if (h_f32 != nullptr)
+    subword_layers_bwd_kernel<float><<<blocks, 256, 0, st>>>(h_f32, layer_stride, words, n_words, row_start,
+                                                             x_mask, W, dy, dy_stride, n_layers, hidden, workspace);
+  else
+    subword_layers_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dy, dy_stride,
+        n_layers, hidden, workspace);
+  RUART_LAUNCH_CHECK();
+  layer_mix_bwd_kernel<<<1, 32, 0, st>>>(workspace, blocks, n_layers, alpha, gamma, dalpha, dgamma, accumulate);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_lstm_recurrence_backward(const float* gates, long long gates_pitch, const float* w_hh,
+                                              const float* dout, long long dout_pitch, float* dxg,
+                                              long long dxg_pitch, int B, int L, int H, int ndir,
+                                              void* stream) {
+  RUART_ARG_CHECK(gates != nullptr && w_hh != nullptr && dout != nullptr && dxg != nullptr);
+  RUART_ARG_CHECK(B > 0 && L > 0 && H > 0 && H <= BP_HP && BP_BT * H <= BP_THREADS && (ndir == 1 || ndir == 2));
+  dim3 grid((B + BP_BT - 1) / BP_BT, ndir);
+  lstm_bptt_kernel<<<grid, BP_THREADS, 0, (cudaStream_t)stream>>>(gates, gates_pitch, w_hh, dout, dout_pitch,
+                                                                 dxg, dxg_pitch, B, L, H);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_lstm_cell_train(const float* gx, const float* gh, float* c, void* h_split, int parts,
+                                     int Kp, int H, int n_rows, const int32_t* last_step, int step,
+                                     const long long* slot_off, float* slots, float* save, void* stream) {
+  RUART_ARG_CHECK(H > 0 && Kp >= H && (Kp % 64) == 0 && parts >= 1 && parts <= 3 && save != nullptr);
+  if (n_rows == 0) return RUART_OK;
+  lstm_cell_train_kernel<<<grid_for(static_cast<long long>(n_rows) * H, 256), 256, 0, (cudaStream_t)stream>>>(
+      gx, gh, c, (__nv_bfloat16*)h_split, parts, Kp, H, n_rows, last_step, step, slot_off, slots, save);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_lstm_cell_backward(const float* save, const float* save_prev, const float* dslots,
+                                        const long long* slot_off, const int32_t* last_step, int step,
+                                        const float* dh_rec, int n_rec, float* dc_carry, float* dgates, int H,
+                                        int n_rows, void* stream) {
+  RUART_ARG_CHECK(save != nullptr && dslots != nullptr && dc_carry != nullptr && dgates != nullptr && H > 0);
+  if (n_rows == 0) return RUART_OK;
+  lstm_cell_bwd_kernel<<<grid_for(static_cast<long long>(n_rows) * H, 256), 256, 0, (cudaStream_t)stream>>>(
+      save, save_prev, dslots, slot_off, last_step, step, dh_rec, n_rec, dc_carry, dgates, H, n_rows);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}

@@ -1120,9 +1120,9 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
   RUART_ARG_CHECK(n_heads > 0);
   if (n_seq == 0) return RUART_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
+  static RuartDeviceOnce attr_set;
   const size_t smem_max = 4 * (2 * ATT_MAX_STAGE * 64 + 64) * sizeof(float);
-  if (!attr_set) {
+  if (!attr_set.done()) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_kernel<float>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_max));
@@ -1135,7 +1135,7 @@ extern "C" int ruart_bert_attention(const float* qkv_f32, const void* qkv_bf16,
     RUART_CUDA_CHECK(cudaFuncSetAttribute(bert_attention_mma16_async_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SHORT_WARPS * 6 * 16 * 128));
-    attr_set = true;
+    attr_set.set();
   }
   // bf16 in, plain bf16 out: sequences of <= 64 tokens run on the warp-level MMA kernels
   int skip_upto = 0;

@@ -45,6 +45,24 @@ void ruart_set_error(const char* fmt, ...);
 
 extern "C" int ruart_num_sms(void);
 
+// Per-DEVICE once-flags.  cudaFuncSetAttribute, __constant__/__device__ symbol uploads and cluster-launch
+// capability are properties of a device (context), not of the process: a process that drives several
+// GPUs must initialise each of them.  Idempotent initialisers may race harmlessly.
+#ifdef __cplusplus
+#include <atomic>
+#define RUART_MAX_DEVICES 64
+inline int ruart_current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= RUART_MAX_DEVICES) return 0;
+  return d;
+}
+struct RuartDeviceOnce {
+  std::atomic<bool> v[RUART_MAX_DEVICES];
+  bool done() const { return v[ruart_current_device()].load(std::memory_order_acquire); }
+  void set() { v[ruart_current_device()].store(true, std::memory_order_release); }
+};
+#endif
+
 #ifdef __CUDACC__
 
 namespace ruart {

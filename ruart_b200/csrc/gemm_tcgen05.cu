@@ -842,8 +842,8 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   // CTA-pair kernel: plain bf16 output, whole 256-column tiles, one MMA term, a full wave of pairs
   static const bool one_cta = getenv("RUART_GEMM_1CTA") != nullptr;  // A/B aid
   GemmKernel kern2 = nullptr;
-  static bool pair_launch_ok = true;
-  if (!one_cta && pair_launch_ok && tma_out && n_terms == 1 && (N % MAX_BN) == 0 && M >= 2 * BM * 8) {
+  static RuartDeviceOnce pair_launch_bad;  // this device rejected the CTA-pair launch
+  if (!one_cta && !pair_launch_bad.done() && tma_out && n_terms == 1 && (N % MAX_BN) == 0 && M >= 2 * BM * 8) {
     if (has_res) kern2 = gemm_bf16_2cta_kernel<K_BIAS, true>;
     else if (kind == K_BIAS) kern2 = gemm_bf16_2cta_kernel<K_BIAS, false>;
     else if (kind == K_GELU_FAST) kern2 = gemm_bf16_2cta_kernel<K_GELU_FAST, false>;
@@ -853,12 +853,12 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
     CUtensorMap tmb2;
     rc = make_tmap_bf16(&tmb2, W, N, (long long)w_parts * Kp, ldw, B2_ROWS);
     if (rc != RUART_OK) return rc;
-    static bool attr2[4] = {};
+    static RuartDeviceOnce attr2[4];
     const int slot2 = has_res ? 2 : (kind == K_BIAS ? 0 : (kind == K_GELU_FAST ? 1 : 3));
-    if (!attr2[slot2]) {
+    if (!attr2[slot2].done()) {
       RUART_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             GEMM2_SMEM_BYTES));
-      attr2[slot2] = true;
+      attr2[slot2].set();
     }
     const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / MAX_BN);
     int grid2 = ruart_num_sms() & ~1;
@@ -873,15 +873,15 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
       ruart_set_error("%s:%d: launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e2));
       return RUART_ERR_CUDA;
     }
-    pair_launch_ok = false;
+    pair_launch_bad.set();
   }
   GemmKernel kern = kernel_for(kind, tma_out, has_res);
-  static bool attr_set[K_NUM][3] = {};
+  static RuartDeviceOnce attr_set[K_NUM][3];
   const int slot = has_res ? 2 : (tma_out ? 1 : 0);
-  if (!attr_set[kind][slot]) {
+  if (!attr_set[kind][slot].done()) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           GEMM_SMEM_BYTES));
-    attr_set[kind][slot] = true;
+    attr_set[kind][slot].set();
   }
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + p.block_n - 1) / p.block_n;

@@ -166,13 +166,18 @@ lstm_recurrence_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*
 // ----------------------------------------------------------------------------------------------
 // Two gate rows per thread (see the header).  KR2 weights of each row in registers, the remaining
 // HP-KR2 columns as float4 quads in shared memory: s_w[(q*2 + r) * 256 + t].
+//
+// SAVE (training): the activated gates and the cell state of every step are also
+// written to `gates` [B*L, ndir*5*H] (row pitch gates_pitch; columns dir*5H + {i,f,g,o,c}*H + j) —
+// what back-propagation through time (lstm_bptt_kernel, backward_kernels.cu) reads.
 constexpr int LSTM2_THREADS = 256;
-template <int BT, int KR2>
+template <int BT, int KR2, bool SAVE = false>
 __global__ void __launch_bounds__(LSTM2_THREADS, 1)
 lstm_recurrence2_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*L, ndir*4H]
                         const float* __restrict__ w_hh,                    // [ndir][4H][H]
                         float* __restrict__ out, long long out_pitch,      // [B*L, >= ndir*H]
-                        int B, int L, int H) {
+                        int B, int L, int H, float* __restrict__ gates = nullptr,
+                        long long gates_pitch = 0) {
   constexpr int NQ2 = (HP - KR2) / 4;
   extern __shared__ __align__(16) float smem[];
   float4* s_w = reinterpret_cast<float4*>(smem);        // [NQ2][2][256] quads
@@ -277,6 +282,11 @@ lstm_recurrence2_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B
       const float s1 = logistic(half ? p1 : 2.0f * p1);
       const float g1 = half ? s1 : fmaf(2.0f, s1, -1.0f);
       const float ig = __shfl_xor_sync(0xffffffffu, g0 * g1, 1);  // half 1 receives i*g
+      if (SAVE && active && b0 + b < B) {
+        float* gr = gates + (static_cast<long long>(b0 + b) * L + tt) * gates_pitch + dir * 5 * H + j;
+        gr[half * H] = g0;          // i (half 0) or f (half 1)
+        gr[(2 + half) * H] = g1;    // g (half 0) or o (half 1)
+      }
       if (half && active) {
         const float cn = fmaf(g0, c[b], ig);
         const float hv = g1 * fmaf(2.0f, logistic(2.0f * cn), -1.0f);
@@ -284,6 +294,8 @@ lstm_recurrence2_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B
         hn[b * HP + j] = hv;
         const int bb = b0 + b;
         if (bb < B) out[(static_cast<long long>(bb) * L + tt) * out_pitch + dir * H + j] = hv;
+        if (SAVE && bb < B)
+          gates[(static_cast<long long>(bb) * L + tt) * gates_pitch + dir * 5 * H + 4 * H + j] = cn;
       }
     }
     __syncthreads();
@@ -291,20 +303,21 @@ lstm_recurrence2_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B
   }
 }
 
-template <int BT, int KR2>
+template <int BT, int KR2, bool SAVE = false>
 int launch2(const float* xg, long long xg_pitch, const float* w_hh, float* out, long long out_pitch,
-            int B, int L, int H, int ndir, cudaStream_t st) {
+            int B, int L, int H, int ndir, cudaStream_t st, float* gates = nullptr,
+            long long gates_pitch = 0) {
   constexpr int NQ2 = (HP - KR2) / 4;
   const size_t smem = (static_cast<size_t>(NQ2) * 2 * LSTM2_THREADS * 4 + 2 * BT * HP) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RUART_CUDA_CHECK(cudaFuncSetAttribute(lstm_recurrence2_kernel<BT, KR2>,
+  static RuartDeviceOnce attr_set;
+  if (!attr_set.done()) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(lstm_recurrence2_kernel<BT, KR2, SAVE>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.set();
   }
   dim3 grid((B + BT - 1) / BT, ndir);
-  lstm_recurrence2_kernel<BT, KR2><<<grid, LSTM2_THREADS, smem, st>>>(xg, xg_pitch, w_hh, out, out_pitch,
-                                                                 B, L, H);
+  lstm_recurrence2_kernel<BT, KR2, SAVE><<<grid, LSTM2_THREADS, smem, st>>>(
+      xg, xg_pitch, w_hh, out, out_pitch, B, L, H, gates, gates_pitch);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
@@ -313,11 +326,11 @@ template <int BT>
 int launch(const float* xg, long long xg_pitch, const float* w_hh, float* out, long long out_pitch,
            int B, int L, int H, int ndir, cudaStream_t st) {
   const size_t smem = (static_cast<size_t>(NQ) * ROWP * 4 + 2 * BT * HP) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static RuartDeviceOnce attr_set;
+  if (!attr_set.done()) {
     RUART_CUDA_CHECK(cudaFuncSetAttribute(lstm_recurrence_kernel<BT>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.set();
   }
   dim3 grid((B + BT - 1) / BT, ndir);
   lstm_recurrence_kernel<BT><<<grid, LSTM_THREADS, smem, st>>>(xg, xg_pitch, w_hh, out, out_pitch,
@@ -345,4 +358,18 @@ extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const 
   // larger batches: several waves of the same kernel (measured 1.45x faster than one wave of the
   // one-row kernel with 8 sequences per CTA: 517 vs 751 us at B = 512, L = 100)
   return launch2<4, 88>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+}
+
+// Training form: same recurrence, additionally saving the activated gates and the
+// cell state of every step (see lstm_recurrence2_kernel<.., SAVE>).
+extern "C" int ruart_lstm_recurrence_train(const float* xg, long long xg_pitch, const float* w_hh,
+                                           float* out, long long out_pitch, int B, int L, int H,
+                                           int ndir, float* gates, long long gates_pitch,
+                                           void* stream) {
+  RUART_ARG_CHECK(B > 0 && L > 0 && H > 0 && H <= 128 && (ndir == 1 || ndir == 2));
+  RUART_ARG_CHECK(gates != nullptr && gates_pitch >= static_cast<long long>(ndir) * 5 * H);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (((B + 1) / 2) * ndir <= ruart_num_sms())
+    return launch2<2, 88, true>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st, gates, gates_pitch);
+  return launch2<4, 88, true>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st, gates, gates_pitch);
 }

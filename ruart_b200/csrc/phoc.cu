@@ -241,8 +241,8 @@ phoc_kernel(const uint8_t* __restrict__ chars, const int32_t* __restrict__ offse
 }
 
 int upload_lut() {
-  static bool done = false;
-  if (done) return RUART_OK;
+  static RuartDeviceOnce done;  // the LUT symbols live in each device's memory
+  if (done.done()) return RUART_OK;
   int8_t lut[36 * 36];
   for (int i = 0; i < 36 * 36; ++i) lut[i] = -1;
   for (int k = 49; k >= 0; --k) {  // first match wins (cphoc.c:78-84): fill back to front
@@ -255,7 +255,7 @@ int upload_lut() {
   lut_init_kernel<<<LUT_N + 1, 32>>>();
   RUART_CUDA_CHECK(cudaGetLastError());
   RUART_CUDA_CHECK(cudaDeviceSynchronize());
-  done = true;
+  done.set();
   return RUART_OK;
 }
 

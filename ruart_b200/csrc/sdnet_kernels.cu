@@ -90,7 +90,8 @@ whole_ln_stats_kernel(const float* __restrict__ x, long long rows, int cols, lon
 
 __global__ void __launch_bounds__(LN_THREADS)
 whole_ln_apply_kernel(float* __restrict__ x, long long rows, int cols, long long pitch,
-                      const double* __restrict__ partials, int n_parts, float eps) {
+                      const double* __restrict__ partials, int n_parts, float eps,
+                      float* __restrict__ stats_out) {
   __shared__ float s_mean, s_inv;
   if (threadIdx.x < 32) {
     double a = 0.0, b = 0.0;
@@ -107,6 +108,10 @@ whole_ln_apply_kernel(float* __restrict__ x, long long rows, int cols, long long
       if (var < 0.0) var = 0.0;
       s_mean = static_cast<float>(mean);
       s_inv = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      if (stats_out != nullptr && blockIdx.x == 0) {   // (mean, rstd) for the backward pass
+        stats_out[0] = s_mean;
+        stats_out[1] = s_inv;
+      }
     }
   }
   __syncthreads();
@@ -795,8 +800,17 @@ extern "C" int ruart_gather_rows(const float* src, long long src_pitch, const vo
   return RUART_OK;
 }
 
+extern "C" int ruart_whole_layernorm_stats(float* x, long long rows, int cols, long long pitch, float eps,
+                                           double* workspace, float* stats_out, void* stream);
+
 extern "C" int ruart_whole_layernorm(float* x, long long rows, int cols, long long pitch, float eps,
                                      double* workspace, void* stream) {
+  return ruart_whole_layernorm_stats(x, rows, cols, pitch, eps, workspace, nullptr, stream);
+}
+
+// Same, also writing (mean, rstd) to stats_out[2] (device) — what the backward pass needs.
+extern "C" int ruart_whole_layernorm_stats(float* x, long long rows, int cols, long long pitch, float eps,
+                                           double* workspace, float* stats_out, void* stream) {
   RUART_ARG_CHECK(x != nullptr && workspace != nullptr && rows > 0 && cols > 0);
   cudaStream_t st = (cudaStream_t)stream;
   long long g = (rows * cols + LN_THREADS * 8 - 1) / (LN_THREADS * 8);
@@ -806,7 +820,7 @@ extern "C" int ruart_whole_layernorm(float* x, long long rows, int cols, long lo
                                                                           workspace);
   RUART_LAUNCH_CHECK();
   whole_ln_apply_kernel<<<cap_grid(rows * cols, LN_THREADS * 4), LN_THREADS, 0, st>>>(
-      x, rows, cols, pitch, workspace, static_cast<int>(g), eps);
+      x, rows, cols, pitch, workspace, static_cast<int>(g), eps, stats_out);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

@@ -18,17 +18,21 @@ def item_index(num_cnt, len_cnt, W, M):
         raise ValueError("every item must have at least one word (len_cnt >= 1)")
     if lens.size and lens.max() > W:
         raise ValueError("len_cnt exceeds the word slots of an item row")
-    if int(num.max()) > M:
+    if B and int(num.max()) > M:
         raise ValueError("num_cnt exceeds the slot count of `position`")
+    if B and int(num.min()) < 0:
+        raise ValueError("num_cnt must be >= 0")
     n_items = lens.size
     item_img = np.repeat(np.arange(B, dtype=np.int64), num)
     first_item = np.cumsum(num) - num
     item_slot = np.arange(n_items, dtype=np.int64) - first_item[item_img]
     word_off = np.cumsum(lens) - lens                      # first word of each item, global
-    img_words = np.add.reduceat(lens, first_item) if n_items else np.zeros(B, np.int64)
-    img_first_word = word_off[first_item]
+    # images WITHOUT items (num_cnt 0: the reference's loops simply skip them, SDNet.py:300-318,498-550)
+    # have 0 words; reduceat / fancy indexing by `first_item` would read the next image's values instead
+    img_words = np.bincount(item_img, weights=lens, minlength=B).astype(np.int64)
+    img_first_word = np.cumsum(img_words) - img_words
     t0_item = word_off - img_first_word[item_img]          # word offset of the item inside its image
-    T_max = int(img_words.max())
+    T_max = int(img_words.max()) if B else 0
     total = int(lens.sum())
     item_of_word = np.repeat(np.arange(n_items, dtype=np.int64), lens)
     w = np.arange(total, dtype=np.int64) - np.repeat(word_off, lens)
@@ -58,9 +62,10 @@ def forward_plan(ocr_num_cnt, ocr_len_cnt, od_num_cnt, od_len_cnt, Wo, Wd, M, M_
     slot_all = np.concatenate([io['item_img'] * M + io['item_slot'],
                                B * M + id_['item_img'] * M_od + id_['item_slot']])
     perm = np.argsort(-lens_all, kind='stable')
-    max_len = int(lens_all.max())
+    max_len = int(lens_all.max()) if lens_all.size else 0
     n_t = [int((lens_all > t).sum()) for t in range(max_len)]
-    a_rows = np.concatenate([base_all[perm[:n]] + t for t, n in enumerate(n_t)])
+    a_rows = np.concatenate([base_all[perm[:n]] + t for t, n in enumerate(n_t)]) if n_t \
+        else np.zeros(0, np.int64)
     i32 = np.concatenate([io['word_src'], io['word_dst'], id_['word_src'], id_['word_dst'], a_rows,
                           lens_all[perm] - 1]).astype(np.int32)
     cuts = np.cumsum([0, io['total_words'], io['total_words'], id_['total_words'], id_['total_words'],

@@ -330,6 +330,11 @@ def shard_batch(batch, rank, world):
     B = len(ocr["num_cnt"])
     per = (B + world - 1) // world
     lo, hi = min(rank * per, B), min((rank + 1) * per, B)
+    if hi <= lo:
+        raise ValueError("rank %d of %d gets an empty shard of a %d-question batch" % (rank, world, B))
+    # keys derived from the WHOLE batch by Utils.collate.attach_index_tensors (forward plan, CSR word
+    # offsets, token counts) cannot be sliced: drop them — run attach_index_tensors again per shard
+    derived = ("ruart_plan", "bert_offsets_csr", "bert_totals")
 
     def cut_items(d):
         if "phoc_chars" in d:
@@ -338,6 +343,8 @@ def shard_batch(batch, rank, world):
         stop = start + sum(d["num_cnt"][lo:hi])
         r = {}
         for k, v in d.items():
+            if k in derived:
+                continue
             if k in ("num_cnt", "len_cnt"):
                 r[k] = v[lo:hi]
             elif k == "position":
@@ -348,7 +355,7 @@ def shard_batch(batch, rank, world):
                 r[k] = v[start:stop]
         return r
 
-    qs = {k: v[lo:hi] for k, v in q.items()}
+    qs = {k: v[lo:hi] for k, v in q.items() if k not in derived}
     return qs, cut_items(ocr), cut_items(od)
 
 

@@ -81,6 +81,11 @@ class FlatAdamax(object):
         with torch.no_grad():
             for p, first, rows in reset:
                 p.data[first:].copy_(rows)
+            # the kernels wrote through raw pointers: tell autograd / the prepared-weight caches of the
+            # inference path (keyed on data_ptr + _version, sdnet_ops.prep_weight, BertEngine._weights_key)
+            # that every parameter changed
+            for p in self.params:
+                torch.autograd.graph.increment_version(p)
 
     def grad_norm(self):
         """Total gradient norm of the last step (a device read-back; for logging only)."""

@@ -134,3 +134,45 @@ def test_collate_drop_in_rebuilds_the_reference_layout():
     opt = synth.make_opt("tiny", max_ocr_len=1)          # an item with 2 words no longer fits: error, like the reference
     with pytest.raises(ValueError):
         VQA_collate(opt).VQA_collate_fun(synth.uncollate(synth.make_batch("tiny")))
+
+
+def test_item_index_handles_images_without_items():
+    # num_cnt[i] == 0 (the reference's loops just skip such an image, SDNet.py:300-318,498-550)
+    W, M = 20, 100
+    num_cnt = [2, 0, 3, 0]
+    len_cnt = [[1, 2], [], [2, 1, 1], []]
+    idx = SDNet._item_index(num_cnt, len_cnt, W, M)
+    assert idx["T_max"] == 4 and idx["total_words"] == 7 and idx["n_items"] == 5
+    src, dst, it = [], [], 0
+    for b in range(4):
+        t = 0
+        for n in len_cnt[b]:
+            for w in range(n):
+                src.append(it * W + w)
+                dst.append(b * 4 + t + w)
+            t += n
+            it += 1
+    assert idx["word_src"].tolist() == src and idx["word_dst"].tolist() == dst
+    assert idx["mask"][1].sum() == 0 and idx["mask"][3].sum() == 0 and idx["mask"][2].sum() == 3
+    # the empty image last, and a wholly empty batch
+    idx2 = SDNet._item_index([1, 0], [[1], []], W, M)
+    assert idx2["T_max"] == 1 and idx2["word_dst"].tolist() == [0]
+    idx3 = SDNet._item_index([], [], W, M)
+    assert idx3["T_max"] == 0 and idx3["n_items"] == 0
+
+
+def test_shard_batch_drops_whole_batch_index_keys_and_rejects_empty_shards():
+    import pytest
+    from ruart_b200.Utils import collate
+    batch = collate.attach_index_tensors(*synth.make_batch("small", ragged=True))
+    for r in range(2):
+        q, ocr, od = synth.shard_batch(batch, r, 2)
+        for d in (q, ocr, od):
+            assert "ruart_plan" not in d and "bert_offsets_csr" not in d and "bert_totals" not in d
+        assert len(ocr["num_cnt"]) == 4 and q["glove"].shape[0] == 4
+        assert ocr["fasttext"].shape[0] == sum(ocr["num_cnt"]) == len(ocr["bert_offsets"])
+        # re-attached per shard
+        q2, ocr2, od2 = collate.attach_index_tensors(q, ocr, od)
+        assert ocr2["ruart_plan"]["key"][0] == 4
+    with pytest.raises(ValueError, match="empty shard"):
+        synth.shard_batch(synth.make_batch("tiny"), 3, 4)
