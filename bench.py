@@ -279,6 +279,138 @@ def run_reference_arm(args, rank, world):
     }))
 
 
+def bce_targets(batch, M, seed):
+    """One-hot BCE targets over the valid OCR slots."""
+    g = torch.Generator().manual_seed(seed)
+    num = batch[1]["num_cnt"]
+    t = torch.zeros(len(num), M + 1)
+    for b, n in enumerate(num):
+        t[b, int(torch.randint(0, max(1, n - 1), (1,), generator=g))] = 1.0
+    return t
+
+
+def run_train(args, rank, world, local_rank):
+    """--train: one `SDNetTrainer.update` per step (SDNetTrainer.py:330-376) on the drop-in — forward with autograd,
+    BCE-with-logits loss on the probabilities (:510-518), backward through the hand-written backward kernels, ONE
+    NCCL all-reduce (mean) of the flat 12.25 M-float gradient buffer, fused clip + Adamax, TUNE_PARTIAL reset.  Every
+    rank holds a different shard of `--cfg` (default cfg5: 32 questions x 200 OCR tokens).  Dropout 0.
+    --verify: rank 0 recomputes the gradients of ALL shards itself and compares their mean with the all-reduced buffer."""
+    import torch.nn.functional as F
+    from ruart_b200.Models.SDNet import SDNet
+    from ruart_b200.train_utils import FlatAdamax
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = args.cfg or "cfg5"
+    opt = synth.make_opt(cfg, BERT_precision="bf16", DROPOUT=0.0, dropout_emb=0.0)
+    torch.manual_seed(1033)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = SDNet(opt, synth.make_embedding(1033))
+    synth.fill_state_dict(net, seed=1033, bert_init="random")
+    net.to(dev)
+    net.train()
+    net.drop_emb = True
+    B = synth.CONFIGS[cfg]["B"]
+    M = opt["max_ocr_num"]
+
+    def shard(r):
+        b = synth.make_batch(cfg, seed=2100 + r, opt=opt)
+        return synth.batch_to(b, dev), bce_targets(b, M, 4242 + r).to(dev)
+
+    batch, targets = shard(rank)
+    # the GRUCell of GetFinalScores never receives a gradient (Layers.py:395-397): 89 tensors are optimised
+    params = [p for n, p in net.named_parameters() if p.requires_grad and not n.startswith("get_answer.rnn.")]
+    fixed = [(net.fast_embed.weight, opt["tune_partial"], net.fixed_embedding_fast.to(dev)),
+             (net.glove_embed.weight, opt["tune_partial"], net.fixed_embedding_glove.to(dev))]
+    fa = FlatAdamax(params, lr=opt["lr"], max_norm=float(opt["grad_clipping"]))
+
+    def grads_of(b, t):
+        scores, _ = net(*tuple(dict(d) for d in b))
+        loss = F.binary_cross_entropy_with_logits(scores, t) * t.size(1)
+        return loss, torch.autograd.grad(loss, params)
+
+    ar_events = []
+
+    def step(verify=False):
+        loss, grads = grads_of(batch, targets)
+        fa.load_grads(list(grads))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fa.allreduce_mean()
+        e1.record()
+        ar_events.append((e0, e1))
+        err = None
+        if verify:
+            if rank == 0:
+                acc = torch.zeros_like(fa.grad)
+                for r in range(world):
+                    b_r, t_r = shard(r)
+                    _, g_r = grads_of(b_r, t_r)
+                    acc += torch.cat([g.reshape(-1) for g in g_r])
+                acc /= world
+                err = float((acc - fa.grad).norm() / acc.norm())
+            if dist is not None:
+                dist.barrier()
+        fa.step(grads=None, reset=fixed, loaded=True)
+        return loss, err
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    _, verify_err = step(verify=args.verify)        # first step doubles as warm-up + the correctness check
+    for _ in range(max(args.warmup - 1, 2)):
+        step()
+    barrier()
+    ar_events.clear()
+    clocks = ClockSampler(local_rank).start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            loss, _ = step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar_events) / max(1, len(ar_events))
+    if dist is not None:
+        t = torch.tensor([ms, ar_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ar_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        n_bytes = fa.n * 4
+        wire = n_bytes * 2 * (world - 1) / world if world > 1 else 0
+        line = {
+            "metric": "ST-VQA training questions/sec (one SDNetTrainer.update per step)", "mode": "train",
+            "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 BERT (locked) / fp32 SDNet stack, 3-part split GEMM operands",
+            "data": "synthetic",
+            "config": {"workload": "%s training step: B=%d questions per GPU, %d+1 OCR items, dropout 0, Adamax lr %g, "
+                                   "grad clip %g, TUNE_PARTIAL %d" % (cfg, B, synth.CONFIGS[cfg]["n_ocr"], opt["lr"],
+                                                                       opt["grad_clipping"], opt["tune_partial"]),
+                       "per_gpu_batch": B, "global_batch": B * world,
+                       "parallelism": "data parallel x%d, one NCCL all-reduce of the flat gradient per step" % world},
+            "clocks": clocks.summary(), "loss_last_step": float(loss),
+            "allreduce": {"elements": fa.n, "bytes": n_bytes, "ms": ar_ms, "wire_bytes_per_rank": wire,
+                          "achieved_GBps_per_rank": (wire / (ar_ms * 1e-3) / 1e9) if ar_ms > 0 and world > 1 else None,
+                          "nvlink5_peak_GBps_per_direction": 900.0,
+                          "share_of_step": ar_ms / (ms / args.steps)},
+            "verify": None if verify_err is None else {
+                "rel_l2_error_vs_single_process_mean_of_all_shards": verify_err, "bound": 1e-4,
+                "ok": verify_err < 1e-4},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -288,6 +420,8 @@ def main():
     ap.add_argument("--cfg", default=None, help="cfg3 (default at N=1), cfg4 (default at N>1: 4096 questions / N), cfg5")
     ap.add_argument("--no-phoc", action="store_true", help="skip the cfg-2 PHOC record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train", action="store_true", help="time the training step (cfg5 by default) instead of inference")
+    ap.add_argument("--verify", action="store_true", help="--train: check the all-reduced gradient on rank 0")
     ap.add_argument("--collate-index", action="store_true",
                     help="prepare the batch with ruart_b200.Utils.collate.attach_index_tensors (CSR word offsets, "
                          "forward plan, host-side token counts: no host sync inside the forward)")
@@ -303,6 +437,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    if args.train:
+        run_train(args, rank, world, local_rank)
+        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -494,9 +631,9 @@ def main():
                          "kernel": "gemm_bf16_2cta_kernel (all %d BERT GEMM launches of the timed steps)" % n_gemm,
                          "kernel_ms_per_step": g_ms / args.steps, "peak_source": peak_src},
             "roofline_step": {"bound": "tensor", "algorithmic_gflop_per_question": STEP_GFLOP_PER_QUESTION,
-                              "achieved": STEP_GFLOP_PER_QUESTION * B / (ms / args.steps) / 1e3 if args.cfg in ("cfg3", "cfg4") else None,
+                              "achieved": STEP_GFLOP_PER_QUESTION * B / (ms / args.steps) if args.cfg in ("cfg3", "cfg4") else None,
                               "peak": peak, "unit": "TFLOP/s",
-                              "frac": (STEP_GFLOP_PER_QUESTION * B / (ms / args.steps) / 1e3 / peak) if args.cfg in ("cfg3", "cfg4") else None,
+                              "frac": (STEP_GFLOP_PER_QUESTION * B / (ms / args.steps) / peak) if args.cfg in ("cfg3", "cfg4") else None,
                               "note": "whole forward (BERT over real tokens + SDNet stack, SURVEY.md §8d) / step time, per GPU"},
             "kernels": dict(kernels, hbm_peak_GBps=hbm, peak_source=hbm_src,
                             note="CUDA events around every launch of the timed steps; bytes are algorithmic (DESIGN.md §4)"),

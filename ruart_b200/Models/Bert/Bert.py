@@ -7,7 +7,7 @@ pytorch_model.bin; the model is put on the GPU and in eval mode.  opt['BERT_MAX_
 accepted and ignored: rows are independent and nothing of size [N, L, 12*768] is materialised, so
 chunking is never needed (it is numerically neutral in the reference, Bert.py:65-85).
 
-Extra (not in the reference): opt['BERT_precision'] in {'bf16' (default), 'fp32'}, and
+Extra (not in the reference): opt['BERT_precision'] in {'bf16' (default), 'bf16x2', 'fp32'}, and
 `encode_into` — the fused entry SDNet uses (subword mean + learned layer sum written straight
 into the embedding concat buffer).
 """

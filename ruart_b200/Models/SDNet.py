@@ -175,7 +175,12 @@ class SDNet(nn.Module):
         self.ques_merger = LinearSelfAttn(ques_final_size)
         ocr_final_size = context_final_size * 2
         self.get_answer = GetFinalScores(ocr_final_size, ques_final_size, yesno=False, no_answer=True, useES=True)
-        self.check_nan = bool(opt.get('CHECK_NAN', True))
+        # NaN guard (the reference's isnan asserts, Layers.py:169,290,430,462,467): True / 'sync' = read the device
+        # flag at the end of every forward (one host sync, what predict()'s `.cpu()` would do anyway);
+        # 'deferred' = copy the flag to pinned memory asynchronously and raise at the START of the next forward /
+        # in check_pending(), so back-to-back forwards overlap (serving loops); False = no check
+        self.check_nan = opt.get('CHECK_NAN', True)
+        self._pending = None
         self.use_streams = bool(opt.get('USE_STREAMS', True))
         self._side = None
         self._warm_version = None
@@ -215,7 +220,27 @@ class SDNet(nn.Module):
             ev.record()
             self.phase_events.append((label, ev))
 
+    def check_pending(self):
+        """Raise what a 'deferred' forward found (NaN scores, stale bert_totals, unknown PHOC unigram)."""
+        pend, self._pending = self._pending, None
+        if pend is None:
+            return
+        ev, host_flags, bert_pack, n_phoc = pend
+        ev.synchronize()
+        self._raise_flags(host_flags, bert_pack, n_phoc)
+
+    @staticmethod
+    def _raise_flags(host_flags, bert_pack, n_phoc):
+        if int(host_flags[0]) != 0:
+            raise AssertionError("NaN in answer scores (reference: assert torch.sum(torch.isnan(...)) == 0)")
+        BertEngine.check_totals(bert_pack)
+        for k in range(n_phoc):  # table-free PHOC channel: unknown unigram, like Utils/cphoc.c:45-50
+            key = int(host_flags[1 + k])
+            if key != -1:
+                raise RuntimeError("Error: unigram %s is unknown" % chr(key & 0xFF))
+
     def forward(self, q_list, ocr_list, od_list, return_score=False):
+        self.check_pending()
         att_score = {} if return_score else None
         dev = ocr_list['fasttext'].device
         if dev.type != 'cuda':
@@ -428,14 +453,19 @@ class SDNet(nn.Module):
                                   nan_flag=nan_flag, want_logits=bool(opt.get('KEEP_LOGITS', False)))
         self._warm_version = ver
         self._phase('scores')
-        if self.check_nan and int(nan_flag.item()) != 0:
-            raise AssertionError("NaN in answer scores (reference: assert torch.sum(torch.isnan(...)) == 0)")
-        if self.check_nan:  # (the nan flag read above synchronised the device)
-            BertEngine.check_totals(bert_pack)
-        for err in phoc_errs:  # table-free PHOC channel: unknown unigram, like Utils/cphoc.c:45-50
-            key = int(err.item())
-            if key != -1:
-                raise RuntimeError("Error: unigram %s is unknown" % chr(key & 0xFF))
+        if self.check_nan or phoc_errs:
+            # ONE read-back of all device flags: [nan flag | PHOC error words] -> pinned host memory
+            flags = torch.cat([nan_flag.to(torch.int64)] + [e.reshape(1) for e in phoc_errs]) if phoc_errs \
+                else nan_flag.to(torch.int64)
+            host_flags = torch.empty(flags.shape, dtype=torch.int64, pin_memory=True)
+            host_flags.copy_(flags, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            if self.check_nan == 'deferred':
+                self._pending = (ev, host_flags, bert_pack, len(phoc_errs))
+            else:
+                ev.synchronize()
+                self._raise_flags(host_flags, bert_pack if self.check_nan else None, len(phoc_errs))
         return score_s, att_score
 
     def linear_sum(self, output, alpha, gamma):

@@ -927,6 +927,148 @@ subword_avg_layers_kernel(const float* h_f32, const __nv_bfloat16* h_b16, long l
   }
 }
 
+// Pipelined form of subword_avg_layers_kernel for bf16 hidden states (the kernel that runs in bf16 mode).
+// The synchronous kernel above keeps one layer's rows in flight per warp (1.5 - 4.5 KB) and sits at
+// 0.33 of the HBM bandwidth (latency-, not bandwidth-bound).  Here every warp owns a
+// 24 KB shared-memory ring of row slots and fetches the word's rows of SEVERAL layers ahead with cp.async
+// (LDGSTS, 16 bytes per lane, the lane that copies a chunk is the lane that reads it back): a one-piece
+// word has all 12 layers (18 KB) in flight at once, a two-piece word 8 layers (24 KB).  Registers no longer
+// bound the bytes in flight.  Words with more than SW_MAX_CNT pieces take the synchronous loop.
+constexpr int SW_WARPS = 8;
+constexpr int SW_MAX_CNT = 4;
+template <int HC>
+struct SwRing {
+  static constexpr int ROW_BYTES = HC * 512;               // one bf16 row
+  static constexpr int SLOTS = (HC == 3) ? 16 : 12;        // 24 KB per warp
+  static constexpr int WARP_BYTES = SLOTS * ROW_BYTES;
+};
+
+template <int HC, int CNT>
+__device__ __forceinline__ void subword_word_async(const __nv_bfloat16* __restrict__ h, long long layer_stride,
+                                                   long long t0, int n_layers, const float* __restrict__ alpha,
+                                                   float mx, float den, float g, uint32_t ring, int lane,
+                                                   RowVec<HC>& tot) {
+  constexpr int H = HC * 256;
+  constexpr int RB = SwRing<HC>::ROW_BYTES;
+  constexpr int S = SwRing<HC>::SLOTS / CNT;               // layers in flight
+  auto issue = [&](int l) {
+    const __nv_bfloat16* src = h + static_cast<long long>(l) * layer_stride + t0 * H + lane * 8;
+    const uint32_t dst = ring + static_cast<uint32_t>((l % S) * CNT) * RB + lane * 16;
+#pragma unroll
+    for (int t = 0; t < CNT; ++t)
+#pragma unroll
+      for (int c = 0; c < HC; ++c)
+        cp_async16_zfill(dst + t * RB + c * 512, src + static_cast<long long>(t) * H + c * 256, true);
+  };
+#pragma unroll 1
+  for (int l = 0; l < S; ++l) {
+    if (l < n_layers) issue(l);
+    cp_async_commit();
+  }
+  const float fc = static_cast<float>(CNT);
+#pragma unroll 1
+  for (int l = 0; l < n_layers; ++l) {
+    cp_async_wait<S - 1>();                                // the group of layer l has landed
+    const float a = expf(alpha[l] - mx) / den;
+    RowVec<HC> acc;
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) acc.v[i] = 0.f;
+    const uint32_t base = ring + static_cast<uint32_t>((l % S) * CNT) * RB + lane * 16;
+#pragma unroll
+    for (int t = 0; t < CNT; ++t) {
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        uint4 u;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                     : "r"(base + t * RB + c * 512));
+        acc.v[c * 8 + 0] += bf16_lo(u.x); acc.v[c * 8 + 1] += bf16_hi(u.x);
+        acc.v[c * 8 + 2] += bf16_lo(u.y); acc.v[c * 8 + 3] += bf16_hi(u.y);
+        acc.v[c * 8 + 4] += bf16_lo(u.z); acc.v[c * 8 + 5] += bf16_hi(u.z);
+        acc.v[c * 8 + 6] += bf16_lo(u.w); acc.v[c * 8 + 7] += bf16_hi(u.w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) {
+      const float mean = (CNT > 1) ? acc.v[i] / fc : acc.v[i];
+      const float term = (mean * a) * g;
+      tot.v[i] = (l == 0) ? term : tot.v[i] + term;
+    }
+    // the slot just consumed is the slot of layer l + S (same lane wrote and read it: no warp sync needed)
+    if (l + S < n_layers) issue(l + S);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+}
+
+template <int HC>
+__global__ void __launch_bounds__(SW_WARPS * 32, 1)
+subword_avg_layers_async_kernel(const __nv_bfloat16* __restrict__ h_b16, long long layer_stride,
+                                const int32_t* __restrict__ words, int n_words,
+                                const int32_t* __restrict__ row_start, const uint8_t* __restrict__ x_mask,
+                                int W, float* __restrict__ dst, long long dst_stride,
+                                const float* __restrict__ alpha, int n_layers,
+                                const float* __restrict__ gamma_p) {
+  extern __shared__ __align__(16) uint8_t sw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ring = smem_u32(sw_smem) + static_cast<uint32_t>(warp) * SwRing<HC>::WARP_BYTES;
+  float mx = -INFINITY;
+  for (int i = 0; i < n_layers; ++i) mx = fmaxf(mx, alpha[i]);
+  float den = 0.f;
+  for (int i = 0; i < n_layers; ++i) den += expf(alpha[i] - mx);
+  const float g = gamma_p[0];
+  for (long long w = static_cast<long long>(blockIdx.x) * SW_WARPS + warp; w < n_words;
+       w += static_cast<long long>(gridDim.x) * SW_WARPS) {
+    const int item = words[w];
+    const int j = words[n_words + w];
+    const int st = words[2LL * n_words + w];
+    const int ed = words[3LL * n_words + w];
+    if (j >= W) continue;
+    float* d = dst + (static_cast<long long>(item) * W + j) * dst_stride;
+    RowVec<HC> tot;
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) tot.v[i] = 0.f;
+    const int cnt = ed - st;
+    // masked word / st >= ed: zeros (Bert.py:155-156,160-165), written explicitly (no zero-fill of dst)
+    if (!(x_mask != nullptr && x_mask[static_cast<long long>(item) * W + j] == 0) && cnt > 0) {
+      const long long t0 = static_cast<long long>(row_start[item]) + st;
+      switch (cnt) {
+        case 1: subword_word_async<HC, 1>(h_b16, layer_stride, t0, n_layers, alpha, mx, den, g, ring, lane, tot); break;
+        case 2: subword_word_async<HC, 2>(h_b16, layer_stride, t0, n_layers, alpha, mx, den, g, ring, lane, tot); break;
+        case 3: subword_word_async<HC, 3>(h_b16, layer_stride, t0, n_layers, alpha, mx, den, g, ring, lane, tot); break;
+        case 4: subword_word_async<HC, 4>(h_b16, layer_stride, t0, n_layers, alpha, mx, den, g, ring, lane, tot); break;
+        default: {
+          const float fc = static_cast<float>(cnt);
+          for (int l = 0; l < n_layers; ++l) {
+            const float a = expf(alpha[l] - mx) / den;
+            RowVec<HC> acc;
+#pragma unroll
+            for (int i = 0; i < HC * 8; ++i) acc.v[i] = 0.f;
+            for (int t = 0; t < cnt; ++t) {
+              RowVec<HC> r;
+              load_row_bf16<HC>(h_b16 + l * layer_stride + (t0 + t) * (HC * 256), lane, r);
+#pragma unroll
+              for (int i = 0; i < HC * 8; ++i) acc.v[i] += r.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < HC * 8; ++i) {
+              const float term = ((acc.v[i] / fc) * a) * g;
+              tot.v[i] = (l == 0) ? term : tot.v[i] + term;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+      *reinterpret_cast<float4*>(d + c * 256 + lane * 8) =
+          make_float4(tot.v[c * 8 + 0], tot.v[c * 8 + 1], tot.v[c * 8 + 2], tot.v[c * 8 + 3]);
+      *reinterpret_cast<float4*>(d + c * 256 + lane * 8 + 4) =
+          make_float4(tot.v[c * 8 + 4], tot.v[c * 8 + 5], tot.v[c * 8 + 6], tot.v[c * 8 + 7]);
+    }
+  }
+}
+
 // Sequence bookkeeping of the packed layout, on the device (replaces a handful of torch integer ops):
 //   seq_lengths_kernel : one warp per row -> number of real tokens of the row and of each of its
 //                        512-token windows (written at the row's / windows' global slots)
@@ -1226,6 +1368,35 @@ extern "C" int ruart_subword_avg_layers(const float* h_f32, const void* h_bf16,
   RUART_ARG_CHECK((dst_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
   if (n_words == 0) return RUART_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // bf16 hidden states: the cp.async-pipelined kernel (RUART_SUBWORD_ASYNC=0: A/B aid, the synchronous one)
+  static const bool use_async = []() {
+    const char* e = getenv("RUART_SUBWORD_ASYNC");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (use_async && h_bf16 != nullptr) {
+    static RuartDeviceOnce attr_set;
+    if (!attr_set.done()) {
+      RUART_CUDA_CHECK(cudaFuncSetAttribute(subword_avg_layers_async_kernel<3>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SW_WARPS * SwRing<3>::WARP_BYTES));
+      RUART_CUDA_CHECK(cudaFuncSetAttribute(subword_avg_layers_async_kernel<4>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SW_WARPS * SwRing<4>::WARP_BYTES));
+      attr_set.set();
+    }
+    int grid = (n_words + SW_WARPS - 1) / SW_WARPS;
+    if (grid > ruart_num_sms()) grid = ruart_num_sms();
+    if (hidden == 768)
+      subword_avg_layers_async_kernel<3><<<grid, SW_WARPS * 32, SW_WARPS * SwRing<3>::WARP_BYTES, st>>>(
+          (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dst, dst_stride,
+          alpha, n_layers, gamma);
+    else
+      subword_avg_layers_async_kernel<4><<<grid, SW_WARPS * 32, SW_WARPS * SwRing<4>::WARP_BYTES, st>>>(
+          (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dst, dst_stride,
+          alpha, n_layers, gamma);
+    RUART_LAUNCH_CHECK();
+    return RUART_OK;
+  }
   if (hidden == 768)
     subword_avg_layers_kernel<3><<<row_grid(n_words), ROWS_PER_CTA * 32, 0, st>>>(
         h_f32, (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dst,

@@ -2,9 +2,9 @@
 TUNE_PARTIAL reset of `SDNetTrainer.update` (Models/SDNetTrainer.py:363-371) on ONE flat fp32 buffer,
 with the data-parallel gradient mean (NCCL all-reduce of that buffer) in front of it.
 
-The backward kernels that would fill the gradients are not built yet; whoever supplies gradients (for
-instance autograd through torch modules sharing these parameters) gets the reference's update rule
-from two kernel launches and no host synchronisation.
+The gradients come from the differentiable path (ruart_b200/autograd_ops.py: hand-written backward kernels
+behind torch.autograd.Function); the reference's update rule is then two kernel launches and no host
+synchronisation.
 """
 import torch
 import torch.distributed as dist
@@ -64,11 +64,13 @@ class FlatAdamax(object):
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
             self.grad.div_(dist.get_world_size())
 
-    def step(self, grads=None, reset=()):
+    def step(self, grads=None, reset=(), loaded=False):
         """One update.  `reset`: iterable of (param, first_row, rows_tensor) restored afterwards —
-        the TUNE_PARTIAL rule (`weight.data[tune_partial:] = fixed_embedding`, SDNetTrainer.py:367-371)."""
-        self.load_grads(grads)
-        self.allreduce_mean()
+        the TUNE_PARTIAL rule (`weight.data[tune_partial:] = fixed_embedding`, SDNetTrainer.py:367-371).
+        loaded=True: the caller already ran load_grads() + allreduce_mean() (e.g. to time the collective)."""
+        if not loaded:
+            self.load_grads(grads)
+            self.allreduce_mean()
         st = current_stream()
         self.step_count += 1
         sq = None

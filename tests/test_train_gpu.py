@@ -47,7 +47,7 @@ def test_training_step_matches_oracle_gradients_and_reference_update():
     g = dict(np.load(os.path.join(GOLDEN, "train_tiny.npz")))
     opt = train_opt("tiny")
     net, _ = build_ours("tiny", seed=1033, bert_init="random", DROPOUT=0.0, dropout_emb=0.0, BERT_precision="fp32")
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}   # (Bert() puts its model on the GPU)
     batch = synth.make_batch("tiny", ragged=True)
     targets = make_targets(batch, opt["max_ocr_num"])
     want_loss, want = train_oracle.loss_and_grads(sd, opt, batch, targets)
@@ -124,7 +124,8 @@ def test_flat_adamax_step_is_seen_by_the_next_forward():
     # path must not serve stale splits afterwards
     from ruart_b200.train_utils import FlatAdamax
     opt = train_opt("tiny")
-    net, _ = build_ours("tiny", seed=1033, device="cuda", DROPOUT=0.0, dropout_emb=0.0, BERT_precision="fp32")
+    net, _ = build_ours("tiny", seed=1033, device="cuda", DROPOUT=0.0, dropout_emb=0.0, BERT_precision="fp32",
+                        KEEP_LOGITS=True)
     batch = synth.make_batch("tiny", ragged=True)
     targets = make_targets(batch, opt["max_ocr_num"]).cuda()
     with torch.no_grad():
@@ -136,7 +137,7 @@ def test_flat_adamax_step_is_seen_by_the_next_forward():
     params = [p for p in net.parameters() if p.requires_grad]
     grads = torch.autograd.grad(loss, params, allow_unused=True)
     live = [(p, gr) for p, gr in zip(params, grads) if gr is not None]
-    fa = FlatAdamax([p for p, _ in live], lr=0.05, max_norm=float(opt["grad_clipping"]))
+    fa = FlatAdamax([p for p, _ in live], lr=0.01, max_norm=float(opt["grad_clipping"]))
     fa.step([gr for _, gr in live])
     net.eval()
     net.drop_emb = False
@@ -144,5 +145,7 @@ def test_flat_adamax_step_is_seen_by_the_next_forward():
         p1, _ = net(*synth.batch_to(copy.deepcopy(batch), "cuda"))
     assert (p1 - p0).abs().max().item() > 1e-4          # the step moved the output ...
     sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-    want_p, _, _ = sdnet_oracle.sdnet_forward(sd, opt, *copy.deepcopy(batch))
-    assert (p1.cpu() - want_p).abs().max().item() < 1e-4   # ... to what the updated weights give
+    want_p, want_l, _ = sdnet_oracle.sdnet_forward(sd, opt, *copy.deepcopy(batch))
+    from helpers import rel_err
+    assert rel_err(net.get_answer.last_logits.cpu(), want_l) < 1e-4   # ... to what the updated weights give
+    assert (p1.cpu() - want_p).abs().max().item() < 5e-4
