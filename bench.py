@@ -217,9 +217,9 @@ def cpu_port_step(cpu_sd, opt, batch):
     return probs
 
 
-def build_net(cfg, device):
+def build_net(cfg, device, check_nan=True):
     from ruart_b200.Models.SDNet import SDNet
-    opt = synth.make_opt(cfg, BERT_precision="bf16")
+    opt = synth.make_opt(cfg, BERT_precision="bf16", CHECK_NAN=check_nan)
     torch.manual_seed(1033)
     with contextlib.redirect_stdout(io.StringIO()):
         net = SDNet(opt, synth.make_embedding(1033))
@@ -420,6 +420,9 @@ def main():
     ap.add_argument("--cfg", default=None, help="cfg3 (default at N=1), cfg4 (default at N>1: 4096 questions / N), cfg5")
     ap.add_argument("--no-phoc", action="store_true", help="skip the cfg-2 PHOC record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-check", action="store_true",
+                    help="read the NaN flag at the end of every forward (one host sync per step, the drop-in's default) "
+                         "instead of one step late (CHECK_NAN='deferred', the serving-loop setting the bench uses)")
     ap.add_argument("--train", action="store_true", help="time the training step (cfg5 by default) instead of inference")
     ap.add_argument("--verify", action="store_true", help="--train: check the all-reduced gradient on rank 0")
     ap.add_argument("--collate-index", action="store_true",
@@ -450,7 +453,7 @@ def main():
 
     from ruart_b200 import _lib
     args.cfg = args.cfg or ("cfg3" if world == 1 else "cfg4")
-    net, opt = build_net(args.cfg, dev)
+    net, opt = build_net(args.cfg, dev, check_nan=True if args.sync_check else "deferred")
     B_global = synth.CONFIGS[args.cfg]["B"]
     strong = args.cfg == "cfg4"
     if strong:
@@ -541,6 +544,7 @@ def main():
             for _ in range(args.steps):
                 probs, _ = net(*fresh(dev_batch))
             e1.record()
+            net.check_pending()     # deferred NaN / token-count flags of the last step
             barrier()
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count - launches0
@@ -564,6 +568,7 @@ def main():
             p, _ = net(*b)
             out_host.copy_(p, non_blocking=True)
         e3.record()
+        net.check_pending()
         barrier()
         ms_e2e = e2.elapsed_time(e3)
 
@@ -619,6 +624,9 @@ def main():
                        "parallelism": "batch-sharded x%d, no collective" % world,
                        "precision": "BERT bf16 operands / fp32 accumulate; SDNet stack fp32 activations, GEMM operands as 2-part bf16 splits (~2^-16)",
                        "l2": "activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "nan_check": ("device flag read at the end of every forward (host sync per step)" if args.sync_check else
+                                     "device flag copied to pinned memory, raised one step late (CHECK_NAN='deferred'); "
+                                     "--sync-check gives the per-step sync"),
                        "batch": ("VQA_collate_fun layout + Utils.collate.attach_index_tensors" if args.collate_index
                                  else "VQA_collate_fun layout (tensors + Python lists), as the reference's collate emits it")},
             "clocks": clocks.summary(),

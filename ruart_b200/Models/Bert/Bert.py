@@ -82,3 +82,14 @@ class Bert(nn.Module):
         segs = pack_handle["segments"] if pack_handle is not None else [Segment(*s) for s in segments]
         return self.engine().encode(segs, sinks, alpha=alpha.detach().float().contiguous(),
                                     gamma=gamma.detach().float().contiguous(), pack_handle=pack_handle)
+
+    def encode_hidden(self, pack_handle):
+        """First half of encode_into: queue the packed encoder; returns (pack, hs_f32 | None, hs_bf16 | None)."""
+        return self.engine().encode_hidden(pack_handle["segments"], pack_handle)
+
+    def mix_into(self, pack_handle, hidden, sinks, alpha, gamma):
+        """Second half: subword mean + learned layer sum of `hidden` (from encode_hidden) into the sinks."""
+        pk, hs_f, hs_b = hidden
+        self.engine().apply_sinks(pack_handle["segments"], pk, hs_f, hs_b, sinks,
+                                  alpha=alpha.detach().float().contiguous(), gamma=gamma.detach().float().contiguous())
+        return pk

@@ -209,15 +209,16 @@ class SDNet(nn.Module):
     phase_log = None  # set to a list to collect (label, seconds since forward start) with device syncs
 
     phase_events = None  # set to a list to collect (label, cuda event) on the main stream, no syncs
+    _phase_stream = None
 
     def _phase(self, label):
         if self.phase_log is not None:
             import time
             torch.cuda.synchronize()
             self.phase_log.append((label, time.perf_counter()))
-        if self.phase_events is not None:
+        if self.phase_events is not None:   # always on the MAIN stream (some phases are queued on side streams)
             ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
+            ev.record(self._phase_stream if self._phase_stream is not None else torch.cuda.current_stream())
             self.phase_events.append((label, ev))
 
     def check_pending(self):
@@ -298,48 +299,75 @@ class SDNet(nn.Module):
             K.gather_rows(self.ent_embedding.weight.detach(), lst['ent'].reshape(-1), buf[..., c_ent:], None,
                           n_rows, ent_dim)
 
-        embed(q_list, 'glove', self.glove_embed, q_in, q_word, B * Wq, PQ)
-        embed(ocr_list, 'fasttext', self.fast_embed, ocr_in, ocr_word, N_ocr * Wo, PX)
-        embed(od_list, 'fasttext', self.fast_embed, od_in, od_word, N_od * Wd, PX)
-        q_list['glove_emb'] = q_word          # side effect of the reference (SDNet.py:449-450,458-459)
-        ocr_list['fasttext_emb'] = ocr_word
-        od_list['fasttext_emb'] = od_word
-
-        self._phase('embed')
-        # ---- BERT: one packed pass, subword mean + layer sum into the concat buffers ------------
-        bert_pack = self.Bert.encode_into(bert_segments,
-                                          [(q_in, QD, PQ + VD), (ocr_in, XD, PX + VD), (od_in, XD, PX + VD)],
-                                          self.alphaBERT, self.gammaBERT, pack_handle=pack_handle)
-
-        self._phase('bert')
-        # ---- host indices (one upload) -------------------------------------------------------
-        plan = ocr_list.get('ruart_plan')   # precomputed by Utils.collate.attach_index_tensors, else here
-        if plan is None:
-            plan = host_index.forward_plan(ocr_list['num_cnt'], ocr_list['len_cnt'], od_list['num_cnt'],
-                                           od_list['len_cnt'], Wo, Wd, M, M_od)
-        if plan['key'] != (B, N_ocr, N_od, Wo, Wd, M, M_od):
-            raise ValueError("num_cnt / len_cnt do not match the item rows of this batch")
-        n_t, n_step_rows, n_all = plan['n_t'], plan['n_step_rows'], plan['n_items']
-        i32_d = K.upload(plan['i32'], dev)
-        i64_d = K.upload(plan['slots'] * self.multi2one_output_size, dev)
-        masks_d = K.upload(plan['masks'], dev)
-        cuts = plan['cuts']
-        ocr_wsrc, ocr_wdst, od_wsrc, od_wdst, a_rows_d, last_d = [i32_d[cuts[i]:cuts[i + 1]] for i in range(6)]
-        ocr_mask = masks_d[:B * M].view(B, M)
-        od_mask = masks_d[B * M:].view(B, M_od)
         q_mask = K.as_u8(q_list['glove_mask'])
+        # anything that invalidates the prepared-weight caches: parameter versions and the split width.  A forward
+        # whose caches are cold (first call / weights changed) runs serially on the main stream so that no branch
+        # reads a prepared weight another branch is still writing.
+        main = torch.cuda.current_stream(dev)
+        self._phase_stream = main
+        ver = (sum(p._version for p in self.parameters()), self.sdnet_parts)
+        concurrent = self.use_streams and self.phase_log is None and self._warm_version == ver
+        if concurrent and self._side is None:
+            # question branch (gates both context branches): high priority; s_emb: embeddings + pre-alignment,
+            # which do not depend on BERT and run underneath its GEMMs
+            self._side = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1),
+                          torch.cuda.Stream(device=dev))
+        s_emb = self._side[2] if concurrent else main
+        fork_emb = torch.cuda.Event()
+        fork_emb.record(main)      # inputs + the zero-filled q_in are ready; recorded BEFORE the encoder is queued
 
-        self._phase('host_index')
-        # ---- word-level pre-alignment (SDNet.py:495-551) --------------------------------------
-        c_pre = PX + VD + BD + pos_dim + ent_dim
-        p2_cache = {}
-        for k, word, wsrc, wdst, buf in ((0, ocr_word, ocr_wsrc, ocr_wdst, ocr_in),
-                                         (1, od_word, od_wsrc, od_wdst, od_in)):
-            T_max, n_words = plan['T_max'][k], plan['total_words'][k]
-            packed = torch.zeros((B, T_max, VD), **f32)
-            K.gather_rows(word, wsrc, packed, wdst, n_words, VD)
-            att = self.pre_align(packed, q_word, q_mask, p2_cache=p2_cache)
-            K.gather_rows(att, wdst, buf[..., c_pre:], wsrc, n_words, VD)
+        # ---- BERT encoder: queued first on the main stream (compute-bound, ~3/4 of the step) -------
+        hidden = self.Bert.encode_hidden(pack_handle)
+        self._phase('bert_layers')
+
+        # ---- embeddings, host indices and word-level pre-alignment on the side stream -------------
+        s_emb.wait_event(fork_emb)
+        with torch.cuda.stream(s_emb):
+            embed(q_list, 'glove', self.glove_embed, q_in, q_word, B * Wq, PQ)
+            embed(ocr_list, 'fasttext', self.fast_embed, ocr_in, ocr_word, N_ocr * Wo, PX)
+            embed(od_list, 'fasttext', self.fast_embed, od_in, od_word, N_od * Wd, PX)
+            q_list['glove_emb'] = q_word          # side effect of the reference (SDNet.py:449-450,458-459)
+            ocr_list['fasttext_emb'] = ocr_word
+            od_list['fasttext_emb'] = od_word
+            self._phase('embed')
+            # host indices (one upload each)
+            plan = ocr_list.get('ruart_plan')   # precomputed by Utils.collate.attach_index_tensors, else here
+            if plan is None:
+                plan = host_index.forward_plan(ocr_list['num_cnt'], ocr_list['len_cnt'], od_list['num_cnt'],
+                                               od_list['len_cnt'], Wo, Wd, M, M_od)
+            if plan['key'] != (B, N_ocr, N_od, Wo, Wd, M, M_od):
+                raise ValueError("num_cnt / len_cnt do not match the item rows of this batch")
+            n_t, n_step_rows, n_all = plan['n_t'], plan['n_step_rows'], plan['n_items']
+            i32_d = K.upload(plan['i32'], dev)
+            i64_d = K.upload(plan['slots'] * self.multi2one_output_size, dev)
+            masks_d = K.upload(plan['masks'], dev)
+            for t in (i32_d, i64_d, masks_d):
+                t.record_stream(main)
+            cuts = plan['cuts']
+            ocr_wsrc, ocr_wdst, od_wsrc, od_wdst, a_rows_d, last_d = [i32_d[cuts[i]:cuts[i + 1]] for i in range(6)]
+            ocr_mask = masks_d[:B * M].view(B, M)
+            od_mask = masks_d[B * M:].view(B, M_od)
+            self._phase('host_index')
+            # word-level pre-alignment (SDNet.py:495-551)
+            c_pre = PX + VD + BD + pos_dim + ent_dim
+            p2_cache = {}
+            for k, word, wsrc, wdst, buf in ((0, ocr_word, ocr_wsrc, ocr_wdst, ocr_in),
+                                             (1, od_word, od_wsrc, od_wdst, od_in)):
+                T_max, n_words = plan['T_max'][k], plan['total_words'][k]
+                packed = torch.zeros((B, T_max, VD), **f32)
+                K.gather_rows(word, wsrc, packed, wdst, n_words, VD)
+                att = self.pre_align(packed, q_word, q_mask, p2_cache=p2_cache)
+                K.gather_rows(att, wdst, buf[..., c_pre:], wsrc, n_words, VD)
+            ev_emb = torch.cuda.Event()
+            ev_emb.record(s_emb)
+
+        # ---- BERT tail: subword mean + layer sum into the concat buffers (host: flatten the offset lists) ----
+        bert_pack = self.Bert.mix_into(pack_handle, hidden,
+                                       [(q_in, QD, PQ + VD), (ocr_in, XD, PX + VD), (od_in, XD, PX + VD)],
+                                       self.alphaBERT, self.gammaBERT)
+        del hidden
+        self._phase('bert')
+        main.wait_event(ev_emb)
 
         self._phase('prealign')
         # ---- multi2one: real word steps only, last step -> slot (SDNet.py:270-271,300-318) ----
@@ -375,15 +403,8 @@ class SDNet(nn.Module):
         # whose weight caches are cold (first call / weights changed) runs serially on the main
         # stream so that no branch reads a prepared weight another branch is still writing.
         L_in = opt['in_rnn_layers']
-        main = torch.cuda.current_stream(dev)
-        # anything that invalidates the prepared-weight caches: parameter versions and the split width
-        ver = (sum(p._version for p in self.parameters()), self.sdnet_parts)
-        concurrent = self.use_streams and self.phase_log is None and self._warm_version == ver
         if concurrent:
-            if self._side is None:
-                # the question branch gates both context branches: high priority
-                self._side = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1))
-            s_od, s_q = self._side
+            s_od, s_q = self._side[0], self._side[1]
             fork = torch.cuda.Event()
             fork.record(main)
             s_od.wait_event(fork)

@@ -287,7 +287,12 @@ class BertEngine(object):
         encoder has been queued, i.e. while the GPU is busy.
         """
         pk, hs_f, hs_b = self.encode_hidden(segments, pack_handle)
-        dev = segments[0].ids.device
+        self.apply_sinks(segments, pk, hs_f, hs_b, sinks, alpha, gamma)
+        return pk
+
+    def apply_sinks(self, segments, pk, hs_f, hs_b, sinks, alpha=None, gamma=None):
+        """Second half of encode(): subword mean (+ learned layer sum) of the kept hidden states into the sinks.
+        Host work first (flattening the Python offset lists), then one kernel per segment."""
         T, H, NL = pk["T"], self.H, self.n_layers
         st = current_stream()
         keep32 = hs_f is not None
@@ -305,7 +310,6 @@ class BertEngine(object):
                     call("ruart_subword_avg_accum", ptr(hf1[li]) if keep32 else None,
                          None if keep32 else ptr(hb1[li]), ptr(wt), nw, ptr(rs), ptr(wmask), sg.W,
                          dst.data_ptr() + 4 * col, stride, None, NL, None, li, 1, H, st)
-        return pk
 
     def word_tables(self, segments, pk):
         """Per segment: (flattened word offsets int32 [4, n] on the device, n, row_start, uint8 word mask).

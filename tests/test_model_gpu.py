@@ -419,3 +419,24 @@ def test_device_answer_selection_matches_reference_predict_goldens():
     d = json.load(open(os.path.join(GOLDEN, "select_answers_cases.json")))
     probs = torch.tensor(d["probs"], dtype=torch.float32)
     assert ops_select(probs, d["num_cnt"]) == d["picks"]
+
+
+def test_nan_guard_sync_and_deferred():
+    # the reference asserts on NaN after every LSTM / attention / score (Layers.py:169,290,430,462,467): here one
+    # device flag, raised at the end of the forward (default) or one step late (CHECK_NAN='deferred')
+    batch = synth.make_batch("tiny")
+    net, opt = build_ours("tiny", device="cuda")
+    with torch.no_grad():
+        net.get_answer.attn.linear.bias[3] = float("nan")
+    with pytest.raises(AssertionError, match="NaN in answer scores"), torch.no_grad():
+        net(*synth.batch_to(copy.deepcopy(batch), "cuda"))
+    net2, _ = build_ours("tiny", device="cuda", CHECK_NAN="deferred")
+    with torch.no_grad():
+        p_ok, _ = net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))
+        net2.check_pending()                                     # clean forward: nothing pending
+        net2.get_answer.attn.linear.bias[3] = float("nan")
+        p_bad, _ = net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))      # returns without a host sync
+        assert torch.isnan(p_bad).any() and not torch.isnan(p_ok).any()
+        with pytest.raises(AssertionError, match="NaN in answer scores"):
+            net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))  # ... and the NEXT forward raises
+        net2.check_pending()
