@@ -258,10 +258,11 @@ RUART_API int ruart_whole_layernorm_backward(const float* y, long long y_pitch, 
                                              const float* stats, double* workspace, float* dx,
                                              long long dx_pitch, void* stream);
 /* nn.Embedding weight gradient (SDNet.py:447-492 lookups): dW[v] (+)= sum_{k: ids[k] == v} dy[k], summed in
- * ascending k by one warp per vocabulary row (deterministic, no atomics).                                  */
+ * ascending k by one warp per vocabulary row (deterministic, no atomics).  workspace: n bytes (flags of the
+ * positions whose gradient row is non-zero; all-zero rows — the pad-word slots — are skipped).             */
 RUART_API int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
-                                   long long dy_pitch, int D, int V, float* dW, long long dw_pitch,
-                                   int accumulate, void* stream);
+                                   long long dy_pitch, int D, int V, uint8_t* workspace, float* dW,
+                                   long long dw_pitch, int accumulate, void* stream);
 /* Gradient of ruart_subword_avg_layers with respect to alpha [n_layers] and gamma [1] (the encoder itself is
  * locked): dy is the gradient of dst (same addressing); workspace >= 256 * n_layers doubles.              */
 RUART_API int ruart_subword_layers_backward(const float* h_f32, const void* h_bf16, long long layer_stride,

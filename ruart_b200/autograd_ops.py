@@ -426,8 +426,9 @@ class EmbeddingFn(Function):
         V, D = ctx.wshape
         dy2 = _c(dy).view(-1, D)
         dw = _f32((V, D), dy.device)
+        flags = torch.empty(max(flat.numel(), 1), dtype=torch.uint8, device=dy.device)
         call("ruart_embedding_grad", ptr(flat), 1 if flat.dtype == torch.int64 else 0, flat.numel(), ptr(dy2), D, D, V,
-             ptr(dw), D, 0, current_stream())
+             ptr(flags), ptr(dw), D, 0, current_stream())
         return None, dw
 
 

@@ -315,13 +315,30 @@ whole_ln_bwd_apply_kernel(const float* __restrict__ y, long long y_pitch, const 
 }
 
 // ------------------------------------------------------------------------------------------ embedding
-// dW[v] (+)= sum over k with ids[k] == v of dy[k], in ascending k (deterministic).  One warp per
-// vocabulary row scans the id list 32 entries at a time.
+// dW[v] (+)= sum over k with ids[k] == v of dy[k], in ascending k (deterministic, no atomics).
+// Pass 1 flags the positions whose gradient row is not all zero (the pad-word slots of an item never reach
+// the output: their rows are exactly zero, and there are ~10x more of them than real words — without the
+// flags the warp of vocabulary row 0 would walk all of them serially).  Pass 2: one warp per vocabulary
+// row scans the (id, flag) list 32 entries at a time and adds the matching rows in order.
+__global__ void __launch_bounds__(256)
+row_nonzero_kernel(const float* __restrict__ dy, long long dy_pitch, long long n, int D,
+                   uint8_t* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long k = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+    const float* row = dy + k * dy_pitch;
+    bool nz = false;
+    for (int c = lane; c < D; c += 32) nz |= (row[c] != 0.f);
+    nz = __any_sync(0xffffffffu, nz);
+    if (lane == 0) flag[k] = nz ? 1 : 0;
+  }
+}
+
 template <typename I>
 __global__ void __launch_bounds__(256)
-embedding_grad_kernel(const I* __restrict__ ids, long long n, const float* __restrict__ dy,
-                      long long dy_pitch, int D, int V, float* __restrict__ dW, long long dw_pitch,
-                      int accumulate) {
+embedding_grad_kernel(const I* __restrict__ ids, const uint8_t* __restrict__ flag, long long n,
+                      const float* __restrict__ dy, long long dy_pitch, int D, int V,
+                      float* __restrict__ dW, long long dw_pitch, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
@@ -331,8 +348,8 @@ embedding_grad_kernel(const I* __restrict__ ids, long long n, const float* __res
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
       for (long long base = 0; base < n; base += 32) {
         const long long k = base + lane;
-        const long long id = (k < n) ? static_cast<long long>(ids[k]) : -1;
-        unsigned m = __ballot_sync(0xffffffffu, id == v);
+        const bool hit = (k < n) && (static_cast<long long>(ids[k]) == v) && (flag[k] != 0);
+        unsigned m = __ballot_sync(0xffffffffu, hit);
         while (m) {
           const int t = __ffs(m) - 1;
           m &= m - 1;
@@ -712,17 +729,22 @@ extern "C" int ruart_whole_layernorm_backward(const float* y, long long y_pitch,
 }
 
 extern "C" int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
-                                    long long dy_pitch, int D, int V, float* dW, long long dw_pitch,
-                                    int accumulate, void* stream) {
+                                    long long dy_pitch, int D, int V, uint8_t* workspace, float* dW,
+                                    long long dw_pitch, int accumulate, void* stream) {
   RUART_ARG_CHECK(ids != nullptr && dy != nullptr && dW != nullptr && n >= 0 && D > 0 && V > 0);
-  const unsigned grid = grid_for(static_cast<long long>(V) * 32, 256);
+  RUART_ARG_CHECK(workspace != nullptr || n == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) {
+    row_nonzero_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(dy, dy_pitch, n, D, workspace);
+    RUART_LAUNCH_CHECK();
+  }
+  const unsigned grid = grid_for(static_cast<long long>(V) * 32, 256);
   if (idx_is_64)
-    embedding_grad_kernel<long long><<<grid, 256, 0, st>>>((const long long*)ids, n, dy, dy_pitch, D, V, dW,
-                                                           dw_pitch, accumulate);
+    embedding_grad_kernel<long long><<<grid, 256, 0, st>>>((const long long*)ids, workspace, n, dy, dy_pitch, D,
+                                                           V, dW, dw_pitch, accumulate);
   else
-    embedding_grad_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)ids, n, dy, dy_pitch, D, V, dW,
-                                                         dw_pitch, accumulate);
+    embedding_grad_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)ids, workspace, n, dy, dy_pitch, D, V,
+                                                         dW, dw_pitch, accumulate);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

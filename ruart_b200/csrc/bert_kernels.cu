@@ -149,44 +149,52 @@ bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict_
 
 // BertSelfOutput / BertOutput tail (modeling.py:260-264, 299-303): LayerNorm(dense_out + input)
 // (the dense bias is already added by the GEMM epilogue).
-template <int HC, bool HAS_RES>
+template <int HC>
 __global__ void __launch_bounds__(ROWS_PER_CTA * 32)
 add_ln_kernel(const float* x_f32, const __nv_bfloat16* x_b16, const float* res_f32,
               const __nv_bfloat16* res_b16, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, int T, float* out_f32,
               __nv_bfloat16* out_b16, int parts) {
-  // Grid-stride over rows, one warp per row, with the NEXT row's loads issued before the current row is
-  // reduced and stored (software pipelining): twice the bytes in flight per warp and no CTA turnover
-  // (the one-row-per-warp, one-CTA-per-8-rows form sat at 0.58-0.62 of the HBM bandwidth).
+  // One warp per row, one CTA per 8 rows.  (Round 2 tried a persistent grid-stride form with the next row's
+  // loads issued before the current row is reduced: 77 registers, 3 CTAs / SM, and SLOWER — 79.9 us vs 72.5 us
+  // for 113 664 rows, gpurun_out/r02_ln.txt — because fewer resident warps hide the shuffle reductions worse.)
   const int lane = threadIdx.x & 31;
-  const long long stride = static_cast<long long>(gridDim.x) * ROWS_PER_CTA;
-  long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
   if (row >= T) return;
-  constexpr bool has_res = HAS_RES;  // false: the GEMM epilogue already added the residual
-  RowVec<HC> x, r;
+  RowVec<HC> x;
   load_act<HC>(x_f32, x_b16, row, lane, x);
-  if (has_res) load_act<HC>(res_f32, res_b16, row, lane, r);
-  while (true) {
-    const long long nxt = row + stride;
-    RowVec<HC> xn, rn;
-    if (nxt < T) {
-      load_act<HC>(x_f32, x_b16, nxt, lane, xn);
-      if (has_res) load_act<HC>(res_f32, res_b16, nxt, lane, rn);
-    }
-    if (has_res) {
+  if (res_f32 != nullptr || res_b16 != nullptr) {  // absent: the GEMM epilogue already added it
+    RowVec<HC> r;
+    load_act<HC>(res_f32, res_b16, row, lane, r);
 #pragma unroll
-      for (int i = 0; i < HC * 8; ++i) x.v[i] += r.v[i];
-    }
-    layer_norm_row<HC>(x, gamma, beta, eps, lane);
-    store_act<HC>(out_f32, out_b16, parts, row, lane, x);
-    if (nxt >= T) break;
-    row = nxt;
+    for (int i = 0; i < HC * 8; ++i) x.v[i] += r.v[i];
+  }
+  layer_norm_row<HC>(x, gamma, beta, eps, lane);
+  store_act<HC>(out_f32, out_b16, parts, row, lane, x);
+}
+
+// bf16 -> bf16 specialisation of add_ln_kernel (residual already fused into the GEMM epilogue, one split part):
+// the form every LayerNorm of the bf16 encoder takes.  Fewer live registers -> more resident warps.
+template <int HC>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32, 6)
+ln_bf16_kernel(const __nv_bfloat16* __restrict__ x_b16, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float eps, int T, __nv_bfloat16* __restrict__ out_b16) {
+  constexpr int H = HC * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (row >= T) return;
+  RowVec<HC> x;
+  load_row_bf16<HC>(x_b16 + row * H, lane, x);
+  layer_norm_row<HC>(x, gamma, beta, eps, lane);
+  __nv_bfloat16* o = out_b16 + row * H;
 #pragma unroll
-    for (int i = 0; i < HC * 8; ++i) x.v[i] = xn.v[i];
-    if (has_res) {
-#pragma unroll
-      for (int i = 0; i < HC * 8; ++i) r.v[i] = rn.v[i];
-    }
+  for (int c = 0; c < HC; ++c) {
+    uint4 u;
+    u.x = pack_bf16x2(x.v[c * 8 + 0], x.v[c * 8 + 1]);
+    u.y = pack_bf16x2(x.v[c * 8 + 2], x.v[c * 8 + 3]);
+    u.z = pack_bf16x2(x.v[c * 8 + 4], x.v[c * 8 + 5]);
+    u.w = pack_bf16x2(x.v[c * 8 + 6], x.v[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(o + c * 256 + lane * 8) = u;
   }
 }
 
@@ -1262,27 +1270,24 @@ extern "C" int ruart_add_layernorm(const float* x_f32, const void* x_bf16, const
   RUART_ARG_CHECK(out_f32 != nullptr || out_bf16 != nullptr);
   if (T == 0) return RUART_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool has_res = res_f32 != nullptr || res_bf16 != nullptr;
-  typedef void (*LnKernel)(const float*, const __nv_bfloat16*, const float*, const __nv_bfloat16*, const float*,
-                           const float*, float, int, float*, __nv_bfloat16*, int);
-  LnKernel kern = (hidden == 768) ? (has_res ? add_ln_kernel<3, true> : add_ln_kernel<3, false>)
-                                  : (has_res ? add_ln_kernel<4, true> : add_ln_kernel<4, false>);
-  // persistent grid: exactly the CTAs that are resident at once (occupancy query, cached per kernel/device)
-  static std::atomic<int> occ[4][RUART_MAX_DEVICES];
-  const int slot = (hidden == 768 ? 0 : 2) + (has_res ? 1 : 0);
-  const int dev = ruart_current_device();
-  int per_sm = occ[slot][dev].load(std::memory_order_relaxed);
-  if (per_sm == 0) {
-    RUART_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROWS_PER_CTA * 32, 0));
-    if (per_sm < 1) per_sm = 1;
-    occ[slot][dev].store(per_sm, std::memory_order_relaxed);
+  if (x_bf16 != nullptr && res_f32 == nullptr && res_bf16 == nullptr && out_f32 == nullptr && out_parts == 1) {
+    if (hidden == 768)
+      ln_bf16_kernel<3><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>((const __nv_bfloat16*)x_bf16, gamma, beta, eps, T,
+                                                                  (__nv_bfloat16*)out_bf16);
+    else
+      ln_bf16_kernel<4><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>((const __nv_bfloat16*)x_bf16, gamma, beta, eps, T,
+                                                                  (__nv_bfloat16*)out_bf16);
+    RUART_LAUNCH_CHECK();
+    return RUART_OK;
   }
-  long long grid = static_cast<long long>(ruart_num_sms()) * per_sm;
-  const long long need = (static_cast<long long>(T) + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-  if (grid > need) grid = need;
-  kern<<<static_cast<unsigned>(grid), ROWS_PER_CTA * 32, 0, st>>>(
-      x_f32, (const __nv_bfloat16*)x_bf16, res_f32, (const __nv_bfloat16*)res_bf16, gamma, beta, eps, T,
-      out_f32, (__nv_bfloat16*)out_bf16, out_parts);
+  if (hidden == 768)
+    add_ln_kernel<3><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        x_f32, (const __nv_bfloat16*)x_bf16, res_f32, (const __nv_bfloat16*)res_bf16, gamma, beta,
+        eps, T, out_f32, (__nv_bfloat16*)out_bf16, out_parts);
+  else
+    add_ln_kernel<4><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        x_f32, (const __nv_bfloat16*)x_bf16, res_f32, (const __nv_bfloat16*)res_bf16, gamma, beta,
+        eps, T, out_f32, (__nv_bfloat16*)out_bf16, out_parts);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
