@@ -145,6 +145,13 @@ RUART_API int ruart_pack_tokens(const long long* ids, const uint8_t* mask, int N
 RUART_API int ruart_split_bf16(const float* src, long long ld, const int32_t* row_idx,
                                long long rows, int K, int Kp, int parts, void* dst, void* stream);
 
+/* Same for the column-wise concatenation of n_src (<= 8) fp32 sources with equal row counts — `torch.cat(xs, 2)`
+ * feeding an nn.Linear / nn.LSTM input (Layers.py:499-501,508,516; SDNet.py:350,380-390): the concatenation is
+ * never materialised.  srcs/pitches/widths are HOST arrays of n_src entries; sum(widths) <= Kp.             */
+RUART_API int ruart_split_concat_bf16(const float* const* srcs_host, const long long* pitches_host,
+                                      const int* widths_host, int n_src, long long rows, int Kp, int parts,
+                                      void* dst, void* stream);
+
 /* ---------------------------------------------------------------- SDNet fusion stack (fp32)
  * Pitches are in floats.  Masks are uint8 (0 = pad), exactly the reference's ByteTensor /
  * bool masks.                                                                                */
@@ -258,11 +265,13 @@ RUART_API int ruart_whole_layernorm_backward(const float* y, long long y_pitch, 
                                              const float* stats, double* workspace, float* dx,
                                              long long dx_pitch, void* stream);
 /* nn.Embedding weight gradient (SDNet.py:447-492 lookups): dW[v] (+)= sum_{k: ids[k] == v} dy[k], summed in
- * ascending k by one warp per vocabulary row (deterministic, no atomics).  workspace: n bytes (flags of the
- * positions whose gradient row is non-zero; all-zero rows — the pad-word slots — are skipped).             */
+ * ascending k by one warp per vocabulary row (deterministic, no atomics).  workspace: >= round_up(n, 16) bytes
+ * (flags of the positions whose gradient row is non-zero; all-zero rows — the pad-word slots — are skipped)
+ * plus, for tables with V < 2048, up to 64 * V * D floats of per-segment partial sums.                      */
 RUART_API int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
-                                   long long dy_pitch, int D, int V, uint8_t* workspace, float* dW,
-                                   long long dw_pitch, int accumulate, void* stream);
+                                   long long dy_pitch, int D, int V, uint8_t* workspace,
+                                   long long workspace_bytes, float* dW, long long dw_pitch, int accumulate,
+                                   void* stream);
 /* Gradient of ruart_subword_avg_layers with respect to alpha [n_layers] and gamma [1] (the encoder itself is
  * locked): dy is the gradient of dst (same addressing); workspace >= 256 * n_layers doubles.              */
 RUART_API int ruart_subword_layers_backward(const float* h_f32, const void* h_bf16, long long layer_stride,

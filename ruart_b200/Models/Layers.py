@@ -122,10 +122,12 @@ class StackedBRNN(nn.Module):
                 [getattr(r, "bias_ih_l0" + s) for s in sfx], [getattr(r, "bias_hh_l0" + s) for s in sfx])
 
     def run_layer(self, i, x, out=None, LN=None):
-        """Layer i on [B, L, in] -> [B, L, ndir*H] (optionally into the strided view `out`)."""
+        """Layer i on [B, L, in] -> [B, L, ndir*H] (optionally into the strided view `out`).  `x` may be a list of
+        [B, L, D_k] tensors standing for their concatenation along the last dim (never materialised)."""
         H = self.hidden_size
+        x0 = x[0] if isinstance(x, (list, tuple)) else x
         if out is None:
-            out = torch.empty((x.shape[0], x.shape[1], self.bidir_coef * H), dtype=torch.float32, device=x.device)
+            out = torch.empty((x0.shape[0], x0.shape[1], self.bidir_coef * H), dtype=torch.float32, device=x0.device)
         w_ih, w_hh, b_ih, b_hh = self._dir_params(i)
         if H <= 128:
             K.lstm_layer(self, x, i, w_ih, w_hh, b_ih, b_hh, H, sdnet_parts, out, whole_ln=bool(LN))
@@ -230,16 +232,17 @@ class AttentionScore(nn.Module):
     def project(self, x, with_diag, a_split=None):
         """relu(x W^T) (* diagonal) for [B, L, D] rows -> fp32 [B*L, hidden]; returns (proj, split)."""
         assert self.correlation_func == 3, "only correlation_func=3 is on RUArt's path"
-        rows = x.shape[0] * x.shape[1]
+        xs = list(x) if isinstance(x, (list, tuple)) else [x]     # a list = its column-wise concatenation
+        rows = xs[0].shape[0] * xs[0].shape[1]
         if a_split is None:
-            a_split = K.split_act(x, sdnet_parts)
+            a_split = K.split_concat(xs, sdnet_parts)
         a, Kp = a_split
         w, _ = K.prep_weight(self, ("w"), [self.linear.weight], sdnet_parts)
-        out = torch.empty((rows, self.hidden_size), dtype=torch.float32, device=x.device)
+        out = torch.empty((rows, self.hidden_size), dtype=torch.float32, device=xs[0].device)
         if with_diag:
             d = K.prep_vector(self, ("d"), lambda: self.diagonal.reshape(-1), [self.diagonal])
         else:
-            d = K.ones(x.device)
+            d = K.ones(xs[0].device)
         K.linear(a, Kp, w, rows, self.hidden_size, sdnet_parts, out, epi=ops.EPI_RELU_SCALE, scale=d)
         return out, a_split
 
@@ -279,7 +282,10 @@ class Attention(nn.Module):
                 raise NotImplementedError("`out=` is an inference-path extension")
             return res
         _no_training(self, dropout_p)
-        B, L1, L2 = x1.shape[0], x1.shape[1], x2.shape[1]
+        # x1 / x2 may be lists of tensors (their concatenation along the last dim, never materialised)
+        x1_0 = x1[0] if isinstance(x1, (list, tuple)) else x1
+        x2_0 = x2[0] if isinstance(x2, (list, tuple)) else x2
+        B, L1, L2 = x1_0.shape[0], x1_0.shape[1], x2_0.shape[1]
         p1, sp = self.scoring.project(x1, True)
         if p2_cache is not None and "p2" in p2_cache:
             p2 = p2_cache["p2"]
@@ -288,7 +294,7 @@ class Attention(nn.Module):
             if p2_cache is not None:
                 p2_cache["p2"] = p2
         if out is None:
-            out = torch.empty((B, L1, x3.shape[2]), dtype=torch.float32, device=x1.device)
+            out = torch.empty((B, L1, x3.shape[2]), dtype=torch.float32, device=x1_0.device)
         K.attention_tail(p1, p2, K.as_u8(x2_mask), x3, out, B, L1, L2, add=add_to_out, parts=sdnet_parts)
         return out
 
@@ -471,13 +477,13 @@ class DeepAttention(nn.Module):
 
     def project_x2(self, x2_word, x2_abstr):
         """relu(x2_att W_i^T) for every head i: [B*L2, heads*hid] (shared by every x1 it is paired with)."""
-        x2_att = K.concat_cols(x2_word + x2_abstr[:-1])
+        srcs = x2_word + x2_abstr[:-1]                 # x2_att = torch.cat(srcs, 2), never materialised
         w, _, hid = self._fused_weights()
         n = len(self.int_attn_list) * hid
-        a, Kp = K.split_act(x2_att, sdnet_parts)
-        rows = x2_att.shape[0] * x2_att.shape[1]
-        p2 = torch.empty((rows, n), dtype=torch.float32, device=x2_att.device)
-        K.linear(a, Kp, w, rows, n, sdnet_parts, p2, epi=ops.EPI_RELU_SCALE, scale=K.ones(x2_att.device))
+        a, Kp = K.split_concat(srcs, sdnet_parts)
+        rows = srcs[0].shape[0] * srcs[0].shape[1]
+        p2 = torch.empty((rows, n), dtype=torch.float32, device=srcs[0].device)
+        K.linear(a, Kp, w, rows, n, sdnet_parts, p2, epi=ops.EPI_RELU_SCALE, scale=K.ones(srcs[0].device))
         return p2
 
     def forward(self, x1_word, x1_abstr, x2_word, x2_abstr, x1_mask, x2_mask, return_bef_rnn=False,
@@ -497,27 +503,28 @@ class DeepAttention(nn.Module):
             x1_hiddens = self.rnn(x1, x1_mask)
             return (x1_hiddens, x1) if return_bef_rnn else x1_hiddens
         _no_training(self, dropout_p)
-        x1_att = K.concat_cols(x1_word + x1_abstr)
-        B, L1, L2 = x1_att.shape[0], x1_att.shape[1], x2_abstr[0].shape[1]
-        widths = [t.shape[2] for t in x1_abstr] + [t.shape[2] for t in x2_abstr]
-        x1 = torch.empty((B, L1, sum(widths)), dtype=torch.float32, device=x1_att.device)
-        col = 0
-        for t in x1_abstr:
-            K.copy_cols(t, x1[:, :, col:col + t.shape[2]])
-            col += t.shape[2]
+        # fused inference form.  Neither x1_att = cat(x1_word + x1_abstr) nor x1 = cat(x1_abstr + attended) is
+        # materialised: the projection GEMM and the BiLSTM's input GEMM read split-bf16 operands built straight
+        # from the pieces (K.split_concat), and `before-rnn` is returned as the LIST of its pieces.
+        srcs = x1_word + x1_abstr
+        B, L1, L2 = srcs[0].shape[0], srcs[0].shape[1], x2_abstr[0].shape[1]
+        dev = srcs[0].device
         w, d, hid = self._fused_weights()
         n = len(self.int_attn_list) * hid
-        a1, Kp = K.split_act(x1_att, sdnet_parts)
-        p1 = torch.empty((B * L1, n), dtype=torch.float32, device=x1_att.device)
+        a1, Kp = K.split_concat(srcs, sdnet_parts)
+        p1 = torch.empty((B * L1, n), dtype=torch.float32, device=dev)
         K.linear(a1, Kp, w, B * L1, n, sdnet_parts, p1, epi=ops.EPI_RELU_SCALE, scale=d)
         p2 = x2_proj if x2_proj is not None else self.project_x2(x2_word, x2_abstr)
         mask = K.as_u8(x2_mask)
+        att = torch.empty((B, L1, sum(t.shape[2] for t in x2_abstr)), dtype=torch.float32, device=dev)
+        col = 0
         for i in range(len(x2_abstr)):
             x3 = x2_abstr[i]
             K.attention_tail(p1[:, i * hid:(i + 1) * hid], p2[:, i * hid:(i + 1) * hid], mask, x3,
-                             x1[:, :, col:col + x3.shape[2]], B, L1, L2, parts=sdnet_parts)
+                             att[:, :, col:col + x3.shape[2]], B, L1, L2, parts=sdnet_parts)
             col += x3.shape[2]
-        x1_hiddens = self.rnn(x1, x1_mask)
+        x1 = list(x1_abstr) + [att]
+        x1_hiddens = self.rnn.run_layer(0, x1) if self.rnn.num_layers == 1 else self.rnn(K.concat_cols(x1), x1_mask)
         if return_bef_rnn:
             return x1_hiddens, x1
         return x1_hiddens

@@ -180,7 +180,7 @@ class SDNet(nn.Module):
         # 'deferred' = copy the flag to pinned memory asynchronously and raise at the START of the next forward /
         # in check_pending(), so back-to-back forwards overlap (serving loops); False = no check
         self.check_nan = opt.get('CHECK_NAN', True)
-        self._pending = None
+        self._pending = []
         self.use_streams = bool(opt.get('USE_STREAMS', True))
         self._side = None
         self._warm_version = None
@@ -221,14 +221,17 @@ class SDNet(nn.Module):
             ev.record(self._phase_stream if self._phase_stream is not None else torch.cuda.current_stream())
             self.phase_events.append((label, ev))
 
-    def check_pending(self):
-        """Raise what a 'deferred' forward found (NaN scores, stale bert_totals, unknown PHOC unigram)."""
-        pend, self._pending = self._pending, None
-        if pend is None:
-            return
-        ev, host_flags, bert_pack, n_phoc = pend
-        ev.synchronize()
-        self._raise_flags(host_flags, bert_pack, n_phoc)
+    def check_pending(self, wait=True):
+        """Raise what 'deferred' forwards found (NaN scores, stale bert_totals, unknown PHOC unigram).
+        wait=False: only look at forwards whose flag copy has already landed (no host block) — what the next
+        forward does on entry, so back-to-back forwards overlap; at most two forwards stay unchecked."""
+        while self._pending:
+            ev, host_flags, bert_pack, n_phoc = self._pending[0]
+            if not wait and len(self._pending) <= 2 and not ev.query():
+                return
+            ev.synchronize()
+            self._pending.pop(0)
+            self._raise_flags(host_flags, bert_pack, n_phoc)
 
     @staticmethod
     def _raise_flags(host_flags, bert_pack, n_phoc):
@@ -241,7 +244,7 @@ class SDNet(nn.Module):
                 raise RuntimeError("Error: unigram %s is unknown" % chr(key & 0xFF))
 
     def forward(self, q_list, ocr_list, od_list, return_score=False):
-        self.check_pending()
+        self.check_pending(wait=False)
         att_score = {} if return_score else None
         dev = ocr_list['fasttext'].device
         if dev.type != 'cuda':
@@ -423,18 +426,16 @@ class SDNet(nn.Module):
             # deep inter-attention + context self-attention (SDNet.py:376-390)
             after, before = self.deep_attn([x], layers, [q_word], q_layers, mask, q_mask, return_bef_rnn=True,
                                            x2_proj=q_proj)
-            s_in = K.concat_cols([after, before, x])
-            DA = self.deep_attn_output_size
-            hl_in = torch.empty((B, Mx, 2 * DA), **f32)
-            K.copy_cols(after, hl_in[:, :, :DA])
-            self.highlvl_self_att(s_in, s_in, mask, x3=after, out=hl_in[:, :, DA:])
-            return self.high_lvl_context_rnn.run_layer(0, hl_in, LN=True)
+            # s_in = cat(after, before-rnn, x) and cat(after, self-attention output) are never materialised:
+            # `before` is the list of its pieces and the GEMM operands are built from the pieces (K.split_concat)
+            s_in = [after] + list(before) + [x]
+            s_out = self.highlvl_self_att(s_in, s_in, mask, x3=after)
+            return self.high_lvl_context_rnn.run_layer(0, [after, s_out], LN=True)
 
         # encoders with whole-tensor LN (SDNet.py:338-350)
         with torch.cuda.stream(s_q):
             q_layers = encode(self.ques_rnn, q_in, L_in)
-            q_cat = K.concat_cols(q_layers)
-            q_high = encode(self.high_lvl_ques_rnn, q_cat, opt['question_high_lvl_rnn_layers'])[-1]
+            q_high = encode(self.high_lvl_ques_rnn, list(q_layers), opt['question_high_lvl_rnn_layers'])[-1]
             q_layers = q_layers + [q_high]
             q_proj = self.deep_attn.project_x2([q_word], q_layers)  # shared by the OCR and OD branches
             ev_q = torch.cuda.Event()
@@ -483,7 +484,7 @@ class SDNet(nn.Module):
             ev = torch.cuda.Event()
             ev.record(main)
             if self.check_nan == 'deferred':
-                self._pending = (ev, host_flags, bert_pack, len(phoc_errs))
+                self._pending.append((ev, host_flags, bert_pack, len(phoc_errs)))
             else:
                 ev.synchronize()
                 self._raise_flags(host_flags, bert_pack if self.check_nan else None, len(phoc_errs))

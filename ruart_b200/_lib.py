@@ -45,6 +45,7 @@ _SIGNATURES = {
                        c_int, c_void_p],
     "ruart_pack_tokens": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ruart_split_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p],
+    "ruart_split_concat_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p],
     "ruart_gather_rows": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_int,
                           c_int, c_void_p],
     "ruart_whole_layernorm": [c_void_p, c_ll, c_int, c_ll, c_float, c_void_p, c_void_p],
@@ -73,7 +74,7 @@ _SIGNATURES = {
     "ruart_whole_layernorm_stats": [c_void_p, c_ll, c_int, c_ll, c_float, c_void_p, c_void_p, c_void_p],
     "ruart_whole_layernorm_backward": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                        c_ll, c_void_p],
-    "ruart_embedding_grad": [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_ll, c_int,
+    "ruart_embedding_grad": [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
                              c_void_p],
     "ruart_subword_layers_backward": [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                       c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
@@ -128,7 +129,7 @@ def check(rc):
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
 _KERNELS_PER_CALL = {"ruart_whole_layernorm": 2, "ruart_whole_layernorm_stats": 2, "ruart_colsum": 2,
-                     "ruart_whole_layernorm_backward": 2, "ruart_subword_layers_backward": 2, "ruart_embedding_grad": 2}
+                     "ruart_whole_layernorm_backward": 2, "ruart_subword_layers_backward": 2, "ruart_embedding_grad": 3}
 launch_count = 0
 _timing_hook = None  # set by bench.py: callable(name, args) -> context manager, or None
 

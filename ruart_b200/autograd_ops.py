@@ -426,9 +426,11 @@ class EmbeddingFn(Function):
         V, D = ctx.wshape
         dy2 = _c(dy).view(-1, D)
         dw = _f32((V, D), dy.device)
-        flags = torch.empty(max(flat.numel(), 1), dtype=torch.uint8, device=dy.device)
-        call("ruart_embedding_grad", ptr(flat), 1 if flat.dtype == torch.int64 else 0, flat.numel(), ptr(dy2), D, D, V,
-             ptr(flags), ptr(dw), D, 0, current_stream())
+        n = flat.numel()
+        ws_bytes = ops.round_up(max(n, 1), 16) + (64 * V * D * 4 if V < 2048 else 0)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
+        call("ruart_embedding_grad", ptr(flat), 1 if flat.dtype == torch.int64 else 0, n, ptr(dy2), D, D, V,
+             ptr(ws), ws_bytes, ptr(dw), D, 0, current_stream())
         return None, dw
 
 

@@ -337,18 +337,26 @@ row_nonzero_kernel(const float* __restrict__ dy, long long dy_pitch, long long n
 template <typename I>
 __global__ void __launch_bounds__(256)
 embedding_grad_kernel(const I* __restrict__ ids, const uint8_t* __restrict__ flag, long long n,
-                      const float* __restrict__ dy, long long dy_pitch, int D, int V,
-                      float* __restrict__ dW, long long dw_pitch, int accumulate) {
+                      const float* __restrict__ dy, long long dy_pitch, int D, int V, int n_seg,
+                      float* __restrict__ partial, float* __restrict__ dW, long long dw_pitch, int accumulate) {
+  // task = (segment of the id list, vocabulary row); n_seg > 1 (small tables: pos / ent embeddings) writes
+  // partial[seg][v][:] and embedding_grad_reduce_kernel adds the segments in order
   const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long tasks = static_cast<long long>(V) * n_seg;
+  const long long seg_len = ((n + n_seg - 1) / n_seg + 31) / 32 * 32;
+  for (long long task = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; task < tasks;
+       task += warps) {
+    const int seg = static_cast<int>(task / V);
+    const int v = static_cast<int>(task - static_cast<long long>(seg) * V);
+    const long long k0 = seg * seg_len, k1 = (k0 + seg_len < n) ? k0 + seg_len : n;
     for (int c0 = 0; c0 < D; c0 += 32 * 8) {
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (long long base = 0; base < n; base += 32) {
+      for (long long base = k0; base < k1; base += 32) {
         const long long k = base + lane;
-        const bool hit = (k < n) && (static_cast<long long>(ids[k]) == v) && (flag[k] != 0);
+        const bool hit = (k < k1) && (static_cast<long long>(ids[k]) == v) && (flag[k] != 0);
         unsigned m = __ballot_sync(0xffffffffu, hit);
         while (m) {
           const int t = __ffs(m) - 1;
@@ -365,11 +373,28 @@ embedding_grad_kernel(const I* __restrict__ ids, const uint8_t* __restrict__ fla
       for (int i = 0; i < 8; ++i) {
         const int c = c0 + lane + 32 * i;
         if (c < D) {
-          float* p = dW + static_cast<long long>(v) * dw_pitch + c;
-          *p = accumulate ? *p + acc[i] : acc[i];
+          if (n_seg > 1) {
+            partial[(static_cast<long long>(seg) * V + v) * D + c] = acc[i];
+          } else {
+            float* p = dW + static_cast<long long>(v) * dw_pitch + c;
+            *p = accumulate ? *p + acc[i] : acc[i];
+          }
         }
       }
     }
+  }
+}
+
+__global__ void embedding_grad_reduce_kernel(const float* __restrict__ partial, int n_seg, int V, int D,
+                                             float* __restrict__ dW, long long dw_pitch, int accumulate) {
+  const long long total = static_cast<long long>(V) * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < n_seg; ++s) t += partial[static_cast<long long>(s) * total + i];
+    const long long v = i / D;
+    float* p = dW + v * dw_pitch + (i - v * D);
+    *p = accumulate ? *p + t : t;
   }
 }
 
@@ -461,6 +486,7 @@ __global__ void layer_mix_bwd_kernel(const double* __restrict__ partials, int n_
 constexpr int BP_THREADS = 512;
 constexpr int BP_BT = 4;
 constexpr int BP_HP = 128;
+constexpr int BP_UNROLL = 32;   // weights in flight per thread in the recurrent-gradient product
 
 __global__ void __launch_bounds__(BP_THREADS, 1)
 lstm_bptt_kernel(const float* __restrict__ gates, long long gates_pitch, const float* __restrict__ w_hh,
@@ -519,12 +545,19 @@ lstm_bptt_kernel(const float* __restrict__ gates, long long gates_pitch, const f
 #pragma unroll
       for (int b = 0; b < BP_BT; ++b) acc[b] = 0.f;
       if (p2) {
+        // W_hh (250 KB) does not fit shared memory: its column k is streamed from L1/L2 with BP_UNROLL
+        // independent loads in flight per thread (5 in flight made a step 20 us; the loads, not the FMAs, bound it)
         const float* wq = W + static_cast<long long>(q) * H * H + k;
-#pragma unroll 5
-        for (int j = 0; j < H; ++j) {
-          const float w = __ldg(wq + static_cast<long long>(j) * H);
+        for (int j0 = 0; j0 < H; j0 += BP_UNROLL) {
+          float w[BP_UNROLL];
 #pragma unroll
-          for (int b = 0; b < BP_BT; ++b) acc[b] = fmaf(s_dg[b][q * BP_HP + j], w, acc[b]);
+          for (int u = 0; u < BP_UNROLL; ++u)
+            w[u] = (j0 + u < H) ? __ldg(wq + static_cast<long long>(j0 + u) * H) : 0.f;
+#pragma unroll
+          for (int u = 0; u < BP_UNROLL; ++u) {
+#pragma unroll
+            for (int b = 0; b < BP_BT; ++b) acc[b] = fmaf(s_dg[b][q * BP_HP + j0 + u], w[u], acc[b]);
+          }
         }
       }
 #pragma unroll
@@ -729,23 +762,41 @@ extern "C" int ruart_whole_layernorm_backward(const float* y, long long y_pitch,
 }
 
 extern "C" int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
-                                    long long dy_pitch, int D, int V, uint8_t* workspace, float* dW,
-                                    long long dw_pitch, int accumulate, void* stream) {
+                                    long long dy_pitch, int D, int V, uint8_t* workspace,
+                                    long long workspace_bytes, float* dW, long long dw_pitch, int accumulate,
+                                    void* stream) {
   RUART_ARG_CHECK(ids != nullptr && dy != nullptr && dW != nullptr && n >= 0 && D > 0 && V > 0);
-  RUART_ARG_CHECK(workspace != nullptr || n == 0);
+  const long long flag_bytes = (n + 15) / 16 * 16;
+  RUART_ARG_CHECK(workspace != nullptr && workspace_bytes >= flag_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   if (n > 0) {
     row_nonzero_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(dy, dy_pitch, n, D, workspace);
     RUART_LAUNCH_CHECK();
   }
-  const unsigned grid = grid_for(static_cast<long long>(V) * 32, 256);
+  // small tables: split the id list into segments so that ~4096 warps have work (50 warps walking 128 k ids
+  // serially cost 4 ms per call); as many segments as the caller's workspace holds partial sums for
+  int n_seg = 1;
+  if (V < 2048) {
+    n_seg = (4096 + V - 1) / V;
+    if (n_seg > 64) n_seg = 64;
+    const long long room = (workspace_bytes - flag_bytes) / (static_cast<long long>(V) * D * 4);
+    if (n_seg > room) n_seg = static_cast<int>(room);
+    if (n_seg < 1) n_seg = 1;
+  }
+  float* partial = reinterpret_cast<float*>(workspace + flag_bytes);
+  const unsigned grid = grid_for(static_cast<long long>(V) * n_seg * 32, 256);
   if (idx_is_64)
     embedding_grad_kernel<long long><<<grid, 256, 0, st>>>((const long long*)ids, workspace, n, dy, dy_pitch, D,
-                                                           V, dW, dw_pitch, accumulate);
+                                                           V, n_seg, partial, dW, dw_pitch, accumulate);
   else
     embedding_grad_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)ids, workspace, n, dy, dy_pitch, D, V,
-                                                         dW, dw_pitch, accumulate);
+                                                         n_seg, partial, dW, dw_pitch, accumulate);
   RUART_LAUNCH_CHECK();
+  if (n_seg > 1) {
+    embedding_grad_reduce_kernel<<<grid_for(static_cast<long long>(V) * D, 256), 256, 0, st>>>(
+        partial, n_seg, V, D, dW, dw_pitch, accumulate);
+    RUART_LAUNCH_CHECK();
+  }
   return RUART_OK;
 }
 

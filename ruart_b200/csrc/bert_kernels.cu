@@ -1233,6 +1233,48 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long long ld,
   }
 }
 
+// fp32 sources laid side by side (torch.cat(..., -1) of up to 8 tensors with equal row counts) -> the bf16 split
+// GEMM operand of their concatenation [rows, parts*Kp], zero padded to Kp per part: the fp32 concatenation is
+// never materialised (one pass instead of n copies + one split; DESIGN.md §8 "operand splits + concat copies").
+struct ConcatSrc {
+  const float* p[8];
+  long long pitch[8];
+  int start[9];   // first column of source k in the concatenation; start[n] = K
+  int n;
+};
+__global__ void split_concat_bf16_kernel(ConcatSrc cs, long long rows, int Kp, int parts,
+                                         __nv_bfloat16* __restrict__ dst) {
+  const int K = cs.start[cs.n];
+  const long long total = rows * (Kp / 2);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / (Kp / 2);
+    const int c = static_cast<int>(i - r * (Kp / 2)) * 2;
+    float x[2] = {0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = c + e;
+      if (col < K) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)      // static indices: the parameter struct stays in the constant bank
+          if (q < cs.n && col >= cs.start[q] && col < cs.start[q + 1])
+            x[e] = cs.p[q][r * cs.pitch[q] + (col - cs.start[q])];
+      }
+    }
+    for (int p = 0; p < parts; ++p) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x[0]);
+      const __nv_bfloat16 h1 = __float2bfloat16_rn(x[1]);
+      __nv_bfloat162 hh;
+      hh.x = h0;
+      hh.y = h1;
+      *reinterpret_cast<__nv_bfloat162*>(dst + r * (static_cast<long long>(parts) * Kp) +
+                                         static_cast<long long>(p) * Kp + c) = hh;
+      x[0] -= __bfloat162float(h0);
+      x[1] -= __bfloat162float(h1);
+    }
+  }
+}
+
 inline unsigned row_grid(long long rows) {
   return static_cast<unsigned>((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
 }
@@ -1482,6 +1524,38 @@ extern "C" int ruart_pack_tokens(const long long* ids, const uint8_t* mask, int 
   if (N == 0) return RUART_OK;
   pack_tokens_kernel<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ids, mask, N, L, row_start,
                                                                     window, out_ids, out_pos, capacity);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_split_concat_bf16(const float* const* srcs_host, const long long* pitches_host,
+                                       const int* widths_host, int n_src, long long rows, int Kp, int parts,
+                                       void* dst, void* stream) {
+  RUART_ARG_CHECK(n_src >= 1 && n_src <= 8 && srcs_host != nullptr && pitches_host != nullptr &&
+                  widths_host != nullptr);
+  RUART_ARG_CHECK(Kp > 0 && (Kp % 64) == 0 && parts >= 1 && parts <= 3 && dst != nullptr);
+  ConcatSrc cs;
+  int col = 0;
+  for (int k = 0; k < 8; ++k) {
+    cs.p[k] = k < n_src ? srcs_host[k] : nullptr;
+    cs.pitch[k] = k < n_src ? pitches_host[k] : 0;
+    cs.start[k] = col;
+    if (k < n_src) {
+      RUART_ARG_CHECK(widths_host[k] > 0 && srcs_host[k] != nullptr);
+      col += widths_host[k];
+    }
+  }
+  cs.start[8] = col;
+  for (int k = n_src; k <= 8; ++k) cs.start[k] = col;
+  cs.n = n_src;
+  RUART_ARG_CHECK(col <= Kp);
+  if (rows == 0) return RUART_OK;
+  const long long total = rows * (Kp / 2);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  split_concat_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
+      cs, rows, Kp, parts, (__nv_bfloat16*)dst);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

@@ -79,6 +79,28 @@ def split_act(x, parts, row_idx=None, n_rows=None):
     return out, Kp
 
 
+def split_concat(tensors, parts):
+    """torch.cat(tensors, -1) -> bf16 split operand [rows, parts*Kp] without materialising the concatenation.
+    tensors: fp32 [.., D_i] with equal leading dims (each may be a pitched view).  Returns (operand, Kp)."""
+    import ctypes
+    if len(tensors) == 1:
+        return split_act(tensors[0], parts)
+    assert len(tensors) <= 8
+    infos = [rows2d(t) for t in tensors]
+    rows = infos[0][0]
+    assert all(i[0] == rows for i in infos), "concatenated tensors need equal row counts"
+    K = sum(i[1] for i in infos)
+    Kp = ops.round_up(K, 64)
+    n = len(tensors)
+    srcs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    pitches = (ctypes.c_longlong * n)(*[i[2] for i in infos])
+    widths = (ctypes.c_int * n)(*[i[1] for i in infos])
+    out = torch.empty((rows, parts * Kp), dtype=torch.bfloat16, device=tensors[0].device)
+    call("ruart_split_concat_bf16", ctypes.addressof(srcs), ctypes.addressof(pitches), ctypes.addressof(widths), n,
+         rows, Kp, parts, ptr(out), current_stream())
+    return out, Kp
+
+
 def _cache_of(owner):
     """Per-module cache (dies with the module: a global cache keyed by id() could be hit by a
     different module that re-uses the id and the freed CUDA addresses)."""
@@ -179,10 +201,12 @@ def as_u8(mask):
 
 def lstm_layer(owner, x, key, w_ih, w_hh, b_ih, b_hh, H, parts, out, whole_ln=False):
     """One (Bi)LSTM layer of StackedBRNN (Layers.py:156-170) for H <= 128 on [B, L, in] input.
-    w_ih/w_hh/b_ih/b_hh are lists over directions.  `out` [B, L, ndir*H] may be a strided view."""
-    B, L = x.shape[0], x.shape[1]
+    w_ih/w_hh/b_ih/b_hh are lists over directions.  `out` [B, L, ndir*H] may be a strided view.
+    x may be a LIST of [B, L, D_i] tensors: the layer runs on their concatenation (never materialised)."""
+    xs = list(x) if isinstance(x, (list, tuple)) else [x]
+    B, L = xs[0].shape[0], xs[0].shape[1]
     ndir = len(w_ih)
-    a, Kp = split_act(x, parts)
+    a, Kp = split_concat(xs, parts)
     w, _ = prep_weight(owner, (key, "w_ih"), w_ih, parts)
     bias = prep_vector(owner, (key, "bias"), lambda: torch.cat([bi + bh for bi, bh in zip(b_ih, b_hh)], 0), b_ih + b_hh)
     whh = prep_vector(owner, (key, "w_hh"), lambda: torch.stack(w_hh, 0), w_hh)

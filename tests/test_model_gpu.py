@@ -437,6 +437,13 @@ def test_nan_guard_sync_and_deferred():
         net2.get_answer.attn.linear.bias[3] = float("nan")
         p_bad, _ = net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))      # returns without a host sync
         assert torch.isnan(p_bad).any() and not torch.isnan(p_ok).any()
+        torch.cuda.synchronize()                                 # (the flag copy has landed)
         with pytest.raises(AssertionError, match="NaN in answer scores"):
-            net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))  # ... and the NEXT forward raises
+            net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))  # ... and the NEXT forward raises on entry
         net2.check_pending()
+        # without waiting for the device: never more than two forwards stay unchecked
+        net2.get_answer.attn.linear.bias[3] = float("nan")
+        with pytest.raises(AssertionError, match="NaN in answer scores"):
+            for _ in range(4):
+                net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))
+            net2.check_pending()
