@@ -210,7 +210,7 @@ def lstm_layer(owner, x, key, w_ih, w_hh, b_ih, b_hh, H, parts, out, whole_ln=Fa
     w, _ = prep_weight(owner, (key, "w_ih"), w_ih, parts)
     bias = prep_vector(owner, (key, "bias"), lambda: torch.cat([bi + bh for bi, bh in zip(b_ih, b_hh)], 0), b_ih + b_hh)
     whh = prep_vector(owner, (key, "w_hh"), lambda: torch.stack(w_hh, 0), w_hh)
-    xg = torch.empty((B * L, ndir * 4 * H), dtype=torch.float32, device=x.device)
+    xg = torch.empty((B * L, ndir * 4 * H), dtype=torch.float32, device=xs[0].device)
     linear(a, Kp, w, B * L, ndir * 4 * H, parts, xg, epi=ops.EPI_BIAS, bias=bias)
     _, _, op = rows2d(out)
     call("ruart_lstm_recurrence", ptr(xg), xg.stride(0), ptr(whh), ptr(out), op, B, L, H, ndir, current_stream())
