@@ -962,12 +962,15 @@ subword_avg_layers_kernel(const float* h_f32, const __nv_bfloat16* h_b16, long l
 // (LDGSTS, 16 bytes per lane, the lane that copies a chunk is the lane that reads it back): a one-piece
 // word has all 12 layers (18 KB) in flight at once, a two-piece word 8 layers (24 KB).  Registers no longer
 // bound the bytes in flight.  Words with more than SW_MAX_CNT pieces take the synchronous loop.
-constexpr int SW_WARPS = 8;
+constexpr int SW_WARPS = 16;
 constexpr int SW_MAX_CNT = 4;
 template <int HC>
 struct SwRing {
   static constexpr int ROW_BYTES = HC * 512;               // one bf16 row
-  static constexpr int SLOTS = (HC == 3) ? 16 : 12;        // 24 KB per warp
+  // 12 KB per warp, 16 warps per CTA (192 KB): the first version (8 warps x 24 KB) had the same bytes in flight but
+  // only 12.5 % of the warp slots, and every word is a serial issue -> wait -> reduce -> store chain (ncu:
+  // profiles/r02_ncu_full2_summary.txt, DRAM 48 %); twice the warps overlap those chains
+  static constexpr int SLOTS = (HC == 3) ? 8 : 6;
   static constexpr int WARP_BYTES = SLOTS * ROW_BYTES;
 };
 
@@ -1208,27 +1211,47 @@ pack_tokens_kernel(const long long* __restrict__ ids, const uint8_t* __restrict_
 }
 
 // fp32 [rows, K] (row stride ld) -> bf16 split [rows, parts*Kp], zero padded to Kp per part.
-__global__ void split_bf16_kernel(const float* __restrict__ src, long long ld,
-                                  const int32_t* __restrict__ row_idx, long long rows, int K,
-                                  int Kp, int parts, __nv_bfloat16* __restrict__ dst) {
-  const long long total = rows * (Kp / 2);
+// 8 columns per thread: four float2 loads (PAIRS: even ld and K, 8-byte aligned base) and one 16-byte store per part.
+template <bool PAIRS>
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ src, long long ld, const int32_t* __restrict__ row_idx,
+                  long long rows, int K, int Kp, int parts, __nv_bfloat16* __restrict__ dst) {
+  const int groups = Kp / 8;
+  const long long total = rows * groups;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / (Kp / 2);
-    const int c = static_cast<int>(i - r * (Kp / 2)) * 2;
+    const long long r = i / groups;
+    const int c0 = static_cast<int>(i - r * groups) * 8;
     const long long sr = row_idx ? static_cast<long long>(row_idx[r]) : r;
-    float x0 = (c < K) ? src[sr * ld + c] : 0.f;
-    float x1 = (c + 1 < K) ? src[sr * ld + c + 1] : 0.f;
+    const float* srow = src + sr * ld;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      const int c = c0 + e;
+      if (PAIRS) {
+        float2 v = make_float2(0.f, 0.f);
+        if (c < K) v = __ldg(reinterpret_cast<const float2*>(srow + c));
+        x[e] = v.x;
+        x[e + 1] = v.y;
+      } else {
+        x[e] = (c < K) ? __ldg(srow + c) : 0.f;
+        x[e + 1] = (c + 1 < K) ? __ldg(srow + c + 1) : 0.f;
+      }
+    }
+    __nv_bfloat16* drow = dst + r * (static_cast<long long>(parts) * Kp) + c0;
     for (int p = 0; p < parts; ++p) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x0);
-      const __nv_bfloat16 h1 = __float2bfloat16_rn(x1);
-      __nv_bfloat162 hh;
-      hh.x = h0;
-      hh.y = h1;
-      *reinterpret_cast<__nv_bfloat162*>(dst + r * (static_cast<long long>(parts) * Kp) +
-                                         static_cast<long long>(p) * Kp + c) = hh;
-      x0 -= __bfloat162float(h0);
-      x1 -= __bfloat162float(h1);
+      uint4 u;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[e]);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(x[e + 1]);
+        w[e / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                   (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        x[e] -= __bfloat162float(h0);
+        x[e + 1] -= __bfloat162float(h1);
+      }
+      *reinterpret_cast<uint4*>(drow + static_cast<long long>(p) * Kp) = u;
     }
   }
 }
@@ -1242,35 +1265,58 @@ struct ConcatSrc {
   int start[9];   // first column of source k in the concatenation; start[n] = K
   int n;
 };
-__global__ void split_concat_bf16_kernel(ConcatSrc cs, long long rows, int Kp, int parts,
-                                         __nv_bfloat16* __restrict__ dst) {
+// Each thread converts 8 consecutive columns of one row: four float2 loads (a pair never straddles two sources
+// when every source starts at an even column — checked by the host; odd layouts take the scalar path) and ONE
+// 16-byte store per split part.  (First version: one column pair per thread with scalar loads — 100 us for the
+// 1800-wide self-attention input, slower than the copies + split it replaced; profiles/r02_launches_summary_v1.txt.)
+template <bool PAIRS>
+__global__ void __launch_bounds__(256)
+split_concat_bf16_kernel(ConcatSrc cs, long long rows, int Kp, int parts, __nv_bfloat16* __restrict__ dst) {
   const int K = cs.start[cs.n];
-  const long long total = rows * (Kp / 2);
+  const int groups = Kp / 8;
+  const long long total = rows * groups;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / (Kp / 2);
-    const int c = static_cast<int>(i - r * (Kp / 2)) * 2;
-    float x[2] = {0.f, 0.f};
+    const long long r = i / groups;
+    const int c0 = static_cast<int>(i - r * groups) * 8;
+    float x[8];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = c + e;
+    for (int e = 0; e < 8; e += 2) {
+      const int col = c0 + e;
+      x[e] = 0.f;
+      x[e + 1] = 0.f;
       if (col < K) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)      // static indices: the parameter struct stays in the constant bank
-          if (q < cs.n && col >= cs.start[q] && col < cs.start[q + 1])
-            x[e] = cs.p[q][r * cs.pitch[q] + (col - cs.start[q])];
+        for (int q = 0; q < 8; ++q) {     // static indices: the parameter struct stays in the constant bank
+          if (q < cs.n && col >= cs.start[q] && col < cs.start[q + 1]) {
+            const float* p = cs.p[q] + r * cs.pitch[q] + (col - cs.start[q]);
+            if (PAIRS) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+              x[e] = v.x;
+              x[e + 1] = v.y;
+            } else {
+              x[e] = __ldg(p);
+            }
+          }
+          if (!PAIRS && q < cs.n && col + 1 >= cs.start[q] && col + 1 < cs.start[q + 1])
+            x[e + 1] = __ldg(cs.p[q] + r * cs.pitch[q] + (col + 1 - cs.start[q]));
+        }
       }
     }
+    __nv_bfloat16* drow = dst + r * (static_cast<long long>(parts) * Kp) + c0;
     for (int p = 0; p < parts; ++p) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x[0]);
-      const __nv_bfloat16 h1 = __float2bfloat16_rn(x[1]);
-      __nv_bfloat162 hh;
-      hh.x = h0;
-      hh.y = h1;
-      *reinterpret_cast<__nv_bfloat162*>(dst + r * (static_cast<long long>(parts) * Kp) +
-                                         static_cast<long long>(p) * Kp + c) = hh;
-      x[0] -= __bfloat162float(h0);
-      x[1] -= __bfloat162float(h1);
+      uint4 u;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[e]);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(x[e + 1]);
+        w[e / 2] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                   (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        x[e] -= __bfloat162float(h0);
+        x[e + 1] -= __bfloat162float(h1);
+      }
+      *reinterpret_cast<uint4*>(drow + static_cast<long long>(p) * Kp) = u;
     }
   }
 }
@@ -1549,13 +1595,23 @@ extern "C" int ruart_split_concat_bf16(const float* const* srcs_host, const long
   for (int k = n_src; k <= 8; ++k) cs.start[k] = col;
   cs.n = n_src;
   RUART_ARG_CHECK(col <= Kp);
+  RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
   if (rows == 0) return RUART_OK;
-  const long long total = rows * (Kp / 2);
+  // float2 loads need every source to start at an even column with an 8-byte aligned base and an even pitch
+  bool pairs = true;
+  for (int k = 0; k < n_src; ++k)
+    pairs = pairs && (cs.start[k] % 2 == 0) && (widths_host[k] % 2 == 0) && (pitches_host[k] % 2 == 0) &&
+            ((reinterpret_cast<uintptr_t>(srcs_host[k]) & 7u) == 0);
+  const long long total = rows * (Kp / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  split_concat_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
-      cs, rows, Kp, parts, (__nv_bfloat16*)dst);
+  if (pairs)
+    split_concat_bf16_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
+        cs, rows, Kp, parts, (__nv_bfloat16*)dst);
+  else
+    split_concat_bf16_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
+        cs, rows, Kp, parts, (__nv_bfloat16*)dst);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
@@ -1563,13 +1619,19 @@ extern "C" int ruart_split_concat_bf16(const float* const* srcs_host, const long
 extern "C" int ruart_split_bf16(const float* src, long long ld, const int32_t* row_idx,
                                 long long rows, int K, int Kp, int parts, void* dst, void* stream) {
   RUART_ARG_CHECK(K > 0 && Kp >= K && (Kp % 64) == 0 && parts >= 1 && parts <= 3);
+  RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
   if (rows == 0) return RUART_OK;
-  const long long total = rows * (Kp / 2);
+  const long long total = rows * (Kp / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  split_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
-      src, ld, row_idx, rows, K, Kp, parts, (__nv_bfloat16*)dst);
+  const bool pairs = (ld % 2 == 0) && (K % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0);
+  if (pairs)
+    split_bf16_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
+        src, ld, row_idx, rows, K, Kp, parts, (__nv_bfloat16*)dst);
+  else
+    split_bf16_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
+        src, ld, row_idx, rows, K, Kp, parts, (__nv_bfloat16*)dst);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
