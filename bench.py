@@ -145,7 +145,7 @@ def phoc_record(n=1_000_000):
 def gemm_traffic():
     """Mean DRAM bytes per BERT GEMM launch from the committed ncu --set full capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")) as f:
             return float(json.load(f)["mean_bytes_per_launch"])
     except Exception:
         return None
