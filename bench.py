@@ -548,8 +548,10 @@ def main():
             return _TimedK("add_ln")
         if name == "ruart_bert_attention":
             return _TimedK("bert_attention")
-        if name == "ruart_subword_avg_layers":
+        if name in ("ruart_subword_avg_layers", "ruart_subword_avg_layers_fold"):
             return _TimedK("subword_avg_layers")
+        if name == "ruart_gemm_bf16_fold":     # the BERT GEMMs with the folded LayerNorms (bf16 mode)
+            return _Timed(2.0 * a[4] * a[5] * a[6])
         if name != "ruart_gemm_bf16":
             return null
         M_, N_, Kp_, terms = a[6], a[7], a[8], a[9]

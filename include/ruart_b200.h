@@ -82,11 +82,44 @@ RUART_API int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const v
                     void* out_bf16, long long ldo_bf16, int out_parts, long long out_part_stride,
                     int fast_gelu, const void* residual_bf16, long long ld_res, void* stream);
 
+/* The CTA-pair GEMM with a FOLDED BertLayerNorm (modeling.py:155-168 fused into its neighbours; bf16 encoder).
+ * LayerNorm is affine per row, y = (v - mu) r gamma + beta, so the encoder keeps the rows v BEFORE each
+ * LayerNorm (bf16) plus 8 float2 partial (sum, sum of squares) per row, and
+ *   fold 2 (BertSelfOutput.dense / BertOutput.dense, modeling.py:260-264,299-303):
+ *       out = A W^T + LayerNorm(residual) + b  written pre-LayerNorm, with its partial sums in out_stats;
+ *       vec = beta + b, vec2 = gamma (of the residual's pending LayerNorm), in_stats = the residual's sums
+ *   fold 1 (query/key/value, BertIntermediate.dense: the consumers of a LayerNorm output, :225-227,287):
+ *       out = act(LayerNorm(A) W0^T + b) computed as r acc - r mu colsum + vec with W = W0 * gamma (host),
+ *       vec = W0 beta + b, vec2 = colsum(W), in_stats = A's sums; epi = RUART_EPI_BIAS or RUART_EPI_BIAS_GELU
+ * Requires M >= 2048, N % 256 == 0, Kp % 64 == 0 (the CTA-pair kernel); RUART_ERR_ARG otherwise.            */
+RUART_API int ruart_gemm_bf16_fold(const void* A, long long lda, const void* W, long long ldw, int M, int N,
+                                   int Kp, int fold, int epi, const float* vec, const float* vec2,
+                                   const float* in_stats, float ln_eps, void* out_bf16, long long ldo,
+                                   const void* residual_bf16, long long ld_res, float* out_stats,
+                                   void* stream);
+
 /* ---------------------------------------------------------------- BERT (packed, pad-free rows)
  * Activations are [T, hidden] row-major over the T real wordpieces of all sequences; every
  * kernel accepts fp32 and/or bf16 pointers (exactly one input representation, any outputs).
  * bf16 outputs may be written as `out_parts` split parts ([T, parts*hidden]).                */
 
+/* Folded-LayerNorm form of ruart_bert_embed_ln: the embedding sum BEFORE its LayerNorm (bf16 [T, hidden]) and
+ * the row's (sum, sum of squares) in slot 0 of out_stats [T][8] float2 (slots 1-7 zero).                    */
+RUART_API int ruart_bert_embed_raw(const int32_t* ids, const int32_t* pos, const float* word_emb,
+                                   const float* pos_emb, const float* type_emb, int T, int hidden,
+                                   void* out_bf16, float* out_stats, void* stream);
+/* Coefficients of ruart_subword_avg_layers_fold: G[l][c] = softmax(alpha)_l * gamma * ln_gamma[l][c],
+ * C[c] = sum_l softmax(alpha)_l * gamma * ln_beta[l][c]  (SDNet.linear_sum, SDNet.py:573-583, times each
+ * layer's output LayerNorm weights).                                                                        */
+RUART_API int ruart_subword_coef(const float* alpha, const float* gamma, int n_layers, const float* ln_gamma,
+                                 const float* ln_beta, int hidden, float* G, float* C, void* stream);
+/* ruart_subword_avg_layers over PRE-LayerNorm layer outputs + their partial sums (folded encoder):
+ * dst[item, j] = sum_l G_l * mean_pieces(v r - mu r) + C.                                                   */
+RUART_API int ruart_subword_avg_layers_fold(const void* h_bf16, long long layer_stride, const float* stats,
+                                            long long stats_layer_stride, float ln_eps, const int32_t* words,
+                                            int n_words, const int32_t* row_start, const uint8_t* x_mask, int W,
+                                            float* dst, long long dst_stride, const float* G, const float* C,
+                                            int n_layers, int hidden, void* stream);
 /* BertEmbeddings.forward, modeling.py:185-199: LN(word[ids] + position[pos] + token_type[0]) */
 RUART_API int ruart_bert_embed_ln(const int32_t* ids, const int32_t* pos, const float* word_emb,
                                   const float* pos_emb, const float* type_emb, const float* gamma,

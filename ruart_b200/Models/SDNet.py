@@ -527,7 +527,7 @@ class SDNet(nn.Module):
             from ..bert_engine import Segment
             segs = [Segment(l['bert'], l['bert_mask'], word_offsets(l), l[m], l.get('bert_totals')) for l, m in lists]
             eng = self.Bert.engine()
-            pk, hs_f, hs_b = eng.encode_hidden(segs)
+            pk, hs_f, hs_b = eng.encode_hidden(segs, allow_fold=False)   # SubwordMixFn reads normalised rows
             packs = eng.subword_packs(segs, pk, hs_f, hs_b)
 
         def embed(lst, key, table, pack):   # get_embedding_from_list, SDNet.py:439-493

@@ -32,6 +32,12 @@ _SIGNATURES = {
     "ruart_gemm_bf16": [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int,
                         c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
                         c_ll, c_int, c_void_p, c_ll, c_void_p],
+    "ruart_gemm_bf16_fold": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_float, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p],
+    "ruart_bert_embed_raw": [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "ruart_subword_coef": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "ruart_subword_avg_layers_fold": [c_void_p, c_ll, c_void_p, c_ll, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "ruart_bert_embed_ln": [c_void_p] * 7 + [c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ruart_add_layernorm": [c_void_p] * 6 + [c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "ruart_bert_attention": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p,

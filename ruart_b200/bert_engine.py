@@ -18,6 +18,7 @@ Three numeric modes
   "fp32"  : activations fp32; GEMM operands are 3-part bf16 splits multiplied as 6 terms (~2^-24)
 """
 import itertools
+import os
 
 import numpy as np
 import torch
@@ -98,6 +99,12 @@ class BertEngine(object):
         assert self.H // self.heads == 64, "attention kernel is specialised for head_dim 64"
         self._key = None
         self._w = None
+        # bf16 mode: the 24 BertLayerNorm passes are folded into the neighbouring GEMMs (fold_weights / the FOLD forms
+        # of the CTA-pair GEMM); needs the pair kernel (T >= FOLD_MIN_T) and 768-wide rows.  RUART_NO_LN_FOLD: A/B aid.
+        self.fold = (mode == "bf16" and not residual_fp32 and self.H == 768
+                     and os.environ.get("RUART_NO_LN_FOLD") is None)
+
+    FOLD_MIN_T = 2048
 
     # ------------------------------------------------------------------ weights
     def _weights_key(self, dev):
@@ -137,8 +144,37 @@ class BertEngine(object):
                 "g2": f(lay.output.LayerNorm.gamma), "b2": f(lay.output.LayerNorm.beta),
                 "eps": float(lay.output.LayerNorm.variance_epsilon),
             })
+        if self.fold:
+            self.fold_weights(W)
         self._key, self._w = key, W
         return W
+
+    def fold_weights(self, W):
+        """Operands of the folded-LayerNorm encoder (ruart_gemm_bf16_fold).  For a LayerNorm (g, b) whose output
+        feeds a dense layer (W0, b0):  LayerNorm(v) W0^T + b0 = r (v (W0 g)^T) - r mu colsum(W0 g) + (W0 b + b0);
+        and where it feeds a residual add, LayerNorm(v) + b0' = (v r - mu r) g + (b + b0')."""
+        m = self.model
+        f = lambda t: t.detach().float().contiguous()
+
+        def consumer(w0, b0, g, b):
+            w0 = f(w0)
+            wf = self._prep_matrix(w0 * g[None, :])                  # bf16(W0 * gamma)
+            return wf, wf.float().sum(1).contiguous(), (w0 @ b + f(b0)).contiguous()
+
+        g_prev, b_prev = W["eg"], W["eb"]                             # layer 0 consumes the embedding LayerNorm
+        ln_g, ln_b = [], []
+        for lay, lw in zip(m.encoder.layer, W["layers"]):
+            s = lay.attention.self
+            wqkv = torch.cat([s.query.weight, s.key.weight, s.value.weight], 0)
+            lw["wqkv_f"], lw["sqkv"], lw["cqkv"] = consumer(wqkv, lw["bqkv"], g_prev, b_prev)
+            lw["res1_g"], lw["res1_b"] = g_prev, (b_prev + lw["bo"]).contiguous()
+            lw["wi_f"], lw["si"], lw["ci"] = consumer(lay.intermediate.dense.weight, lw["bi"], lw["g1"], lw["b1"])
+            lw["res2_g"], lw["res2_b"] = lw["g1"], (lw["b1"] + lw["bd"]).contiguous()
+            g_prev, b_prev = lw["g2"], lw["b2"]
+            ln_g.append(lw["g2"])
+            ln_b.append(lw["b2"])
+        W["ln2_g"] = torch.stack(ln_g).contiguous()                   # [n_layers, H] for ruart_subword_coef
+        W["ln2_b"] = torch.stack(ln_b).contiguous()
 
     # ------------------------------------------------------------------ packing
     _pack_streams = {}
@@ -286,7 +322,7 @@ class BertEngine(object):
         once at the end; the Python word-offset lists are flattened on the host AFTER the whole
         encoder has been queued, i.e. while the GPU is busy.
         """
-        pk, hs_f, hs_b = self.encode_hidden(segments, pack_handle)
+        pk, hs_f, hs_b = self.encode_hidden(segments, pack_handle, allow_fold=alpha is not None)
         self.apply_sinks(segments, pk, hs_f, hs_b, sinks, alpha, gamma)
         return pk
 
@@ -297,6 +333,23 @@ class BertEngine(object):
         st = current_stream()
         keep32 = hs_f is not None
         layer_stride = T * H
+        fold = pk.get("fold")
+        if fold is not None:
+            # hs_b holds the rows BEFORE each layer's output LayerNorm: the subword kernel normalises them
+            if alpha is None:
+                raise RuntimeError("per-layer outputs need the unfolded encoder (encode_hidden(allow_fold=False))")
+            W = self._w
+            dev = hs_b.device
+            G = torch.empty((NL, H), dtype=torch.float32, device=dev)
+            C = torch.empty((H,), dtype=torch.float32, device=dev)
+            call("ruart_subword_coef", ptr(alpha), ptr(gamma), NL, ptr(W["ln2_g"]), ptr(W["ln2_b"]), H, ptr(G), ptr(C), st)
+            stats = fold["stats"]
+            for k, (sg, (wt, nw, rs, wmask)) in enumerate(zip(segments, self.word_tables(segments, pk))):
+                dst, stride, col = sinks[k]
+                call("ruart_subword_avg_layers_fold", ptr(hs_b[1:]), layer_stride, ptr(stats[1:]), T * 8,
+                     W["layers"][0]["eps"], ptr(wt), nw, ptr(rs), ptr(wmask), sg.W, dst.data_ptr() + 4 * col, stride,
+                     ptr(G), ptr(C), NL, H, st)
+            return
         for k, (sg, (wt, nw, rs, wmask)) in enumerate(zip(segments, self.word_tables(segments, pk))):
             hf1 = hs_f[1:] if keep32 else None
             hb1 = None if keep32 else hs_b[1:]
@@ -332,9 +385,51 @@ class BertEngine(object):
         return [(hf1, hb1, T * H, wt, nw, rs, wmask, sg.N, sg.W, NL, H)
                 for sg, (wt, nw, rs, wmask) in zip(segments, self.word_tables(segments, pk))]
 
-    def encode_hidden(self, segments, pack_handle=None):
+    def _gemm_fold(self, a, w, T, N, K, fold, epi, vec, vec2, in_stats, eps, residual=None, out=None, out_stats=None):
+        if out is None:
+            out = torch.empty((T, N), dtype=torch.bfloat16, device=a.device)
+        call("ruart_gemm_bf16_fold", ptr(a), a.stride(0), ptr(w), w.stride(0), T, N, K, fold, epi, ptr(vec), ptr(vec2),
+             ptr(in_stats), eps, ptr(out), out.stride(0), ptr(residual), 0 if residual is None else residual.stride(0),
+             ptr(out_stats), current_stream())
+        return out
+
+    def _encode_hidden_fold(self, pk, W):
+        """bf16 encoder with every BertLayerNorm folded into its neighbours: 4 GEMMs + the attention per layer.
+        Returns hs_raw bf16 [NL + 1, T, H] (rows BEFORE the embedding / each layer's output LayerNorm) and their
+        partial sums [NL + 1, T, 8, 2]."""
+        T, H, I, NL = pk["T"], self.H, self.I, self.n_layers
+        dev = pk["ids"].device
+        st = current_stream()
+        hs = torch.empty((NL + 1, T, H), dtype=torch.bfloat16, device=dev)
+        stats = torch.empty((NL + 1, T, 8, 2), dtype=torch.float32, device=dev)
+        call("ruart_bert_embed_raw", ptr(pk["ids"]), ptr(pk["pos"]), ptr(W["word"]), ptr(W["pos"]), ptr(W["type"]),
+             T, H, ptr(hs[0]), ptr(stats[0]), st)
+        eps0 = W["eps"]
+        stats1 = torch.empty((T, 8, 2), dtype=torch.float32, device=dev)
+        raw1 = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
+        scale = 1.0 / 8.0
+        for li, lw in enumerate(W["layers"]):
+            eps_in = eps0 if li == 0 else W["layers"][li - 1]["eps"]
+            qkv = self._gemm_fold(hs[li], lw["wqkv_f"], T, 3 * H, H, 1, ops.EPI_BIAS, lw["cqkv"], lw["sqkv"],
+                                  stats[li], eps_in)
+            ctx = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
+            for s0, s1, mlen in pk["att_groups"]:
+                cu = pk["cu_seqlens"][s0:s1 + 1]
+                call("ruart_bert_attention", None, ptr(qkv), ptr(cu), s1 - s0, self.heads, scale, mlen, None,
+                     ptr(ctx), 1, st)
+            self._gemm_fold(ctx, lw["wo"], T, H, H, 2, ops.EPI_BIAS, lw["res1_b"], lw["res1_g"], stats[li], eps_in,
+                            residual=hs[li], out=raw1, out_stats=stats1)
+            ff = self._gemm_fold(raw1, lw["wi_f"], T, I, H, 1, ops.EPI_BIAS_GELU, lw["ci"], lw["si"], stats1, lw["eps"])
+            self._gemm_fold(ff, lw["wd"], T, H, I, 2, ops.EPI_BIAS, lw["res2_b"], lw["res2_g"], stats1, lw["eps"],
+                            residual=raw1, out=hs[li + 1], out_stats=stats[li + 1])
+        pk["fold"] = {"stats": stats}
+        return pk, None, hs
+
+    def encode_hidden(self, segments, pack_handle=None, allow_fold=True):
         """The encoder alone: returns (pack, hs_f32 or None, hs_bf16 or None) with hs [n_layers + 1, T, H]
-        (index 0 = embedding output, 1.. = encoder layers)."""
+        (index 0 = embedding output, 1.. = encoder layers).  With the folded LayerNorms (bf16 mode, T >= FOLD_MIN_T,
+        allow_fold) hs_bf16 holds the rows BEFORE each LayerNorm and pack["fold"]["stats"] their partial sums —
+        apply_sinks() is the only consumer that understands that form."""
         dev = segments[0].ids.device
         if dev.type != "cuda":
             raise RuntimeError("ruart_b200 BERT runs on CUDA only; there is no CPU fallback")
@@ -342,6 +437,23 @@ class BertEngine(object):
         pk = self.pack_finish(pack_handle) if pack_handle is not None else self.pack(segments)
         T, H, I, NL = pk["T"], self.H, self.I, self.n_layers
         st = current_stream()
+        scale = 1.0 / 8.0
+        # attention launches: adjacent segments of short sequences (<= 16 tokens: the paired-MMA
+        # kernel) are merged into one call.  (Running the question segment on a side stream next to
+        # them was measured: no gain, its 192 KB CTAs and the item kernel's CTAs exclude each other.)
+        att_groups = []
+        for sgm in pk["segments"]:
+            if sgm["seq1"] == sgm["seq0"]:
+                continue
+            short = sgm["max_len"] <= 16
+            if att_groups and short and att_groups[-1][2] <= 16 and att_groups[-1][1] == sgm["seq0"]:
+                g = att_groups[-1]
+                att_groups[-1] = (g[0], sgm["seq1"], max(g[2], sgm["max_len"]))
+            else:
+                att_groups.append((sgm["seq0"], sgm["seq1"], sgm["max_len"]))
+        pk["att_groups"] = att_groups
+        if self.fold and allow_fold and T >= self.FOLD_MIN_T and self.gelu_mode == 2:
+            return self._encode_hidden_fold(pk, W)
         fp32 = self.mode != "bf16"            # fp32 activations + split GEMM operands ("fp32" and "bf16x2")
         keep32 = fp32 or self.residual_fp32   # fp32 copy of the residual stream
         parts = self.parts
@@ -360,20 +472,6 @@ class BertEngine(object):
         h_f, h_b = layer_bufs(0)
         call("ruart_bert_embed_ln", ptr(pk["ids"]), ptr(pk["pos"]), ptr(W["word"]), ptr(W["pos"]),
              ptr(W["type"]), ptr(W["eg"]), ptr(W["eb"]), W["eps"], T, H, ptr(h_f), ptr(h_b), parts, st)
-        scale = 1.0 / 8.0
-        # attention launches: adjacent segments of short sequences (<= 16 tokens: the paired-MMA
-        # kernel) are merged into one call.  (Running the question segment on a side stream next to
-        # them was measured: no gain, its 192 KB CTAs and the item kernel's CTAs exclude each other.)
-        att_groups = []
-        for sgm in pk["segments"]:
-            if sgm["seq1"] == sgm["seq0"]:
-                continue
-            short = sgm["max_len"] <= 16
-            if att_groups and short and att_groups[-1][2] <= 16 and att_groups[-1][1] == sgm["seq0"]:
-                g = att_groups[-1]
-                att_groups[-1] = (g[0], sgm["seq1"], max(g[2], sgm["max_len"]))
-            else:
-                att_groups.append((sgm["seq0"], sgm["seq1"], sgm["max_len"]))
         for li, lw in enumerate(W["layers"]):
             q_f, q_b = self._gemm(h_b, lw["wqkv"], lw["bqkv"], 3 * H, H, ops.EPI_BIAS, "act")
             ctx = torch.empty((T, parts * H), dtype=torch.bfloat16, device=dev)

@@ -147,6 +147,47 @@ bert_embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict_
   store_act<HC>(out_f32, out_b16, parts, row, lane, w);
 }
 
+// Folded-LayerNorm form (bf16 encoder, see gemm_tcgen05.cu): the embedding sum is stored BEFORE its LayerNorm
+// (bf16) together with the row's (sum, sum of squares) in slot 0 of its 8-slot partial-sum row; the first
+// layer's query/key/value GEMM and the first residual add finish the normalisation.
+template <int HC>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+bert_embed_raw_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ pos,
+                      const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
+                      const float* __restrict__ type_emb, int T, __nv_bfloat16* __restrict__ out_b16,
+                      float2* __restrict__ out_stats) {
+  constexpr int H = HC * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (row >= T) return;
+  const int id = ids[row];
+  const int ps = pos[row];
+  RowVec<HC> w, p, t;
+  load_row_f32<HC>(word_emb + static_cast<long long>(id) * H, lane, w);
+  load_row_f32<HC>(pos_emb + static_cast<long long>(ps) * H, lane, p);
+  load_row_f32<HC>(type_emb, lane, t);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < HC * 8; ++i) {
+    w.v[i] = (w.v[i] + p.v[i]) + t.v[i];
+    s1 += w.v[i];
+    s2 = fmaf(w.v[i], w.v[i], s2);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane < 8) out_stats[row * 8 + lane] = (lane == 0) ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+  __nv_bfloat16* o = out_b16 + row * H;
+#pragma unroll
+  for (int c = 0; c < HC; ++c) {
+    uint4 u;
+    u.x = pack_bf16x2(w.v[c * 8 + 0], w.v[c * 8 + 1]);
+    u.y = pack_bf16x2(w.v[c * 8 + 2], w.v[c * 8 + 3]);
+    u.z = pack_bf16x2(w.v[c * 8 + 4], w.v[c * 8 + 5]);
+    u.w = pack_bf16x2(w.v[c * 8 + 6], w.v[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(o + c * 256 + lane * 8) = u;
+  }
+}
+
 // BertSelfOutput / BertOutput tail (modeling.py:260-264, 299-303): LayerNorm(dense_out + input)
 // (the dense bias is already added by the GEMM epilogue).
 template <int HC>
@@ -1100,6 +1141,212 @@ subword_avg_layers_async_kernel(const __nv_bfloat16* __restrict__ h_b16, long lo
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Folded-LayerNorm form of the kernel above (bf16 encoder with fused LayerNorms, gemm_tcgen05.cu): the kept
+// layer outputs are the rows BEFORE each layer's output LayerNorm plus their partial sums, so the normalisation
+// happens here.  With a_l = softmax(alpha)_l * gamma and y = (v r - mu r) g_l + b_l (BertLayerNorm, modeling.py:155-168)
+//     dst = sum_l a_l * mean_pieces(y)  =  sum_l G_l * mean_pieces(v r - mu r)  +  C,
+//     G_l[c] = a_l g_l[c]   (table [n_layers][H], built by subword_coef_kernel),   C[c] = sum_l a_l b_l[c]
+// i.e. ONE fma per element for the row's (r, -mu r) — the same count as the plain sum — and one fma per layer
+// and column for G.  G lives in shared memory (36 KB for 12 x 768), every ring slot carries the row's 64 bytes
+// of partial sums behind its 1536 bytes of data (fetched by the same cp.async group).
+constexpr int SWF_WARPS = 16;
+template <int HC>
+struct SwFoldRing {
+  static constexpr int DATA_BYTES = HC * 512;
+  static constexpr int SLOT_BYTES = DATA_BYTES + 64;          // + 8 float2 partial sums of the row
+  static constexpr int SLOTS = 7;
+  static constexpr int WARP_BYTES = SLOTS * SLOT_BYTES;
+};
+
+__global__ void __launch_bounds__(256)
+subword_coef_kernel(const float* __restrict__ alpha, const float* __restrict__ gamma_p, int n_layers,
+                    const float* __restrict__ ln_g, const float* __restrict__ ln_b, int H,
+                    float* __restrict__ G, float* __restrict__ C) {
+  // ln_g / ln_b: [n_layers][H] output-LayerNorm weights of the encoder layers
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float mx = -INFINITY;
+  for (int i = 0; i < n_layers; ++i) mx = fmaxf(mx, alpha[i]);
+  float den = 0.f;
+  for (int i = 0; i < n_layers; ++i) den += expf(alpha[i] - mx);
+  const float g = gamma_p[0];
+  float cc = 0.f;
+  for (int l = 0; l < n_layers; ++l) {
+    const float a = (expf(alpha[l] - mx) / den) * g;
+    G[static_cast<long long>(l) * H + c] = a * ln_g[static_cast<long long>(l) * H + c];
+    cc = fmaf(a, ln_b[static_cast<long long>(l) * H + c], cc);
+  }
+  C[c] = cc;
+}
+
+__device__ __forceinline__ void row_norm_from_partials(const float4 a, const float4 b, const float4 c, float inv_dim,
+                                                       float eps, float& r, float& nmr) {
+  const float s1 = ((a.x + a.z) + (b.x + b.z)) + (c.x + c.z);
+  const float s2 = ((a.y + a.w) + (b.y + b.w)) + (c.y + c.w);
+  const float mu = s1 * inv_dim;
+  const float var = fmaxf(fmaf(-mu, mu, s2 * inv_dim), 0.0f);
+  r = rsqrtf(var + eps);
+  nmr = -mu * r;
+}
+
+template <int HC, int CNT>
+__device__ __forceinline__ void subword_word_fold(const __nv_bfloat16* __restrict__ h, long long layer_stride,
+                                                  const float2* __restrict__ stats, long long stats_layer_stride,
+                                                  long long t0, int n_layers, const float* __restrict__ Gs,
+                                                  float eps, uint32_t ring, int lane, RowVec<HC>& tot) {
+  constexpr int H = HC * 256;
+  constexpr int SB = SwFoldRing<HC>::SLOT_BYTES;
+  constexpr int DB = SwFoldRing<HC>::DATA_BYTES;
+  constexpr int S = SwFoldRing<HC>::SLOTS / CNT;             // layers in flight
+  auto issue = [&](int l) {
+    const __nv_bfloat16* src = h + static_cast<long long>(l) * layer_stride + t0 * H + lane * 8;
+    const float2* ssrc = stats + static_cast<long long>(l) * stats_layer_stride + t0 * 8 + lane * 2;
+    const uint32_t dst = ring + static_cast<uint32_t>((l % S) * CNT) * SB;
+#pragma unroll
+    for (int t = 0; t < CNT; ++t) {
+#pragma unroll
+      for (int c = 0; c < HC; ++c)
+        cp_async16_zfill(dst + t * SB + c * 512 + lane * 16, src + static_cast<long long>(t) * H + c * 256, true);
+      // lanes 0-3 also fetch the row's 64 bytes of partial sums; every lane reads them back, hence the
+      // __syncwarp() after the wait below
+      if (lane < 4) cp_async16_zfill(dst + t * SB + DB + lane * 16, ssrc + static_cast<long long>(t) * 8, true);
+    }
+  };
+#pragma unroll 1
+  for (int l = 0; l < S; ++l) {
+    if (l < n_layers) issue(l);
+    cp_async_commit();
+  }
+  const float inv_cnt = 1.0f / static_cast<float>(CNT);
+#pragma unroll 1
+  for (int l = 0; l < n_layers; ++l) {
+    cp_async_wait<S - 1>();                                  // the group of layer l has landed (this lane's copies)
+    __syncwarp();                                            // ... and lanes 0-3's copies of the partial sums
+    RowVec<HC> acc;
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) acc.v[i] = 0.f;
+    const uint32_t base = ring + static_cast<uint32_t>((l % S) * CNT) * SB;
+#pragma unroll
+    for (int t = 0; t < CNT; ++t) {
+      float4 pa, pb, pc;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pa.x), "=f"(pa.y), "=f"(pa.z), "=f"(pa.w)
+                   : "r"(base + t * SB + DB));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pb.x), "=f"(pb.y), "=f"(pb.z), "=f"(pb.w)
+                   : "r"(base + t * SB + DB + 16));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pc.x), "=f"(pc.y), "=f"(pc.z), "=f"(pc.w)
+                   : "r"(base + t * SB + DB + 32));
+      float r, nmr;
+      row_norm_from_partials(pa, pb, pc, 1.0f / H, eps, r, nmr);
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {
+        uint4 u;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                     : "r"(base + t * SB + c * 512 + lane * 16));
+        acc.v[c * 8 + 0] += fmaf(bf16_lo(u.x), r, nmr); acc.v[c * 8 + 1] += fmaf(bf16_hi(u.x), r, nmr);
+        acc.v[c * 8 + 2] += fmaf(bf16_lo(u.y), r, nmr); acc.v[c * 8 + 3] += fmaf(bf16_hi(u.y), r, nmr);
+        acc.v[c * 8 + 4] += fmaf(bf16_lo(u.z), r, nmr); acc.v[c * 8 + 5] += fmaf(bf16_hi(u.z), r, nmr);
+        acc.v[c * 8 + 6] += fmaf(bf16_lo(u.w), r, nmr); acc.v[c * 8 + 7] += fmaf(bf16_hi(u.w), r, nmr);
+      }
+    }
+    __syncwarp();                                            // all lanes have read the partial sums of this slot
+    const float* gl = Gs + l * H;
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gl + c * 256 + lane * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gl + c * 256 + lane * 8 + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mean = (CNT > 1) ? acc.v[c * 8 + i] * inv_cnt : acc.v[c * 8 + i];
+        tot.v[c * 8 + i] = fmaf(mean, g[i], tot.v[c * 8 + i]);
+      }
+    }
+    if (l + S < n_layers) issue(l + S);
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+}
+
+template <int HC>
+__global__ void __launch_bounds__(SWF_WARPS * 32, 1)
+subword_avg_layers_fold_kernel(const __nv_bfloat16* __restrict__ h_b16, long long layer_stride,
+                               const float2* __restrict__ stats, long long stats_layer_stride, float eps,
+                               const int32_t* __restrict__ words, int n_words,
+                               const int32_t* __restrict__ row_start, const uint8_t* __restrict__ x_mask,
+                               int W, float* __restrict__ dst, long long dst_stride,
+                               const float* __restrict__ G, const float* __restrict__ C, int n_layers) {
+  constexpr int H = HC * 256;
+  extern __shared__ __align__(16) uint8_t sw_smem[];
+  float* Gs = reinterpret_cast<float*>(sw_smem);             // [n_layers][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n_layers * H / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(Gs)[i] = __ldg(reinterpret_cast<const float4*>(G) + i);
+  __syncthreads();
+  const uint32_t ring = smem_u32(sw_smem) + static_cast<uint32_t>(n_layers * H * 4) +
+                        static_cast<uint32_t>(warp) * SwFoldRing<HC>::WARP_BYTES;
+  for (long long w = static_cast<long long>(blockIdx.x) * SWF_WARPS + warp; w < n_words;
+       w += static_cast<long long>(gridDim.x) * SWF_WARPS) {
+    const int item = words[w];
+    const int j = words[n_words + w];
+    const int st = words[2LL * n_words + w];
+    const int ed = words[3LL * n_words + w];
+    if (j >= W) continue;
+    float* d = dst + (static_cast<long long>(item) * W + j) * dst_stride;
+    RowVec<HC> tot;
+#pragma unroll
+    for (int i = 0; i < HC * 8; ++i) tot.v[i] = 0.f;
+    const int cnt = ed - st;
+    // masked word / st >= ed: zeros (Bert.py:155-156,160-165), written explicitly (no zero-fill of dst)
+    if (!(x_mask != nullptr && x_mask[static_cast<long long>(item) * W + j] == 0) && cnt > 0) {
+      const long long t0 = static_cast<long long>(row_start[item]) + st;
+#pragma unroll
+      for (int c = 0; c < HC; ++c) {                         // C = sum_l a_l beta_l
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(C + c * 256 + lane * 8));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(C + c * 256 + lane * 8 + 4));
+        tot.v[c * 8 + 0] = c0.x; tot.v[c * 8 + 1] = c0.y; tot.v[c * 8 + 2] = c0.z; tot.v[c * 8 + 3] = c0.w;
+        tot.v[c * 8 + 4] = c1.x; tot.v[c * 8 + 5] = c1.y; tot.v[c * 8 + 6] = c1.z; tot.v[c * 8 + 7] = c1.w;
+      }
+      switch (cnt) {
+        case 1: subword_word_fold<HC, 1>(h_b16, layer_stride, stats, stats_layer_stride, t0, n_layers, Gs, eps, ring, lane, tot); break;
+        case 2: subword_word_fold<HC, 2>(h_b16, layer_stride, stats, stats_layer_stride, t0, n_layers, Gs, eps, ring, lane, tot); break;
+        case 3: subword_word_fold<HC, 3>(h_b16, layer_stride, stats, stats_layer_stride, t0, n_layers, Gs, eps, ring, lane, tot); break;
+        default: {
+          const float inv_cnt = 1.0f / static_cast<float>(cnt);
+          for (int l = 0; l < n_layers; ++l) {
+            RowVec<HC> acc;
+#pragma unroll
+            for (int i = 0; i < HC * 8; ++i) acc.v[i] = 0.f;
+            for (int t = 0; t < cnt; ++t) {
+              const float4* sp = reinterpret_cast<const float4*>(stats + l * stats_layer_stride + (t0 + t) * 8);
+              float r, nmr;
+              row_norm_from_partials(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2), 1.0f / H, eps, r, nmr);
+              RowVec<HC> x;
+              load_row_bf16<HC>(h_b16 + l * layer_stride + (t0 + t) * H, lane, x);
+#pragma unroll
+              for (int i = 0; i < HC * 8; ++i) acc.v[i] += fmaf(x.v[i], r, nmr);
+            }
+            const float* gl = Gs + l * H;
+#pragma unroll
+            for (int c = 0; c < HC; ++c)
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                tot.v[c * 8 + i] = fmaf(acc.v[c * 8 + i] * inv_cnt, gl[c * 256 + lane * 8 + i], tot.v[c * 8 + i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < HC; ++c) {
+      *reinterpret_cast<float4*>(d + c * 256 + lane * 8) =
+          make_float4(tot.v[c * 8 + 0], tot.v[c * 8 + 1], tot.v[c * 8 + 2], tot.v[c * 8 + 3]);
+      *reinterpret_cast<float4*>(d + c * 256 + lane * 8 + 4) =
+          make_float4(tot.v[c * 8 + 4], tot.v[c * 8 + 5], tot.v[c * 8 + 6], tot.v[c * 8 + 7]);
+    }
+  }
+}
+
 // Sequence bookkeeping of the packed layout, on the device (replaces a handful of torch integer ops):
 //   seq_lengths_kernel : one warp per row -> number of real tokens of the row and of each of its
 //                        512-token windows (written at the row's / windows' global slots)
@@ -1344,6 +1591,69 @@ extern "C" int ruart_bert_embed_ln(const int32_t* ids, const int32_t* pos, const
     bert_embed_ln_kernel<4><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
         ids, pos, word_emb, pos_emb, type_emb, gamma, beta, eps, T, out_f32,
         (__nv_bfloat16*)out_bf16, out_parts);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_bert_embed_raw(const int32_t* ids, const int32_t* pos, const float* word_emb,
+                                    const float* pos_emb, const float* type_emb, int T, int hidden,
+                                    void* out_bf16, float* out_stats, void* stream) {
+  RUART_ARG_CHECK(hidden == 768 || hidden == 1024);
+  RUART_ARG_CHECK(out_bf16 != nullptr && out_stats != nullptr);
+  if (T == 0) return RUART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hidden == 768)
+    bert_embed_raw_kernel<3><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        ids, pos, word_emb, pos_emb, type_emb, T, (__nv_bfloat16*)out_bf16, (float2*)out_stats);
+  else
+    bert_embed_raw_kernel<4><<<row_grid(T), ROWS_PER_CTA * 32, 0, st>>>(
+        ids, pos, word_emb, pos_emb, type_emb, T, (__nv_bfloat16*)out_bf16, (float2*)out_stats);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_subword_coef(const float* alpha, const float* gamma, int n_layers, const float* ln_gamma,
+                                  const float* ln_beta, int hidden, float* G, float* C, void* stream) {
+  RUART_ARG_CHECK(alpha != nullptr && gamma != nullptr && ln_gamma != nullptr && ln_beta != nullptr);
+  RUART_ARG_CHECK(G != nullptr && C != nullptr && n_layers >= 1 && hidden > 0);
+  subword_coef_kernel<<<(hidden + 255) / 256, 256, 0, (cudaStream_t)stream>>>(alpha, gamma, n_layers, ln_gamma,
+                                                                            ln_beta, hidden, G, C);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_subword_avg_layers_fold(const void* h_bf16, long long layer_stride, const float* stats,
+                                             long long stats_layer_stride, float ln_eps, const int32_t* words,
+                                             int n_words, const int32_t* row_start, const uint8_t* x_mask, int W,
+                                             float* dst, long long dst_stride, const float* G, const float* C,
+                                             int n_layers, int hidden, void* stream) {
+  RUART_ARG_CHECK(hidden == 768 || hidden == 1024);
+  RUART_ARG_CHECK(h_bf16 != nullptr && stats != nullptr && G != nullptr && C != nullptr && n_layers >= 1);
+  RUART_ARG_CHECK((dst_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+  RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(stats) & 15u) == 0 && (reinterpret_cast<uintptr_t>(G) & 15u) == 0);
+  if (n_words == 0) return RUART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ring = hidden == 768 ? SwFoldRing<3>::WARP_BYTES : SwFoldRing<4>::WARP_BYTES;
+  const size_t smem = static_cast<size_t>(n_layers) * hidden * 4 + SWF_WARPS * ring;
+  RUART_ARG_CHECK(smem <= 232448);
+  static RuartDeviceOnce attr_set;
+  if (!attr_set.done()) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(subword_avg_layers_fold_kernel<3>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(subword_avg_layers_fold_kernel<4>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set.set();
+  }
+  int grid = (n_words + SWF_WARPS - 1) / SWF_WARPS;
+  if (grid > ruart_num_sms()) grid = ruart_num_sms();
+  if (hidden == 768)
+    subword_avg_layers_fold_kernel<3><<<grid, SWF_WARPS * 32, smem, st>>>(
+        (const __nv_bfloat16*)h_bf16, layer_stride, (const float2*)stats, stats_layer_stride, ln_eps, words, n_words,
+        row_start, x_mask, W, dst, dst_stride, G, C, n_layers);
+  else
+    subword_avg_layers_fold_kernel<4><<<grid, SWF_WARPS * 32, smem, st>>>(
+        (const __nv_bfloat16*)h_bf16, layer_stride, (const float2*)stats, stats_layer_stride, ln_eps, words, n_words,
+        row_start, x_mask, W, dst, dst_stride, G, C, n_layers);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

@@ -96,6 +96,16 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote)
                : "memory");
 }
+// Same, without the release fence (MEMBAR.ALL.GPU + ERRBAR in SASS, which also drains the arriving thread's
+// outstanding bulk stores): for hand-offs whose only payload is TMEM that has already been read into
+// registers (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order it) — ncu showed the peer CTA's
+// elected epilogue thread spending 37 % of its time in that fence (profiles/r02_gemm_stalls.txt).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -347,9 +357,11 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // usual "tanh GELU" constants): max |gelu error| 2.5e-5 over all x before the MUFU.TANH rounding
 // (<= 2^-11 relative).  6 FMA-pipe + 2 ALU + 1 MUFU instructions; used for bf16 outputs only.
 __device__ __forceinline__ float gelu_erf_tanhfit(float x) {
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);  // the quartic turns over beyond |x| ~ 11
-  const float x2 = xc * xc;
-  const float u = xc * fmaf(fmaf(-0.00035151681f, x2, 0.0370056462f), x2, 0.797507884f);
+  // the quartic in x^2 peaks at x^2 = c1 / (2 |c2|) = 52.64 (|x| = 7.26, u = 12.8: tanh is 1 to fp32
+  // precision) and turns over beyond: clamping x^2 there keeps u monotone with ONE min instead of the
+  // two-sided clamp of x
+  const float x2 = fminf(x * x, 52.6f);
+  const float u = x * fmaf(fmaf(-0.00035151681f, x2, 0.0370056462f), x2, 0.797507884f);
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx(u), hx);
 }

@@ -69,6 +69,13 @@ struct GemmParams {
   long long out_part_stride;  // elements between parts inside one row
   const __nv_bfloat16* residual;  // TMA_OUT only: added (fp32) before rounding, or nullptr
   long long ld_res;
+  // folded LayerNorm (CTA-pair kernel, FOLD != 0; see the comment above gemm_bf16_2cta_kernel)
+  const float2* in_stats;   // [M][8] partial (sum, sum of squares) of the rows whose LayerNorm is pending:
+                            // FOLD 1: the rows of A; FOLD 2: the rows of the residual
+  const float* vec2;        // FOLD 1: colsum[n] = sum_k W'[n,k]; FOLD 2: gamma[n] of the residual's LayerNorm
+  float2* out_stats;        // FOLD 2: [M][8] partial sums of the rows written here (slot 2 * n_blk + group)
+  float ln_inv_dim;         // 1 / (width of the normalised rows)
+  float ln_eps;
 };
 
 template <int EPI>
@@ -81,6 +88,16 @@ __device__ __forceinline__ float epi_fn(float acc, float v) {
   if constexpr (EPI == K_RELU_SCALE) return fmaxf(acc, 0.0f) * v;
   if constexpr (EPI == K_BIAS_RELU) return fmaxf(acc + v, 0.0f);
   return acc;
+}
+
+// activation only (the folded-LayerNorm epilogue has already formed the pre-activation)
+template <int EPI>
+__device__ __forceinline__ float epi_act(float x) {
+  if constexpr (EPI == K_GELU_FAST) return gelu_erf_fast(x);
+  if constexpr (EPI == K_GELU_EXACT) return gelu_erf(x);
+  if constexpr (EPI == K_GELU_TANHFIT) return gelu_erf_tanhfit(x);
+  if constexpr (EPI == K_BIAS_RELU) return fmaxf(x, 0.0f);
+  return x;
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -426,7 +443,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 //   tmem_empty (leader's) 4 arrivals: one elected thread per epilogue group of each CTA (the peer's
 //                         arrive remotely)
 // The epilogue is the TMA-store epilogue of the kernel above, per CTA on its own 128 rows.
-template <int EPI, bool HAS_RES>
+//
+// Folded LayerNorm (FOLD != 0, bf16 BERT).  BertLayerNorm is affine per row, y = (v - mu) r gamma + beta, so it
+// never has to be materialised between two GEMMs:
+//   FOLD 2 (BertSelfOutput / BertOutput dense, modeling.py:260-264,299-303): the epilogue adds the residual
+//           and writes the PRE-LayerNorm rows v (bf16) plus, per row and per 128-column half-tile, the partial
+//           sums (sum v, sum v^2) taken from the fp32 values; the residual itself is still "pending" its own
+//           LayerNorm, which is applied on the fly from ITS partial sums: res = (v~ r - mu r) gamma + (beta + bias)
+//   FOLD 1 (the GEMM that consumes LayerNorm(v): query/key/value, BertIntermediate): A = v~ as stored,
+//           W' = W * gamma (folded on the host), and the epilogue finishes the normalisation,
+//           out = r acc - r mu colsum(W') + (W beta + bias)
+// 24 LayerNorm passes per forward (1.6 ms, 8.4 GB of DRAM traffic at cfg-3) disappear.  Shared memory is full
+// (6 stages + 2 staging buffers), so the two per-column vectors of a FOLD tile are single-buffered and one more
+// 256-thread barrier per tile protects them.
+template <int EPI, bool HAS_RES, int FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b,
@@ -544,6 +574,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (both CTAs)
+    static_assert(FOLD == 0 || (FOLD == 1 && !HAS_RES) || (FOLD == 2 && HAS_RES && EPI == K_BIAS), "fold forms");
     const int grp = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int et = threadIdx.x - 128 - grp * 128;
@@ -558,11 +589,32 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = tile - m_pair * n_tiles;
       const int m_blk = 2 * m_pair + static_cast<int>(rank);
       const int tile_col0 = n_blk * MAX_BN;
-      float* vec = s_vec + (tile_ctr & 1u) * MAX_BN;
+      float* vec = s_vec + (FOLD ? 0u : (tile_ctr & 1u) * MAX_BN);
+      float* vec2 = s_vec + MAX_BN;  // FOLD only
+      if (FOLD) epi_all_bar_sync();  // single-buffered vectors: the previous tile's readers are done
       if (EPI != K_NONE) {
-        for (int i = et + grp * 128; i < MAX_BN; i += 256)
+        for (int i = et + grp * 128; i < MAX_BN; i += 256) {
           vec[i] = __ldg(p.vec + static_cast<long long>(tile_col0 + i) * p.vec_stride);
+          if (FOLD) vec2[i] = __ldg(p.vec2 + tile_col0 + i);
+        }
       }
+      // pending LayerNorm of this thread's row: r = rstd, nmr = -mean * rstd
+      float ln_r = 1.0f, ln_nmr = 0.0f;
+      if constexpr (FOLD != 0) {
+        const int row = m_blk * BM + r_local;
+        float s1 = 0.f, s2 = 1.0f / p.ln_inv_dim;  // harmless unit-variance stand-in for rows past M
+        if (row < p.M) {
+          const float4* sp = reinterpret_cast<const float4*>(p.in_stats + static_cast<long long>(row) * 8);
+          const float4 a = __ldg(sp), b = __ldg(sp + 1), c = __ldg(sp + 2);
+          s1 = ((a.x + a.z) + (b.x + b.z)) + (c.x + c.z);
+          s2 = ((a.y + a.w) + (b.y + b.w)) + (c.y + c.w);
+        }
+        const float mu = s1 * p.ln_inv_dim;
+        const float var = fmaxf(fmaf(-mu, mu, s2 * p.ln_inv_dim), 0.0f);
+        ln_r = rsqrtf(var + p.ln_eps);
+        ln_nmr = -mu * ln_r;
+      }
+      float st1 = 0.f, st2 = 0.f;  // FOLD 2: this thread's partial sums over its 128 columns
       epi_all_bar_sync();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -586,7 +638,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           grp_bar_sync(grp);
           if (issuer) {
             if (leader) mbar_arrive(&tmem_empty_bar[acc]);
-            else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else mbar_arrive_cluster_relaxed(&tmem_empty_bar[acc], 0);
           }
         }
         uint8_t* row_ptr = cbuf + r_local * 128;
@@ -598,10 +650,18 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int j = c * 8 + q * 2;
-              const float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
-              const float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
+              float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+              float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
               const float2 bv = *reinterpret_cast<const float2*>(vec + c0 + j);
-              pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x), epi_fn<EPI>(x1, bv.y));
+              if constexpr (FOLD == 1) {
+                // LayerNorm(v) W^T + b  =  r acc + (-mu r) colsum + (W beta + b)
+                const float2 cs = *reinterpret_cast<const float2*>(vec2 + c0 + j);
+                x0 = fmaf(ln_r, x0, fmaf(ln_nmr, cs.x, bv.x));
+                x1 = fmaf(ln_r, x1, fmaf(ln_nmr, cs.y, bv.y));
+                pk[q] = pack_bf16x2(epi_act<EPI>(x0), epi_act<EPI>(x1));
+              } else {
+                pk[q] = pack_bf16x2(epi_fn<EPI>(x0, bv.x), epi_fn<EPI>(x1, bv.y));
+              }
             }
             pk4[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
@@ -611,14 +671,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int c = 0; c < 8; ++c)
             *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r_local & 7)) << 4)) = pk4[c];
         } else {
+          if constexpr (FOLD == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 b0 = *reinterpret_cast<const float2*>(vec + c0 + j);
-            const float2 b1 = *reinterpret_cast<const float2*>(vec + c0 + 32 + j);
-            v0[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j]), b0.x));
-            v0[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j + 1]), b0.y));
-            v1[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j]), b1.x));
-            v1[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j + 1]), b1.y));
+            for (int j = 0; j < 32; j += 2) {
+              const float2 b0 = *reinterpret_cast<const float2*>(vec + c0 + j);
+              const float2 b1 = *reinterpret_cast<const float2*>(vec + c0 + 32 + j);
+              v0[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j]), b0.x));
+              v0[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v0[j + 1]), b0.y));
+              v1[j] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j]), b1.x));
+              v1[j + 1] = __float_as_uint(epi_fn<EPI>(__uint_as_float(v1[j + 1]), b1.y));
+            }
           }
           mbar_wait(&res_bar[grp], res_phase);
           res_phase ^= 1u;
@@ -631,9 +693,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int j = c * 8 + q * 2;
-              const float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
-              const float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
-              pk[q] = pack_bf16x2(x0 + bf16_lo(rw[q]), x1 + bf16_hi(rw[q]));
+              float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+              float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
+              if constexpr (FOLD == 2) {
+                // residual = LayerNorm(stored rows) = (v~ r - mu r) gamma + beta; vec holds beta + dense bias
+                const float2 gm = *reinterpret_cast<const float2*>(vec2 + c0 + j);
+                const float2 bt = *reinterpret_cast<const float2*>(vec + c0 + j);
+                x0 += fmaf(fmaf(bf16_lo(rw[q]), ln_r, ln_nmr), gm.x, bt.x);
+                x1 += fmaf(fmaf(bf16_hi(rw[q]), ln_r, ln_nmr), gm.y, bt.y);
+                st1 += x0 + x1;
+                st2 = fmaf(x0, x0, fmaf(x1, x1, st2));
+              } else {
+                x0 += bf16_lo(rw[q]);
+                x1 += bf16_hi(rw[q]);
+              }
+              pk[q] = pack_bf16x2(x0, x1);
             }
             *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
@@ -644,6 +718,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tma_store_2d(&tmap_c, cbuf, tile_col0 + c0, m_blk * BM);
           bulk_commit();
         }
+      }
+      if constexpr (FOLD == 2) {
+        const int row = m_blk * BM + r_local;
+        if (row < p.M) p.out_stats[static_cast<long long>(row) * 8 + n_blk * 2 + grp] = make_float2(st1, st2);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -815,6 +893,11 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   p.out_part_stride = out_part_stride;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16);
   p.ld_res = ld_res;
+  p.in_stats = nullptr;
+  p.vec2 = nullptr;
+  p.out_stats = nullptr;
+  p.ln_inv_dim = 0.f;
+  p.ln_eps = 0.f;
   if (residual_bf16 != nullptr) {
     // fused residual: staged TMA-store epilogue only, whole 64-column chunks, 16-byte aligned rows
     RUART_ARG_CHECK(tma_out && kind == K_BIAS && (N % 64) == 0 && (ld_res % 8) == 0 &&
@@ -844,10 +927,10 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   GemmKernel kern2 = nullptr;
   static RuartDeviceOnce pair_launch_bad;  // this device rejected the CTA-pair launch
   if (!one_cta && !pair_launch_bad.done() && tma_out && n_terms == 1 && (N % MAX_BN) == 0 && M >= 2 * BM * 8) {
-    if (has_res) kern2 = gemm_bf16_2cta_kernel<K_BIAS, true>;
-    else if (kind == K_BIAS) kern2 = gemm_bf16_2cta_kernel<K_BIAS, false>;
-    else if (kind == K_GELU_FAST) kern2 = gemm_bf16_2cta_kernel<K_GELU_FAST, false>;
-    else if (kind == K_GELU_TANHFIT) kern2 = gemm_bf16_2cta_kernel<K_GELU_TANHFIT, false>;
+    if (has_res) kern2 = gemm_bf16_2cta_kernel<K_BIAS, true, 0>;
+    else if (kind == K_BIAS) kern2 = gemm_bf16_2cta_kernel<K_BIAS, false, 0>;
+    else if (kind == K_GELU_FAST) kern2 = gemm_bf16_2cta_kernel<K_GELU_FAST, false, 0>;
+    else if (kind == K_GELU_TANHFIT) kern2 = gemm_bf16_2cta_kernel<K_GELU_TANHFIT, false, 0>;
   }
   if (kern2 != nullptr) {
     CUtensorMap tmb2;
@@ -888,6 +971,76 @@ extern "C" int ruart_gemm_bf16(const void* A, long long lda, int a_parts, const 
   const int total = m_tiles * n_tiles;
   const int grid = total < ruart_num_sms() ? total : ruart_num_sms();
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, tmr, p);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+// CTA-pair GEMM with a folded LayerNorm (see the comment above gemm_bf16_2cta_kernel; bf16 BERT encoder only).
+//   fold 1: out = act( LayerNorm(A) W^T + b )   given A = the stored pre-LayerNorm rows, W = W0 * gamma (host),
+//           vec = W0 beta + b, vec2 = colsum(W), in_stats = partial sums of A's rows (ln_dim = K)
+//           act: RUART_EPI_BIAS (none) or RUART_EPI_BIAS_GELU (fitted-tanh erf-GELU)
+//   fold 2: out = A W^T + LayerNorm(residual) + b, pre-LayerNorm rows + their partial sums (out_stats):
+//           vec = beta + b, vec2 = gamma, in_stats = partial sums of the residual's rows (ln_dim = N)
+// Needs the CTA-pair kernel (M >= 2048, N % 256 == 0, cluster launch available): returns RUART_ERR_ARG
+// otherwise and the caller keeps the explicit LayerNorm pass.
+extern "C" int ruart_gemm_bf16_fold(const void* A, long long lda, const void* W, long long ldw, int M, int N,
+                                    int Kp, int fold, int epi, const float* vec, const float* vec2,
+                                    const float* in_stats, float ln_eps, void* out_bf16, long long ldo,
+                                    const void* residual_bf16, long long ld_res, float* out_stats,
+                                    void* stream) {
+  RUART_ARG_CHECK(M >= 2 * BM * 8 && N > 0 && (N % MAX_BN) == 0 && Kp > 0 && (Kp % BK) == 0);
+  RUART_ARG_CHECK((lda % 8) == 0 && (ldw % 8) == 0 && (ldo % 8) == 0);
+  RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_bf16) & 15u) == 0);
+  RUART_ARG_CHECK(vec != nullptr && vec2 != nullptr && in_stats != nullptr &&
+                  (reinterpret_cast<uintptr_t>(in_stats) & 15u) == 0);
+  RUART_ARG_CHECK(fold == 1 || fold == 2);
+  RUART_ARG_CHECK((fold == 1 ? Kp : N) == 768);  // the epilogues sum 6 partial-sum slots = 3 column tiles x 2 groups
+  GemmKernel kern = nullptr;
+  int slot = 0;
+  if (fold == 1) {
+    RUART_ARG_CHECK(residual_bf16 == nullptr && (epi == RUART_EPI_BIAS || epi == RUART_EPI_BIAS_GELU));
+    if (epi == RUART_EPI_BIAS) { kern = gemm_bf16_2cta_kernel<K_BIAS, false, 1>; slot = 0; }
+    else { kern = gemm_bf16_2cta_kernel<K_GELU_TANHFIT, false, 1>; slot = 1; }
+  } else {
+    RUART_ARG_CHECK(residual_bf16 != nullptr && out_stats != nullptr && epi == RUART_EPI_BIAS && (ld_res % 8) == 0 &&
+                    (reinterpret_cast<uintptr_t>(residual_bf16) & 15u) == 0 && N <= 4 * MAX_BN);
+    kern = gemm_bf16_2cta_kernel<K_BIAS, true, 2>;
+    slot = 2;
+  }
+  GemmParams p;
+  p.M = M; p.N = N; p.Kp = Kp; p.block_n = MAX_BN; p.n_terms = 1; p.term_a = 0; p.term_b = 0;
+  p.vec = vec; p.vec_stride = 1;
+  p.out_f32 = nullptr; p.ldo_f32 = 0;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ldo_bf16 = ldo; p.out_parts = 1; p.out_part_stride = 0;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual_bf16); p.ld_res = ld_res;
+  p.in_stats = reinterpret_cast<const float2*>(in_stats);
+  p.vec2 = vec2;
+  p.out_stats = reinterpret_cast<float2*>(out_stats);
+  p.ln_inv_dim = 1.0f / static_cast<float>(fold == 1 ? Kp : N);
+  p.ln_eps = ln_eps;
+  if (M == 0) return RUART_OK;
+  CUtensorMap tma, tmb, tmc, tmr;
+  int rc = make_tmap_bf16(&tma, A, M, Kp, lda, BM);
+  if (rc != RUART_OK) return rc;
+  rc = make_tmap_bf16(&tmb, W, N, Kp, ldw, B2_ROWS);
+  if (rc != RUART_OK) return rc;
+  rc = make_tmap_bf16(&tmc, out_bf16, M, N, ldo, BM);
+  if (rc != RUART_OK) return rc;
+  tmr = tmc;
+  if (residual_bf16 != nullptr) {
+    rc = make_tmap_bf16(&tmr, residual_bf16, M, N, ld_res, BM);
+    if (rc != RUART_OK) return rc;
+  }
+  static RuartDeviceOnce attr[3];
+  if (!attr[slot].done()) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+    attr[slot].set();
+  }
+  const int pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / MAX_BN);
+  int grid2 = ruart_num_sms() & ~1;
+  if (grid2 > 2 * pair_tiles) grid2 = 2 * pair_tiles;
+  kern<<<grid2, GEMM_THREADS, GEMM2_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, tmr, p);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

@@ -81,3 +81,109 @@ def test_add_layernorm_and_embed():
     s = (y - u).pow(2).mean(-1, keepdim=True)
     want = g * ((y - u) / torch.sqrt(s + 1e-12)) + b
     assert (out - want).abs().max().item() < 1e-4
+
+
+def test_embed_raw_and_folded_subword_mix():
+    """ruart_bert_embed_raw / ruart_subword_coef / ruart_subword_avg_layers_fold (the ends of the folded-LayerNorm
+    encoder) against torch: LayerNorm of the stored rows, subword mean (Bert.py:149-165), learned layer sum
+    (SDNet.py:573-583)."""
+    from ruart_b200._lib import call, current_stream, ptr
+    st = current_stream()
+    T, H, NL, eps = 3300, 768, 12, 1e-12
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    ids = torch.randint(0, 3000, (T,), device="cuda", dtype=torch.int32)
+    pos = torch.randint(0, 512, (T,), device="cuda", dtype=torch.int32)
+    we, pe, te = rnd(3000, H), rnd(512, H), rnd(2, H)
+    raw = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+    stats = torch.full((T, 8, 2), 9.0, device="cuda")
+    call("ruart_bert_embed_raw", ptr(ids), ptr(pos), ptr(we), ptr(pe), ptr(te), T, H, ptr(raw), ptr(stats), st)
+    y = we[ids.long()] + pe[pos.long()] + te[0]
+    assert (raw.float() - y).abs().max().item() < 2e-2 * y.abs().max().item()
+    assert (stats[:, 0, 0] - y.sum(1)).abs().max().item() < 1e-2
+    assert ((stats[:, 0, 1] - (y * y).sum(1)).abs() / (y * y).sum(1)).max().item() < 1e-5
+    assert (stats[:, 1:] == 0).all()
+    # ---- layer mix over NL stored (pre-LayerNorm) layers
+    hs = (rnd(NL, T, H) * 1.7 + 0.3).bfloat16()
+    x = hs.float()
+    stt = torch.zeros(NL, T, 8, 2, device="cuda")
+    for k, chunk in enumerate(x.split(128, dim=2)):
+        stt[:, :, k, 0] = chunk.sum(2)
+        stt[:, :, k, 1] = (chunk * chunk).sum(2)
+    ln_g, ln_b = rnd(NL, H) * 0.4 + 1.0, rnd(NL, H) * 0.2
+    alpha, gam = rnd(NL), torch.tensor([[1.3]], device="cuda")
+    G = torch.empty(NL, H, device="cuda")
+    C = torch.empty(H, device="cuda")
+    call("ruart_subword_coef", ptr(alpha), ptr(gam), NL, ptr(ln_g), ptr(ln_b), H, ptr(G), ptr(C), st)
+    a = torch.softmax(alpha, 0) * 1.3
+    assert (G - a[:, None] * ln_g).abs().max().item() < 1e-5 and (C - (a[:, None] * ln_b).sum(0)).abs().max().item() < 1e-5
+    # items of 1..6 pieces (1-3: pipelined path, 4+: synchronous path), one masked word, one st == ed word
+    N, Wd = 300, 3
+    words, row_start, t0 = [], [], 0
+    for it in range(N):
+        row_start.append(t0)
+        o = 0
+        for j in range(Wd):
+            cnt = (it + j) % 6 + 1
+            words.append((it, j, o, o + (0 if (it, j) == (7, 1) else cnt)))
+            o += cnt
+        t0 += o
+    assert t0 <= T
+    wt = torch.tensor(words, dtype=torch.int32, device="cuda").t().contiguous()
+    rs = torch.tensor(row_start, dtype=torch.int32, device="cuda")
+    wmask = torch.ones(N, Wd, dtype=torch.uint8, device="cuda")
+    wmask[5, 2] = 0
+    dst = torch.full((N, Wd, H + 4), 5.0, device="cuda")
+    call("ruart_subword_avg_layers_fold", ptr(hs), T * H, ptr(stt), T * 8, eps, ptr(wt), len(words), ptr(rs), ptr(wmask), Wd,
+         dst.data_ptr(), H + 4, ptr(G), ptr(C), NL, H, st)
+    torch.cuda.synchronize()
+    u = x.mean(-1, keepdim=True)
+    yn = (x - u) / torch.sqrt((x - u).pow(2).mean(-1, keepdim=True) + eps) * ln_g[:, None, :] + ln_b[:, None, :]
+    for it, j, s, e in words[:60] + words[-30:]:
+        got = dst[it, j, :H]
+        if wmask[it, j] == 0 or e <= s:
+            assert (got == 0).all()
+            continue
+        want = sum(a[l] * yn[l, row_start[it] + s:row_start[it] + e].mean(0) for l in range(NL))
+        assert (got - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item()), (it, j, s, e)
+    assert (dst[..., H:] == 5.0).all()
+
+
+def test_folded_layernorm_encoder_matches_unfolded():
+    """The bf16 encoder with every LayerNorm folded into the neighbouring GEMMs (BertEngine._encode_hidden_fold)
+    against the explicit-LayerNorm bf16 encoder and the fp32-mode encoder on the same packed batch."""
+    import contextlib, io
+    from ruart_b200.Models.Bert.Bert import Bert
+    from ruart_b200.bert_engine import Segment
+    torch.manual_seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        bert = Bert({'BERT_LINEAR_COMBINE': True, 'BERT_num_layers': 3, 'BERT_model_file': ''})
+    for p in bert.parameters():                     # non-trivial LayerNorm weights
+        if p.dim() == 1:
+            p.data.add_(torch.randn_like(p) * 0.2)
+    N, L, Wd, H = 700, 8, 3, 768
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(3, L + 1, (N,), generator=g)
+    ids = torch.randint(1000, 30000, (N, L), generator=g)
+    mask = torch.arange(L)[None, :] < lens[:, None]
+    ids = (ids * mask).cuda()
+    offsets = [[[1 + j, 2 + j] for j in range(min(Wd, int(lens[i]) - 2))] for i in range(N)]
+    wmask = torch.tensor([[j < len(o) for j in range(Wd)] for o in offsets]).cuda()
+    seg = lambda: [Segment(ids, mask.cuda(), offsets, wmask)]
+    alpha = torch.randn(3).cuda()
+    gamma = torch.tensor([[0.9]]).cuda()
+    outs = {}
+    for name, prec, fold in (("fold", "bf16", True), ("plain", "bf16", False), ("fp32", "fp32", False)):
+        bert.precision = prec
+        eng = bert.engine()
+        eng.fold = fold and eng.fold
+        dst = torch.zeros(N, Wd, H, device="cuda")
+        pk = eng.encode(seg(), [(dst, H, 0)], alpha=alpha, gamma=gamma)
+        assert ("fold" in pk) == (name == "fold")
+        outs[name] = dst
+        bert._engine = None
+    torch.cuda.synchronize()
+    scale = outs["fp32"].abs().max().item()
+    e_fold = (outs["fold"] - outs["fp32"]).abs().max().item() / scale
+    e_plain = (outs["plain"] - outs["fp32"]).abs().max().item() / scale
+    assert e_plain < 3e-2 and e_fold < max(1.5 * e_plain, 1e-2), (e_fold, e_plain)

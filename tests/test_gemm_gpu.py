@@ -147,3 +147,74 @@ def test_gemm_cta_pair_path(M, N, K, kind):
     assert (out[rows].float() - want).abs().max().item() < 1e-2 * max(1.0, want.abs().max().item())
     assert (buf[M] == 7.0).all() and (buf[:, N:] == 7.0).all()
     assert torch.isfinite(out.float()).all()
+
+
+def _partials(x, slots=6):
+    """[M, H] fp32 -> [M, 8, 2] partial (sum, sum of squares) spread over `slots` column groups."""
+    M, H = x.shape
+    st = torch.zeros(M, 8, 2, device=x.device)
+    for k, chunk in enumerate(x.split(H // slots, dim=1)):
+        st[:, k, 0] = chunk.sum(1)
+        st[:, k, 1] = (chunk * chunk).sum(1)
+    return st.contiguous()
+
+
+def _ln(x, g, b, eps=1e-12):
+    u = x.mean(-1, keepdim=True)
+    s = (x - u).pow(2).mean(-1, keepdim=True)
+    return (x - u) / torch.sqrt(s + eps) * g + b
+
+
+@pytest.mark.parametrize("M", [2048, 5000, 20011])
+def test_gemm_folded_layernorm_forms(M):
+    """ruart_gemm_bf16_fold (the CTA-pair GEMM with BertLayerNorm folded in, modeling.py:155-168,260-264,287,299-303)
+    against LayerNorm + matmul in torch fp32 on the same bf16-rounded operands."""
+    from ruart_b200._lib import call, current_stream, ptr
+    H, eps = 768, 1e-12
+    g = torch.Generator(device="cuda").manual_seed(M)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    gamma, beta = rnd(H) * 0.5 + 1.0, rnd(H) * 0.3
+    # ---- fold 2: out = A W^T + LayerNorm(residual) + b (pre-LayerNorm rows) + partial sums of out
+    for K in (768, 3072):
+        a = (rnd(M, K) * 0.5).bfloat16()
+        w = (rnd(H, K) * 0.03).bfloat16()
+        bias = rnd(H)
+        raw = (rnd(M, H) * 2.0 + 0.7).bfloat16()                     # stored rows whose LayerNorm is pending
+        st_in = _partials(raw.float())
+        out = torch.full((M + 1, H), 7.0, device="cuda", dtype=torch.bfloat16)
+        st_out = torch.zeros(M + 1, 8, 2, device="cuda")
+        call("ruart_gemm_bf16_fold", ptr(a), K, ptr(w), K, M, H, K, 2, 1, ptr((beta + bias).contiguous()), ptr(gamma),
+             ptr(st_in), eps, ptr(out), H, ptr(raw), H, ptr(st_out), current_stream())
+        torch.cuda.synchronize()
+        want = a.float() @ w.float().t() + _ln(raw.float(), gamma, beta, eps) + bias
+        scale = want.abs().max().item()
+        assert (out[:M].float() - want).abs().max().item() < 1e-2 * scale
+        assert (out[M] == 7.0).all() and (st_out[M] == 0).all()      # nothing past the last row
+        s1, s2 = st_out[:M, :6, 0].sum(1), st_out[:M, :6, 1].sum(1)
+        assert (s1 - want.sum(1)).abs().max().item() < 2e-3 * scale * H ** 0.5
+        assert ((s2 - (want * want).sum(1)).abs() / (want * want).sum(1)).max().item() < 1e-3
+    # ---- fold 1: out = act(LayerNorm(A) W0^T + b) from the stored rows A, W0 * gamma, colsum and W0 beta + b
+    for N, epi in ((2304, 1), (3072, 2)):
+        raw = (rnd(M, H) * 1.5 - 0.4).bfloat16()
+        w0 = rnd(N, H) * 0.03
+        bias = rnd(N)
+        wf = (w0 * gamma[None, :]).bfloat16().contiguous()
+        colsum = wf.float().sum(1).contiguous()
+        cvec = (w0 @ beta + bias).contiguous()
+        st_in = _partials(raw.float(), slots=3)
+        out = torch.full((M + 1, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        call("ruart_gemm_bf16_fold", ptr(raw), H, ptr(wf), H, M, N, H, 1, epi, ptr(cvec), ptr(colsum), ptr(st_in), eps,
+             ptr(out), N, None, 0, None, current_stream())
+        torch.cuda.synchronize()
+        # the same algebra in fp32 on the same rounded operands (tight), and the unfolded definition (bf16-level)
+        x = raw.float()
+        u = x.mean(-1, keepdim=True)
+        r = torch.rsqrt((x * x).mean(-1, keepdim=True) - u * u + eps)
+        pre = r * (x @ wf.float().t()) - (r * u) * colsum + cvec
+        ref = _ln(x, gamma, beta, eps) @ w0.t() + bias
+        if epi == 2:
+            pre, ref = torch.nn.functional.gelu(pre), torch.nn.functional.gelu(ref)
+        scale = ref.abs().max().item()
+        assert (out[:M].float() - pre).abs().max().item() < 6e-3 * scale
+        assert (out[:M].float() - ref).abs().max().item() < 2.5e-2 * scale
+        assert (out[M] == 7.0).all()

@@ -51,3 +51,36 @@ for name, N, K, epi, has_res in shapes:
     print("%-12s M=%d N=%d K=%d  ours %.3f ms  %.1f TFLOP/s | cublas %.3f ms %.1f TFLOP/s" %
           (name, M, N, K, t, fl / t / 1e9, tc, fl / tc / 1e9))
 print("layer total: %.3f ms, %.1f TFLOP/s ; x12 layers = %.1f ms" % (tot_t, tot_f / tot_t / 1e9, 12 * tot_t))
+
+# ---- the same four GEMMs with the folded BertLayerNorm epilogues (ruart_gemm_bf16_fold)
+from ruart_b200._lib import call, current_stream, ptr  # noqa: E402
+H = 768
+stats = torch.zeros(M, 8, 2, device="cuda")
+stats[:, 0, 1] = H
+stats2 = torch.zeros(M, 8, 2, device="cuda")
+tot_t = 0.0
+for name, N, K, epi, fold in [("qkv", 2304, 768, 1, 1), ("attn_out+res", 768, 768, 1, 2), ("ffn_up+gelu", 3072, 768, 2, 1),
+                              ("ffn_down+res", 768, 3072, 1, 2)]:
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    v1, v2 = torch.randn(N, device="cuda"), torch.randn(N, device="cuda")
+    o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(M, N, device="cuda").bfloat16() if fold == 2 else None
+    run = lambda: call("ruart_gemm_bf16_fold", ptr(a), K, ptr(w), K, M, N, K, fold, epi, ptr(v1), ptr(v2), ptr(stats), 1e-12,
+                       ptr(o), N, ptr(res), N if fold == 2 else 0, ptr(stats2) if fold == 2 else None, current_stream())
+    for _ in range(3):
+        run()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = sorted(ts)[len(ts) // 2]
+    tot_t += t
+    print("fold %-12s N=%d K=%d  %.3f ms  %.1f TFLOP/s" % (name, N, K, t, 2.0 * M * N * K / t / 1e9))
+print("folded layer total: %.3f ms ; x12 layers = %.1f ms (no LayerNorm passes)" % (tot_t, 12 * tot_t))
