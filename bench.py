@@ -552,6 +552,8 @@ def main():
             return _TimedK("subword_avg_layers")
         if name == "ruart_gemm_bf16_fold":     # the BERT GEMMs with the folded LayerNorms (bf16 mode)
             return _Timed(2.0 * a[4] * a[5] * a[6])
+        if name == "ruart_qkv_attention_fold":  # query/key/value GEMM with the attention in its epilogue: projection FLOPs only
+            return _Timed(2.0 * a[4] * a[5] * (a[6] * 192))
         if name != "ruart_gemm_bf16":
             return null
         M_, N_, Kp_, terms = a[6], a[7], a[8], a[9]

@@ -98,6 +98,23 @@ RUART_API int ruart_gemm_bf16_fold(const void* A, long long lda, const void* W, 
                                    const void* residual_bf16, long long ld_res, float* out_stats,
                                    void* stream);
 
+/* Fused query/key/value projection + self-attention of the folded bf16 encoder (BertSelfAttention.forward,
+ * modeling.py:224-250): ctx = softmax(Q K^T / 8 + mask) V per sequence and head, with Q|K|V = LayerNorm(A) W0^T + b
+ * computed tile by tile and never written to memory.  A = the stored pre-LayerNorm rows + in_stats (as fold 1 of
+ * ruart_gemm_bf16_fold); W = (W0 * gamma) with rows permuted head-major [q_h / 8 ; k_h ; v_h] (192 rows per head),
+ * vec / vec2 = W0 beta + b and colsum(W) permuted / scaled alike; tile_meta / tok_bounds from ruart_seq_tiles.
+ * Needs M >= 2048, Kp == 768, every sequence <= 128 tokens.                                                   */
+RUART_API int ruart_qkv_attention_fold(const void* A, long long lda, const void* W, long long ldw, int M, int Kp,
+                                       int n_heads, const float* vec, const float* vec2, const float* in_stats,
+                                       float ln_eps, const int32_t* tile_meta, const int32_t* tok_bounds,
+                                       void* out_bf16, long long ldo, void* stream);
+/* Row tiles for ruart_qkv_attention_fold from the sequence offsets cu_seq[S + 1] of the packed layout: whole
+ * consecutive sequences, at most 128 rows per tile (greedy).  meta[0] = number of tiles n, meta[1 .. n] = first row
+ * of each tile, meta[n + 1] = cu_seq[S]; capacity (ints) >= 2 * T / 128 + 8.  tok_bounds [T][2] = (first row, end
+ * row) of every token's sequence.                                                                             */
+RUART_API int ruart_seq_tiles(const int32_t* cu_seq, int S, int32_t* meta, int capacity, int32_t* tok_bounds,
+                              void* stream);
+
 /* ---------------------------------------------------------------- BERT (packed, pad-free rows)
  * Activations are [T, hidden] row-major over the T real wordpieces of all sequences; every
  * kernel accepts fp32 and/or bf16 pointers (exactly one input representation, any outputs).

@@ -74,7 +74,8 @@ class Bert(nn.Module):
     def pack_begin(self, segments):
         """Start the token packing of `segments` on a side stream (see BertEngine.pack_begin)."""
         segs = [Segment(*s) for s in segments]
-        return self.engine().pack_begin(segs)
+        eng = self.engine()
+        return eng.pack_begin(segs, want_tiles=eng.fuse_attn)
 
     def encode_into(self, segments, sinks, alpha, gamma, pack_handle=None):
         """Fused path: segments = [(ids, mask, offsets, word_mask)], sinks = [(dst, stride, col)].

@@ -34,6 +34,9 @@ _SIGNATURES = {
                         c_ll, c_int, c_void_p, c_ll, c_void_p],
     "ruart_gemm_bf16_fold": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_float, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p],
+    "ruart_qkv_attention_fold": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_float, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
+    "ruart_seq_tiles": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "ruart_bert_embed_raw": [c_void_p] * 5 + [c_int, c_int, c_void_p, c_void_p, c_void_p],
     "ruart_subword_coef": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "ruart_subword_avg_layers_fold": [c_void_p, c_ll, c_void_p, c_ll, c_float, c_void_p, c_int, c_void_p, c_void_p,
@@ -134,7 +137,7 @@ def check(rc):
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-_KERNELS_PER_CALL = {"ruart_whole_layernorm": 2, "ruart_whole_layernorm_stats": 2, "ruart_colsum": 2,
+_KERNELS_PER_CALL = {"ruart_seq_tiles": 2, "ruart_whole_layernorm": 2, "ruart_whole_layernorm_stats": 2, "ruart_colsum": 2,
                      "ruart_whole_layernorm_backward": 2, "ruart_subword_layers_backward": 2, "ruart_embedding_grad": 3}
 launch_count = 0
 _timing_hook = None  # set by bench.py: callable(name, args) -> context manager, or None

@@ -103,6 +103,9 @@ class BertEngine(object):
         # of the CTA-pair GEMM); needs the pair kernel (T >= FOLD_MIN_T) and 768-wide rows.  RUART_NO_LN_FOLD: A/B aid.
         self.fold = (mode == "bf16" and not residual_fp32 and self.H == 768
                      and os.environ.get("RUART_NO_LN_FOLD") is None)
+        # ... and the attention runs inside the query/key/value GEMM's epilogue (ruart_qkv_attention_fold) when every
+        # sequence fits one 128-row accumulator tile.  RUART_NO_ATTN_FUSE: A/B aid.
+        self.fuse_attn = self.fold and os.environ.get("RUART_NO_ATTN_FUSE") is None
 
     FOLD_MIN_T = 2048
 
@@ -167,6 +170,16 @@ class BertEngine(object):
             s = lay.attention.self
             wqkv = torch.cat([s.query.weight, s.key.weight, s.value.weight], 0)
             lw["wqkv_f"], lw["sqkv"], lw["cqkv"] = consumer(wqkv, lw["bqkv"], g_prev, b_prev)
+            # head-major row order [q_h / 8 ; k_h ; v_h] for the fused attention epilogue (the scale 1 / sqrt(64) is a
+            # power of two: folding it into the query rows is exact)
+            H, nh = self.H, self.heads
+            perm = torch.cat([torch.arange(64, device=wqkv.device) + part * H + h * 64
+                              for h in range(nh) for part in range(3)])
+            qscale = torch.ones(3 * H, device=wqkv.device)
+            qscale[:H] = 0.125
+            lw["wqkv_p"] = (lw["wqkv_f"].float() * qscale[:, None])[perm].to(torch.bfloat16).contiguous()
+            lw["sqkv_p"] = (lw["sqkv"] * qscale)[perm].contiguous()
+            lw["cqkv_p"] = (lw["cqkv"] * qscale)[perm].contiguous()
             lw["res1_g"], lw["res1_b"] = g_prev, (b_prev + lw["bo"]).contiguous()
             lw["wi_f"], lw["si"], lw["ci"] = consumer(lay.intermediate.dense.weight, lw["bi"], lw["g1"], lw["b1"])
             lw["res2_g"], lw["res2_b"] = lw["g1"], (lw["b1"] + lw["bd"]).contiguous()
@@ -180,7 +193,7 @@ class BertEngine(object):
     _pack_streams = {}
 
     @classmethod
-    def pack_begin(cls, segments):
+    def pack_begin(cls, segments, want_tiles=False):
         """First half of the token packing: row / window lengths (ruart_seq_lengths) and their prefix
         sums + totals (ruart_seq_scan) on a SIDE stream, and an async copy of the totals into pinned
         memory.  The caller can queue unrelated work on the compute stream before pack_finish()."""
@@ -233,8 +246,21 @@ class BertEngine(object):
             done = torch.cuda.Event()
             done.record(side)
             keep = (row_len, win_len, totals, masks, row0, seq0)
+            tiles = None
+            if want_tiles:
+                # row tiles of whole sequences + per-token sequence bounds for the fused attention epilogue
+                # (ruart_seq_tiles: one CTA, ~0.2 ms at cfg-3) — queued AFTER `done`, so that it runs under the token
+                # packing and the embedding kernel; sized by the padded token count (the real one is not known here)
+                padded = sum(sg.N * sg.L for sg in segments)
+                cap = 2 * padded // 128 + 8
+                meta = torch.empty(cap, dtype=torch.int32, device=dev)
+                bounds = torch.empty((max(padded, 1), 2), dtype=torch.int32, device=dev)
+                call("ruart_seq_tiles", ptr(cu_seq), S, ptr(meta), cap, ptr(bounds), st)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                tiles = (meta, bounds, ev)
         return {"segments": segments, "cu_rows": cu_rows, "cu_seq": cu_seq, "host": host, "done": done,
-                "nwins": nwins, "keep": keep, "host_known": host_known, "check": check}
+                "nwins": nwins, "keep": keep, "host_known": host_known, "check": check, "tiles": tiles}
 
     @staticmethod
     def pack_finish(h):
@@ -275,7 +301,7 @@ class BertEngine(object):
             r0 += sg.N
             s0 += sg.N * nwins[k]
         return {"ids": ids, "pos": pos, "cu_seqlens": cu_seq, "T": T, "segments": segs,
-                "check": (h["check"], list(host)) if h["host_known"] else None}
+                "check": (h["check"], list(host)) if h["host_known"] else None, "tiles": h.get("tiles")}
 
     @staticmethod
     def check_totals(pk):
@@ -289,8 +315,8 @@ class BertEngine(object):
                                "Utils.collate.attach_index_tensors" % (host, [int(v) for v in dev_totals]))
 
     @classmethod
-    def pack(cls, segments):
-        return cls.pack_finish(cls.pack_begin(segments))
+    def pack(cls, segments, want_tiles=False):
+        return cls.pack_finish(cls.pack_begin(segments, want_tiles))
 
     # ------------------------------------------------------------------ forward
     def _gemm(self, a, w, bias, N, K, epi, out_kind, fast_gelu=False, residual=None):
@@ -408,21 +434,40 @@ class BertEngine(object):
         stats1 = torch.empty((T, 8, 2), dtype=torch.float32, device=dev)
         raw1 = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
         scale = 1.0 / 8.0
+        fuse = self.fuse_attn and max([sg["max_len"] for sg in pk["segments"]] + [0]) <= 128
+        if fuse:
+            # row tiles of whole sequences (<= 128 rows) + per-token sequence bounds, once per batch: normally
+            # already queued on the packing stream (pack_begin(want_tiles=True))
+            if pk.get("tiles") is not None:
+                meta, bounds, ev = pk["tiles"]
+                main = torch.cuda.current_stream(dev)
+                main.wait_event(ev)
+                meta.record_stream(main)
+                bounds.record_stream(main)
+            else:
+                cap = 2 * T // 128 + 8
+                meta = torch.empty(cap, dtype=torch.int32, device=dev)
+                bounds = torch.empty((T, 2), dtype=torch.int32, device=dev)
+                call("ruart_seq_tiles", ptr(pk["cu_seqlens"]), pk["cu_seqlens"].numel() - 1, ptr(meta), cap, ptr(bounds), st)
         for li, lw in enumerate(W["layers"]):
             eps_in = eps0 if li == 0 else W["layers"][li - 1]["eps"]
-            qkv = self._gemm_fold(hs[li], lw["wqkv_f"], T, 3 * H, H, 1, ops.EPI_BIAS, lw["cqkv"], lw["sqkv"],
-                                  stats[li], eps_in)
             ctx = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
-            for s0, s1, mlen in pk["att_groups"]:
-                cu = pk["cu_seqlens"][s0:s1 + 1]
-                call("ruart_bert_attention", None, ptr(qkv), ptr(cu), s1 - s0, self.heads, scale, mlen, None,
-                     ptr(ctx), 1, st)
+            if fuse:
+                call("ruart_qkv_attention_fold", ptr(hs[li]), H, ptr(lw["wqkv_p"]), H, T, H, self.heads,
+                     ptr(lw["cqkv_p"]), ptr(lw["sqkv_p"]), ptr(stats[li]), eps_in, ptr(meta), ptr(bounds), ptr(ctx), H, st)
+            else:
+                qkv = self._gemm_fold(hs[li], lw["wqkv_f"], T, 3 * H, H, 1, ops.EPI_BIAS, lw["cqkv"], lw["sqkv"],
+                                      stats[li], eps_in)
+                for s0, s1, mlen in pk["att_groups"]:
+                    cu = pk["cu_seqlens"][s0:s1 + 1]
+                    call("ruart_bert_attention", None, ptr(qkv), ptr(cu), s1 - s0, self.heads, scale, mlen, None,
+                         ptr(ctx), 1, st)
             self._gemm_fold(ctx, lw["wo"], T, H, H, 2, ops.EPI_BIAS, lw["res1_b"], lw["res1_g"], stats[li], eps_in,
                             residual=hs[li], out=raw1, out_stats=stats1)
             ff = self._gemm_fold(raw1, lw["wi_f"], T, I, H, 1, ops.EPI_BIAS_GELU, lw["ci"], lw["si"], stats1, lw["eps"])
             self._gemm_fold(ff, lw["wd"], T, H, I, 2, ops.EPI_BIAS, lw["res2_b"], lw["res2_g"], stats1, lw["eps"],
                             residual=raw1, out=hs[li + 1], out_stats=stats[li + 1])
-        pk["fold"] = {"stats": stats}
+        pk["fold"] = {"stats": stats, "fused_attention": fuse}
         return pk, None, hs
 
     def encode_hidden(self, segments, pack_handle=None, allow_fold=True):
@@ -434,7 +479,7 @@ class BertEngine(object):
         if dev.type != "cuda":
             raise RuntimeError("ruart_b200 BERT runs on CUDA only; there is no CPU fallback")
         W = self.prepare(dev)
-        pk = self.pack_finish(pack_handle) if pack_handle is not None else self.pack(segments)
+        pk = self.pack_finish(pack_handle) if pack_handle is not None else self.pack(segments, self.fuse_attn)
         T, H, I, NL = pk["T"], self.H, self.I, self.n_layers
         st = current_stream()
         scale = 1.0 / 8.0

@@ -1431,6 +1431,73 @@ seq_scan_kernel(const int32_t* __restrict__ row_len, int R, const int32_t* __res
   }
 }
 
+// Row tiles of the fused query/key/value + attention GEMM (gemm_tcgen05.cu): consecutive WHOLE sequences are
+// grouped greedily into tiles of at most 128 token rows, so that every sequence has its Q, K and V rows inside
+// one accumulator tile.  The packed layout itself is untouched: a tile simply starts at its first sequence's row
+// and the MMA computes (and discards) up to 127 rows of the next tile.
+//   meta[0] = number of tiles n, meta[1 .. n + 1] = first token row of each tile, meta[n + 1] = T.
+// ONE CTA: cu_seq is staged through shared memory in chunks; warp 0 walks it 32 sequences at a time (ballot of
+// "still fits in the current tile"), i.e. sequential only in the number of tiles.
+constexpr int TILE_ROWS = 128;
+constexpr int TILES_CHUNK = 32768;
+__global__ void __launch_bounds__(1024)
+seq_tiles_kernel(const int32_t* __restrict__ cu_seq, int S, int32_t* __restrict__ meta, int capacity) {
+  extern __shared__ int32_t s_cu[];  // cu_seq[base .. base + n] of the current chunk
+  __shared__ int s_state[2];         // row0 of the open tile, tiles closed so far
+  if (threadIdx.x == 0) {
+    s_state[0] = cu_seq[0];
+    s_state[1] = 0;
+    meta[1] = cu_seq[0];
+  }
+  for (int base = 0; base < S; base += TILES_CHUNK) {
+    const int n = min(TILES_CHUNK, S - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) s_cu[i] = cu_seq[base + i];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      int row0 = s_state[0], closed = s_state[1];
+      int s = 0;
+      while (s < n) {
+        const int i = s + lane;
+        const bool fits = (i < n) && (s_cu[i + 1] - row0 <= TILE_ROWS);
+        const unsigned bad = __ballot_sync(0xffffffffu, !fits);
+        if (bad == 0u) { s += 32; continue; }
+        const int k = __ffs(bad) - 1;
+        if (s + k >= n) break;              // everything left in this chunk fits
+        const int start = s_cu[s + k];      // sequence s + k opens a new tile
+        if (k == 0 && start == row0) {      // a single sequence longer than a tile (the caller excludes it): skip it
+          s += 1;
+          continue;
+        }
+        closed += 1;
+        row0 = start;
+        if (lane == 0 && 1 + closed < capacity) meta[1 + closed] = row0;
+        s += k;
+      }
+      if (lane == 0) {
+        s_state[0] = row0;
+        s_state[1] = closed;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n_tiles = s_state[1] + 1;
+    meta[0] = min(n_tiles, capacity - 2);
+    if (1 + n_tiles < capacity) meta[1 + n_tiles] = cu_seq[S];
+  }
+}
+
+// (first row, end row) of its sequence for every packed token
+__global__ void __launch_bounds__(256)
+seq_token_bounds_kernel(const int32_t* __restrict__ cu_seq, int S, int2* __restrict__ bounds) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int a = cu_seq[s], b = cu_seq[s + 1];
+  for (int t = a; t < b; ++t) bounds[t] = make_int2(a, b);
+}
+
 // Token packing: ids [N, L] + mask [N, L] -> the real tokens of every row, in row order, at
 // out[row_start[r] ...]; position id = column index inside its 512-token window (the reference
 // restarts positions per window, Bert.py:96-99,135-138 + modeling.py:186-187).  One warp per row.
@@ -1870,6 +1937,25 @@ extern "C" int ruart_seq_scan(const int32_t* row_len, int R, const int32_t* win_
   seq_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_len, R, win_len, S, seg, cu_rows, cu_seq,
                                                         totals, max_total);
   RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+extern "C" int ruart_seq_tiles(const int32_t* cu_seq, int S, int32_t* meta, int capacity, int32_t* tok_bounds,
+                               void* stream) {
+  RUART_ARG_CHECK(S >= 0 && meta != nullptr && capacity >= 4 && tok_bounds != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  static RuartDeviceOnce attr_set;
+  const size_t smem = (TILES_CHUNK + 2) * sizeof(int32_t);
+  if (!attr_set.done()) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(seq_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.set();
+  }
+  seq_tiles_kernel<<<1, 1024, smem, st>>>(cu_seq, S, meta, capacity);
+  RUART_LAUNCH_CHECK();
+  if (S > 0) {
+    seq_token_bounds_kernel<<<(S + 255) / 256, 256, 0, st>>>(cu_seq, S, reinterpret_cast<int2*>(tok_bounds));
+    RUART_LAUNCH_CHECK();
+  }
   return RUART_OK;
 }
 

@@ -737,6 +737,376 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused query/key/value projection + self-attention (BertSelfAttention.forward, modeling.py:224-250) for the
+// bf16 encoder: the [T, 2304] Q|K|V matrix is never written to memory.
+//
+// The weight rows are permuted head-major on the host ([Wq_h / 8 ; Wk_h ; Wv_h], 192 rows per head, the softmax
+// scale folded into the query rows), so one 192-column accumulator tile holds one head's Q, K and V of the tile's
+// rows.  Row tiles come from ruart_seq_tiles: consecutive WHOLE sequences, at most 128 token rows, so every
+// sequence meets all of its keys inside one CTA's 128 TMEM lanes (RUArt's sequences are 3-10 wordpieces for
+// items, <= 50 for questions).  16 warps:
+//   0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocation — the CTA-pair pipeline of the kernel above with
+//     N = 192 and a 4-stage ring;
+//   4-7 "converters": read the accumulator (tcgen05.ld, one TMEM lane quadrant each), finish the pending LayerNorm
+//     of the A rows (FOLD 1 above), round to bf16 and store Q, K, V as three XOR-swizzled [128 x 64] tiles in
+//     one of TWO shared-memory buffers; they release the TMEM buffer as soon as it is read;
+//   8-15 "attention": 16 query rows per warp: S = Q K^T and O = P V on mma.sync.m16n8k16 (the register layout of
+//     the stand-alone kernels in bert_kernels.cu), masked by the rows' sequence bounds, online softmax over the
+//     16-key blocks of the rows' key range only; O is staged through the warp's own Q rows and written as
+//     128-byte rows of ctx[:, 64 h : 64 h + 64].
+// Converters and attention warps hand the tile buffers over with bar.arrive / bar.sync pairs, so the attention of
+// tile i runs under the conversion of tile i + 1 and the MMAs of tiles i + 1, i + 2.  (First version: one buffer,
+// all eight epilogue warps doing both phases in turn — 0.53 ms per layer at cfg-3 against 0.29 ms for the GEMM
+// alone, tools/bench_qkv_attn.py; the MMAs were not the cost: without them the attention phase took as long.)
+constexpr int QA_THREADS = 512;
+constexpr int QA_BN = 192;
+constexpr int QA_B_ROWS = QA_BN / 2;
+constexpr int QA_B_STAGE = QA_B_ROWS * BK * 2;  // 12 KB
+constexpr int QA_STAGES = 4;
+constexpr int QA_TILE = 128 * 128;              // one [128 x 64] bf16 tile
+constexpr int QA_BUF = 3 * QA_TILE;             // Q | K | V
+constexpr int QA_OFF_B = QA_STAGES * A_STAGE_BYTES;
+constexpr int QA_OFF_T = QA_OFF_B + QA_STAGES * QA_B_STAGE;
+constexpr int QA_OFF_VEC = QA_OFF_T + 2 * QA_BUF;
+constexpr int QA_OFF_BAR = QA_OFF_VEC + 2 * QA_BN * 4;
+constexpr int QA_SMEM_BYTES = QA_OFF_BAR + 256;
+static_assert(QA_SMEM_BYTES <= 232448 && (QA_OFF_T % 1024) == 0 && (QA_B_STAGE % 1024) == 0, "qkv+attention smem");
+// named barriers: 1 = the four converter warps; 2, 3 = tile buffer 0 / 1 written; 4, 5 = tile buffer 0 / 1 read
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct QaParams {
+  int M, Kp, n_heads;
+  const int32_t* meta;      // ruart_seq_tiles: [0] = tiles, [1 ..] = first row of each tile, then M
+  const int2* bounds;       // [M] (first row, end row) of each token's sequence
+  const float2* in_stats;   // [M][8] partial sums of the A rows (pending LayerNorm)
+  const float* vec;         // [n_heads * 192] W0 beta + b, permuted like the weight rows
+  const float* vec2;        // [n_heads * 192] colsum(W)
+  float ln_inv_dim, ln_eps;
+  __nv_bfloat16* out;       // ctx [M, n_heads * 64]
+  long long ldo;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(QA_THREADS, 1)
+qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const QaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + QA_OFF_B;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QA_OFF_BAR);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + QA_STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * QA_STAGES;
+  uint64_t* tmem_empty_bar = bars + 2 * QA_STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * QA_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < QA_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2);  // one elected converter thread per CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n_mtiles = __ldg(p.meta);
+  const int m_pairs = (n_mtiles + 1) >> 1;
+  const int total_tiles = m_pairs * p.n_heads;
+  const int k_blocks = p.Kp / BK;
+  const int tile0 = blockIdx.x >> 1;
+  const int tile_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int m_pair = tile / p.n_heads;
+        const int h = tile - m_pair * p.n_heads;
+        const int mt = 2 * m_pair + static_cast<int>(rank);
+        const int row_a = (mt < n_mtiles) ? __ldg(p.meta + 1 + mt) : p.M;  // past the end: zero-filled tile
+        const int row_b = h * QA_BN + static_cast<int>(rank) * QA_B_ROWS;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint32_t full_leader;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                       : "=r"(full_leader)
+                       : "r"(smem_u32(&full_bar[stage])), "r"(0));
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + QA_B_STAGE));
+          tma_load_2d_2sm(&tmap_a, full_leader, smem_a + stage * A_STAGE_BYTES, kb * BK, row_a);
+          tma_load_2d_2sm(&tmap_b, full_leader, smem_b + stage * QA_B_STAGE, kb * BK, row_b);
+          if (++stage == QA_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(2 * BM, QA_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * MAX_BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * QA_B_STAGE));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 0x3);
+          if (++stage == QA_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2sm(&tmem_full_bar[acc], 0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ converters (both CTAs)
+    const int ew = warp & 3;               // TMEM lane quadrant
+    const int ct = threadIdx.x - 128;      // 0..127 = the tile row this thread converts
+    float* vec = reinterpret_cast<float*>(smem + QA_OFF_VEC);
+    float* vec2 = vec + QA_BN;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t tile_ctr = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tile_ctr) {
+      const int m_pair = tile / p.n_heads;
+      const int h = tile - m_pair * p.n_heads;
+      const int mt = 2 * m_pair + static_cast<int>(rank);
+      const int row0 = (mt < n_mtiles) ? __ldg(p.meta + 1 + mt) : p.M;
+      const int buf = tile_ctr & 1u;
+      // the previous tile's conversion is over (group barrier at its end): the vectors may be replaced
+      for (int i = ct; i < QA_BN; i += 128) {
+        vec[i] = __ldg(p.vec + h * QA_BN + i);
+        vec2[i] = __ldg(p.vec2 + h * QA_BN + i);
+      }
+      float ln_r, ln_nmr;
+      {
+        const int row = row0 + ct;
+        float s1 = 0.f, s2 = 1.0f / p.ln_inv_dim;
+        if (row < p.M) {
+          const float4* sp = reinterpret_cast<const float4*>(p.in_stats + static_cast<long long>(row) * 8);
+          const float4 a = __ldg(sp), b = __ldg(sp + 1), c = __ldg(sp + 2);
+          s1 = ((a.x + a.z) + (b.x + b.z)) + (c.x + c.z);
+          s2 = ((a.y + a.w) + (b.y + b.w)) + (c.y + c.w);
+        }
+        const float mu = s1 * p.ln_inv_dim;
+        const float var = fmaxf(fmaf(-mu, mu, s2 * p.ln_inv_dim), 0.0f);
+        ln_r = rsqrtf(var + p.ln_eps);
+        ln_nmr = -mu * ln_r;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      if (tile_ctr >= 2) named_bar_sync(4 + buf, 384);  // the attention warps have finished with this buffer
+      uint8_t* sT = smem + QA_OFF_T + buf * QA_BUF;
+      const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * MAX_BN);
+#pragma unroll 1
+      for (int cc = 0; cc < 3; ++cc) {       // Q, K, V: 64 columns each
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(tmem_acc + cc * 64, v0);
+        tmem_ld_32x32b_x32(tmem_acc + cc * 64 + 32, v1);
+        tmem_ld_wait();
+        uint8_t* trow = sT + cc * QA_TILE;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = c * 8 + q * 2;
+            const float x0 = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
+            const float x1 = __uint_as_float(j < 32 ? v0[j + 1] : v1[j - 31]);
+            const float2 bv = *reinterpret_cast<const float2*>(vec + cc * 64 + j);
+            const float2 cs = *reinterpret_cast<const float2*>(vec2 + cc * 64 + j);
+            pk[q] = pack_bf16x2(fmaf(ln_r, x0, fmaf(ln_nmr, cs.x, bv.x)), fmaf(ln_r, x1, fmaf(ln_nmr, cs.y, bv.y)));
+          }
+          *reinterpret_cast<uint4*>(trow + tile_off(ct, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tc_fence_before();
+      named_bar_arrive(2 + buf, 384);        // Q, K, V of this tile are in buffer `buf`
+      named_bar_sync(1, 128);                // every converter's TMEM reads are done
+      if (ct == 0) {
+        if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+        else mbar_arrive_cluster_relaxed(&tmem_empty_bar[acc], 0);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ attention (both CTAs)
+    const int q0 = (warp - 8) * 16;        // this warp's query rows [q0, q0 + 16) of the tile
+    const int g = lane >> 2, t = lane & 3;
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int a_chk = lane >> 4;
+    const int b_row = lane & 7;
+    const int b_chk = lane >> 3;
+    uint32_t tile_ctr = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tile_ctr) {
+      const int m_pair = tile / p.n_heads;
+      const int h = tile - m_pair * p.n_heads;
+      const int mt = 2 * m_pair + static_cast<int>(rank);
+      const int row0 = (mt < n_mtiles) ? __ldg(p.meta + 1 + mt) : p.M;
+      const int n_valid = (mt < n_mtiles) ? __ldg(p.meta + 2 + mt) - row0 : 0;
+      const int buf = tile_ctr & 1u;
+      // sequence bounds of this thread's two rows (tile-local), fetched before the buffer is waited for
+      int2 bA = make_int2(q0 + g, q0 + g + 1), bB = make_int2(q0 + g + 8, q0 + g + 9);
+      if (row0 + q0 + g < p.M) {
+        const int2 gb = __ldg(p.bounds + row0 + q0 + g);
+        bA = make_int2(max(gb.x - row0, 0), min(gb.y - row0, 128));
+      }
+      if (row0 + q0 + g + 8 < p.M) {
+        const int2 gb = __ldg(p.bounds + row0 + q0 + g + 8);
+        bB = make_int2(max(gb.x - row0, 0), min(gb.y - row0, 128));
+      }
+      named_bar_sync(2 + buf, 384);          // the converters have written buffer `buf`
+      if (q0 < n_valid) {
+        uint8_t* sQ = smem + QA_OFF_T + buf * QA_BUF;
+        const uint32_t aQ = smem_u32(sQ), aK = aQ + QA_TILE, aV = aK + QA_TILE;
+        uint32_t qa[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ldsm_x4(aQ + tile_off(q0 + a_row, 2 * ks + a_chk), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+        // rows are in sequence order: the warp's key range runs from its first row's sequence start (lane 0 holds
+        // row q0) to its last row's sequence end (lanes 28-31 hold row q0 + 15)
+        const int klo = __shfl_sync(0xffffffffu, bA.x, 0), khi = __shfl_sync(0xffffffffu, bB.y, 28);
+        float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
+        float o[8][4];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+        for (int kb = klo & ~15; kb < khi; kb += 16) {
+          float s[2][4];
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            uint32_t kf[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+              ldsm_x4(aK + tile_off(kb + nt * 8 + b_row, 4 * kh + b_chk), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2)
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt)
+                mma_bf16_16816(s[nt], qa[2 * kh + k2][0], qa[2 * kh + k2][1], qa[2 * kh + k2][2], qa[2 * kh + k2][3],
+                               kf[nt][2 * k2], kf[nt][2 * k2 + 1]);
+          }
+          float bmA = -INFINITY, bmB = -INFINITY;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const int k0 = kb + nt * 8 + 2 * t;
+            s[nt][0] = (k0 >= bA.x && k0 < bA.y) ? s[nt][0] : -INFINITY;
+            s[nt][1] = (k0 + 1 >= bA.x && k0 + 1 < bA.y) ? s[nt][1] : -INFINITY;
+            s[nt][2] = (k0 >= bB.x && k0 < bB.y) ? s[nt][2] : -INFINITY;
+            s[nt][3] = (k0 + 1 >= bB.x && k0 + 1 < bB.y) ? s[nt][3] : -INFINITY;
+            bmA = fmaxf(bmA, fmaxf(s[nt][0], s[nt][1]));
+            bmB = fmaxf(bmB, fmaxf(s[nt][2], s[nt][3]));
+          }
+          bmA = fmaxf(bmA, __shfl_xor_sync(0xffffffffu, bmA, 1));
+          bmA = fmaxf(bmA, __shfl_xor_sync(0xffffffffu, bmA, 2));
+          bmB = fmaxf(bmB, __shfl_xor_sync(0xffffffffu, bmB, 1));
+          bmB = fmaxf(bmB, __shfl_xor_sync(0xffffffffu, bmB, 2));
+          const float nmA = fmaxf(mA, bmA), nmB = fmaxf(mB, bmB);
+          // rows whose sequence has not started yet in this key block keep (m, l, o) = (-inf, 0, 0)
+          const float fA = (nmA == -INFINITY) ? 1.0f : __expf(mA - nmA);
+          const float fB = (nmB == -INFINITY) ? 1.0f : __expf(mB - nmB);
+          const float zA = (nmA == -INFINITY) ? 0.0f : nmA, zB = (nmB == -INFINITY) ? 0.0f : nmB;
+          mA = nmA;
+          mB = nmB;
+          float psA = 0.f, psB = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            s[nt][0] = __expf(s[nt][0] - zA);
+            s[nt][1] = __expf(s[nt][1] - zA);
+            s[nt][2] = __expf(s[nt][2] - zB);
+            s[nt][3] = __expf(s[nt][3] - zB);
+            psA += s[nt][0] + s[nt][1];
+            psB += s[nt][2] + s[nt][3];
+          }
+          lA = fmaf(lA, fA, psA);
+          lB = fmaf(lB, fB, psB);
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            o[d][0] *= fA; o[d][1] *= fA;
+            o[d][2] *= fB; o[d][3] *= fB;
+          }
+          const uint32_t p0 = pack_bf16x2(s[0][0], s[0][1]), p1 = pack_bf16x2(s[0][2], s[0][3]);
+          const uint32_t p2 = pack_bf16x2(s[1][0], s[1][1]), p3 = pack_bf16x2(s[1][2], s[1][3]);
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(aV + tile_off(kb + a_row, 2 * dp + a_chk), b0, b1, b2, b3);
+            mma_bf16_16816(o[2 * dp], p0, p1, p2, p3, b0, b1);
+            mma_bf16_16816(o[2 * dp + 1], p0, p1, p2, p3, b2, b3);
+          }
+        }
+        lA += __shfl_xor_sync(0xffffffffu, lA, 1);
+        lA += __shfl_xor_sync(0xffffffffu, lA, 2);
+        lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+        lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+        const float iA = lA > 0.f ? __fdividef(1.0f, lA) : 0.f, iB = lB > 0.f ? __fdividef(1.0f, lB) : 0.f;
+        __syncwarp();  // this warp's Q fragments are in registers: its 16 Q rows become the O staging rows
+        const int rA = q0 + g, rB = rA + 8;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          *reinterpret_cast<uint32_t*>(sQ + tile_off(rA, d) + 4 * t) = pack_bf16x2(o[d][0] * iA, o[d][1] * iA);
+          *reinterpret_cast<uint32_t*>(sQ + tile_off(rB, d) + 4 * t) = pack_bf16x2(o[d][2] * iB, o[d][3] * iB);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = q0 + (lane >> 3) + 4 * i;
+          if (r < n_valid) {
+            const uint4 o4 = *reinterpret_cast<const uint4*>(sQ + tile_off(r, lane & 7));
+            *(reinterpret_cast<uint4*>(p.out + static_cast<long long>(row0 + r) * p.ldo + h * 64) + (lane & 7)) = o4;
+          }
+        }
+      }
+      named_bar_arrive(4 + buf, 384);        // this warp no longer touches buffer `buf`
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+  }
+}
+
 // --------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1041,6 +1411,50 @@ extern "C" int ruart_gemm_bf16_fold(const void* A, long long lda, const void* W,
   int grid2 = ruart_num_sms() & ~1;
   if (grid2 > 2 * pair_tiles) grid2 = 2 * pair_tiles;
   kern<<<grid2, GEMM_THREADS, GEMM2_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, tmc, tmr, p);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+// Fused query/key/value GEMM + self-attention of the folded bf16 encoder (qkv_attn_2cta_kernel above).
+//   A [M, Kp] bf16: the stored pre-LayerNorm rows; in_stats their partial sums
+//   W [n_heads * 192, Kp] bf16: (W0 * gamma) with the rows permuted head-major [q_h / 8 ; k_h ; v_h]
+//   vec / vec2 [n_heads * 192]: W0 beta + b and colsum(W), permuted and scaled the same way
+//   tile_meta / tok_bounds: from ruart_seq_tiles (every sequence <= 128 tokens)
+//   out [M, n_heads * 64] bf16: the attention context (input of BertSelfOutput.dense)
+extern "C" int ruart_qkv_attention_fold(const void* A, long long lda, const void* W, long long ldw, int M, int Kp,
+                                        int n_heads, const float* vec, const float* vec2, const float* in_stats,
+                                        float ln_eps, const int32_t* tile_meta, const int32_t* tok_bounds,
+                                        void* out_bf16, long long ldo, void* stream) {
+  RUART_ARG_CHECK(M >= 2 * BM * 8 && Kp == 768 && n_heads >= 1 && n_heads <= 64);
+  RUART_ARG_CHECK((lda % 8) == 0 && (ldw % 8) == 0 && (ldo % 8) == 0);
+  RUART_ARG_CHECK((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(W) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_bf16) & 15u) == 0);
+  RUART_ARG_CHECK(vec != nullptr && vec2 != nullptr && in_stats != nullptr && tile_meta != nullptr &&
+                  tok_bounds != nullptr && (reinterpret_cast<uintptr_t>(in_stats) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(tok_bounds) & 7u) == 0);
+  QaParams p;
+  p.M = M; p.Kp = Kp; p.n_heads = n_heads;
+  p.meta = tile_meta;
+  p.bounds = reinterpret_cast<const int2*>(tok_bounds);
+  p.in_stats = reinterpret_cast<const float2*>(in_stats);
+  p.vec = vec; p.vec2 = vec2;
+  p.ln_inv_dim = 1.0f / static_cast<float>(Kp);
+  p.ln_eps = ln_eps;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.ldo = ldo;
+  CUtensorMap tma, tmb;
+  int rc = make_tmap_bf16(&tma, A, M, Kp, lda, BM);
+  if (rc != RUART_OK) return rc;
+  rc = make_tmap_bf16(&tmb, W, (long long)n_heads * QA_BN, Kp, ldw, QA_B_ROWS);
+  if (rc != RUART_OK) return rc;
+  static RuartDeviceOnce attr;
+  if (!attr.done()) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(qkv_attn_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          QA_SMEM_BYTES));
+    attr.set();
+  }
+  const int grid = ruart_num_sms() & ~1;  // persistent; the tile count is read from tile_meta on the device
+  qkv_attn_2cta_kernel<<<grid, QA_THREADS, QA_SMEM_BYTES, (cudaStream_t)stream>>>(tma, tmb, p);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }

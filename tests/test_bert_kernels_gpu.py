@@ -187,3 +187,86 @@ def test_folded_layernorm_encoder_matches_unfolded():
     e_fold = (outs["fold"] - outs["fp32"]).abs().max().item() / scale
     e_plain = (outs["plain"] - outs["fp32"]).abs().max().item() / scale
     assert e_plain < 3e-2 and e_fold < max(1.5 * e_plain, 1e-2), (e_fold, e_plain)
+
+
+@pytest.mark.parametrize("lens", [[3, 5, 8, 1, 2, 7, 6, 4] * 300, [33, 20, 42, 5, 64, 3, 16, 17, 128, 1, 127, 2, 100, 28] * 40,
+                                  [128] * 20 + [1] * 300 + [0, 0, 5] * 50, [7] * 4000])
+def test_seq_tiles(lens):
+    """ruart_seq_tiles: greedy tiles of whole sequences, <= 128 rows each, and per-token sequence bounds."""
+    from ruart_b200._lib import call, current_stream, ptr
+    cu = [0]
+    for l in lens:
+        cu.append(cu[-1] + l)
+    T, S = cu[-1], len(lens)
+    cu_d = torch.tensor(cu, dtype=torch.int32, device="cuda")
+    cap = 2 * T // 128 + 8
+    meta = torch.full((cap,), -7, dtype=torch.int32, device="cuda")
+    bounds = torch.full((T, 2), -1, dtype=torch.int32, device="cuda")
+    call("ruart_seq_tiles", ptr(cu_d), S, ptr(meta), cap, ptr(bounds), current_stream())
+    torch.cuda.synchronize()
+    m = meta.cpu().tolist()
+    n = m[0]
+    starts = m[1:n + 2]
+    # host restatement of the greedy rule
+    want, row0 = [0], 0
+    for s in range(S):
+        if cu[s + 1] - row0 > 128:
+            row0 = cu[s]
+            want.append(row0)
+    want.append(T)
+    assert starts == want and n == len(want) - 1
+    assert all(b - a <= 128 for a, b in zip(starts[:-1], starts[1:]))
+    b = bounds.cpu()
+    for s in (0, 1, S // 2, S - 1):
+        if lens[s]:
+            assert b[cu[s]:cu[s + 1]].tolist() == [[cu[s], cu[s + 1]]] * lens[s]
+
+
+@pytest.mark.parametrize("lens", [[3, 5, 8, 1, 2, 7, 6, 4] * 80, [33, 20, 42, 5, 64, 3, 16, 17, 128, 1, 127, 2, 100, 28] * 6,
+                                  [50] * 30 + [4, 6] * 200])
+def test_qkv_attention_fold(lens):
+    """ruart_qkv_attention_fold (query/key/value GEMM with the folded LayerNorm and the attention in its epilogue,
+    modeling.py:224-250) against LayerNorm -> three Linears -> per-sequence softmax attention in torch fp32."""
+    from ruart_b200._lib import call, current_stream, ptr
+    st = current_stream()
+    heads, H, eps = 12, 768, 1e-12
+    cu = [0]
+    for l in lens:
+        cu.append(cu[-1] + l)
+    T, S = cu[-1], len(lens)
+    assert T >= 2048
+    g = torch.Generator(device="cuda").manual_seed(T)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    raw = (rnd(T, H) * 1.3 + 0.2).bfloat16()
+    x = raw.float()
+    stats = torch.zeros(T, 8, 2, device="cuda")
+    for k, chunk in enumerate(x.split(128, dim=1)):
+        stats[:, k, 0] = chunk.sum(1)
+        stats[:, k, 1] = (chunk * chunk).sum(1)
+    gamma, beta = rnd(H) * 0.3 + 1.0, rnd(H) * 0.2
+    w0, b0 = rnd(3 * H, H) * 0.04, rnd(3 * H) * 0.1
+    wf = (w0 * gamma[None, :]).bfloat16()
+    colsum = wf.float().sum(1)
+    cvec = w0 @ beta + b0
+    perm = torch.cat([torch.arange(64, device="cuda") + part * H + h * 64 for h in range(heads) for part in range(3)])
+    qs = torch.ones(3 * H, device="cuda")
+    qs[:H] = 0.125
+    w_p = (wf.float() * qs[:, None])[perm].bfloat16().contiguous()
+    s_p, c_p = (colsum * qs)[perm].contiguous(), (cvec * qs)[perm].contiguous()
+    cu_d = torch.tensor(cu, dtype=torch.int32, device="cuda")
+    cap = 2 * T // 128 + 8
+    meta = torch.empty(cap, dtype=torch.int32, device="cuda")
+    bounds = torch.empty((T, 2), dtype=torch.int32, device="cuda")
+    call("ruart_seq_tiles", ptr(cu_d), S, ptr(meta), cap, ptr(bounds), st)
+    ctx = torch.full((T + 1, H), 7.0, device="cuda", dtype=torch.bfloat16)
+    call("ruart_qkv_attention_fold", ptr(raw), H, ptr(w_p), H, T, H, heads, ptr(c_p), ptr(s_p), ptr(stats), eps,
+         ptr(meta), ptr(bounds), ptr(ctx), H, st)
+    torch.cuda.synchronize()
+    u = x.mean(-1, keepdim=True)
+    ln = (x - u) / torch.sqrt((x - u).pow(2).mean(-1, keepdim=True) + eps) * gamma + beta
+    qkv = (ln @ w0.t() + b0).bfloat16()            # the unfused path rounds Q|K|V to bf16 as well
+    want = _ref_attention(qkv, cu, heads)
+    assert torch.isfinite(ctx[:T].float()).all()
+    err = (ctx[:T].float() - want).abs().max().item()
+    assert err < 3e-2 * max(1.0, want.abs().max().item()), err
+    assert (ctx[T] == 7.0).all()
