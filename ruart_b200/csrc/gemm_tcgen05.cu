@@ -975,23 +975,37 @@ qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int b_row = lane & 7;
     const int b_chk = lane >> 3;
     uint32_t tile_ctr = 0;
+    // (row0, n_valid, this thread's two sequence bounds) of a tile; fetched one tile AHEAD so that the two dependent
+    // L2 round trips (tile table -> bounds) are off the critical path
+    struct TileInfo { int row0, n_valid; int2 bA, bB; };
+    auto fetch = [&](int tile) {
+      TileInfo ti;
+      const int m_pair = tile / p.n_heads;
+      const int mt = 2 * m_pair + static_cast<int>(rank);
+      const bool live = tile < total_tiles && mt < n_mtiles;
+      ti.row0 = live ? __ldg(p.meta + 1 + mt) : p.M;
+      ti.n_valid = live ? __ldg(p.meta + 2 + mt) - ti.row0 : 0;
+      ti.bA = make_int2(q0 + g, q0 + g + 1);
+      ti.bB = make_int2(q0 + g + 8, q0 + g + 9);
+      if (ti.row0 + q0 + g < p.M) {
+        const int2 gb = __ldg(p.bounds + ti.row0 + q0 + g);
+        ti.bA = make_int2(max(gb.x - ti.row0, 0), min(gb.y - ti.row0, 128));
+      }
+      if (ti.row0 + q0 + g + 8 < p.M) {
+        const int2 gb = __ldg(p.bounds + ti.row0 + q0 + g + 8);
+        ti.bB = make_int2(max(gb.x - ti.row0, 0), min(gb.y - ti.row0, 128));
+      }
+      return ti;
+    };
+    TileInfo nxt = fetch(tile0);
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tile_ctr) {
       const int m_pair = tile / p.n_heads;
       const int h = tile - m_pair * p.n_heads;
-      const int mt = 2 * m_pair + static_cast<int>(rank);
-      const int row0 = (mt < n_mtiles) ? __ldg(p.meta + 1 + mt) : p.M;
-      const int n_valid = (mt < n_mtiles) ? __ldg(p.meta + 2 + mt) - row0 : 0;
+      const TileInfo cur = nxt;
+      const int row0 = cur.row0, n_valid = cur.n_valid;
+      const int2 bA = cur.bA, bB = cur.bB;
       const int buf = tile_ctr & 1u;
-      // sequence bounds of this thread's two rows (tile-local), fetched before the buffer is waited for
-      int2 bA = make_int2(q0 + g, q0 + g + 1), bB = make_int2(q0 + g + 8, q0 + g + 9);
-      if (row0 + q0 + g < p.M) {
-        const int2 gb = __ldg(p.bounds + row0 + q0 + g);
-        bA = make_int2(max(gb.x - row0, 0), min(gb.y - row0, 128));
-      }
-      if (row0 + q0 + g + 8 < p.M) {
-        const int2 gb = __ldg(p.bounds + row0 + q0 + g + 8);
-        bB = make_int2(max(gb.x - row0, 0), min(gb.y - row0, 128));
-      }
+      nxt = fetch(tile + tile_step);
       named_bar_sync(2 + buf, 384);          // the converters have written buffer `buf`
       if (q0 < n_valid) {
         uint8_t* sQ = smem + QA_OFF_T + buf * QA_BUF;
@@ -1007,7 +1021,9 @@ qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         float o[8][4];
 #pragma unroll
         for (int d = 0; d < 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
-        for (int kb = klo & ~15; kb < khi; kb += 16) {
+        // 16-key blocks start at the first key (not at a multiple of 16): ceil(range / 16) blocks; rows past the tile
+        // (all masked) are clamped to its last row
+        for (int kb = klo; kb < khi; kb += 16) {
           float s[2][4];
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -1016,7 +1032,7 @@ qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             uint32_t kf[2][4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
-              ldsm_x4(aK + tile_off(kb + nt * 8 + b_row, 4 * kh + b_chk), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
+              ldsm_x4(aK + tile_off(min(kb + nt * 8 + b_row, 127), 4 * kh + b_chk), kf[nt][0], kf[nt][1], kf[nt][2], kf[nt][3]);
 #pragma unroll
             for (int k2 = 0; k2 < 2; ++k2)
 #pragma unroll
@@ -1068,7 +1084,7 @@ qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
           for (int dp = 0; dp < 4; ++dp) {
             uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(aV + tile_off(kb + a_row, 2 * dp + a_chk), b0, b1, b2, b3);
+            ldsm_x4_t(aV + tile_off(min(kb + a_row, 127), 2 * dp + a_chk), b0, b1, b2, b3);
             mma_bf16_16816(o[2 * dp], p0, p1, p2, p3, b0, b1);
             mma_bf16_16816(o[2 * dp + 1], p0, p1, p2, p3, b2, b3);
           }
