@@ -584,6 +584,33 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
     uint32_t tile_ctr = 0;
+    // FOLD: the tile's two per-column vectors (one element each per thread) and the row's partial sums are fetched
+    // ONE TILE AHEAD into registers: at the top of a tile they would cost two exposed L2 round trips (ncu: 18 % of
+    // the epilogue warps' time on the first use of the sums, profiles/r02b_ncu_full_summary.txt)
+    float pf_v = 0.f, pf_v2 = 0.f;
+    float4 pf_a = make_float4(0.f, 0.f, 0.f, 0.f), pf_b = pf_a, pf_c = pf_a;
+    auto prefetch = [&](int tile) {
+      if constexpr (FOLD != 0) {
+        if (tile < total_tiles) {
+          const int m_pair = tile / n_tiles;
+          const int n_blk = tile - m_pair * n_tiles;
+          const int col = n_blk * MAX_BN + et + grp * 128;
+          pf_v = __ldg(p.vec + col);
+          pf_v2 = __ldg(p.vec2 + col);
+          const int row = (2 * m_pair + static_cast<int>(rank)) * BM + r_local;
+          if (row < p.M) {
+            const float4* sp = reinterpret_cast<const float4*>(p.in_stats + static_cast<long long>(row) * 8);
+            pf_a = __ldg(sp);
+            pf_b = __ldg(sp + 1);
+            pf_c = __ldg(sp + 2);
+          } else {  // harmless unit-variance stand-in for rows past M
+            pf_a = make_float4(0.f, 1.0f / p.ln_inv_dim, 0.f, 0.f);
+            pf_b = pf_c = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+    };
+    prefetch(tile0);
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tile_ctr) {
       const int m_pair = tile / n_tiles;
       const int n_blk = tile - m_pair * n_tiles;
@@ -591,28 +618,22 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int tile_col0 = n_blk * MAX_BN;
       float* vec = s_vec + (FOLD ? 0u : (tile_ctr & 1u) * MAX_BN);
       float* vec2 = s_vec + MAX_BN;  // FOLD only
-      if (FOLD) epi_all_bar_sync();  // single-buffered vectors: the previous tile's readers are done
-      if (EPI != K_NONE) {
-        for (int i = et + grp * 128; i < MAX_BN; i += 256) {
-          vec[i] = __ldg(p.vec + static_cast<long long>(tile_col0 + i) * p.vec_stride);
-          if (FOLD) vec2[i] = __ldg(p.vec2 + tile_col0 + i);
-        }
-      }
       // pending LayerNorm of this thread's row: r = rstd, nmr = -mean * rstd
       float ln_r = 1.0f, ln_nmr = 0.0f;
       if constexpr (FOLD != 0) {
-        const int row = m_blk * BM + r_local;
-        float s1 = 0.f, s2 = 1.0f / p.ln_inv_dim;  // harmless unit-variance stand-in for rows past M
-        if (row < p.M) {
-          const float4* sp = reinterpret_cast<const float4*>(p.in_stats + static_cast<long long>(row) * 8);
-          const float4 a = __ldg(sp), b = __ldg(sp + 1), c = __ldg(sp + 2);
-          s1 = ((a.x + a.z) + (b.x + b.z)) + (c.x + c.z);
-          s2 = ((a.y + a.w) + (b.y + b.w)) + (c.y + c.w);
-        }
+        epi_all_bar_sync();  // single-buffered vectors: the previous tile's readers are done
+        vec[et + grp * 128] = pf_v;
+        vec2[et + grp * 128] = pf_v2;
+        const float s1 = ((pf_a.x + pf_a.z) + (pf_b.x + pf_b.z)) + (pf_c.x + pf_c.z);
+        const float s2 = ((pf_a.y + pf_a.w) + (pf_b.y + pf_b.w)) + (pf_c.y + pf_c.w);
         const float mu = s1 * p.ln_inv_dim;
         const float var = fmaxf(fmaf(-mu, mu, s2 * p.ln_inv_dim), 0.0f);
         ln_r = rsqrtf(var + p.ln_eps);
         ln_nmr = -mu * ln_r;
+        prefetch(tile + tile_step);
+      } else if (EPI != K_NONE) {
+        for (int i = et + grp * 128; i < MAX_BN; i += 256)
+          vec[i] = __ldg(p.vec + static_cast<long long>(tile_col0 + i) * p.vec_stride);
       }
       float st1 = 0.f, st2 = 0.f;  // FOLD 2: this thread's partial sums over its 128 columns
       epi_all_bar_sync();
@@ -902,32 +923,54 @@ qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t tile_ctr = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tile_ctr) {
+    // the tile's vectors (192 + 192 floats over 128 threads: 3 elements each) and the row's partial sums, fetched one
+    // tile ahead into registers (two dependent L2 round trips: tile table -> partial sums)
+    float pf_v[3], pf_v2[3];
+    float4 pf_a, pf_b, pf_c;
+    auto prefetch = [&](int tile) {
+      if (tile >= total_tiles) return;
       const int m_pair = tile / p.n_heads;
       const int h = tile - m_pair * p.n_heads;
       const int mt = 2 * m_pair + static_cast<int>(rank);
-      const int row0 = (mt < n_mtiles) ? __ldg(p.meta + 1 + mt) : p.M;
+      const int row = ((mt < n_mtiles) ? __ldg(p.meta + 1 + mt) : p.M) + ct;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = ct + 128 * k;          // i < 192 for k = 0, and for k = 1 when ct < 64
+        pf_v[k] = (i < QA_BN) ? __ldg(p.vec + h * QA_BN + i) : 0.f;
+        pf_v2[k] = (i < QA_BN) ? __ldg(p.vec2 + h * QA_BN + i) : 0.f;
+      }
+      if (row < p.M) {
+        const float4* sp = reinterpret_cast<const float4*>(p.in_stats + static_cast<long long>(row) * 8);
+        pf_a = __ldg(sp);
+        pf_b = __ldg(sp + 1);
+        pf_c = __ldg(sp + 2);
+      } else {
+        pf_a = make_float4(0.f, 1.0f / p.ln_inv_dim, 0.f, 0.f);
+        pf_b = pf_c = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    prefetch(tile0);
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tile_ctr) {
       const int buf = tile_ctr & 1u;
       // the previous tile's conversion is over (group barrier at its end): the vectors may be replaced
-      for (int i = ct; i < QA_BN; i += 128) {
-        vec[i] = __ldg(p.vec + h * QA_BN + i);
-        vec2[i] = __ldg(p.vec2 + h * QA_BN + i);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = ct + 128 * k;
+        if (i < QA_BN) {
+          vec[i] = pf_v[k];
+          vec2[i] = pf_v2[k];
+        }
       }
       float ln_r, ln_nmr;
       {
-        const int row = row0 + ct;
-        float s1 = 0.f, s2 = 1.0f / p.ln_inv_dim;
-        if (row < p.M) {
-          const float4* sp = reinterpret_cast<const float4*>(p.in_stats + static_cast<long long>(row) * 8);
-          const float4 a = __ldg(sp), b = __ldg(sp + 1), c = __ldg(sp + 2);
-          s1 = ((a.x + a.z) + (b.x + b.z)) + (c.x + c.z);
-          s2 = ((a.y + a.w) + (b.y + b.w)) + (c.y + c.w);
-        }
+        const float s1 = ((pf_a.x + pf_a.z) + (pf_b.x + pf_b.z)) + (pf_c.x + pf_c.z);
+        const float s2 = ((pf_a.y + pf_a.w) + (pf_b.y + pf_b.w)) + (pf_c.y + pf_c.w);
         const float mu = s1 * p.ln_inv_dim;
         const float var = fmaxf(fmaf(-mu, mu, s2 * p.ln_inv_dim), 0.0f);
         ln_r = rsqrtf(var + p.ln_eps);
         ln_nmr = -mu * ln_r;
       }
+      prefetch(tile + tile_step);
       named_bar_sync(1, 128);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
