@@ -19,8 +19,10 @@ N > 1 is launched with torchrun, one rank per GPU; rank 0 prints ONE JSON line.
              The events are recorded in a second pass of the same K steps right after the timed region
              (a pair of events per launch slows a step by ~2 ms, so `value` is timed without them)
   roofline_step  whole-step algorithmic work (77.5 GFLOP per question) / step time / peak
-  kernels    live CUDA-event time and algorithmic GB/s of the memory-bound BERT kernels (LayerNorm,
-             attention, subword mean + layer sum) against the measured HBM bandwidth
+  kernels    live CUDA-event time and algorithmic GB/s of the memory-bound BERT kernels against the measured HBM
+             bandwidth.  In the default bf16 mode only the subword mean + layer sum is left: the LayerNorms are folded
+             into the GEMM epilogues and the attention runs inside the query/key/value GEMM (RUART_NO_LN_FOLD /
+             RUART_NO_ATTN_FUSE bring the separate kernels — and their lines here — back)
   phoc       BASELINE configs[1]: 1 M synthetic strings through the PHOC kernel (strings/s, fraction of
              HBM bandwidth, bit-exact check against the C oracle on a sample, CPU cphoc baseline)
   cpu_baseline  the CPU oracle port (oracle/sdnet_oracle.py, plain torch fp32 on all host threads)
@@ -145,7 +147,7 @@ def phoc_record(n=1_000_000):
 def gemm_traffic():
     """Mean DRAM bytes per BERT GEMM launch from the committed ncu --set full capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02b_gemm_traffic.json")) as f:
             return float(json.load(f)["mean_bytes_per_launch"])
     except Exception:
         return None
@@ -683,7 +685,8 @@ def main():
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                          "frac": (ach / peak) if ach else None, "traffic": gemm_traffic(),
                          "traffic_unit": "bytes per launch (mean of the 4 BERT GEMM shapes, ncu dram read+write)",
-                         "kernel": "gemm_bf16_2cta_kernel (all %d BERT GEMM launches of %d steps)" % (n_gemm, args.steps),
+                         "kernel": "gemm_bf16_2cta_kernel<EPI, RES, FOLD> + qkv_attn_2cta_kernel (all %d BERT GEMM launches of %d steps; "
+                                   "the query/key/value GEMM carries the attention in its epilogue, its FLOPs are the projection's only)" % (n_gemm, args.steps),
                          "kernel_ms_per_step": g_ms / args.steps, "peak_source": peak_src,
                          "instrumented_ms_per_step": ms_instr / args.steps,
                          "how": "CUDA events around every launch, in a second pass of the same steps right after the "
