@@ -208,7 +208,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {  // whole warp walks the loop, one elected lane issues (see gemm_bf16_2cta_kernel)
       const uint32_t idesc = make_idesc_bf16_f32(BM, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
@@ -224,18 +224,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tc_fence_after();
           const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
-            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+              umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (elect_one_sync()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -543,7 +547,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader only)
-    if (leader && lane == 0) {
+    // The WHOLE warp walks the loop (uniform control flow, every operand provably warp-uniform) and one elected lane
+    // issues.  With a single-lane loop (`lane == 0`) the compiler cannot keep the descriptors in uniform registers
+    // and wraps every tcgen05.mma in an ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY waterfall: ~95 instructions per
+    // k-block on a scheduler shared with two epilogue warps — ncu showed the issuing warp busy 87 % of the time and
+    // the tensor pipe idling in proportion to the epilogue's instruction count ("MMA issue loop").
+    if (leader) {
       const uint32_t idesc = make_idesc_bf16_f32(2 * BM, MAX_BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -558,16 +567,20 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tc_fence_after();
           const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * B2_STAGE_BYTES));
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage], 0x3);  // frees the slot in BOTH CTAs
+          }
+          __syncwarp();
           if (++stage == STAGES2) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit_2sm(&tmem_full_bar[acc], 0x3);  // both CTAs' epilogues
+        if (elect_one_sync()) umma_commit_2sm(&tmem_full_bar[acc], 0x3);  // both CTAs' epilogues
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -885,7 +898,10 @@ qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader only)
+    // single-lane loop here: the whole-warp / elected-lane form that helps the GEMM kernels above measured SLOWER in
+    // this kernel (0.400 vs 0.377 ms per layer, tools/bench_qkv_attn.py) — its schedulers are shared with 12 busy warps
     if (leader && lane == 0) {
+      {
       const uint32_t idesc = make_idesc_bf16_f32(2 * BM, QA_BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -912,6 +928,7 @@ qkv_attn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         umma_commit_2sm(&tmem_full_bar[acc], 0x3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
+      }
       }
     }
   } else if (warp >= 4 && warp < 8) {
