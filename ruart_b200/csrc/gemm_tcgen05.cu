@@ -559,11 +559,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_warp(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * MAX_BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_warp(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * B2_STAGE_BYTES));
