@@ -599,7 +599,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t tile_ctr = 0;
     // FOLD: the tile's two per-column vectors (one element each per thread) and the row's partial sums are fetched
     // ONE TILE AHEAD into registers: at the top of a tile they would cost two exposed L2 round trips (ncu: 18 % of
-    // the epilogue warps' time on the first use of the sums, profiles/r02b_ncu_full_summary.txt)
+    // the epilogue warps' time on the first use of the sums, profiles/r02c_ncu_full_summary.txt)
     float pf_v = 0.f, pf_v2 = 0.f;
     float4 pf_a = make_float4(0.f, 0.f, 0.f, 0.f), pf_b = pf_a, pf_c = pf_a;
     auto prefetch = [&](int tile) {
