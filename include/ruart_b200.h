@@ -226,6 +226,13 @@ RUART_API int ruart_attention_tail(const float* p1, long long p1_pitch, const fl
                                    const float* x3, long long x3_pitch, int D3, float* out,
                                    long long out_pitch, int B, int L1, int L2, int add_to_out,
                                    int split_parts, void* stream);
+/* The n_heads (<= 4) Attention modules of one DeepAttention call (Layers.py:493-524) in one launch: head z reads
+ * columns [z hidden, (z+1) hidden) of the stacked projections p1 / p2 and x3s_host[z] ([B, L2, D3], common pitch),
+ * and writes out[:, :, z D3 : (z+1) D3].  Tensor-core form only (L2 <= 128).                                  */
+RUART_API int ruart_attention_tail_heads(const float* p1, long long p1_pitch, const float* p2,
+                                         long long p2_pitch, int hidden, int n_heads, const uint8_t* mask,
+                                         const float* const* x3s_host, long long x3_pitch, int D3, float* out,
+                                         long long out_pitch, int B, int L1, int L2, void* stream);
 /* LinearSelfAttn + weighted_avg (Layers.py:328-341,529-534): out[b] = softmax(mask(x w + b)) x  */
 RUART_API int ruart_self_attn_pool(const float* x, long long x_pitch, int B, int L, int D,
                                    const uint8_t* mask, const float* w, const float* bias,

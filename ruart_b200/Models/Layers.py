@@ -286,13 +286,24 @@ class Attention(nn.Module):
         x1_0 = x1[0] if isinstance(x1, (list, tuple)) else x1
         x2_0 = x2[0] if isinstance(x2, (list, tuple)) else x2
         B, L1, L2 = x1_0.shape[0], x1_0.shape[1], x2_0.shape[1]
-        p1, sp = self.scoring.project(x1, True)
-        if p2_cache is not None and "p2" in p2_cache:
-            p2 = p2_cache["p2"]
+        if x2 is x1 and p2_cache is None:
+            # self-attention (SDNet.py:380-390,411): both sides project the SAME rows through the same Linear, so
+            # relu(x W^T) is computed once and the query side is that result times the diagonal — the product the
+            # GEMM epilogue would form (relu(acc) * d), hence bit-identical, for a 10 us pass instead of a GEMM
+            p2, _ = self.scoring.project(x1, False)
+            d = K.prep_vector(self.scoring, ("d"), lambda: self.scoring.diagonal.reshape(-1), [self.scoring.diagonal])
+            p1 = torch.empty_like(p2)
+            hid = p2.shape[1]
+            call("ruart_eltwise", 3, ptr(p2), hid, None, 0, ptr(d), d.numel(), ptr(p1), hid, p2.shape[0], hid,
+                 current_stream())
         else:
-            p2, _ = self.scoring.project(x2, False, a_split=sp if x2 is x1 else None)
-            if p2_cache is not None:
-                p2_cache["p2"] = p2
+            p1, sp = self.scoring.project(x1, True)
+            if p2_cache is not None and "p2" in p2_cache:
+                p2 = p2_cache["p2"]
+            else:
+                p2, _ = self.scoring.project(x2, False)
+                if p2_cache is not None:
+                    p2_cache["p2"] = p2
         if out is None:
             out = torch.empty((B, L1, x3.shape[2]), dtype=torch.float32, device=x1_0.device)
         K.attention_tail(p1, p2, K.as_u8(x2_mask), x3, out, B, L1, L2, add=add_to_out, parts=sdnet_parts)
@@ -517,12 +528,22 @@ class DeepAttention(nn.Module):
         p2 = x2_proj if x2_proj is not None else self.project_x2(x2_word, x2_abstr)
         mask = K.as_u8(x2_mask)
         att = torch.empty((B, L1, sum(t.shape[2] for t in x2_abstr)), dtype=torch.float32, device=dev)
-        col = 0
-        for i in range(len(x2_abstr)):
-            x3 = x2_abstr[i]
-            K.attention_tail(p1[:, i * hid:(i + 1) * hid], p2[:, i * hid:(i + 1) * hid], mask, x3,
-                             att[:, :, col:col + x3.shape[2]], B, L1, L2, parts=sdnet_parts)
-            col += x3.shape[2]
+        nh = len(x2_abstr)
+        x3s = [K.rows2d(t) for t in x2_abstr]          # (2-D view, width, pitch)
+        if (sdnet_parts == 2 and L2 <= 128 and nh <= 4 and len({(r[1], r[2]) for r in x3s}) == 1):
+            # the heads share p1 / p2 / mask and have equally shaped x3: ONE launch with the head on grid.z
+            # (three 66 us launches of a latency-bound kernel -> one; same arithmetic per head)
+            import ctypes
+            ptrs = (ctypes.c_void_p * nh)(*[t.data_ptr() for t in x2_abstr])
+            call("ruart_attention_tail_heads", ptr(p1), n, ptr(p2), K.rows2d(p2)[2], hid, nh, ptr(mask), ptrs,
+                 x3s[0][2], x3s[0][1], ptr(att), K.rows2d(att)[2], B, L1, L2, current_stream())
+        else:
+            col = 0
+            for i in range(nh):
+                x3 = x2_abstr[i]
+                K.attention_tail(p1[:, i * hid:(i + 1) * hid], p2[:, i * hid:(i + 1) * hid], mask, x3,
+                                 att[:, :, col:col + x3.shape[2]], B, L1, L2, parts=sdnet_parts)
+                col += x3.shape[2]
         x1 = list(x1_abstr) + [att]
         x1_hiddens = self.rnn.run_layer(0, x1) if self.rnn.num_layers == 1 else self.rnn(K.concat_cols(x1), x1_mask)
         if return_bef_rnn:

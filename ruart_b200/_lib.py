@@ -60,6 +60,8 @@ _SIGNATURES = {
     "ruart_whole_layernorm": [c_void_p, c_ll, c_int, c_ll, c_float, c_void_p, c_void_p],
     "ruart_attention_tail": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_int,
                              c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "ruart_attention_tail_heads": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_ll, c_int,
+                                   c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "ruart_self_attn_pool": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_ll, c_void_p],
     "ruart_final_scores": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,

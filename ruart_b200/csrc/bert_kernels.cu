@@ -1594,6 +1594,37 @@ split_concat_bf16_kernel(ConcatSrc cs, long long rows, int Kp, int parts, __nv_b
     const long long r = i / groups;
     const int c0 = static_cast<int>(i - r * groups) * 8;
     float x[8];
+    // fast path (PAIRS): the whole 8-column group lies inside ONE source -> one source search, four float2 loads
+    // (the kernel was issue-bound on the per-pair search: 81 % issue slots busy, profiles/r02c_ncu_full2_summary.txt)
+    bool done = false;
+    if (PAIRS && c0 + 8 <= K) {
+      int q = 0;
+#pragma unroll
+      for (int k = 1; k < 8; ++k) q += (k < cs.n && c0 >= cs.start[k]) ? 1 : 0;
+      // select the source's fields with static indices (the struct stays in the constant bank)
+      const float* base = cs.p[0];
+      long long pitch = cs.pitch[0];
+      int st = cs.start[0], en = cs.start[1];
+#pragma unroll
+      for (int k = 1; k < 8; ++k)
+        if (q == k) {
+          base = cs.p[k];
+          pitch = cs.pitch[k];
+          st = cs.start[k];
+          en = cs.start[k + 1];
+        }
+      if (c0 + 8 <= en) {
+        const float2* src = reinterpret_cast<const float2*>(base + r * pitch + (c0 - st));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 v = __ldg(src + e);
+          x[2 * e] = v.x;
+          x[2 * e + 1] = v.y;
+        }
+        done = true;
+      }
+    }
+    if (!done)
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
       const int col = c0 + e;

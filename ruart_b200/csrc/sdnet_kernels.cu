@@ -404,12 +404,22 @@ __device__ __forceinline__ void stage_split_chunk(const float* __restrict__ src,
   }
 }
 
+struct TailX3 {
+  const float* p[4];
+};
+
 __global__ void __launch_bounds__(ATM_THREADS)
 attention_tail_mma_kernel(const float* __restrict__ p1, long long p1_pitch,
                           const float* __restrict__ p2, long long p2_pitch, int Hd,
-                          const uint8_t* __restrict__ mask, const float* __restrict__ x3,
+                          const uint8_t* __restrict__ mask, const TailX3 x3s,
                           long long x3_pitch, int D3, float* __restrict__ out, long long out_pitch,
                           int L1, int L2, int add_to_out) {
+  // blockIdx.z = attention head of a DeepAttention group (Layers.py:493-524): head z reads columns
+  // [z Hd, (z + 1) Hd) of the stacked projections, its own x3 and writes columns [z D3, (z + 1) D3) of out
+  p1 += blockIdx.z * Hd;
+  p2 += blockIdx.z * Hd;
+  out += blockIdx.z * D3;
+  const float* __restrict__ x3 = x3s.p[blockIdx.z];
   // [p1 hi | p1 lo] 2 x 8 KB, [p2 / x3 hi | lo] 2 x 16 KB
   __shared__ __align__(128) uint8_t s_q[2][ATM_Q * 128];
   __shared__ __align__(128) uint8_t s_k[2][ATM_L2 * 128];
@@ -834,8 +844,9 @@ extern "C" int ruart_attention_tail(const float* p1, long long p1_pitch, const f
   static const bool no_mma = getenv("RUART_TAIL_NO_MMA") != nullptr;  // A/B aid
   if (split_parts == 2 && L2 <= ATM_L2 && !no_mma) {
     dim3 grid((L1 + ATM_Q - 1) / ATM_Q, B);
+    TailX3 xs = {{x3, nullptr, nullptr, nullptr}};
     attention_tail_mma_kernel<<<grid, ATM_THREADS, 0, (cudaStream_t)stream>>>(
-        p1, p1_pitch, p2, p2_pitch, hidden, mask, x3, x3_pitch, D3, out, out_pitch, L1, L2,
+        p1, p1_pitch, p2, p2_pitch, hidden, mask, xs, x3_pitch, D3, out, out_pitch, L1, L2,
         add_to_out);
     RUART_LAUNCH_CHECK();
     return RUART_OK;
@@ -861,6 +872,28 @@ extern "C" int ruart_attention_tail(const float* p1, long long p1_pitch, const f
   attention_tail_kernel<<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(
       p1, p1_pitch, p2, p2_pitch, hidden, mask, x3, x3_pitch, D3, out, out_pitch, L1, L2,
       add_to_out);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
+// The n_heads (<= 4) attention heads of one DeepAttention call in ONE launch (grid.z = head): head z takes the
+// columns [z hidden, (z + 1) hidden) of the stacked projections p1 / p2, x3s[z] (all [B, L2, D3], pitch x3_pitch)
+// and writes out[:, :, z D3 : (z + 1) D3].  Tensor-core form only (2-part operands, L2 <= 128): RUART_ERR_ARG
+// otherwise and the caller launches the heads one by one.
+extern "C" int ruart_attention_tail_heads(const float* p1, long long p1_pitch, const float* p2,
+                                          long long p2_pitch, int hidden, int n_heads, const uint8_t* mask,
+                                          const float* const* x3s_host, long long x3_pitch, int D3, float* out,
+                                          long long out_pitch, int B, int L1, int L2, void* stream) {
+  RUART_ARG_CHECK(B > 0 && L1 > 0 && L2 > 0 && hidden > 0 && D3 > 0 && n_heads >= 1 && n_heads <= 4);
+  RUART_ARG_CHECK(L2 <= ATM_L2 && x3s_host != nullptr);
+  TailX3 xs = {{nullptr, nullptr, nullptr, nullptr}};
+  for (int i = 0; i < n_heads; ++i) {
+    RUART_ARG_CHECK(x3s_host[i] != nullptr);
+    xs.p[i] = x3s_host[i];
+  }
+  dim3 grid((L1 + ATM_Q - 1) / ATM_Q, B, n_heads);
+  attention_tail_mma_kernel<<<grid, ATM_THREADS, 0, (cudaStream_t)stream>>>(
+      p1, p1_pitch, p2, p2_pitch, hidden, mask, xs, x3_pitch, D3, out, out_pitch, L1, L2, 0);
   RUART_LAUNCH_CHECK();
   return RUART_OK;
 }
