@@ -149,9 +149,12 @@ def test_embed_raw_and_folded_subword_mix():
     assert (dst[..., H:] == 5.0).all()
 
 
-def test_folded_layernorm_encoder_matches_unfolded():
+@pytest.mark.parametrize("long_row", [False, True])
+def test_folded_layernorm_encoder_matches_unfolded(long_row):
     """The bf16 encoder with every LayerNorm folded into the neighbouring GEMMs (BertEngine._encode_hidden_fold)
-    against the explicit-LayerNorm bf16 encoder and the fp32-mode encoder on the same packed batch."""
+    against the explicit-LayerNorm bf16 encoder and the fp32-mode encoder on the same packed batch.
+    long_row: one 200-token row -> the attention cannot be fused into the query/key/value GEMM (a sequence must fit
+    one 128-row accumulator tile) and the folded encoder runs with the stand-alone attention kernels."""
     import contextlib, io
     from ruart_b200.Models.Bert.Bert import Bert
     from ruart_b200.bert_engine import Segment
@@ -161,9 +164,11 @@ def test_folded_layernorm_encoder_matches_unfolded():
     for p in bert.parameters():                     # non-trivial LayerNorm weights
         if p.dim() == 1:
             p.data.add_(torch.randn_like(p) * 0.2)
-    N, L, Wd, H = 700, 8, 3, 768
+    N, L, Wd, H = 700, (200 if long_row else 8), 3, 768
     g = torch.Generator().manual_seed(5)
-    lens = torch.randint(3, L + 1, (N,), generator=g)
+    lens = torch.randint(3, 9, (N,), generator=g)
+    if long_row:
+        lens[17] = 200
     ids = torch.randint(1000, 30000, (N, L), generator=g)
     mask = torch.arange(L)[None, :] < lens[:, None]
     ids = (ids * mask).cuda()
@@ -180,6 +185,8 @@ def test_folded_layernorm_encoder_matches_unfolded():
         dst = torch.zeros(N, Wd, H, device="cuda")
         pk = eng.encode(seg(), [(dst, H, 0)], alpha=alpha, gamma=gamma)
         assert ("fold" in pk) == (name == "fold")
+        if name == "fold":
+            assert pk["fold"]["fused_attention"] == (not long_row)
         outs[name] = dst
         bert._engine = None
     torch.cuda.synchronize()
