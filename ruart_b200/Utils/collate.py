@@ -119,3 +119,46 @@ def to_cuda(batch, device="cuda"):
     """ToCUDA (SDNetTrainer.py:208-230) with non_blocking copies; host lists / plans stay on the host."""
     return tuple({k: (v.to(device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in d.items()}
                  for d in batch)
+
+
+class CudaPrefetcher(object):
+    """`ToCUDA` (SDNetTrainer.py:208-230) one batch AHEAD: the host -> device copies of batch i + 1 run on a copy
+    stream while batch i is on the compute stream ("pinned-memory async H2D in ToCUDA").
+
+        for q, ocr, od in CudaPrefetcher(pinned_batches):      # pinned_batches: iterable of pin(...)-ed batches
+            scores, _ = network(q, ocr, od)
+
+    The yielded tensors were allocated and written on the copy stream: the compute stream waits for that stream and
+    the tensors are recorded on it (caching-allocator lifetime), so they are used like the result of to_cuda()."""
+
+    def __init__(self, batches, device="cuda"):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            self._next = to_cuda(host, self.device)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream)
+        batch = self._next
+        for d in batch:
+            for v in d.values():
+                if torch.is_tensor(v):
+                    v.record_stream(cur)
+        self._preload()
+        return batch

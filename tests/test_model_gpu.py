@@ -447,3 +447,23 @@ def test_nan_guard_sync_and_deferred():
             for _ in range(4):
                 net2(*synth.batch_to(copy.deepcopy(batch), "cuda"))
             net2.check_pending()
+
+
+def test_cuda_prefetcher_yields_what_to_cuda_does():
+    """Utils.collate.CudaPrefetcher (ToCUDA one batch ahead on a copy stream): same tensors as
+    to_cuda(), usable on the compute stream, and the forward gives bit-identical probabilities."""
+    from ruart_b200.Utils import collate
+    net, opt = build_ours("tiny", device="cuda", BERT_precision="fp32")
+    batches = [collate.pin(synth.make_batch("tiny", seed=s, ragged=True)) for s in (11, 12, 13)]
+    want = []
+    with torch.no_grad():
+        for hb in batches:
+            d = collate.to_cuda(hb)
+            want.append((net(*d)[0].clone(), d[1]["fasttext"].clone()))
+        got = []
+        for d in collate.CudaPrefetcher(iter(batches)):
+            got.append((net(*d)[0].clone(), d[1]["fasttext"].clone()))
+    torch.cuda.synchronize()
+    assert len(got) == 3
+    for (p0, f0), (p1, f1) in zip(want, got):
+        assert torch.equal(f0, f1) and torch.equal(p0, p1)
