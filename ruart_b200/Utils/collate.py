@@ -128,13 +128,21 @@ class CudaPrefetcher(object):
         for q, ocr, od in CudaPrefetcher(pinned_batches):      # pinned_batches: iterable of pin(...)-ed batches
             scores, _ = network(q, ocr, od)
 
-    The yielded tensors were allocated and written on the copy stream: the compute stream waits for that stream and
-    the tensors are recorded on it (caching-allocator lifetime), so they are used like the result of to_cuda()."""
+    The device tensors live in TWO reusable sets of staging buffers (re-allocated only when a shape changes): set
+    i % 2 is overwritten by batch i + 2 only after the compute stream has passed the point where batch i + 1 was
+    requested, i.e. after everything that was queued for batch i.  (Fresh allocations on the copy stream +
+    record_stream were measured first: the caching allocator cannot recycle those blocks while the host runs
+    steps ahead of the GPU and the loop degenerated into cudaMalloc calls — 29 vs 24 ms per step.)
+    The yielded dicts are new objects each time (SDNet.forward adds keys to them); the tensors inside are only
+    valid until the batch after next is requested."""
 
     def __init__(self, batches, device="cuda"):
         self.it = iter(batches)
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self._sets = [{}, {}]
+        self._free = [None, None]     # event on the compute stream after which set k may be overwritten
+        self._n = 0
         self._next = None
         self._preload()
 
@@ -144,8 +152,29 @@ class CudaPrefetcher(object):
         except StopIteration:
             self._next = None
             return
+        k = self._n % 2
+        self._n += 1
+        bufs = self._sets[k]
+        if self._free[k] is not None:
+            self.stream.wait_event(self._free[k])
+        out = []
         with torch.cuda.stream(self.stream):
-            self._next = to_cuda(host, self.device)
+            for di, d in enumerate(host):
+                o = {}
+                for key, v in d.items():
+                    if torch.is_tensor(v):
+                        b = bufs.get((di, key))
+                        if b is None or b.shape != v.shape or b.dtype != v.dtype:
+                            b = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                            bufs[(di, key)] = b
+                        b.copy_(v, non_blocking=True)
+                        o[key] = b
+                    else:
+                        o[key] = v
+                out.append(o)
+        ready = torch.cuda.Event()
+        ready.record(self.stream)
+        self._next = (tuple(out), ready, k)
 
     def __iter__(self):
         return self
@@ -153,12 +182,12 @@ class CudaPrefetcher(object):
     def __next__(self):
         if self._next is None:
             raise StopIteration
+        batch, ready, k = self._next
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_stream(self.stream)
-        batch = self._next
-        for d in batch:
-            for v in d.values():
-                if torch.is_tensor(v):
-                    v.record_stream(cur)
+        # everything queued so far used (at most) the OTHER set: it may be overwritten once the stream gets here
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._free[1 - k] = done
+        cur.wait_event(ready)
         self._preload()
         return batch
