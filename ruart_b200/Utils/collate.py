@@ -136,15 +136,25 @@ class CudaPrefetcher(object):
     The yielded dicts are new objects each time (SDNet.forward adds keys to them); the tensors inside are only
     valid until the batch after next is requested."""
 
-    def __init__(self, batches, device="cuda"):
-        self.it = iter(batches)
+    def __init__(self, batches=None, device="cuda"):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self._sets = [{}, {}]
         self._free = [None, None]     # event on the compute stream after which set k may be overwritten
         self._n = 0
         self._next = None
+        self.it = iter(())
+        if batches is not None:
+            self.feed(batches)
+
+    def feed(self, batches):
+        """Start over on another iterable of pinned batches, KEEPING the copy stream and the staging buffers (a
+        data loader's next epoch; bench.py's warm-up and timed loops).  Returns self, so `for b in pf.feed(x)`."""
+        if self._next is not None:
+            raise RuntimeError("CudaPrefetcher.feed(): the previous iterable is not exhausted")
+        self.it = iter(batches)
         self._preload()
+        return self
 
     def _preload(self):
         try:

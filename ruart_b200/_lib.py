@@ -166,6 +166,19 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = None
+
+
 def current_stream():
-    import torch
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device, as an int.  torch.cuda.current_stream() costs
+    ~14 us of Python per call and the forward asks ~170 times: the raw accessor is two C calls."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+        get_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        get_dev = getattr(torch._C, "_cuda_getDevice", None)
+        if get_stream is not None and get_dev is not None:
+            _raw_stream = lambda: get_stream(get_dev())
+        else:
+            _raw_stream = lambda: torch.cuda.current_stream().cuda_stream
+    return _raw_stream()

@@ -99,6 +99,7 @@ class BertEngine(object):
         assert self.H // self.heads == 64, "attention kernel is specialised for head_dim 64"
         self._key = None
         self._w = None
+        self._params = None
         # bf16 mode: the 24 BertLayerNorm passes are folded into the neighbouring GEMMs (fold_weights / the FOLD forms
         # of the CTA-pair GEMM); needs the pair kernel (T >= FOLD_MIN_T) and 768-wide rows.  RUART_NO_LN_FOLD: A/B aid.
         self.fold = (mode == "bf16" and not residual_fp32 and self.H == 768
@@ -111,8 +112,12 @@ class BertEngine(object):
 
     # ------------------------------------------------------------------ weights
     def _weights_key(self, dev):
-        return (str(dev), self.mode, tuple(p._version for p in self.model.parameters()),
-                tuple(p.data_ptr() for p in self.model.parameters()))
+        # the Parameter OBJECTS are fixed after construction (load_state_dict / .to() / optimizers change their
+        # data in place): walking the module tree on every forward cost ~1.3 ms of host time
+        ps = self._params
+        if ps is None:
+            ps = self._params = tuple(self.model.parameters())
+        return (str(dev), self.mode, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
 
     def _prep_matrix(self, w):
         """fp32 [N, K] -> bf16 GEMM operand ([N, K] or 3-part split [N, 3K])."""
