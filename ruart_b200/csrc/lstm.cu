@@ -16,6 +16,7 @@
 // broadcast h load now feeds four FFMA2 instead of two, and 88 weights of each row sit in
 // registers, so the shared-memory loads per FMA halve: 3.75 -> 2.61 us per time step at B = 256,
 // H = 125 (profiles/r01_lstm_microbench.txt).
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -303,6 +304,231 @@ lstm_recurrence2_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Tensor-core form — the kernel that runs for inference.  One CTA owns 8 sequences of one direction
+// for all steps.  The gate pre-activations of a step are  W_hh [4H x H] · h^T [H x 8]  on mma.sync
+// m16n8k16 with W_hh as the A operand: gate rows are the M dimension, the 8 sequences are N, so no
+// column of the tile is padding.  fp32 fidelity comes from the bf16 hi|lo split the SDNet GEMMs use:
+// W·h = Wh·hh + Wh·hl + Wl·hh (the dropped Wl·hl term is 2^-16 relative).
+//
+// 8 warps; warp w owns units 16w .. 16w+15 as four 16-row tiles: tile (ug, 0) = rows {i of units
+// 16w+8ug+0..7 ; f of the same units}, tile (ug, 1) = {g ; o}.  In the accumulator layout lane
+// (g = lane/4, c = lane%4) then holds i, f, g, o of unit 16w+8ug+g for sequences 2c and 2c+1: the cell
+// update needs no shuffle.  The hi halves of the thread's A fragments stay in REGISTERS for the whole
+// sequence (128 registers), the lo halves of the first KLO_REG k-steps too; the other lo fragments
+// sit in shared memory in fragment order (one conflict-free LDS.128 each).  h_{t-1} lives in shared
+// memory as bf16 hi and lo rows [sequence][unit] (pitch 272 B: ldmatrix rows on distinct banks) and is
+// the B operand through ldmatrix.x4.  xg rows (x W_ih^T + b, from the tcgen05 GEMM) arrive through a
+// 3-stage ring of 1-D TMA bulk copies, three steps ahead, and initialise the accumulators.
+// Activations: E_x = 2^(-x log2 e) on MUFU.EX2, and  s(i)·tanh(g) = (1-E_g) / ((1+E_i)(1+E_g))  shares
+// one MUFU.RCP between two gates (likewise s(o)·tanh(c)): 8 MUFU per cell instead of 10.
+constexpr int LM_THREADS = 256;
+constexpr int LM_BT = 8;      // sequences per CTA = N of the MMA
+constexpr int LM_HS = 136;    // bf16 pitch of an h row
+constexpr int LM_XS = 3;      // xg ring stages
+constexpr int LM_XST = LM_BT * 4 * HP;  // floats per ring stage
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int KLO_REG>
+constexpr size_t lstm_mma_smem() {
+  return static_cast<size_t>(8 - KLO_REG) * 4 * LM_THREADS * 16 + 2 * 2 * LM_BT * LM_HS * 2 +
+         static_cast<size_t>(LM_XS) * LM_XST * 4 + LM_XS * 8;
+}
+
+template <int KLO_REG>
+__global__ void __launch_bounds__(LM_THREADS, 1)
+lstm_recurrence_mma_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B*L, ndir*4H]
+                           const float* __restrict__ w_hh,                    // [ndir][4H][H]
+                           float* __restrict__ out, long long out_pitch,      // [B*L, >= ndir*H]
+                           int B, int L, int H) {
+  constexpr int KS = 8;
+  constexpr int KLO_SM = KS - KLO_REG;
+  extern __shared__ __align__(128) unsigned char lm_smem[];
+  uint4* s_wlo = reinterpret_cast<uint4*>(lm_smem);                                    // [KLO_SM][4][256]
+  __nv_bfloat16* s_h = reinterpret_cast<__nv_bfloat16*>(lm_smem + KLO_SM * 4 * LM_THREADS * 16);  // [2][hi|lo][8][LM_HS]
+  float* s_x = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_h) + 2 * 2 * LM_BT * LM_HS * 2);
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(s_x + LM_XS * LM_XST);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int dir = blockIdx.y;
+  const int b0 = blockIdx.x * LM_BT;
+  const int nb = min(LM_BT, B - b0);
+  const int rs = 4 * H;  // floats per sequence row of a ring stage
+  const float* W = w_hh + static_cast<long long>(dir) * 4 * H * H;
+
+  uint32_t whi[4][KS][4];
+  uint32_t wlo[4][KLO_REG > 0 ? KLO_REG : 1][4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int unit = 16 * w + 8 * (t >> 1) + g;
+    const bool uok = unit < H;
+    const float* r0 = W + (static_cast<long long>(2 * (t & 1)) * H + unit) * H;
+    const float* r1 = r0 + static_cast<long long>(H) * H;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t lo4[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int k = 16 * ks + 8 * hf + 2 * c;
+        const float v00 = (uok && k < H) ? __ldg(r0 + k) : 0.f;
+        const float v01 = (uok && k + 1 < H) ? __ldg(r0 + k + 1) : 0.f;
+        const float v10 = (uok && k < H) ? __ldg(r1 + k) : 0.f;
+        const float v11 = (uok && k + 1 < H) ? __ldg(r1 + k + 1) : 0.f;
+        const uint32_t h0 = pack_bf16x2(v00, v01), h1 = pack_bf16x2(v10, v11);
+        whi[t][ks][2 * hf] = h0;
+        whi[t][ks][2 * hf + 1] = h1;
+        lo4[2 * hf] = pack_bf16x2(v00 - bf16_lo(h0), v01 - bf16_hi(h0));
+        lo4[2 * hf + 1] = pack_bf16x2(v10 - bf16_lo(h1), v11 - bf16_hi(h1));
+      }
+      if (ks < KLO_REG) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wlo[t][ks < KLO_REG ? ks : 0][i] = lo4[i];
+      } else {
+        s_wlo[((ks - KLO_REG) * 4 + t) * LM_THREADS + tid] = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+      }
+    }
+  }
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(s_h);
+    for (int i = tid; i < 2 * 2 * LM_BT * LM_HS / 2; i += LM_THREADS) z[i] = 0u;
+    if (nb < LM_BT)  // rows of absent sequences are never loaded: keep them finite
+      for (int i = tid; i < LM_XS * LM_XST; i += LM_THREADS) s_x[i] = 0.f;
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < LM_XS; ++i) mbar_init(&xbar[i], LM_THREADS / 32);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  auto step_time = [&](int s) { return dir == 0 ? s : (L - 1 - s); };
+  // lane 0 of warp n: the xg row of sequence n at step s into ring stage s % LM_XS (every warp arrives, so
+  // no warp carries all eight copies on the critical path of a step)
+  auto issue = [&](int s) {
+    const int stg = s % LM_XS;
+    if (w < nb) {
+      const uint32_t bytes = static_cast<uint32_t>(rs) * 4u;
+      mbar_arrive_expect_tx(&xbar[stg], bytes);
+      bulk_load_1d(s_x + stg * LM_XST + w * rs,
+                   xg + (static_cast<long long>(b0 + w) * L + step_time(s)) * xg_pitch +
+                       static_cast<long long>(dir) * rs,
+                   bytes, &xbar[stg]);
+    } else {
+      mbar_arrive(&xbar[stg]);
+    }
+  };
+  if (lane == 0)
+    for (int s = 0; s < LM_XS && s < L; ++s) issue(s);
+
+  float cst[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) cst[i][0] = cst[i][1] = 0.f;
+  // ldmatrix lane address inside an h half-buffer: matrix m = lane / 8 covers k = 8m .. 8m+7 of the pair of k-steps
+  const uint32_t h_base = smem_u32(s_h);
+  const uint32_t lane_off = static_cast<uint32_t>(((lane & 7) * LM_HS + 8 * (lane >> 3)) * 2);
+  constexpr uint32_t HBUF = 2 * LM_BT * LM_HS * 2;  // bytes per buffer (hi rows then lo rows)
+  constexpr uint32_t HLO = LM_BT * LM_HS * 2;
+  int cur = 0;
+  for (int s = 0; s < L; ++s) {
+    const int stg = s % LM_XS;
+    mbar_wait(&xbar[stg], (s / LM_XS) & 1);
+    const float* xs = s_x + stg * LM_XST;
+    float acc[4][4], sm[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int unit = 16 * w + 8 * (t >> 1) + g;
+      const bool uok = unit < H;
+      const float* x0 = xs + (2 * c) * rs + (2 * (t & 1)) * H + unit;
+      acc[t][0] = uok ? x0[0] : 0.f;
+      acc[t][1] = uok ? x0[rs] : 0.f;
+      acc[t][2] = uok ? x0[H] : 0.f;
+      acc[t][3] = uok ? x0[rs + H] : 0.f;
+      sm[t][0] = sm[t][1] = sm[t][2] = sm[t][3] = 0.f;
+    }
+    const uint32_t hb = h_base + cur * HBUF + lane_off;
+#pragma unroll
+    for (int kp = 0; kp < KS / 2; ++kp) {
+      uint32_t bh[4], bl[4];
+      ldsm_x4(hb + kp * 64, bh[0], bh[1], bh[2], bh[3]);
+      ldsm_x4(hb + HLO + kp * 64, bl[0], bl[1], bl[2], bl[3]);
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = 2 * kp + kk;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          mma_bf16_16816(acc[t], whi[t][ks][0], whi[t][ks][1], whi[t][ks][2], whi[t][ks][3], bh[2 * kk], bh[2 * kk + 1]);
+          mma_bf16_16816(sm[t], whi[t][ks][0], whi[t][ks][1], whi[t][ks][2], whi[t][ks][3], bl[2 * kk], bl[2 * kk + 1]);
+          if (ks < KLO_REG) {
+            const int kr = ks < KLO_REG ? ks : 0;
+            mma_bf16_16816(sm[t], wlo[t][kr][0], wlo[t][kr][1], wlo[t][kr][2], wlo[t][kr][3], bh[2 * kk], bh[2 * kk + 1]);
+          } else {
+            const uint4 l4 = s_wlo[((ks - KLO_REG) * 4 + t) * LM_THREADS + tid];
+            mma_bf16_16816(sm[t], l4.x, l4.y, l4.z, l4.w, bh[2 * kk], bh[2 * kk + 1]);
+          }
+        }
+      }
+    }
+    __nv_bfloat16* hn = s_h + (cur ^ 1) * (2 * LM_BT * LM_HS);
+    const int tt = step_time(s);
+    constexpr float L2E = 1.4426950408889634f;
+#pragma unroll
+    for (int ug = 0; ug < 2; ++ug) {
+      const int unit = 16 * w + 8 * ug + g;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float pi = acc[2 * ug][e] + sm[2 * ug][e];
+        const float pf = acc[2 * ug][2 + e] + sm[2 * ug][2 + e];
+        const float pg = acc[2 * ug + 1][e] + sm[2 * ug + 1][e];
+        const float po = acc[2 * ug + 1][2 + e] + sm[2 * ug + 1][2 + e];
+        // exponents capped at 2^60 so that the shared denominators stay finite
+        const float Ei = ex2_approx(fminf(-L2E * pi, 60.f));
+        const float Eg = ex2_approx(fminf(-2.f * L2E * pg, 60.f));
+        const float Ef = ex2_approx(-L2E * pf);
+        const float Eo = ex2_approx(fminf(-L2E * po, 60.f));
+        const float ig = (1.f - Eg) * rcp_approx((1.f + Ei) * (1.f + Eg));
+        const float fg = rcp_approx(1.f + Ef);
+        const float cn = fmaf(fg, cst[ug][e], ig);
+        const float Ec = ex2_approx(fminf(-2.f * L2E * cn, 60.f));
+        const float hv = (1.f - Ec) * rcp_approx((1.f + Eo) * (1.f + Ec));
+        cst[ug][e] = cn;
+        if (unit < H) {
+          const int n = 2 * c + e;
+          const __nv_bfloat16 hh = __float2bfloat16_rn(hv);
+          hn[n * LM_HS + unit] = hh;
+          hn[LM_BT * LM_HS + n * LM_HS + unit] = __float2bfloat16_rn(hv - __bfloat162float(hh));
+          if (n < nb)
+            out[(static_cast<long long>(b0 + n) * L + tt) * out_pitch + dir * H + unit] = hv;
+        }
+      }
+    }
+    __syncthreads();
+    if (lane == 0 && s + LM_XS < L) issue(s + LM_XS);
+    cur ^= 1;
+  }
+}
+
+template <int KLO_REG>
+int launch_mma(const float* xg, long long xg_pitch, const float* w_hh, float* out, long long out_pitch,
+               int B, int L, int H, int ndir, cudaStream_t st) {
+  constexpr size_t smem = lstm_mma_smem<KLO_REG>();
+  static RuartDeviceOnce attr_set;
+  if (!attr_set.done()) {
+    RUART_CUDA_CHECK(cudaFuncSetAttribute(lstm_recurrence_mma_kernel<KLO_REG>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set.set();
+  }
+  dim3 grid((B + LM_BT - 1) / LM_BT, ndir);
+  lstm_recurrence_mma_kernel<KLO_REG><<<grid, LM_THREADS, smem, st>>>(xg, xg_pitch, w_hh, out, out_pitch,
+                                                                       B, L, H);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
 template <int BT, int KR2, bool SAVE = false>
 int launch2(const float* xg, long long xg_pitch, const float* w_hh, float* out, long long out_pitch,
             int B, int L, int H, int ndir, cudaStream_t st, float* gates = nullptr,
@@ -348,6 +574,15 @@ extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const 
   cudaStream_t st = (cudaStream_t)stream;
   // fewest sequences per CTA that still fits one wave of CTAs on the device
   const int sms = ruart_num_sms();
+  // tensor-core form unless switched off (A/B aid) or the xg rows cannot be bulk-copied (16-byte alignment)
+  static const char* fma_env = getenv("RUART_LSTM_FMA");
+  static const char* klo_env = getenv("RUART_LSTM_KLO");
+  if (!fma_env && (xg_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(xg) & 15) == 0) {
+    const int klo = klo_env ? atoi(klo_env) : 2;
+    if (klo == 0) return launch_mma<0>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+    if (klo == 3) return launch_mma<3>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+    return launch_mma<2>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+  }
   static const bool one_row = getenv("RUART_LSTM_ONE_ROW") != nullptr;  // A/B aid: the 512-thread kernel
   if (one_row) {
     if (((B + 1) / 2) * ndir <= sms) return launch<2>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);

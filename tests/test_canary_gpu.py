@@ -131,7 +131,7 @@ def test_new_kernels_stay_inside_their_outputs():
     gates.check("lstm_recurrence_train gates")
     plain = torch.empty(B, L, 2 * H, device="cuda")
     call("ruart_lstm_recurrence", ptr(xg), 8 * H, ptr(whh), ptr(plain), 2 * H, B, L, H, 2, st)
-    assert torch.equal(plain, o.view)                  # saving the gates does not change the recurrence
+    assert torch.allclose(plain, o.view, atol=5e-6)    # inference runs the tensor-core form of the same recurrence
     dxg = Guarded((B * L, 8 * H))
     dout = R(B, L, 2 * H)
     call("ruart_lstm_recurrence_backward", ptr(gates.view), 10 * H, ptr(whh), ptr(dout), 2 * H, ptr(dxg.view),

@@ -25,6 +25,38 @@ def test_stacked_brnn_layer_matches_oracle(B, L, I, H, bidir):
     assert (got.cpu() - want).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("B,L,H,ndir", [(7, 9, 125, 2), (256, 101, 125, 2), (1, 1, 125, 2), (20, 5, 128, 1),
+                                        (37, 40, 17, 2), (9, 3, 64, 1), (300, 4, 89, 2)])
+def test_lstm_tensor_core_recurrence_matches_fp32_fma_recurrence(B, L, H, ndir):
+    """ruart_lstm_recurrence (mma.sync on bf16 hi|lo splits, shared reciprocals) against the fp32-FMA kernel
+    that the training path keeps (ruart_lstm_recurrence_train), on a strided output and xg with row padding."""
+    from ruart_b200._lib import current_stream, ptr
+    from ruart_b200.ops import call
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + L)
+    pitch = ndir * 4 * H + 4 * (B % 3)                     # multiple of 4 floats: the TMA path
+    xg = torch.randn(B * L, pitch, device="cuda", generator=g) * 1.5
+    xg[:, :3] *= 30                                         # saturated gates: the capped exponents
+    whh = (torch.rand(ndir, 4 * H, H, device="cuda", generator=g) * 2 - 1) / H ** 0.5
+    want = torch.zeros(B, L, ndir * H + 3, device="cuda")
+    got = torch.zeros_like(want)
+    gates = torch.empty(B * L, ndir * 5 * H, device="cuda")
+    st = current_stream()
+    call("ruart_lstm_recurrence_train", ptr(xg), pitch, ptr(whh), ptr(want), ndir * H + 3, B, L, H, ndir,
+         ptr(gates), ndir * 5 * H, st)
+    call("ruart_lstm_recurrence", ptr(xg), pitch, ptr(whh), ptr(got), ndir * H + 3, B, L, H, ndir, st)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert (got[..., ndir * H:] == 0).all()                 # nothing written past the row
+    assert (got - want).abs().max().item() < 5e-6
+    # rows that cannot be bulk-copied (pitch not a multiple of 4 floats) take the FMA kernel: same result
+    if H % 2 == 1 and ndir == 2:
+        xg2 = torch.empty(B * L, pitch + 1, device="cuda")
+        xg2[:, :pitch] = xg
+        got2 = torch.zeros_like(want)
+        call("ruart_lstm_recurrence", ptr(xg2), pitch + 1, ptr(whh), ptr(got2), ndir * H + 3, B, L, H, ndir, st)
+        assert torch.equal(got2, want)
+
+
 def test_attention_module_matches_oracle():
     from ruart_b200.Models import Layers
     Layers.set_dropout_prob(0.0)

@@ -33,7 +33,21 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3
-        res.append({"B": B, "L": L, "H": H, "us": round(us, 1), "us_per_step": round(us / L, 3)})
+        gates = torch.empty(B * L, 10 * H, device=dev)
+        ref = torch.empty_like(out)
+        old = lambda: call("ruart_lstm_recurrence_train", ptr(xg), 8 * H, ptr(w), ptr(ref), 2 * H, B, L, H, 2,
+                           ptr(gates), 10 * H, st)
+        old()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            old()
+        e1.record()
+        torch.cuda.synchronize()
+        us_old = e0.elapsed_time(e1) / 5 * 1e3
+        res.append({"B": B, "L": L, "H": H, "us": round(us, 1), "us_per_step": round(us / L, 3),
+                    "fma_kernel_with_saved_gates_us": round(us_old, 1),
+                    "max_abs_diff": float((out - ref).abs().max())})
     print(json.dumps(res))
 
 
