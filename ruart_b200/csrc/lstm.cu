@@ -318,14 +318,26 @@ lstm_recurrence2_kernel(const float* __restrict__ xg, long long xg_pitch,  // [B
 // sequence (128 registers), the lo halves of the first KLO_REG k-steps too; the other lo fragments
 // sit in shared memory in fragment order (one conflict-free LDS.128 each).  h_{t-1} lives in shared
 // memory as bf16 hi and lo rows [sequence][unit] (pitch 272 B: ldmatrix rows on distinct banks) and is
-// the B operand through ldmatrix.x4.  xg rows (x W_ih^T + b, from the tcgen05 GEMM) arrive through a
-// 3-stage ring of 1-D TMA bulk copies, three steps ahead, and initialise the accumulators.
-// Activations: E_x = 2^(-x log2 e) on MUFU.EX2, and  s(i)·tanh(g) = (1-E_g) / ((1+E_i)(1+E_g))  shares
-// one MUFU.RCP between two gates (likewise s(o)·tanh(c)): 8 MUFU per cell instead of 10.
+// the B operand through ldmatrix.x4.  The HMMAs are issued term by term over the four tiles, so two
+// HMMAs on the same accumulator sit four issues apart.  xg rows (x W_ih^T + b, from the tcgen05 GEMM)
+// arrive through a 4-stage ring of 1-D TMA bulk copies, three steps ahead, and are added while the tensor
+// pipe drains.
+// Activations: E_x = 2^(-x log2 e) on MUFU.EX2 — the factor -log2 e (-2 log2 e for the g gate: tanh) is
+// folded into the W_hh fragments when they are loaded and into the xg add — and
+// s(i)·tanh(g) = (1-E_g) / ((1+E_i)(1+E_g))  shares one MUFU.RCP between two gates (likewise s(o)·tanh(c)):
+// 8 MUFU per cell instead of 10.  The four cells of a thread are computed together (independent MUFU
+// chains), the stores that follow are branch-free.
+//
+// Measured (profiles/r02_lstm_microbench.txt): 1.5 us per step against 2.6 for the FMA kernel, on half
+// the CTAs (64 for B = 256, both directions), so two of the three branch LSTMs run side by side.  A step
+// is ~1500 clk of HMMA (192 per scheduler at 8 clk, the legacy tensor path) + ~800 clk of cell update +
+// the barrier; publishing the two halves of h behind separate mbarriers so that one warp of a scheduler
+// could run its cell update under the other's HMMAs was tried: the phase offset decays to lockstep within
+// a few steps and nothing is gained.
 constexpr int LM_THREADS = 256;
 constexpr int LM_BT = 8;      // sequences per CTA = N of the MMA
 constexpr int LM_HS = 136;    // bf16 pitch of an h row
-constexpr int LM_XS = 3;      // xg ring stages
+constexpr int LM_XS = 4;      // xg ring stages
 constexpr int LM_XST = LM_BT * 4 * HP;  // floats per ring stage
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -347,6 +359,7 @@ lstm_recurrence_mma_kernel(const float* __restrict__ xg, long long xg_pitch,  //
                            int B, int L, int H) {
   constexpr int KS = 8;
   constexpr int KLO_SM = KS - KLO_REG;
+  constexpr float L2E = 1.4426950408889634f;
   extern __shared__ __align__(128) unsigned char lm_smem[];
   uint4* s_wlo = reinterpret_cast<uint4*>(lm_smem);                                    // [KLO_SM][4][256]
   __nv_bfloat16* s_h = reinterpret_cast<__nv_bfloat16*>(lm_smem + KLO_SM * 4 * LM_THREADS * 16);  // [2][hi|lo][8][LM_HS]
@@ -366,18 +379,19 @@ lstm_recurrence_mma_kernel(const float* __restrict__ xg, long long xg_pitch,  //
   for (int t = 0; t < 4; ++t) {
     const int unit = 16 * w + 8 * (t >> 1) + g;
     const bool uok = unit < H;
-    const float* r0 = W + (static_cast<long long>(2 * (t & 1)) * H + unit) * H;
-    const float* r1 = r0 + static_cast<long long>(H) * H;
+    const float* r0 = W + (static_cast<long long>(2 * (t & 1)) * H + unit) * H;   // gate i or g
+    const float* r1 = r0 + static_cast<long long>(H) * H;                          // gate f or o
+    const float sc0 = (t & 1) ? -2.f * L2E : -L2E, sc1 = -L2E;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t lo4[4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int k = 16 * ks + 8 * hf + 2 * c;
-        const float v00 = (uok && k < H) ? __ldg(r0 + k) : 0.f;
-        const float v01 = (uok && k + 1 < H) ? __ldg(r0 + k + 1) : 0.f;
-        const float v10 = (uok && k < H) ? __ldg(r1 + k) : 0.f;
-        const float v11 = (uok && k + 1 < H) ? __ldg(r1 + k + 1) : 0.f;
+        const float v00 = (uok && k < H) ? sc0 * __ldg(r0 + k) : 0.f;
+        const float v01 = (uok && k + 1 < H) ? sc0 * __ldg(r0 + k + 1) : 0.f;
+        const float v10 = (uok && k < H) ? sc1 * __ldg(r1 + k) : 0.f;
+        const float v11 = (uok && k + 1 < H) ? sc1 * __ldg(r1 + k + 1) : 0.f;
         const uint32_t h0 = pack_bf16x2(v00, v01), h1 = pack_bf16x2(v10, v11);
         whi[t][ks][2 * hf] = h0;
         whi[t][ks][2 * hf + 1] = h1;
@@ -408,22 +422,25 @@ lstm_recurrence_mma_kernel(const float* __restrict__ xg, long long xg_pitch,  //
 
   auto step_time = [&](int s) { return dir == 0 ? s : (L - 1 - s); };
   // lane 0 of warp n: the xg row of sequence n at step s into ring stage s % LM_XS (every warp arrives, so
-  // no warp carries all eight copies on the critical path of a step)
+  // no warp carries all eight copies on the critical path of a step); steps are issued in order, the source
+  // pointer walks one row per step
+  const long long xstep = (dir == 0 ? 1 : -1) * xg_pitch;
+  const float* xsrc = xg + (static_cast<long long>(b0 + (w < nb ? w : 0)) * L + step_time(0)) * xg_pitch +
+                      static_cast<long long>(dir) * rs;
   auto issue = [&](int s) {
     const int stg = s % LM_XS;
     if (w < nb) {
       const uint32_t bytes = static_cast<uint32_t>(rs) * 4u;
       mbar_arrive_expect_tx(&xbar[stg], bytes);
-      bulk_load_1d(s_x + stg * LM_XST + w * rs,
-                   xg + (static_cast<long long>(b0 + w) * L + step_time(s)) * xg_pitch +
-                       static_cast<long long>(dir) * rs,
-                   bytes, &xbar[stg]);
+      bulk_load_1d(s_x + stg * LM_XST + w * rs, xsrc, bytes, &xbar[stg]);
+      xsrc += xstep;
     } else {
       mbar_arrive(&xbar[stg]);
     }
   };
+  constexpr int AHEAD = LM_XS - 1;  // steps the copies run ahead
   if (lane == 0)
-    for (int s = 0; s < LM_XS && s < L; ++s) issue(s);
+    for (int s = 0; s < AHEAD && s < L; ++s) issue(s);
 
   float cst[2][2];
 #pragma unroll
@@ -433,81 +450,94 @@ lstm_recurrence_mma_kernel(const float* __restrict__ xg, long long xg_pitch,  //
   const uint32_t lane_off = static_cast<uint32_t>(((lane & 7) * LM_HS + 8 * (lane >> 3)) * 2);
   constexpr uint32_t HBUF = 2 * LM_BT * LM_HS * 2;  // bytes per buffer (hi rows then lo rows)
   constexpr uint32_t HLO = LM_BT * LM_HS * 2;
+  // units >= H read the xg value of unit H-1 (finite; their W rows are zero and nothing of theirs is stored)
+  const int ux0 = min(16 * w + g, H - 1), ux1 = min(16 * w + 8 + g, H - 1);
+  float* orow = out + (static_cast<long long>(b0 + 2 * c) * L + step_time(0)) * out_pitch + dir * H + 16 * w + g;
+  const long long ostep = (dir == 0 ? 1 : -1) * out_pitch;
+  const long long oseq = static_cast<long long>(L) * out_pitch;
   int cur = 0;
   for (int s = 0; s < L; ++s) {
-    const int stg = s % LM_XS;
-    mbar_wait(&xbar[stg], (s / LM_XS) & 1);
-    const float* xs = s_x + stg * LM_XST;
-    float acc[4][4], sm[4][4];
+    float acc[4][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int unit = 16 * w + 8 * (t >> 1) + g;
-      const bool uok = unit < H;
-      const float* x0 = xs + (2 * c) * rs + (2 * (t & 1)) * H + unit;
-      acc[t][0] = uok ? x0[0] : 0.f;
-      acc[t][1] = uok ? x0[rs] : 0.f;
-      acc[t][2] = uok ? x0[H] : 0.f;
-      acc[t][3] = uok ? x0[rs + H] : 0.f;
-      sm[t][0] = sm[t][1] = sm[t][2] = sm[t][3] = 0.f;
-    }
-    const uint32_t hb = h_base + cur * HBUF + lane_off;
+    for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+    if (s > 0) {  // h_{-1} = 0
+      const uint32_t hb = h_base + cur * HBUF + lane_off;
 #pragma unroll
-    for (int kp = 0; kp < KS / 2; ++kp) {
-      uint32_t bh[4], bl[4];
-      ldsm_x4(hb + kp * 64, bh[0], bh[1], bh[2], bh[3]);
-      ldsm_x4(hb + HLO + kp * 64, bl[0], bl[1], bl[2], bl[3]);
+      for (int kp = 0; kp < KS / 2; ++kp) {
+        uint32_t bh[4], bl[4];
+        ldsm_x4(hb + kp * 64, bh[0], bh[1], bh[2], bh[3]);
+        ldsm_x4(hb + HLO + kp * 64, bl[0], bl[1], bl[2], bl[3]);
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int ks = 2 * kp + kk;
+        for (int kk = 0; kk < 2; ++kk) {
+          const int ks = 2 * kp + kk;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          mma_bf16_16816(acc[t], whi[t][ks][0], whi[t][ks][1], whi[t][ks][2], whi[t][ks][3], bh[2 * kk], bh[2 * kk + 1]);
-          mma_bf16_16816(sm[t], whi[t][ks][0], whi[t][ks][1], whi[t][ks][2], whi[t][ks][3], bl[2 * kk], bl[2 * kk + 1]);
-          if (ks < KLO_REG) {
-            const int kr = ks < KLO_REG ? ks : 0;
-            mma_bf16_16816(sm[t], wlo[t][kr][0], wlo[t][kr][1], wlo[t][kr][2], wlo[t][kr][3], bh[2 * kk], bh[2 * kk + 1]);
-          } else {
-            const uint4 l4 = s_wlo[((ks - KLO_REG) * 4 + t) * LM_THREADS + tid];
-            mma_bf16_16816(sm[t], l4.x, l4.y, l4.z, l4.w, bh[2 * kk], bh[2 * kk + 1]);
+          for (int t = 0; t < 4; ++t)
+            mma_bf16_16816(acc[t], whi[t][ks][0], whi[t][ks][1], whi[t][ks][2], whi[t][ks][3], bh[2 * kk], bh[2 * kk + 1]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            mma_bf16_16816(acc[t], whi[t][ks][0], whi[t][ks][1], whi[t][ks][2], whi[t][ks][3], bl[2 * kk], bl[2 * kk + 1]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (ks < KLO_REG) {
+              const int kr = ks < KLO_REG ? ks : 0;
+              mma_bf16_16816(acc[t], wlo[t][kr][0], wlo[t][kr][1], wlo[t][kr][2], wlo[t][kr][3], bh[2 * kk], bh[2 * kk + 1]);
+            } else {
+              const uint4 l4 = s_wlo[((ks - KLO_REG) * 4 + t) * LM_THREADS + tid];
+              mma_bf16_16816(acc[t], l4.x, l4.y, l4.z, l4.w, bh[2 * kk], bh[2 * kk + 1]);
+            }
           }
         }
       }
     }
+    // while the tensor pipe drains: the next copy goes out (its stage was last read in the cell update of step
+    // s-1, which every warp has left) and this step's xg rows are fetched from the ring
+    if (lane == 0 && s + AHEAD < L) issue(s + AHEAD);
+    const int stg = s % LM_XS;
+    mbar_wait(&xbar[stg], (s / LM_XS) & 1);
+    const float* xs = s_x + stg * LM_XST + (2 * c) * rs;
     __nv_bfloat16* hn = s_h + (cur ^ 1) * (2 * LM_BT * LM_HS);
-    const int tt = step_time(s);
-    constexpr float L2E = 1.4426950408889634f;
+    float hv[2][2];
+#pragma unroll
+    for (int ug = 0; ug < 2; ++ug) {
+      const float* x0 = xs + (ug ? ux1 : ux0);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float* xe = x0 + e * rs;
+        // pre-activations times -log2 e (-2 log2 e for g); exponents capped at 2^60 so that the shared
+        // denominators stay finite
+        const float pi = fmaf(-L2E, xe[0], acc[2 * ug][e]);
+        const float pf = fmaf(-L2E, xe[H], acc[2 * ug][2 + e]);
+        const float pg = fmaf(-2.f * L2E, xe[2 * H], acc[2 * ug + 1][e]);
+        const float po = fmaf(-L2E, xe[3 * H], acc[2 * ug + 1][2 + e]);
+        const float Ei = ex2_approx(fminf(pi, 60.f));
+        const float Eg = ex2_approx(fminf(pg, 60.f));
+        const float Ef = ex2_approx(pf);
+        const float Eo = ex2_approx(fminf(po, 60.f));
+        const float ig = (1.f - Eg) * rcp_approx((1.f + Ei) * (1.f + Eg));
+        const float fg = rcp_approx(1.f + Ef);
+        const float cn = fmaf(fg, cst[ug][e], ig);
+        const float Ec = ex2_approx(fminf(-2.f * L2E * cn, 60.f));
+        hv[ug][e] = (1.f - Ec) * rcp_approx((1.f + Eo) * (1.f + Ec));
+        cst[ug][e] = cn;
+      }
+    }
+    // units >= H produce finite values that meet zero columns of W_hh in the next step: the shared-memory
+    // stores need no predicate
 #pragma unroll
     for (int ug = 0; ug < 2; ++ug) {
       const int unit = 16 * w + 8 * ug + g;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const float pi = acc[2 * ug][e] + sm[2 * ug][e];
-        const float pf = acc[2 * ug][2 + e] + sm[2 * ug][2 + e];
-        const float pg = acc[2 * ug + 1][e] + sm[2 * ug + 1][e];
-        const float po = acc[2 * ug + 1][2 + e] + sm[2 * ug + 1][2 + e];
-        // exponents capped at 2^60 so that the shared denominators stay finite
-        const float Ei = ex2_approx(fminf(-L2E * pi, 60.f));
-        const float Eg = ex2_approx(fminf(-2.f * L2E * pg, 60.f));
-        const float Ef = ex2_approx(-L2E * pf);
-        const float Eo = ex2_approx(fminf(-L2E * po, 60.f));
-        const float ig = (1.f - Eg) * rcp_approx((1.f + Ei) * (1.f + Eg));
-        const float fg = rcp_approx(1.f + Ef);
-        const float cn = fmaf(fg, cst[ug][e], ig);
-        const float Ec = ex2_approx(fminf(-2.f * L2E * cn, 60.f));
-        const float hv = (1.f - Ec) * rcp_approx((1.f + Eo) * (1.f + Ec));
-        cst[ug][e] = cn;
-        if (unit < H) {
-          const int n = 2 * c + e;
-          const __nv_bfloat16 hh = __float2bfloat16_rn(hv);
-          hn[n * LM_HS + unit] = hh;
-          hn[LM_BT * LM_HS + n * LM_HS + unit] = __float2bfloat16_rn(hv - __bfloat162float(hh));
-          if (n < nb)
-            out[(static_cast<long long>(b0 + n) * L + tt) * out_pitch + dir * H + unit] = hv;
-        }
+        const int n = 2 * c + e;
+        const float v = hv[ug][e];
+        const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+        hn[n * LM_HS + unit] = hh;
+        hn[LM_BT * LM_HS + n * LM_HS + unit] = __float2bfloat16_rn(v - __bfloat162float(hh));
+        if (unit < H && n < nb) orow[e * oseq + 8 * ug] = v;
       }
     }
+    orow += ostep;
     __syncthreads();
-    if (lane == 0 && s + LM_XS < L) issue(s + LM_XS);
     cur ^= 1;
   }
 }
@@ -578,10 +608,10 @@ extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const 
   static const char* fma_env = getenv("RUART_LSTM_FMA");
   static const char* klo_env = getenv("RUART_LSTM_KLO");
   if (!fma_env && (xg_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(xg) & 15) == 0) {
-    const int klo = klo_env ? atoi(klo_env) : 2;
+    const int klo = klo_env ? atoi(klo_env) : 3;  // lo fragments of that many k-steps in registers (A/B aid)
     if (klo == 0) return launch_mma<0>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
-    if (klo == 3) return launch_mma<3>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
-    return launch_mma<2>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+    if (klo == 2) return launch_mma<2>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+    return launch_mma<3>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
   }
   static const bool one_row = getenv("RUART_LSTM_ONE_ROW") != nullptr;  // A/B aid: the 512-thread kernel
   if (one_row) {
