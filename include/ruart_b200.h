@@ -250,7 +250,9 @@ RUART_API int ruart_lstm_cell(const float* gx, const int32_t* row_gx, const floa
                               const int32_t* last_step, int step, const long long* slot_off,
                               float* slots, void* stream);
 /* Persistent (Bi)LSTM recurrence of StackedBRNN (Layers.py:137,166): xg = x W_ih^T + b_ih + b_hh
- * [B*L, ndir*4H] -> out[:, dir*H + j]; w_hh [ndir][4H][H]; H <= 128; pads are processed.      */
+ * [B*L, ndir*4H] -> out[:, dir*H + j]; w_hh [ndir][4H][H]; H <= 128; pads are processed.
+ * Runs on tensor cores (mma.sync on bf16 hi|lo splits of W_hh and h, ~1e-6 from the fp32 recurrence)
+ * when xg is 16-byte aligned with xg_pitch % 4 == 0; otherwise the fp32 FMA kernel.              */
 RUART_API int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const float* w_hh,
                                     float* out, long long out_pitch, int B, int L, int H,
                                     int ndir, void* stream);

@@ -12,7 +12,7 @@ ncu --set full --clock-control none --import-source on --profile-from-start off 
     --launch-skip 16 --launch-count 12 -f -o gpurun_out/${T}_full python tools/profile_step.py cfg3 > gpurun_out/${T}_ncu_full.log 2>&1
 python tools/summarize_ncu_full.py gpurun_out/${T}_full.ncu-rep > gpurun_out/${T}_ncu_full_summary.txt 2>&1
 ncu --set full --clock-control none --profile-from-start off \
-    -k regex:"subword_avg_layers_fold|lstm_recurrence2|attention_tail_mma|seq_tiles|split_concat" --launch-count 10 -f -o gpurun_out/${T}_full2 \
+    -k regex:"subword_avg_layers_fold|lstm_recurrence|attention_tail_mma|seq_tiles|split_concat" --launch-count 10 -f -o gpurun_out/${T}_full2 \
     python tools/profile_step.py cfg3 > gpurun_out/${T}_ncu_full2.log 2>&1
 python tools/summarize_ncu_full.py gpurun_out/${T}_full2.ncu-rep > gpurun_out/${T}_ncu_full2_summary.txt 2>&1
 rm -f gpurun_out/${T}_full2.ncu-rep
