@@ -1666,6 +1666,116 @@ split_concat_bf16_kernel(ConcatSrc cs, long long rows, int Kp, int parts, __nv_b
   }
 }
 
+// Row-tiled form of the same conversion (the one that runs when float2 loads are legal and Kp <= 4096): a CTA walks
+// tiles of RB = 256 SLOTS / (Kp / 8) rows, and a thread keeps the SAME (row within the tile, 8-column group) slots in
+// every tile, so the index division and the source search happen once per thread instead of once per 8 columns (the
+// flat form shows 69 % of the issue slots busy in ncu, profiles/r02d_movers_summary.txt).  All loads of a thread's
+// slots are issued before the conversions.  Worth 5-10 % (3.5-4.8 TB/s of mixed read/write traffic; four slots per
+// thread cost the occupancy and run at half the speed): profiles/r02_split_concat_microbench.txt.
+template <int SCR_SLOTS>
+__global__ void __launch_bounds__(256)
+split_concat_rows_kernel(ConcatSrc cs, long long rows, int Kp, int parts, int RB, __nv_bfloat16* __restrict__ dst) {
+  const int K = cs.start[cs.n];
+  const int groups = Kp / 8;
+  const int items = RB * groups;
+  const long long dpitch = static_cast<long long>(parts) * Kp;
+  const float* sp[SCR_SLOTS];      // source of the slot's 8 columns at row 0 of a tile (nullptr: zero columns / slow path)
+  long long spitch[SCR_SLOTS];
+  int rl[SCR_SLOTS], c0s[SCR_SLOTS];
+  bool slow[SCR_SLOTS];
+#pragma unroll
+  for (int j = 0; j < SCR_SLOTS; ++j) {
+    const int it = threadIdx.x + 256 * j;
+    rl[j] = -1;
+    sp[j] = nullptr;
+    spitch[j] = 0;
+    c0s[j] = 0;
+    slow[j] = false;
+    if (it < items) {
+      rl[j] = it / groups;
+      const int c0 = (it - rl[j] * groups) * 8;
+      c0s[j] = c0;
+      if (c0 + 8 <= K) {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) q += (k < cs.n && c0 >= cs.start[k]) ? 1 : 0;
+        const float* base = cs.p[0];
+        long long pitch = cs.pitch[0];
+        int st = cs.start[0], en = cs.start[1];
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+          if (q == k) {
+            base = cs.p[k];
+            pitch = cs.pitch[k];
+            st = cs.start[k];
+            en = cs.start[k + 1];
+          }
+        if (c0 + 8 <= en) {
+          sp[j] = base + (c0 - st);
+          spitch[j] = pitch;
+        } else {
+          slow[j] = true;
+        }
+      } else if (c0 < K) {
+        slow[j] = true;
+      }
+    }
+  }
+  for (long long row0 = static_cast<long long>(blockIdx.x) * RB; row0 < rows; row0 += static_cast<long long>(gridDim.x) * RB) {
+    float x[SCR_SLOTS][8];
+#pragma unroll
+    for (int j = 0; j < SCR_SLOTS; ++j) {
+      const long long r = row0 + rl[j];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[j][e] = 0.f;
+      if (rl[j] >= 0 && r < rows) {
+        if (sp[j] != nullptr) {
+          const float2* src = reinterpret_cast<const float2*>(sp[j] + r * spitch[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 v = __ldg(src + e);
+            x[j][2 * e] = v.x;
+            x[j][2 * e + 1] = v.y;
+          }
+        } else if (slow[j]) {  // the group straddles two sources or the end of the concatenation
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const int col = c0s[j] + e;
+            if (col < K) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (q < cs.n && col >= cs.start[q] && col < cs.start[q + 1]) {
+                  const float2 v = __ldg(reinterpret_cast<const float2*>(cs.p[q] + r * cs.pitch[q] + (col - cs.start[q])));
+                  x[j][e] = v.x;
+                  x[j][e + 1] = v.y;
+                }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < SCR_SLOTS; ++j) {
+      const long long r = row0 + rl[j];
+      if (rl[j] >= 0 && r < rows) {
+        __nv_bfloat16* drow = dst + r * dpitch + c0s[j];
+        for (int p = 0; p < parts; ++p) {
+          uint4 u;
+          uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const uint32_t h = pack_bf16x2(x[j][e], x[j][e + 1]);
+            w[e / 2] = h;
+            x[j][e] -= bf16_lo(h);
+            x[j][e + 1] -= bf16_hi(h);
+          }
+          *reinterpret_cast<uint4*>(drow + static_cast<long long>(p) * Kp) = u;
+        }
+      }
+    }
+  }
+}
+
 inline unsigned row_grid(long long rows) {
   return static_cast<unsigned>((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
 }
@@ -2033,7 +2143,22 @@ extern "C" int ruart_split_concat_bf16(const float* const* srcs_host, const long
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(ruart_num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  if (pairs)
+  static const char* sc_env = getenv("RUART_SPLIT_CONCAT_SLOTS");  // A/B aid: 0 = the first (flat-index) form
+  const int groups = Kp / 8;
+  int slots = groups <= 64 ? 1 : groups <= 512 ? 2 : 0;  // measured: profiles/r02_split_concat_microbench.txt
+  if (sc_env) slots = atoi(sc_env);
+  if (pairs && slots > 0 && groups <= 256 * slots) {
+    const int RB = (256 * slots) / groups;
+    long long tiles = (rows + RB - 1) / RB;
+    const long long cap2 = static_cast<long long>(ruart_num_sms()) * 16;
+    const unsigned grid = static_cast<unsigned>(tiles < cap2 ? tiles : cap2);
+    if (slots == 1)
+      split_concat_rows_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(cs, rows, Kp, parts, RB, (__nv_bfloat16*)dst);
+    else if (slots == 2)
+      split_concat_rows_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(cs, rows, Kp, parts, RB, (__nv_bfloat16*)dst);
+    else
+      split_concat_rows_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(cs, rows, Kp, parts, RB, (__nv_bfloat16*)dst);
+  } else if (pairs)
     split_concat_bf16_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
         cs, rows, Kp, parts, (__nv_bfloat16*)dst);
   else

@@ -57,6 +57,30 @@ def test_lstm_tensor_core_recurrence_matches_fp32_fma_recurrence(B, L, H, ndir):
         assert torch.equal(got2, want)
 
 
+@pytest.mark.parametrize("rows,widths,parts", [(37, (300, 250, 250), 3), (1000, (768, 300, 12, 8, 300), 3),
+                                               (1, (2, 6, 10), 2), (513, (250,) * 7, 3), (5, (1000,) * 8, 2),
+                                               (9, (1250,) * 8, 3), (130, (126, 2), 1)])
+def test_split_concat_operand_is_the_exact_bf16_split_of_the_concatenation(rows, widths, parts):
+    """ruart_split_concat_bf16 (row-tiled kernel; flat kernel beyond Kp = 8192) on pitched sources, 8-column groups
+    that straddle two sources, a ragged last tile: every part bit-identical to the torch restatement."""
+    from ruart_b200 import sdnet_ops as K
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    pieces = []
+    for i, w in enumerate(widths):
+        full = torch.randn(rows, w + 2 * (i % 3), device="cuda", generator=g) * (10.0 ** (i % 4 - 2))
+        pieces.append(full[:, :w])                                  # pitched view, even pitch
+    got, Kp = K.split_concat(pieces, parts)
+    Ksum = sum(widths)
+    assert Kp == (Ksum + 63) // 64 * 64 and got.shape == (rows, parts * Kp)
+    x = torch.cat(pieces, 1)
+    for p in range(parts):
+        h = x.to(torch.bfloat16)
+        part = got[:, p * Kp:(p + 1) * Kp]
+        assert torch.equal(part[:, :Ksum], h), "part %d" % p
+        assert (part[:, Ksum:] == 0).all()
+        x = x - h.float()
+
+
 def test_attention_module_matches_oracle():
     from ruart_b200.Models import Layers
     Layers.set_dropout_prob(0.0)
