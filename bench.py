@@ -524,8 +524,9 @@ def main():
     H = 768
 
     class _Timed(object):
-        def __init__(self, flops):
+        def __init__(self, flops, shape="other"):
             self.flops = flops
+            self.shape = shape
 
         def __enter__(self):
             self.e0 = torch.cuda.Event(enable_timing=True)
@@ -534,7 +535,7 @@ def main():
 
         def __exit__(self, *a):
             self.e1.record()
-            gemm_events.append((self.e0, self.e1, self.flops))
+            gemm_events.append((self.e0, self.e1, self.flops, self.shape))
 
     null = contextlib.nullcontext()
 
@@ -559,9 +560,10 @@ def main():
         if name in ("ruart_subword_avg_layers", "ruart_subword_avg_layers_fold"):
             return _TimedK("subword_avg_layers")
         if name == "ruart_gemm_bf16_fold":     # the BERT GEMMs with the folded LayerNorms (bf16 mode)
-            return _Timed(2.0 * a[4] * a[5] * a[6])
+            shape = "ffn_up+gelu" if a[5] == 4 * H else ("ffn_down+residual" if a[6] == 4 * H else "attn_out+residual")
+            return _Timed(2.0 * a[4] * a[5] * a[6], shape)
         if name == "ruart_qkv_attention_fold":  # query/key/value GEMM with the attention in its epilogue: projection FLOPs only
-            return _Timed(2.0 * a[4] * a[5] * (a[6] * 192))
+            return _Timed(2.0 * a[4] * a[5] * (a[6] * 192), "qkv+attention")
         if name != "ruart_gemm_bf16":
             return null
         M_, N_, Kp_, terms = a[6], a[7], a[8], a[9]
@@ -636,9 +638,15 @@ def main():
         barrier()
         _lib.set_timing_hook(None)
         ms_instr = i0.elapsed_time(i1)
-        g_ms = sum(a.elapsed_time(b) for a, b, _ in gemm_events)
-        g_fl = sum(f for _, _, f in gemm_events)
+        g_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_events)
+        g_fl = sum(f for _, _, f, _ in gemm_events)
         n_gemm = len(gemm_events)
+        by_shape = {}
+        for a, b, f, sh in gemm_events:
+            rec = by_shape.setdefault(sh, [0, 0.0, 0.0])
+            rec[0] += 1
+            rec[1] += a.elapsed_time(b)
+            rec[2] += f
         k_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in kern_events.items()}
         k_n = {k: len(v) // args.steps for k, v in kern_events.items()}
 
@@ -715,6 +723,9 @@ def main():
                          "kernel": "gemm_bf16_2cta_kernel<EPI, RES, FOLD> + qkv_attn_2cta_kernel (all %d BERT GEMM launches of %d steps; "
                                    "the query/key/value GEMM carries the attention in its epilogue, its FLOPs are the projection's only)" % (n_gemm, args.steps),
                          "kernel_ms_per_step": g_ms / args.steps, "peak_source": peak_src,
+                         "by_shape": {sh: {"launches_per_step": r[0] // args.steps, "ms_per_step": r[1] / args.steps,
+                                           "achieved": r[2] / (r[1] * 1e-3) / 1e12, "frac": r[2] / (r[1] * 1e-3) / 1e12 / peak}
+                                      for sh, r in sorted(by_shape.items()) if r[1] > 0},
                          "instrumented_ms_per_step": ms_instr / args.steps,
                          "how": "CUDA events around every launch, in a second pass of the same steps right after the "
                                 "timed region (events between kernels slow a step by ~2 ms, so they stay out of `value`)"},

@@ -256,6 +256,10 @@ RUART_API int ruart_lstm_cell(const float* gx, const int32_t* row_gx, const floa
 RUART_API int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const float* w_hh,
                                     float* out, long long out_pitch, int B, int L, int H,
                                     int ndir, void* stream);
+/* Same recurrence on the fp32 FMA kernel only (the fp32 mode of the stack, SDNET_precision 'fp32').   */
+RUART_API int ruart_lstm_recurrence_f32(const float* xg, long long xg_pitch, const float* w_hh,
+                                        float* out, long long out_pitch, int B, int L, int H,
+                                        int ndir, void* stream);
 
 /* Answer-index rule of SDNetTrainer.predict (SDNetTrainer.py:402-412): out_idx[b] = index of the
  * largest probability among {last column (if label_no_answer)} U {i < num_cnt[b] - 1}.          */

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "ruart_lstm_cell": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                         c_int, c_void_p, c_void_p, c_void_p],
     "ruart_lstm_recurrence": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p],
+    "ruart_lstm_recurrence_f32": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p],
     "ruart_grad_sqnorm": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
     "ruart_adamax_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int,
                           c_void_p, c_float, c_void_p],

@@ -583,6 +583,220 @@ lstm_bptt_kernel(const float* __restrict__ gates, long long gates_pitch, const f
   }
 }
 
+// Tensor-core form of the same backward recurrence — the kernel that runs.  Mirror image of
+// lstm_recurrence_mma_kernel (lstm.cu): per step  dh_rec^T [H x 8] = W_hh^T [H x 4H] · d_pre^T [4H x 8]  on
+// mma.sync.m16n8k16 with W_hh^T as the A operand.  8 warps, 8 sequences per CTA (= N).  Warp w owns units
+// 16w .. 16w+15 (one 16-row tile); the K dimension is the four gates, each padded to 128 rows (32 k-steps).
+// The hi halves of the thread's A fragments live in registers for the whole sequence (128 registers), the lo
+// halves of BPM_KLO k-steps too, the others in shared memory in fragment order.  In the accumulator layout the
+// thread holds dh_rec of units (16w+g, 16w+8+g) for sequences (2c, 2c+1): exactly the four cells whose gate
+// gradients it computes next — no shuffle, no shared-memory round trip for dh.  Four accumulator chains
+// (k-step mod 4) keep dependent HMMAs apart.  d_pre is published as bf16 hi | lo rows [sequence][gate*128+unit]
+// (double buffered, ldmatrix.x4 as the B operand); the three product terms hi·hi + hi·lo + lo·hi give ~2^-16.
+// The saved activations (i, f, g, o, c) and dout of a thread's cells are staged two steps ahead by the
+// thread itself with 4-byte cp.async into a private slot of a 3-deep ring (c of the earlier time step — the
+// c_prev of the forget-gate gradient — is then already there), so no global latency sits inside a step.
+// Measured: profiles/r02_lstm_microbench.txt.
+constexpr int BPM_THREADS = 256;
+constexpr int BPM_BT = 8;
+constexpr int BPM_KS = 32;            // k-steps: 4 gates x 128 padded units / 16
+constexpr int BPM_KLO = 2;            // k-steps whose lo fragments stay in registers
+constexpr int BPM_DS = 520;           // bf16 pitch of a d_pre row (1040 B: ldmatrix rows on distinct banks)
+constexpr int BPM_SLOTS = 24;         // staged floats per thread and step: 4 cells x (i, f, g, o, c, dout)
+constexpr size_t BPM_SMEM = static_cast<size_t>(BPM_KS - BPM_KLO) * BPM_THREADS * 16 +
+                            2 * 2 * BPM_BT * BPM_DS * 2 + 3 * BPM_SLOTS * BPM_THREADS * 4;
+
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(BPM_THREADS, 1)
+lstm_bptt_mma_kernel(const float* __restrict__ gates, long long gates_pitch, const float* __restrict__ w_hh,
+                     const float* __restrict__ dout, long long dout_pitch, float* __restrict__ dxg,
+                     long long dxg_pitch, int B, int L, int H) {
+  extern __shared__ __align__(128) unsigned char bpm_smem[];
+  uint4* s_wlo = reinterpret_cast<uint4*>(bpm_smem);                                         // [KS-KLO][256]
+  __nv_bfloat16* s_dg = reinterpret_cast<__nv_bfloat16*>(bpm_smem + (BPM_KS - BPM_KLO) * BPM_THREADS * 16);  // [2][hi|lo][8][DS]
+  float* s_st = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_dg) + 2 * 2 * BPM_BT * BPM_DS * 2);  // [3][SLOTS][256]
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int dir = blockIdx.y;
+  const int b0 = blockIdx.x * BPM_BT;
+  const float* W = w_hh + static_cast<long long>(dir) * 4 * H * H;
+
+  // A = W_hh^T: A[unit u][kk = q*128 + j] = W_hh[q*H + j][u]
+  uint32_t whi[BPM_KS][4];
+  uint32_t wlo[BPM_KLO][4];
+  {
+    const int u0 = 16 * w + g, u1 = u0 + 8;
+#pragma unroll
+    for (int ks = 0; ks < BPM_KS; ++ks) {
+      uint32_t lo4[4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int kk = 16 * ks + 8 * hf + 2 * c;
+        const int q = kk >> 7, j = kk & 127;
+        const float* r = W + (static_cast<long long>(q) * H + j) * H;
+        const float v00 = (j < H && u0 < H) ? __ldg(r + u0) : 0.f;
+        const float v01 = (j + 1 < H && u0 < H) ? __ldg(r + H + u0) : 0.f;
+        const float v10 = (j < H && u1 < H) ? __ldg(r + u1) : 0.f;
+        const float v11 = (j + 1 < H && u1 < H) ? __ldg(r + H + u1) : 0.f;
+        const uint32_t h0 = pack_bf16x2(v00, v01), h1 = pack_bf16x2(v10, v11);
+        whi[ks][2 * hf] = h0;
+        whi[ks][2 * hf + 1] = h1;
+        lo4[2 * hf] = pack_bf16x2(v00 - bf16_lo(h0), v01 - bf16_hi(h0));
+        lo4[2 * hf + 1] = pack_bf16x2(v10 - bf16_lo(h1), v11 - bf16_hi(h1));
+      }
+      if (ks < BPM_KLO) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wlo[ks < BPM_KLO ? ks : 0][i] = lo4[i];
+      } else {
+        s_wlo[(ks - BPM_KLO) * BPM_THREADS + tid] = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+      }
+    }
+  }
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(s_dg);
+    for (int i = tid; i < 2 * 2 * BPM_BT * BPM_DS / 2; i += BPM_THREADS) z[i] = 0u;
+  }
+  __syncthreads();
+
+  // the thread's four cells: (unit 16w + 8ug + g, sequence 2c + e); staged slot v = (ug*2 + e)*6 + {i,f,g,o,c,dout}
+  long long rowL[2];   // (sequence of column e) * L, 0 when the sequence is outside the batch
+  int uu[2];           // unit of group ug, 0 when beyond H
+  bool ok[2][2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) rowL[e] = static_cast<long long>(b0 + 2 * c + e < B ? b0 + 2 * c + e : 0) * L;
+#pragma unroll
+  for (int ug = 0; ug < 2; ++ug) {
+    const int unit = 16 * w + 8 * ug + g;
+    uu[ug] = unit < H ? unit : 0;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) ok[ug][e] = unit < H && b0 + 2 * c + e < B;
+  }
+  const uint32_t st_base = smem_u32(s_st) + tid * 4;
+  auto stage = [&](int it) {   // iteration it handles step s = L-1-it, i.e. time index tt
+    if (it < L) {
+      const int s = L - 1 - it;
+      const long long tt = dir == 0 ? s : (L - 1 - s);
+      const uint32_t dst = st_base + (it % 3) * (BPM_SLOTS * BPM_THREADS * 4);
+#pragma unroll
+      for (int ug = 0; ug < 2; ++ug)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float* gr = gates + (rowL[e] + tt) * gates_pitch + dir * 5 * H + uu[ug];
+          const int v0 = (ug * 2 + e) * 6;
+#pragma unroll
+          for (int q = 0; q < 5; ++q)
+            cp_async4_zfill(dst + (v0 + q) * (BPM_THREADS * 4), gr + q * H, ok[ug][e]);
+          cp_async4_zfill(dst + (v0 + 5) * (BPM_THREADS * 4), dout + (rowL[e] + tt) * dout_pitch + dir * H + uu[ug],
+                          ok[ug][e]);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0);
+  stage(1);
+
+  float dh_rec[2][2], dc_carry[2][2];
+#pragma unroll
+  for (int ug = 0; ug < 2; ++ug) dh_rec[ug][0] = dh_rec[ug][1] = dc_carry[ug][0] = dc_carry[ug][1] = 0.f;
+  const uint32_t dg_base = smem_u32(s_dg);
+  const uint32_t lane_off = static_cast<uint32_t>(((lane & 7) * BPM_DS + 8 * (lane >> 3)) * 2);
+  constexpr uint32_t DBUF = 2 * BPM_BT * BPM_DS * 2;   // bytes per buffer (hi rows then lo rows)
+  constexpr uint32_t DLO = BPM_BT * BPM_DS * 2;
+  constexpr float L2E = 1.4426950408889634f;
+  for (int it = 0; it < L; ++it) {
+    const int s = L - 1 - it;
+    const long long tt = dir == 0 ? s : (L - 1 - s);
+    stage(it + 2);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // the groups of iterations it and it+1 have landed
+    const float* cur = s_st + (it % 3) * (BPM_SLOTS * BPM_THREADS) + tid;
+    const float* nxt = s_st + ((it + 1) % 3) * (BPM_SLOTS * BPM_THREADS) + tid;
+    __nv_bfloat16* dgw = s_dg + (it & 1) * (2 * BPM_BT * BPM_DS);
+#pragma unroll
+    for (int ug = 0; ug < 2; ++ug)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int v0 = (ug * 2 + e) * 6;
+        const float gi = cur[(v0 + 0) * BPM_THREADS], gf = cur[(v0 + 1) * BPM_THREADS];
+        const float gg = cur[(v0 + 2) * BPM_THREADS], go = cur[(v0 + 3) * BPM_THREADS];
+        const float cc = cur[(v0 + 4) * BPM_THREADS];
+        const float c_prev = (s > 0) ? nxt[(v0 + 4) * BPM_THREADS] : 0.f;
+        const float dh = cur[(v0 + 5) * BPM_THREADS] + dh_rec[ug][e];
+        const float E = ex2_approx(fminf(-2.f * L2E * cc, 80.f));
+        const float tc = (1.f - E) * rcp_approx(1.f + E);
+        const float d_o = dh * tc;
+        const float dc = fmaf(dh * go, 1.0f - tc * tc, dc_carry[ug][e]);
+        const float dai = dc * gg * gi * (1.0f - gi);
+        const float daf = dc * c_prev * gf * (1.0f - gf);
+        const float dag = dc * gi * (1.0f - gg * gg);
+        const float dao = d_o * go * (1.0f - go);
+        dc_carry[ug][e] = dc * gf;
+        if (ok[ug][e]) {
+          float* xr = dxg + (rowL[e] + tt) * dxg_pitch + dir * 4 * H + uu[ug];
+          xr[0] = dai;
+          xr[H] = daf;
+          xr[2 * H] = dag;
+          xr[3 * H] = dao;
+        }
+        // cells outside the batch / beyond H staged zeros: their gradients are zero
+        const int unit = 16 * w + 8 * ug + g, n = 2 * c + e;
+        __nv_bfloat16* dr = dgw + n * BPM_DS + unit;
+        const float da[4] = {dai, daf, dag, dao};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat16 hh = __float2bfloat16_rn(da[q]);
+          dr[q * 128] = hh;
+          dr[BPM_BT * BPM_DS + q * 128] = __float2bfloat16_rn(da[q] - __bfloat162float(hh));
+        }
+      }
+    __syncthreads();
+    if (s > 0) {   // the recurrent gradient is not needed before the first step
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      const uint32_t db = dg_base + (it & 1) * DBUF + lane_off;
+#pragma unroll
+      for (int kp = 0; kp < BPM_KS / 2; ++kp) {
+        if (((32 * kp) & 127) < H) {   // both k-steps of a pair lie in one gate; all-padding pairs are skipped
+          uint32_t bh[4], bl[4];
+          ldsm_x4(db + kp * 64, bh[0], bh[1], bh[2], bh[3]);
+          ldsm_x4(db + DLO + kp * 64, bl[0], bl[1], bl[2], bl[3]);
+          // chains: (kp even, kk) -> 0, 1 ; (kp odd, kk) -> 2, 3, each takes its three terms two issues apart
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int ks = 2 * kp + kk;
+            mma_bf16_16816(acc[2 * (kp & 1) + kk], whi[ks][0], whi[ks][1], whi[ks][2], whi[ks][3], bh[2 * kk], bh[2 * kk + 1]);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int ks = 2 * kp + kk;
+            mma_bf16_16816(acc[2 * (kp & 1) + kk], whi[ks][0], whi[ks][1], whi[ks][2], whi[ks][3], bl[2 * kk], bl[2 * kk + 1]);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int ks = 2 * kp + kk;
+            if (ks < BPM_KLO) {
+              const int kr = ks < BPM_KLO ? ks : 0;
+              mma_bf16_16816(acc[2 * (kp & 1) + kk], wlo[kr][0], wlo[kr][1], wlo[kr][2], wlo[kr][3], bh[2 * kk], bh[2 * kk + 1]);
+            } else {
+              const uint4 l4 = s_wlo[(ks - BPM_KLO) * BPM_THREADS + tid];
+              mma_bf16_16816(acc[2 * (kp & 1) + kk], l4.x, l4.y, l4.z, l4.w, bh[2 * kk], bh[2 * kk + 1]);
+            }
+          }
+        }
+      }
+      dh_rec[0][0] = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+      dh_rec[0][1] = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+      dh_rec[1][0] = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+      dh_rec[1][1] = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------ multi2one
 // Training form of lstm_cell_kernel (sdnet_kernels.cu): same update with accurate expf / tanhf, also
 // saving (i, f, g, o, c, h) of the step in save[r][6H].
@@ -841,6 +1055,20 @@ extern "C" int ruart_lstm_recurrence_backward(const float* gates, long long gate
                                               void* stream) {
   RUART_ARG_CHECK(gates != nullptr && w_hh != nullptr && dout != nullptr && dxg != nullptr);
   RUART_ARG_CHECK(B > 0 && L > 0 && H > 0 && H <= BP_HP && BP_BT * H <= BP_THREADS && (ndir == 1 || ndir == 2));
+  static const bool fma_form = getenv("RUART_LSTM_BPTT_FMA") != nullptr;   // A/B aid: the fp32 FMA kernel
+  if (!fma_form) {
+    static RuartDeviceOnce attr_set;
+    if (!attr_set.done()) {
+      RUART_CUDA_CHECK(cudaFuncSetAttribute(lstm_bptt_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)BPM_SMEM));
+      attr_set.set();
+    }
+    dim3 grid((B + BPM_BT - 1) / BPM_BT, ndir);
+    lstm_bptt_mma_kernel<<<grid, BPM_THREADS, BPM_SMEM, (cudaStream_t)stream>>>(gates, gates_pitch, w_hh, dout,
+                                                                               dout_pitch, dxg, dxg_pitch, B, L, H);
+    RUART_LAUNCH_CHECK();
+    return RUART_OK;
+  }
   dim3 grid((B + BP_BT - 1) / BP_BT, ndir);
   lstm_bptt_kernel<<<grid, BP_THREADS, 0, (cudaStream_t)stream>>>(gates, gates_pitch, w_hh, dout, dout_pitch,
                                                                  dxg, dxg_pitch, B, L, H);

@@ -597,9 +597,9 @@ int launch(const float* xg, long long xg_pitch, const float* w_hh, float* out, l
 
 }  // namespace
 
-extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const float* w_hh,
-                                     float* out, long long out_pitch, int B, int L, int H,
-                                     int ndir, void* stream) {
+static int lstm_recurrence_dispatch(const float* xg, long long xg_pitch, const float* w_hh,
+                                    float* out, long long out_pitch, int B, int L, int H,
+                                    int ndir, void* stream, bool tensor_cores) {
   RUART_ARG_CHECK(B > 0 && L > 0 && H > 0 && H <= 128 && (ndir == 1 || ndir == 2));
   cudaStream_t st = (cudaStream_t)stream;
   // fewest sequences per CTA that still fits one wave of CTAs on the device
@@ -607,7 +607,7 @@ extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const 
   // tensor-core form unless switched off (A/B aid) or the xg rows cannot be bulk-copied (16-byte alignment)
   static const char* fma_env = getenv("RUART_LSTM_FMA");
   static const char* klo_env = getenv("RUART_LSTM_KLO");
-  if (!fma_env && (xg_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(xg) & 15) == 0) {
+  if (tensor_cores && !fma_env && (xg_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(xg) & 15) == 0) {
     const int klo = klo_env ? atoi(klo_env) : 3;  // lo fragments of that many k-steps in registers (A/B aid)
     if (klo == 0) return launch_mma<0>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
     if (klo == 2) return launch_mma<2>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
@@ -623,6 +623,21 @@ extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const 
   // larger batches: several waves of the same kernel (measured 1.45x faster than one wave of the
   // one-row kernel with 8 sequences per CTA: 517 vs 751 us at B = 512, L = 100)
   return launch2<4, 88>(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, st);
+}
+
+// The production form: tensor cores, W_hh and h as bf16 hi | lo splits (~2^-16 relative, the precision of the 2-part
+// SDNet stack next to a bf16 BERT).
+extern "C" int ruart_lstm_recurrence(const float* xg, long long xg_pitch, const float* w_hh,
+                                     float* out, long long out_pitch, int B, int L, int H,
+                                     int ndir, void* stream) {
+  return lstm_recurrence_dispatch(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, stream, true);
+}
+
+// fp32 FMA recurrence (the fp32 mode of the stack, 3-part operands everywhere else): same arguments.
+extern "C" int ruart_lstm_recurrence_f32(const float* xg, long long xg_pitch, const float* w_hh,
+                                         float* out, long long out_pitch, int B, int L, int H,
+                                         int ndir, void* stream) {
+  return lstm_recurrence_dispatch(xg, xg_pitch, w_hh, out, out_pitch, B, L, H, ndir, stream, false);
 }
 
 // Training form: same recurrence, additionally saving the activated gates and the

@@ -213,7 +213,9 @@ def lstm_layer(owner, x, key, w_ih, w_hh, b_ih, b_hh, H, parts, out, whole_ln=Fa
     xg = torch.empty((B * L, ndir * 4 * H), dtype=torch.float32, device=xs[0].device)
     linear(a, Kp, w, B * L, ndir * 4 * H, parts, xg, epi=ops.EPI_BIAS, bias=bias)
     _, _, op = rows2d(out)
-    call("ruart_lstm_recurrence", ptr(xg), xg.stride(0), ptr(whh), ptr(out), op, B, L, H, ndir, current_stream())
+    # fp32 mode (3-part operands): the fp32 FMA recurrence; otherwise the tensor-core one (bf16 hi|lo, ~2^-16)
+    call("ruart_lstm_recurrence_f32" if parts == 3 else "ruart_lstm_recurrence", ptr(xg), xg.stride(0), ptr(whh),
+         ptr(out), op, B, L, H, ndir, current_stream())
     if whole_ln:
         whole_layernorm_(out)
     return out

@@ -57,6 +57,47 @@ def test_lstm_tensor_core_recurrence_matches_fp32_fma_recurrence(B, L, H, ndir):
         assert torch.equal(got2, want)
 
 
+@pytest.mark.parametrize("B,L,H,ndir", [(7, 9, 125, 2), (33, 12, 128, 2), (1, 1, 125, 2), (9, 2, 17, 1), (20, 3, 64, 2)])
+def test_lstm_bptt_tensor_core_kernel_matches_torch_autograd(B, L, H, ndir):
+    """ruart_lstm_recurrence_backward (mma.sync on bf16 hi|lo splits of W_hh^T and the gate gradients) on the gates
+    saved by ruart_lstm_recurrence_train, against torch autograd through a plain restatement of the recurrence."""
+    from ruart_b200._lib import current_stream, ptr
+    from ruart_b200.ops import call
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + L)
+    xg = (torch.randn(B, L, ndir * 4 * H, device="cuda", generator=g) * 0.8).requires_grad_(True)
+    whh = (torch.rand(ndir, 4 * H, H, device="cuda", generator=g) * 2 - 1) / H ** 0.5
+    dout = torch.randn(B, L, ndir * H, device="cuda", generator=g)
+    outs = []
+    for d in range(ndir):
+        h = torch.zeros(B, H, device="cuda")
+        c = torch.zeros(B, H, device="cuda")
+        hs = [None] * L
+        for s in range(L):
+            t = s if d == 0 else L - 1 - s
+            pre = xg[:, t, d * 4 * H:(d + 1) * 4 * H] + h @ whh[d].t()
+            i, f, gg, o = pre.split(H, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            hs[t] = h
+        outs.append(torch.stack(hs, 1))
+    ref_out = torch.cat(outs, 2)
+    want = torch.autograd.grad(ref_out, xg, dout)[0].reshape(B * L, ndir * 4 * H)
+    st = current_stream()
+    out = torch.empty(B, L, ndir * H, device="cuda")
+    gates = torch.empty(B * L, ndir * 5 * H, device="cuda")
+    xg2 = xg.detach().reshape(B * L, -1).contiguous()
+    call("ruart_lstm_recurrence_train", ptr(xg2), ndir * 4 * H, ptr(whh), ptr(out), ndir * H, B, L, H, ndir,
+         ptr(gates), ndir * 5 * H, st)
+    assert (out - ref_out).abs().max().item() < 2e-5
+    got = torch.full((B * L, ndir * 4 * H + 2), 7.0, device="cuda")
+    call("ruart_lstm_recurrence_backward", ptr(gates), ndir * 5 * H, ptr(whh), ptr(dout), ndir * H, ptr(got),
+         ndir * 4 * H + 2, B, L, H, ndir, st)
+    torch.cuda.synchronize()
+    assert (got[:, ndir * 4 * H:] == 7.0).all()             # nothing written past the row
+    err = (got[:, :ndir * 4 * H] - want).abs().max().item()
+    assert err < 2e-5 * max(1.0, want.abs().max().item()), err
+
+
 @pytest.mark.parametrize("rows,widths,parts", [(37, (300, 250, 250), 3), (1000, (768, 300, 12, 8, 300), 3),
                                                (1, (2, 6, 10), 2), (513, (250,) * 7, 3), (5, (1000,) * 8, 2),
                                                (9, (1250,) * 8, 3), (130, (126, 2), 1)])
