@@ -412,7 +412,7 @@ def run_train(args, rank, world, local_rank):
             "metric": "ST-VQA training questions/sec (one SDNetTrainer.update per step)", "mode": "train",
             "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 BERT (locked) / fp32 SDNet stack, 3-part split GEMM operands",
+            "vs_baseline": None, "dtype": "bf16 BERT (locked) / fp32 SDNet stack, GEMM operands (forward, dgrad, wgrad) as 2-part bf16 splits (~2^-16), like the inference path",
             "data": "synthetic",
             "config": {"workload": "%s training step: B=%d questions per GPU, %d+1 OCR items, dropout 0, Adamax lr %g, "
                                    "grad clip %g, TUNE_PARTIAL %d" % (cfg, B, synth.CONFIGS[cfg]["n_ocr"], opt["lr"],

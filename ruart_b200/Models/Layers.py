@@ -52,6 +52,14 @@ def set_sdnet_precision(parts):
 train_parts = 3  # split width of the GEMM operands in the differentiable form (3 = fp32 grade)
 
 
+def set_train_precision(parts):
+    """Split width of the differentiable form's GEMM operands (forward, dgrad, wgrad): 3 = fp32 grade (6 products),
+    2 = ~2^-16 relative (3 products) — what SDNet picks next to a bf16 BERT, like the inference path."""
+    global train_parts
+    assert parts in (2, 3)
+    train_parts = parts
+
+
 def grad_mode(module=None):
     """True when the differentiable form must run: autograd is recording and the module trains."""
     return torch.is_grad_enabled() and (module is None or module.training)

@@ -252,6 +252,7 @@ class SDNet(nn.Module):
                                "there is no CPU fallback")
         if Layers.grad_mode(self):
             # SDNetTrainer.update (SDNetTrainer.py:332-337): network.train(), autograd recording
+            Layers.set_train_precision(max(2, self.sdnet_parts))
             return self._forward_differentiable(q_list, ocr_list, od_list), att_score
         if self.training and (Layers.dropout_p > 0 or (self.drop_emb and self.opt.get('dropout_emb', 0) > 0)):
             raise NotImplementedError("train-mode dropout needs autograd enabled (the differentiable form); "

@@ -105,6 +105,36 @@ def test_training_step_matches_oracle_gradients_and_reference_update():
     assert (probs.cpu() - want_p).abs().max().item() < 1e-4
 
 
+def test_two_part_training_precision_tracks_the_fp32_grade_gradients():
+    """SDNET_precision 'bf16x2' (what a bf16 BERT selects; bench.py --train): forward, dgrad and wgrad GEMMs on 2-part
+    splits (~2^-16).  Same net, same batch, fp32 BERT in both runs: every gradient within 1e-3 of the 3-part run."""
+    opt = train_opt("tiny")
+    batch = synth.make_batch("tiny", ragged=True)
+    targets = make_targets(batch, opt["max_ocr_num"]).cuda()
+    res = {}
+    for prec in ("fp32", "bf16x2"):
+        net, _ = build_ours("tiny", seed=1033, device="cuda", DROPOUT=0.0, dropout_emb=0.0, BERT_precision="fp32",
+                            SDNET_precision=prec)
+        net.train()
+        net.drop_emb = True
+        scores, _ = net(*synth.batch_to(copy.deepcopy(batch), "cuda"))
+        loss = F.binary_cross_entropy_with_logits(scores, targets) * targets.size(1)
+        named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+        grads = torch.autograd.grad(loss, [p for _, p in named], allow_unused=True)
+        res[prec] = (float(loss), {n: g_ for (n, _), g_ in zip(named, grads) if g_ is not None})
+    from ruart_b200.Models import Layers
+    assert Layers.train_parts == 2
+    assert abs(res["fp32"][0] - res["bf16x2"][0]) < 1e-4 * abs(res["fp32"][0])
+    assert res["fp32"][1].keys() == res["bf16x2"][1].keys()
+    differs = False
+    for n, a in res["fp32"][1].items():
+        b = res["bf16x2"][1][n]
+        if float(a.norm()) > 1e-6:
+            assert float((a - b).norm() / a.norm()) < 1e-3, n
+        differs = differs or not torch.equal(a, b)
+    assert differs                                                # the 2-part path really ran
+
+
 def test_differentiable_forward_equals_fused_inference_forward():
     net, opt = build_ours("small", seed=77, device="cuda", DROPOUT=0.0, dropout_emb=0.0, BERT_precision="fp32",
                           KEEP_LOGITS=True)
