@@ -24,10 +24,31 @@ TOTALS_KEY = "bert_totals"     # (real wordpieces of the list, longest 512-token
 WINDOW = 512                   # Bert.BERT_MAX_LEN (Bert.py:18)
 
 
+def check_offsets(csr, mask):
+    """The packed encoder keeps only the real wordpieces of a row, so (a) `bert_mask` must be a contiguous
+    prefix of each row (what `~ids.eq(0)` gives for the reference's right-padded ids, VQA_Dataset.py:476-542)
+    and (b) a word's [st, ed) must lie inside its row's real wordpieces.  The reference would read a pad
+    position's hidden state for an offset past them (Bert.py:153-165); here that position does not exist, so it
+    is an error instead of a silent read of the neighbouring row.  Degenerate spans (st >= ed) read nothing."""
+    mask = mask.numpy() if torch.is_tensor(mask) else np.asarray(mask)
+    if mask.size and (mask[:, 1:] & ~mask[:, :-1]).any():
+        raise ValueError("bert_mask must be a contiguous prefix of every row (right-padded wordpiece ids)")
+    if csr.shape[1] == 0:
+        return
+    lens = mask.sum(1)
+    live = csr[2] < csr[3]
+    bad = live & ((csr[2] < 0) | (csr[3] > lens[csr[0]]))
+    if bad.any():
+        k = int(np.flatnonzero(bad)[0])
+        raise ValueError("bert_offsets: word %d of row %d spans wordpieces [%d, %d) but the row has %d"
+                         % (csr[1, k], csr[0, k], csr[2, k], csr[3, k], lens[csr[0, k]]))
+
+
 def attach_index_tensors(q_list, ocr_list, od_list):
     for d in (q_list, ocr_list, od_list):
         d[CSR_KEY] = flatten_offsets(d["bert_offsets"], len(d["bert_offsets"]))
         m = d["bert_mask"].cpu() != 0
+        check_offsets(d[CSR_KEY], m)
         longest = max((int(m[:, p:p + WINDOW].sum(1).max()) for p in range(0, m.shape[1], WINDOW)), default=0) \
             if m.shape[0] else 0
         d[TOTALS_KEY] = (int(m.sum()), longest)

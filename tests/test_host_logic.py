@@ -176,3 +176,25 @@ def test_shard_batch_drops_whole_batch_index_keys_and_rejects_empty_shards():
         assert ocr2["ruart_plan"]["key"][0] == 4
     with pytest.raises(ValueError, match="empty shard"):
         synth.shard_batch(synth.make_batch("tiny"), 3, 4)
+
+
+def test_collate_rejects_offsets_past_the_real_wordpieces_and_non_prefix_masks():
+    # the packed encoder has no pad positions: what the reference would read from one (Bert.py:153-165) is an
+    # error here, raised on the host before anything is uploaded; degenerate spans (st >= ed) stay legal
+    import copy
+    import pytest
+    from ruart_b200.Utils import collate
+    q, ocr, od = synth.make_batch("tiny", ragged=True)
+    collate.attach_index_tensors(*copy.deepcopy((q, ocr, od)))            # the synthetic batch itself is clean
+    row_len = int(ocr["bert_mask"][0].sum())
+    bad = copy.deepcopy((q, ocr, od))
+    bad[1]["bert_offsets"][0][0] = [1, row_len + 1]
+    with pytest.raises(ValueError, match="spans wordpieces"):
+        collate.attach_index_tensors(*bad)
+    ok = copy.deepcopy((q, ocr, od))
+    ok[1]["bert_offsets"][0][0] = [row_len + 3, row_len + 3]               # st == ed: reads nothing
+    collate.attach_index_tensors(*ok)
+    holes = copy.deepcopy((q, ocr, od))
+    holes[0]["bert_mask"][0, 1] = False                                    # a hole inside the row
+    with pytest.raises(ValueError, match="contiguous prefix"):
+        collate.attach_index_tensors(*holes)
