@@ -275,7 +275,8 @@ def run_reference_arm(args, rank, world):
     sample = "%d questions of the %s shape per step (fp32, torch CPU, %d threads)" % (n_q, args.cfg, threads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.cfg == "cfg4" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload_desc(args.cfg, world)},
         "cpu_baseline": dict({"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                              **port_vs_reference()),
