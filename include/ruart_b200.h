@@ -327,10 +327,14 @@ RUART_API int ruart_whole_layernorm_backward(const float* y, long long y_pitch, 
                                              long long dy_pitch, long long rows, int cols,
                                              const float* stats, double* workspace, float* dx,
                                              long long dx_pitch, void* stream);
-/* nn.Embedding weight gradient (SDNet.py:447-492 lookups): dW[v] (+)= sum_{k: ids[k] == v} dy[k], summed in
- * ascending k by one warp per vocabulary row (deterministic, no atomics).  workspace: >= round_up(n, 16) bytes
- * (flags of the positions whose gradient row is non-zero; all-zero rows — the pad-word slots — are skipped)
- * plus, for tables with V < 2048, up to 64 * V * D floats of per-segment partial sums.                      */
+/* nn.Embedding weight gradient (the backward of SDNet.py:447-492's lookups): dW[v] (+)= sum of dy[k] over the
+ * positions k with ids[k] == v, in an order that depends on the ids alone (deterministic, no floating-point
+ * atomics).  All-zero gradient rows (the pad-word slots) and ids outside [0, V) are skipped.
+ * workspace >= ruart_embedding_grad_workspace_bytes(n, V, D) selects the sorted form (counting sort of the live
+ * positions by row, then one warp per 64 consecutive sorted positions: work ~ n, not V x n).  A smaller workspace
+ * — at least round_up(n, 16) bytes, plus up to 64 * V * D floats of per-segment partial sums for V < 2048 — runs the
+ * first form, one warp per vocabulary row scanning the id list in ascending k.                                  */
+RUART_API long long ruart_embedding_grad_workspace_bytes(long long n, int V, int D);
 RUART_API int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
                                    long long dy_pitch, int D, int V, uint8_t* workspace,
                                    long long workspace_bytes, float* dW, long long dw_pitch, int accumulate,

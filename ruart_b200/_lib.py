@@ -86,6 +86,7 @@ _SIGNATURES = {
     "ruart_whole_layernorm_stats": [c_void_p, c_ll, c_int, c_ll, c_float, c_void_p, c_void_p, c_void_p],
     "ruart_whole_layernorm_backward": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                        c_ll, c_void_p],
+    "ruart_embedding_grad_workspace_bytes": [c_ll, c_int, c_int],
     "ruart_embedding_grad": [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int,
                              c_void_p],
     "ruart_subword_layers_backward": [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
@@ -100,7 +101,7 @@ _SIGNATURES = {
     "ruart_lstm_cell_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"ruart_last_error": ctypes.c_char_p}
+_RESTYPES = {"ruart_last_error": ctypes.c_char_p, "ruart_embedding_grad_workspace_bytes": ctypes.c_longlong}
 
 
 def declared_symbols():
@@ -141,7 +142,7 @@ def check(rc):
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
 _KERNELS_PER_CALL = {"ruart_seq_tiles": 2, "ruart_whole_layernorm": 2, "ruart_whole_layernorm_stats": 2, "ruart_colsum": 2,
-                     "ruart_whole_layernorm_backward": 2, "ruart_subword_layers_backward": 2, "ruart_embedding_grad": 3}
+                     "ruart_whole_layernorm_backward": 2, "ruart_subword_layers_backward": 2, "ruart_embedding_grad": 6}
 launch_count = 0
 _timing_hook = None  # set by bench.py: callable(name, args) -> context manager, or None
 

@@ -15,7 +15,7 @@ grade, the default for training: gradients within 1e-4 of the fp32 reference).
 import torch
 from torch.autograd import Function
 
-from . import ops
+from . import _lib, ops
 from . import sdnet_ops as K
 from ._lib import current_stream, ptr
 from .ops import call
@@ -427,7 +427,7 @@ class EmbeddingFn(Function):
         dy2 = _c(dy).view(-1, D)
         dw = _f32((V, D), dy.device)
         n = flat.numel()
-        ws_bytes = ops.round_up(max(n, 1), 16) + (64 * V * D * 4 if V < 2048 else 0)
+        ws_bytes = int(_lib.lib().ruart_embedding_grad_workspace_bytes(n, V, D))      # the sorted form
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dy.device)
         call("ruart_embedding_grad", ptr(flat), 1 if flat.dtype == torch.int64 else 0, n, ptr(dy2), D, D, V,
              ptr(ws), ws_bytes, ptr(dw), D, 0, current_stream())

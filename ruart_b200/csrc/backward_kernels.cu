@@ -398,6 +398,186 @@ __global__ void embedding_grad_reduce_kernel(const float* __restrict__ partial, 
   }
 }
 
+// Sorted form (the default): work proportional to the number of live positions instead of V x n.
+//   1. flag + count    live positions per vocabulary row (integer atomics: the COUNTS are deterministic)
+//   2. scan            start[v] = exclusive prefix of the counts, start[V] = number of live positions
+//   3. fill            the live positions of row v land in pos[start[v] .. start[v+1]) in arbitrary order
+//   4. rank            every entry counts the smaller entries of its own bucket -> sorted[] holds each bucket in
+//                      ascending k (one thread per entry: a heavy bucket is ranked by as many threads as it has
+//                      entries, all reading the same addresses)
+//   5. slab sums       one warp per EG_SLAB consecutive entries of sorted[], whatever rows they belong to: rows
+//                      lying inside one slab are written straight to dW, a row that crosses slab borders leaves one
+//                      partial sum per slab (at most the first and the last run of a slab can be such)
+//   6. combine         rows that cross slab borders: partial sums added in slab order; rows without a live
+//                      position: zeros
+// The summation order is a function of the ids alone (ascending k inside a slab, slabs in ascending order), so the
+// result is deterministic, and equal bit for bit to the one-warp-per-row walk for every row inside one slab.
+constexpr int EG_SLAB = 64;
+constexpr int EG_ACC = 10;   // columns per lane and pass: D <= 320 (the 300-wide word tables) in one pass
+
+template <typename I>
+__global__ void __launch_bounds__(256)
+eg_flag_count_kernel(const float* __restrict__ dy, long long dy_pitch, long long n, int D,
+                     const I* __restrict__ ids, int V, uint8_t* __restrict__ flag, int* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long k = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+    const float* row = dy + k * dy_pitch;
+    bool nz = false;
+    for (int c = lane; c < D; c += 32) nz |= (row[c] != 0.f);
+    nz = __any_sync(0xffffffffu, nz);
+    if (lane == 0) {
+      const long long v = static_cast<long long>(ids[k]);
+      const bool live = nz && v >= 0 && v < V;      // ids outside the table have no row to add to
+      flag[k] = live ? 1 : 0;
+      if (live) atomicAdd(cnt + v, 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) eg_scan_kernel(int* __restrict__ cnt, int* __restrict__ start, int V) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (V + 1023) / 1024;
+  const int b = tid * per, e = (b + per < V) ? b + per : V;
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += cnt[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int add = (tid >= off) ? s_part[tid - off] : 0;
+    __syncthreads();
+    s_part[tid] += add;
+    __syncthreads();
+  }
+  int run = s_part[tid] - sum;
+  for (int i = b; i < e; ++i) {
+    const int c = cnt[i];
+    start[i] = run;
+    cnt[i] = 0;          // becomes the fill cursor
+    run += c;
+  }
+  if (tid == 1023) start[V] = s_part[1023];
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256)
+eg_fill_kernel(const I* __restrict__ ids, const uint8_t* __restrict__ flag, long long n,
+               const int* __restrict__ start, int* __restrict__ cursor, int* __restrict__ pos) {
+  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (flag[k]) {
+      const int v = static_cast<int>(ids[k]);
+      pos[start[v] + atomicAdd(cursor + v, 1)] = static_cast<int>(k);
+    }
+  }
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256)
+eg_rank_kernel(const I* __restrict__ ids, const int* __restrict__ start, int V, const int* __restrict__ pos,
+               int* __restrict__ sorted) {
+  const int total = start[V];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = pos[i];
+    const int v = static_cast<int>(ids[k]);
+    const int s = start[v], e = start[v + 1];
+    int rank = 0;
+    for (int j = s; j < e; ++j) rank += (pos[j] < k) ? 1 : 0;
+    sorted[s + rank] = k;
+  }
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256)
+eg_slab_kernel(const I* __restrict__ ids, const int* __restrict__ start, int V, const int* __restrict__ sorted,
+               const float* __restrict__ dy, long long dy_pitch, int D, float* __restrict__ partial,
+               float* __restrict__ dW, long long dw_pitch, int accumulate) {
+  __shared__ int s_k[8][EG_SLAB];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int total = start[V];
+  const int n_slabs = (total + EG_SLAB - 1) / EG_SLAB;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_slabs; t += warps) {
+    const int b0 = t * EG_SLAB, b1 = (b0 + EG_SLAB < total) ? b0 + EG_SLAB : total;
+    for (int j = lane; j < b1 - b0; j += 32) s_k[w][j] = sorted[b0 + j];
+    __syncwarp();
+    for (int c0 = 0; c0 < D; c0 += 32 * EG_ACC) {
+      int j = 0;
+      while (j < b1 - b0) {
+        const int v = static_cast<int>(ids[s_k[w][j]]);
+        const int s = start[v], e = start[v + 1];
+        const int j2 = ((e < b1) ? e : b1) - b0;            // the run of row v inside this slab is [j, j2)
+        float acc[EG_ACC];
+#pragma unroll
+        for (int i = 0; i < EG_ACC; ++i) acc[i] = 0.f;
+        int jj = j;
+        for (; jj + 4 <= j2; jj += 4) {                       // four gradient rows in flight, added in order
+          float r[4][EG_ACC];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* row = dy + static_cast<long long>(s_k[w][jj + u]) * dy_pitch;
+#pragma unroll
+            for (int i = 0; i < EG_ACC; ++i) {
+              const int c = c0 + lane + 32 * i;
+              r[u][i] = (c < D) ? row[c] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < EG_ACC; ++i) acc[i] += r[u][i];
+        }
+        for (; jj < j2; ++jj) {
+          const float* row = dy + static_cast<long long>(s_k[w][jj]) * dy_pitch;
+#pragma unroll
+          for (int i = 0; i < EG_ACC; ++i) {
+            const int c = c0 + lane + 32 * i;
+            if (c < D) acc[i] += row[c];
+          }
+        }
+        const bool complete = (s >= b0) && (e <= b1);
+        float* out = complete ? dW + static_cast<long long>(v) * dw_pitch
+                              : partial + static_cast<long long>(j == 0 ? 2 * t : 2 * t + 1) * D;
+#pragma unroll
+        for (int i = 0; i < EG_ACC; ++i) {
+          const int c = c0 + lane + 32 * i;
+          if (c < D) out[c] = (complete && accumulate) ? out[c] + acc[i] : acc[i];
+        }
+        j = j2;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+eg_combine_kernel(const int* __restrict__ start, int V, const float* __restrict__ partial, int D,
+                  float* __restrict__ dW, long long dw_pitch, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
+    const int s = start[v], e = start[v + 1];
+    float* out = dW + static_cast<long long>(v) * dw_pitch;
+    if (e == s) {
+      if (!accumulate)
+        for (int c = lane; c < D; c += 32) out[c] = 0.f;
+      continue;
+    }
+    const int ta = s / EG_SLAB, tb = (e - 1) / EG_SLAB;
+    if (ta == tb) continue;                                   // inside one slab: written by eg_slab_kernel
+    for (int c = lane; c < D; c += 32) {
+      float sum = 0.f;
+      for (int t = ta; t <= tb; ++t)
+        sum += partial[static_cast<long long>(s <= t * EG_SLAB ? 2 * t : 2 * t + 1) * D + c];
+      out[c] = accumulate ? out[c] + sum : sum;
+    }
+  }
+}
+
+inline long long eg_round16(long long x) { return (x + 15) / 16 * 16; }
+
 // ------------------------------------------------------------------------------------------ subword
 // s[l] = sum over words of < dy[word], mean_{t in [st,ed)} h_l[row_start[item] + t] >   (Bert.py:149-165):
 // the only quantity the gradients of alphaBERT / gammaBERT need (SDNet.py:573-583).  One warp per word.
@@ -431,6 +611,78 @@ subword_layers_bwd_kernel(const T* __restrict__ h, long long layer_stride, const
         float sum = 0.f;
         for (int t = 0; t < cnt; ++t) sum += static_cast<float>(hl[static_cast<long long>(t) * hidden + c]);
         dot = fmaf(sum * inv, g[c], dot);
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) s_acc[wid][l] += dot;   // per-warp accumulator, words in a fixed order
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_layers) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_acc[w][threadIdx.x];
+    partials[static_cast<long long>(blockIdx.x) * n_layers + threadIdx.x] = t;
+  }
+}
+
+// bf16 hidden states, hidden a multiple of 256 (768 for BERT-base): every lane owns hidden/256 groups of 8
+// consecutive columns, so a token row is read with 16-byte loads (hidden/256 per lane, all independent), the
+// gradient row is held in registers for the twelve layers, and two layers are in flight at a time.
+constexpr int SWV_MAX = 4;   // hidden <= 1024
+__global__ void __launch_bounds__(256)
+subword_layers_bwd_bf16v_kernel(const __nv_bfloat16* __restrict__ h, long long layer_stride,
+                                const int32_t* __restrict__ words, int n_words,
+                                const int32_t* __restrict__ row_start, const uint8_t* __restrict__ x_mask, int W,
+                                const float* __restrict__ dy, long long dy_stride, int n_layers, int hidden,
+                                double* __restrict__ partials) {
+  __shared__ double s_acc[8][SW_MAX_LAYERS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nv = hidden >> 8;
+  if (lane < SW_MAX_LAYERS) s_acc[wid][lane] = 0.0;
+  __syncwarp();
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+    const int item = words[w];
+    const int j = words[1LL * n_words + w];
+    const int st = words[2LL * n_words + w];
+    const int ed = words[3LL * n_words + w];
+    if (j >= W || x_mask[static_cast<long long>(item) * W + j] == 0 || ed <= st) continue;
+    const int cnt = ed - st;
+    const float inv = (cnt > 1) ? 1.0f / static_cast<float>(cnt) : 1.0f;
+    const float* g = dy + (static_cast<long long>(item) * W + j) * dy_stride;
+    float gr[SWV_MAX][8];
+#pragma unroll
+    for (int i = 0; i < SWV_MAX; ++i) {
+      if (i < nv) {
+        const float4 a = *reinterpret_cast<const float4*>(g + (lane + 32 * i) * 8);
+        const float4 b = *reinterpret_cast<const float4*>(g + (lane + 32 * i) * 8 + 4);
+        gr[i][0] = a.x * inv; gr[i][1] = a.y * inv; gr[i][2] = a.z * inv; gr[i][3] = a.w * inv;
+        gr[i][4] = b.x * inv; gr[i][5] = b.y * inv; gr[i][6] = b.z * inv; gr[i][7] = b.w * inv;
+      }
+    }
+    const long long t0 = static_cast<long long>(row_start[item]) + st;
+#pragma unroll 2
+    for (int l = 0; l < n_layers; ++l) {
+      const __nv_bfloat16* hl = h + static_cast<long long>(l) * layer_stride + t0 * hidden;
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < SWV_MAX; ++i) {
+        if (i < nv) {
+          float sum[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sum[u] = 0.f;
+          for (int t = 0; t < cnt; ++t) {
+            const uint4 v = *reinterpret_cast<const uint4*>(hl + static_cast<long long>(t) * hidden + (lane + 32 * i) * 8);
+            const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = __bfloat1622float2(p[u]);
+              sum[2 * u] += f.x;
+              sum[2 * u + 1] += f.y;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dot = fmaf(sum[u], gr[i][u], dot);
+        }
       }
       dot = warp_sum(dot);
       if (lane == 0) s_acc[wid][l] += dot;   // per-warp accumulator, words in a fixed order
@@ -984,6 +1236,41 @@ extern "C" int ruart_whole_layernorm_backward(const float* y, long long y_pitch,
   return RUART_OK;
 }
 
+extern "C" long long ruart_embedding_grad_workspace_bytes(long long n, int V, int D) {
+  if (n < 0 || V <= 0 || D <= 0) return -1;
+  const long long slabs = (n + EG_SLAB - 1) / EG_SLAB;
+  return eg_round16(n) + eg_round16((2LL * V + 1 + 2 * n) * 4) + 2 * slabs * D * 4;
+}
+
+template <typename I>
+static int embedding_grad_sorted(const I* ids, long long n, const float* dy, long long dy_pitch, int D, int V,
+                                 uint8_t* workspace, float* dW, long long dw_pitch, int accumulate,
+                                 cudaStream_t st) {
+  uint8_t* flag = workspace;
+  int* cnt = reinterpret_cast<int*>(workspace + eg_round16(n));
+  int* start = cnt + V;
+  int* pos = start + V + 1;
+  int* sorted = pos + n;
+  float* partial = reinterpret_cast<float*>(workspace + eg_round16(n) + eg_round16((2LL * V + 1 + 2 * n) * 4));
+  RUART_CUDA_CHECK(cudaMemsetAsync(cnt, 0, static_cast<size_t>(V) * 4, st));
+  eg_flag_count_kernel<I><<<grid_for(n * 32, 256), 256, 0, st>>>(dy, dy_pitch, n, D, ids, V, flag, cnt);
+  RUART_LAUNCH_CHECK();
+  eg_scan_kernel<<<1, 1024, 0, st>>>(cnt, start, V);
+  RUART_LAUNCH_CHECK();
+  eg_fill_kernel<I><<<grid_for(n, 256), 256, 0, st>>>(ids, flag, n, start, cnt, pos);
+  RUART_LAUNCH_CHECK();
+  eg_rank_kernel<I><<<grid_for(n, 256), 256, 0, st>>>(ids, start, V, pos, sorted);
+  RUART_LAUNCH_CHECK();
+  const long long slabs = (n + EG_SLAB - 1) / EG_SLAB;
+  eg_slab_kernel<I><<<grid_for(slabs * 32, 256), 256, 0, st>>>(ids, start, V, sorted, dy, dy_pitch, D, partial, dW,
+                                                               dw_pitch, accumulate);
+  RUART_LAUNCH_CHECK();
+  eg_combine_kernel<<<grid_for(static_cast<long long>(V) * 32, 256), 256, 0, st>>>(start, V, partial, D, dW,
+                                                                                   dw_pitch, accumulate);
+  RUART_LAUNCH_CHECK();
+  return RUART_OK;
+}
+
 extern "C" int ruart_embedding_grad(const void* ids, int idx_is_64, long long n, const float* dy,
                                     long long dy_pitch, int D, int V, uint8_t* workspace,
                                     long long workspace_bytes, float* dW, long long dw_pitch, int accumulate,
@@ -992,6 +1279,16 @@ extern "C" int ruart_embedding_grad(const void* ids, int idx_is_64, long long n,
   const long long flag_bytes = (n + 15) / 16 * 16;
   RUART_ARG_CHECK(workspace != nullptr && workspace_bytes >= flag_bytes);
   cudaStream_t st = (cudaStream_t)stream;
+  // sorted form whenever the caller's workspace holds it (ruart_embedding_grad_workspace_bytes); the
+  // one-warp-per-row scan below stays for smaller workspaces and as the A/B aid RUART_EMBGRAD_SCAN
+  static const bool scan_form = getenv("RUART_EMBGRAD_SCAN") != nullptr;
+  if (!scan_form && n > 0 && n < (1LL << 31) - EG_SLAB &&
+      workspace_bytes >= ruart_embedding_grad_workspace_bytes(n, V, D)) {
+    return idx_is_64 ? embedding_grad_sorted<long long>((const long long*)ids, n, dy, dy_pitch, D, V, workspace, dW,
+                                                        dw_pitch, accumulate, st)
+                     : embedding_grad_sorted<int32_t>((const int32_t*)ids, n, dy, dy_pitch, D, V, workspace, dW,
+                                                      dw_pitch, accumulate, st);
+  }
   if (n > 0) {
     row_nonzero_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(dy, dy_pitch, n, D, workspace);
     RUART_LAUNCH_CHECK();
@@ -1039,6 +1336,12 @@ extern "C" int ruart_subword_layers_backward(const float* h_f32, const void* h_b
   if (h_f32 != nullptr)
     subword_layers_bwd_kernel<float><<<blocks, 256, 0, st>>>(h_f32, layer_stride, words, n_words, row_start,
                                                              x_mask, W, dy, dy_stride, n_layers, hidden, workspace);
+  else if (hidden % 256 == 0 && hidden <= 256 * SWV_MAX && dy_stride % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(h_bf16) & 15) == 0 &&
+           layer_stride % 8 == 0 && getenv("RUART_SUBWORD_BWD_SCALAR") == nullptr)
+    subword_layers_bwd_bf16v_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)h_bf16, layer_stride, words, n_words,
+                                                            row_start, x_mask, W, dy, dy_stride, n_layers, hidden,
+                                                            workspace);
   else
     subword_layers_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
         (const __nv_bfloat16*)h_bf16, layer_stride, words, n_words, row_start, x_mask, W, dy, dy_stride,

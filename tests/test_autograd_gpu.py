@@ -196,14 +196,19 @@ def test_multi2one_real_steps_matches_padded_lstm_and_its_gradients():
         assert rel(a_, b_) < 1e-4
 
 
-def test_subword_mix_gradients_for_alpha_and_gamma():
-    # Bert.py:149-165 + SDNet.py:573-583 on synthetic hidden states: values and d/d(alpha, gamma)
+@pytest.mark.parametrize("bf16", [False, True])
+def test_subword_mix_gradients_for_alpha_and_gamma(bf16):
+    # Bert.py:149-165 + SDNet.py:573-583 on synthetic hidden states: values and d/d(alpha, gamma); bf16 hidden states
+    # (what the bf16 encoder keeps) take the 16-byte-load backward kernel
     from ruart_b200 import autograd_ops as A
     g = torch.Generator().manual_seed(8)
     NL, H, N, W = 12, 768, 4, 5
     lens = [6, 9, 4, 7]
     T = sum(lens)
     hs = torch.randn(NL, T, H, generator=g).cuda()
+    hs_b = hs.bfloat16() if bf16 else None
+    if bf16:
+        hs = hs_b.float()
     row_start = torch.tensor(np.cumsum([0] + lens[:-1]), dtype=torch.int32).cuda()
     words = []  # (item, j, st, ed)
     for i, n in enumerate(lens):
@@ -220,7 +225,7 @@ def test_subword_mix_gradients_for_alpha_and_gamma():
     wmask = wmask.cuda()
     alpha = leaf(NL, gen=g)
     gamma = leaf(1, 1, gen=g)
-    pack = (hs, None, T * H, wt, wt.shape[1], row_start, wmask, N, W, NL, H)
+    pack = (None if bf16 else hs, hs_b, T * H, wt, wt.shape[1], row_start, wmask, N, W, NL, H)
     out = A.subword_mix(alpha, gamma, pack)
     ref_layers = []
     for l in range(NL):
@@ -355,3 +360,66 @@ def test_train_mode_dropout_masks_scale_and_gradient():
     y2 = Layers.dropout(x, p=0.5, training=True)
     assert not torch.equal((y2 != 0)[:, 0], (y2 != 0)[:, 17])
     Layers.set_seq_dropout(True)
+
+
+@pytest.mark.parametrize("V,D,n,ids_kind,dtype", [
+    (5000, 300, 40000, "uniform", torch.int64),      # the word tables of a cfg-5 step
+    (5000, 300, 20000, "zipf", torch.int64),         # a few rows own most positions (buckets across many slabs)
+    (60000, 300, 3000, "uniform", torch.int32),      # real-vocabulary size: most rows empty
+    (50, 12, 30000, "uniform", torch.int64),         # pos table: every bucket spans slabs
+    (20, 8, 777, "single", torch.int64),             # one row owns everything
+    (7, 33, 64, "uniform", torch.int64), (7, 33, 65, "uniform", torch.int64), (3, 5, 1, "uniform", torch.int64),
+    (700, 321, 5000, "out_of_range", torch.int64),   # D > one column pass; ids outside the table are skipped
+])
+def test_embedding_grad_sorted_form(V, D, n, ids_kind, dtype):
+    """ruart_embedding_grad, sorted form (counting sort of the live positions + slab sums) against an fp64
+    index_add, against the first form (one warp per row, taken with a small workspace) and against itself
+    (deterministic: bit-identical repeats); `accumulate` adds to what dW holds."""
+    from ruart_b200 import _lib
+    from ruart_b200._lib import current_stream, ptr
+    from ruart_b200.ops import call
+    g = torch.Generator().manual_seed(V * 31 + n)
+    if ids_kind == "uniform":
+        ids = torch.randint(0, V, (n,), generator=g)
+    elif ids_kind == "zipf":
+        ids = torch.from_numpy(np.minimum(np.random.default_rng(n).zipf(1.2, n) - 1, V - 1))
+    elif ids_kind == "single":
+        ids = torch.full((n,), V - 1)
+    else:
+        ids = torch.randint(-3, V + 3, (n,), generator=g)
+    ids = ids.to(dtype).cuda()
+    dy = torch.randn(n, D, generator=g).cuda()
+    dy[torch.rand(n, generator=g).cuda() < 0.4] = 0          # pad-word slots: exactly zero rows
+    valid = (ids >= 0) & (ids < V)
+    ref = torch.zeros(V, D, dtype=torch.float64, device="cuda").index_add_(0, ids[valid].long(), dy[valid].double())
+    big = int(_lib.lib().ruart_embedding_grad_workspace_bytes(n, V, D))
+    small = (n + 15) // 16 * 16 + (64 * V * D * 4 if V < 2048 else 0)
+    assert big > small or V < 2048
+    is64 = 1 if dtype == torch.int64 else 0
+
+    def run(ws_bytes, accumulate=0, init=None):
+        ws = torch.empty(ws_bytes + 64, dtype=torch.uint8, device="cuda")
+        ws[ws_bytes:] = 0x5A                                   # guard band behind the workspace
+        dw = torch.full((V + 2, D), 7.25, device="cuda")       # guard rows around the table
+        if init is not None:
+            dw[1:V + 1] = init
+        call("ruart_embedding_grad", ptr(ids), is64, n, ptr(dy), D, D, V, ptr(ws), ws_bytes, dw.data_ptr() + 4 * D, D,
+             accumulate, current_stream())
+        torch.cuda.synchronize()
+        assert (ws[ws_bytes:] == 0x5A).all() and (dw[0] == 7.25).all() and (dw[V + 1] == 7.25).all()
+        return dw[1:V + 1].clone()
+
+    got = run(big)
+    scale = float(ref.abs().max().clamp_min(1.0))
+    assert float((got.double() - ref).abs().max()) < 2e-5 * scale
+    assert torch.equal(got, run(big))                          # deterministic
+    first = run(small) if small < big else None                # the scan form
+    if first is not None:
+        assert float((first.double() - ref).abs().max()) < 2e-5 * scale
+        # rows whose live positions fit one 64-entry slab are summed in the same order by both forms
+        cnt = torch.bincount(ids[valid & (dy != 0).any(1)].long(), minlength=V)
+        light = cnt <= 1
+        assert torch.equal(got[light], first[light])
+    init = torch.randn(V, D, generator=g).cuda()
+    acc = run(big, accumulate=1, init=init)
+    assert float((acc.double() - (ref + init.double())).abs().max()) < 2e-5 * scale

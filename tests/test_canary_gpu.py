@@ -113,12 +113,15 @@ def test_new_kernels_stay_inside_their_outputs():
         dyr = R(777, D)
         dyr[::3] = 0
         dw = Guarded((V, D))
-        ws_bytes = 784 + (64 * V * D * 4 if V < 2048 else 0)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
-        call("ruart_embedding_grad", ptr(ids), 1, 777, ptr(dyr), D, D, V, ptr(ws), ws_bytes, ptr(dw.view), D, 0, st)
-        dw.check("embedding_grad V=%d" % V)
         ref = torch.zeros(V, D, device="cuda").index_add_(0, ids, dyr)
-        assert torch.allclose(dw.view, ref, atol=1e-5)
+        from ruart_b200 import _lib
+        sorted_bytes = int(_lib.lib().ruart_embedding_grad_workspace_bytes(777, V, D))
+        for ws_bytes in (784 + (64 * V * D * 4 if V < 2048 else 0), sorted_bytes):   # first form, sorted form
+            ws = Guarded((ws_bytes // 4,))
+            call("ruart_embedding_grad", ptr(ids), 1, 777, ptr(dyr), D, D, V, ptr(ws.view), ws_bytes, ptr(dw.view), D, 0, st)
+            dw.check("embedding_grad V=%d" % V)
+            ws.check("embedding_grad workspace V=%d" % V, all_written=False)
+            assert torch.allclose(dw.view, ref, atol=1e-5)
 
     # LSTM with saved gates + BPTT: B not a multiple of the CTA's sequence count, H = 125
     B, L, H = 7, 9, 125
