@@ -1282,7 +1282,7 @@ extern "C" int ruart_embedding_grad(const void* ids, int idx_is_64, long long n,
   // sorted form whenever the caller's workspace holds it (ruart_embedding_grad_workspace_bytes); the
   // one-warp-per-row scan below stays for smaller workspaces and as the A/B aid RUART_EMBGRAD_SCAN
   static const bool scan_form = getenv("RUART_EMBGRAD_SCAN") != nullptr;
-  if (!scan_form && n > 0 && n < (1LL << 31) - EG_SLAB &&
+  if (!scan_form && n > 0 && n < (1LL << 31) - EG_SLAB && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
       workspace_bytes >= ruart_embedding_grad_workspace_bytes(n, V, D)) {
     return idx_is_64 ? embedding_grad_sorted<long long>((const long long*)ids, n, dy, dy_pitch, D, V, workspace, dW,
                                                         dw_pitch, accumulate, st)
@@ -1330,6 +1330,7 @@ extern "C" int ruart_subword_layers_backward(const float* h_f32, const void* h_b
   RUART_ARG_CHECK(n_layers >= 1 && n_layers <= SW_MAX_LAYERS && workspace != nullptr);
   RUART_ARG_CHECK(alpha != nullptr && gamma != nullptr && dalpha != nullptr && dgamma != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool scalar_form = getenv("RUART_SUBWORD_BWD_SCALAR") != nullptr;   // A/B aid
   int blocks = (n_words + 7) / 8;
   if (blocks > 256) blocks = 256;
   if (blocks < 1) blocks = 1;
@@ -1338,7 +1339,7 @@ extern "C" int ruart_subword_layers_backward(const float* h_f32, const void* h_b
                                                              x_mask, W, dy, dy_stride, n_layers, hidden, workspace);
   else if (hidden % 256 == 0 && hidden <= 256 * SWV_MAX && dy_stride % 4 == 0 &&
            (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(h_bf16) & 15) == 0 &&
-           layer_stride % 8 == 0 && getenv("RUART_SUBWORD_BWD_SCALAR") == nullptr)
+           layer_stride % 8 == 0 && !scalar_form)
     subword_layers_bwd_bf16v_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)h_bf16, layer_stride, words, n_words,
                                                             row_start, x_mask, W, dy, dy_stride, n_layers, hidden,
                                                             workspace);
